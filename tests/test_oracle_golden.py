@@ -1,0 +1,118 @@
+"""Pins the CPU oracle against outputs of the UNMODIFIED reference (tests/golden/*.npz, made by
+tests/golden/make_golden.py in the build container).  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+
+def _knn_sets_equal(pts, qry, idx_a, idx_b, oracle):
+    """index sets identical except where the k-th distance ties"""
+    da = np.sort(oracle.sq_dist_f32(qry[:, None, :], pts[idx_a]), axis=1)
+    db = np.sort(oracle.sq_dist_f32(qry[:, None, :], pts[idx_b]), axis=1)
+    np.testing.assert_array_equal(da, db)
+    for r in range(idx_a.shape[0]):
+        if set(idx_a[r]) != set(idx_b[r]):
+            diff = set(idx_a[r]) ^ set(idx_b[r])
+            kth = da[r, -1]
+            d = oracle.sq_dist_f32(qry[r][None], pts[list(diff)])
+            assert np.all(d == kth), 'row {} differs outside a tie'.format(r)
+
+
+def test_param_inventory(oracle, weights):
+    spec = oracle.param_spec()
+    assert len(spec) == 455
+    assert sum(int(np.prod(s)) for s in spec.values()) == 13774258
+    assert list(spec) == list(weights)
+
+
+def test_knn(oracle):
+    g = load_golden('knn')
+    idx, d2 = oracle.knn(g['pts'], g['qry'], 64)
+    assert np.all(np.diff(d2, axis=1) >= 0)
+    _knn_sets_equal(g['pts'], g['qry'], idx, g['idx64'].astype(np.int64), oracle)
+    idx1, _ = oracle.knn(g['pts'], g['qry'], 1)
+    _knn_sets_equal(g['pts'], g['qry'], idx1, g['idx1'].astype(np.int64), oracle)
+    # k > N is clamped to N (source/poco_utils.py:259-260)
+    idx_s, _ = oracle.knn(g['pts'][:10], g['qry'][:5], 16)
+    assert idx_s.shape == (5, 10)
+    np.testing.assert_array_equal(idx_s, g['idx_small'])
+
+
+def test_patches(oracle):
+    g = load_golden('patches')
+    loc = oracle.get_pts_local_ps(g['pts'], g['qry'], 50)
+    # the same 50 neighbours in the same order and the same fp32 arithmetic: bit exact unless ties reorder
+    np.testing.assert_allclose(np.sort(loc, axis=1), np.sort(g['pts_local_ps'], axis=1), rtol=0, atol=0)
+    assert np.abs(np.linalg.norm(loc, axis=2).max(axis=1) - 1).max() < 1e-6
+
+
+def test_fkaconv_layer_and_resblock(oracle, weights, weights_digest):
+    g = load_golden('fkaconv')
+    assert str(g['digest']) == weights_digest
+    pts, sup = g['pts'].T[None], g['support'].T[None]
+    ids = g['ids'].astype(np.int64)[None]
+    y = oracle.fkaconv_layer(weights, 'encoder.resnetb01.cv1', g['x32'], pts, sup, ids)
+    np.testing.assert_allclose(y, g['y_fka'], rtol=1e-4, atol=1e-5 * np.abs(g['y_fka']).max())
+    y = oracle.residual_block(weights, 'encoder.resnetb10', g['x64'], pts, sup, ids)
+    np.testing.assert_allclose(y, g['y_rb'], rtol=1e-4, atol=1e-5 * np.abs(g['y_rb']).max())
+    ids_same = g['ids_same'].astype(np.int64)[None]
+    y = oracle.residual_block(weights, 'encoder.resnetb01', g['x64'], pts, pts, ids_same)
+    np.testing.assert_allclose(y, g['y_rb_same'], rtol=1e-4, atol=1e-5 * np.abs(g['y_rb_same']).max())
+
+
+def test_encoder(oracle, weights, weights_digest):
+    g = load_golden('encoder')
+    assert str(g['digest']) == weights_digest
+    data = {k: (v.astype(np.int64) if k.startswith('ids') else v) for k, v in g.items() if k not in ('latents', 'digest')}
+    lat = oracle.fkaconv_network(weights, data)
+    scale = np.abs(g['latents']).max()
+    assert np.abs(lat - g['latents']).max() < 2e-5 * scale
+
+
+def test_decode(oracle, weights, weights_digest):
+    g = load_golden('decode')
+    assert str(g['digest']) == weights_digest
+    latents = np.random.default_rng(int(g['latents_seed'])).standard_normal((1, 256, g['pts'].shape[0])).astype(np.float32)
+    assert abs(latents.astype(np.float64).sum() - float(g['latents_sum'])) < 1e-6
+    pts = g['pts'].T[None]
+    ids = g['proj_ids'].astype(np.int64)[None]
+    fp = oracle.interp_attention(weights, latents, pts, g['qry'][None], ids)
+    assert np.abs(fp - g['feat_proj']).max() < 2e-5 * max(1.0, np.abs(g['feat_proj']).max())
+    fn = oracle.pointnet_feat(weights, np.swapaxes(g['pts_local_ps'], 1, 2))
+    assert np.abs(fn - g['feat_pn']).max() < 2e-5 * max(1.0, np.abs(g['feat_pn']).max())
+    data = {'pts': pts, 'latents': latents, 'pts_query': g['qry'][None],
+            'pts_local_ps': oracle.get_pts_local_ps(g['pts'], g['qry'], 50)[None]}
+    logits = oracle.from_latent(weights, data)
+    assert np.abs(logits - g['logits']).max() < 1e-4  # the north-star tolerance, fp32 vs fp32
+    assert np.abs(oracle.occupancy_from_logits(logits) - g['occ']).max() < 1e-4
+    # the float64 oracle is at least as close to the reference as the fp32 one is
+    logits64 = oracle.from_latent(weights, dict(data), dtype=np.float64)
+    assert np.abs(logits64 - g['logits']).max() < 1e-4
+
+
+def test_region_growing(oracle):
+    g = load_golden('volume')
+
+    def predict(q):
+        return np.tanh(20.0 * (np.linalg.norm(q, axis=1) - 0.4)).astype(np.float32)
+
+    step, bmin_pad, _ = oracle.grid_definition(g['pts'], 17, 1)
+    assert np.float32(step) == g['step'] and np.float32(bmin_pad) == g['bmin_pad']
+    vol = oracle.create_volume(predict, g['pts'], 17, padding=1)
+    np.testing.assert_array_equal(np.isnan(vol), np.isnan(g['volume']))
+    np.testing.assert_array_equal(np.nan_to_num(vol), np.nan_to_num(g['volume']))
+    dense = oracle.dense_grid_queries(g['pts'], 17, 1)
+    assert dense.shape == (19 ** 3, 3)
+
+
+def test_latent_schedule(oracle):
+    rng = np.random.default_rng(3)
+    sched = oracle.latent_loop_schedule(25000, 10000, 3, rng)
+    counts = np.zeros(25000, dtype=np.int64)
+    for ids in sched:
+        assert ids.shape[0] == 10000
+        counts[np.unique(ids)] += 1
+    assert counts.min() >= 3
+    small = oracle.latent_loop_schedule(500, 10000, 2, rng)
+    assert len(small) == 2 and all(np.array_equal(s, np.arange(500)) for s in small)
