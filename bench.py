@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""Benchmark of the PPSurf occupancy decode (BASELINE.json metric): Mquery-pts/s over the dense (129+2)^3 marching-cubes
+grid of a 100k-point synthetic cloud, ppsurf_50nn, latents and points resident on the device.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--path 0|1]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One step = one pass of the hot path (kNN k=64 -> patches -> both branches -> MLP -> softmax difference) over this rank's
+contiguous slab of the grid.  N>1: the grid is split into N slabs (strong scaling of the fixed 131^3 volume), rank 0
+encodes the cloud and the latents travel in ONE NCCL broadcast before the timed region; the decode itself needs no
+collective.  Prints one JSON line (rank 0).  `--impl reference` times the CPU restatement of the reference (oracle/,
+torch-CPU ops + scipy kd-tree, all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'Mquery-pts/sec occupancy decode, ppsurf_50nn 129^3 grid'
+UNIT = 'Mquery/s'
+# algorithmic work of the reference formulation per query and of the formulation actually executed
+FLOP_PER_QUERY_REFERENCE = 53.24e6
+GEMM_FLOP_PER_ROW = 2.0 * (256 * 256 * 2 + 256 * 64)  # fc2 + fc3 + fc_query on one (query, neighbour) row
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--path', type=int, default=int(os.environ.get('PPS_DECODE_PATH', '0')))
+    ap.add_argument('--points', type=int, default=100000)
+    ap.add_argument('--resolution', type=int, default=129)
+    ap.add_argument('--num-pts-local', type=int, default=50)
+    ap.add_argument('--chunk', type=int, default=16384)
+    ap.add_argument('--latents', default='encoder', choices=['encoder', 'random'])
+    ap.add_argument('--cpu-sample', type=int, default=4096, help='queries of the CPU baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {'bf16_tflops': d.get('bf16_tflops_sustained', d.get('bf16_tflops')), 'hbm_gbs': d.get('hbm_gbs'),
+                'source': 'measured (MEASURED_PEAKS.json, sustained bf16)'}
+    return {'bf16_tflops': 1400.0, 'hbm_gbs': 6650.0, 'source': 'fallback (B200_PROFILING.md)'}
+
+
+class ClockSampler:
+    """samples nvidia-smi while the timed region runs"""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def __enter__(self):
+        q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == 'active'})
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+def grid_shard(total, world, rank):
+    """contiguous slab [first, first+count) of the flattened C-order vertex list"""
+    first = total * rank // world
+    return first, total * (rank + 1) // world - first
+
+
+def workload_name(args):
+    r = args.resolution + 2
+    return 'ppsurf_{}nn predict decode, {}k-pt synthetic sphere cloud, dense {}^3={} grid vertices (gen_resolution_global={})'.format(
+        args.num_pts_local, args.points // 1000, r, r ** 3, args.resolution)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU legs (oracle = checker / baseline only)
+# ---------------------------------------------------------------------------------------------------------------------
+
+def cpu_decode(oracle, weights, pts, latents_cn, queries, num_pts_local):
+    """the reference's per-batch work on the host cores: kd-tree build + k=64 / k=P queries, patch normalisation, both
+    branches, MLP, softmax difference (reference formulation, torch CPU ops on all threads)"""
+    import torch
+    from oracle import ppsurf_oracle_torch as oracle_torch
+    kmax = max(64, num_pts_local)
+    idx, _ = oracle.knn_kdtree(pts, queries, kmax)
+    loc = oracle.normalize_patches(pts[idx[:, :num_pts_local]], queries)
+    occ, _ = oracle_torch.from_latent(weights, torch.from_numpy(pts), torch.from_numpy(np.ascontiguousarray(latents_cn.T)),
+                                      torch.from_numpy(queries), torch.from_numpy(idx[:, :64].copy()), torch.from_numpy(loc))
+    return occ.numpy()
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from oracle import ppsurf_oracle as oracle
+    weights = oracle.make_state_dict(42)
+    pts = oracle.synthetic_cloud(args.points, 42)
+    rng = np.random.default_rng(7)
+    latents = rng.standard_normal((256, args.points)).astype(np.float32)
+    grid = oracle.dense_grid_queries(pts, args.resolution, 1)
+    sample = args.cpu_sample
+    times = []
+    for s in range(args.warmup + args.steps):
+        q = grid[rng.choice(grid.shape[0], sample, replace=False)]
+        t0 = time.perf_counter()
+        cpu_decode(oracle, weights, pts, latents, q, args.num_pts_local)
+        dt = time.perf_counter() - t0
+        if s >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = sample / (ms * 1e-3) / 1e6
+    cores = os.cpu_count()
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': workload_name(args), 'step': 'bounded sample of {} grid vertices per step'.format(sample)},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': '{} random vertices of the same grid per step, torch-CPU oracle + scipy cKDTree'.format(sample)},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0}))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------------------------
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import ppsurf_b200
+    from ppsurf_b200 import _lib, ops, synthetic
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    ops.require_device()
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _lib.lib
+
+    model = ppsurf_b200.PPSurfModel(
+        pointnet_latent_size=256, output_names=['imp_surf_sign'], in_channels=3, out_channels=2, k=64, lambda_l1=0.0,
+        debug=False, in_file='bench', results_dir='results', padding_factor=0.05, name='ppsurf_50nn',
+        network_latent_size=256, gen_subsample_manifold_iter=10, gen_subsample_manifold=10000,
+        gen_resolution_global=args.resolution, num_pts_local=args.num_pts_local, rec_batch_size=50000, gen_refine_iter=10,
+        workers=8)
+    net = model.network
+    sd = synthetic.make_state_dict(net, 42)
+    net.load_state_dict(sd, strict=True)
+    model = model.to(dev)
+    net.decode_chunk, net.decode_path = args.chunk, args.path
+    pts_np = synthetic.synthetic_cloud(args.points, 42)
+    pts_bcn = torch.from_numpy(pts_np.T[None].copy()).to(dev)
+
+    # ---- encode on rank 0, one NCCL broadcast of the latent table (SURVEY.md §8e option A)
+    encoder_s = None
+    latents = torch.empty((1, 256, args.points), dtype=torch.float32, device=dev)
+    if rank == 0:
+        if args.latents == 'encoder':
+            net.sampling_seed = 42
+            gen = torch.Generator().manual_seed(42)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            latents = model.encode_cloud(pts_bcn, generator=gen).contiguous()
+            torch.cuda.synchronize()
+            encoder_s = time.perf_counter() - t0
+        else:
+            latents = torch.from_numpy(np.random.default_rng(7).standard_normal((1, 256, args.points)).astype(np.float32)).to(dev)
+    broadcast_ms = None
+    if world > 1:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        e0.record()
+        dist.broadcast(latents, src=0)
+        e1.record()
+        torch.cuda.synchronize()
+        broadcast_ms = e0.elapsed_time(e1)
+
+    dec = net.decoder_for(pts_bcn, latents)
+    r = args.resolution + 2
+    total = r ** 3
+    first, count = grid_shard(total, world, rank)
+    step, bmin_pad, _ = model.grid_definition(pts_np, args.resolution, 1)
+    queries = ops.grid_queries(r, step, bmin_pad, first=first, count=count, device=dev)
+    occ = torch.empty((count,), dtype=torch.float32, device=dev)
+    ws = dec.workspace(min(args.chunk, count))
+    stream = torch.cuda.current_stream()
+
+    def one_step():
+        _lib.check(lib.pps_decoder_decode(dec.packed.ref, dec.index.buf.data_ptr(), dec.pts.data_ptr(), dec.table.data_ptr(),
+                                          dec.n, queries.data_ptr(), count, min(args.chunk, count), ws.data_ptr(), ws.numel(),
+                                          None, occ.data_ptr(), None, args.path, stream.cuda_stream))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    barrier()
+    launches0 = lib.pps_launch_count()
+    lib.pps_profile_enable(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            one_step()
+        e1.record()
+        barrier()
+    elapsed_ms = e0.elapsed_time(e1)
+    import ctypes
+    dom_ms, brackets = ctypes.c_double(0), ctypes.c_longlong(0)
+    _lib.check(lib.pps_profile_read(ctypes.byref(dom_ms), ctypes.byref(brackets)))
+    lib.pps_profile_enable(0)
+    launches = lib.pps_launch_count() - launches0
+
+    # ---- end to end through the public host-buffer call: pinned host queries in, pinned host occupancy out
+    q_host = queries.cpu().pin_memory()
+    occ_host = torch.empty((count,), dtype=torch.float32).pin_memory()
+    dec.decode_host(q_host, occ_host)  # warm (allocates staging)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        dec.decode_host(q_host, occ_host)
+    e3.record()
+    barrier()
+    e2e_ms = e2.elapsed_time(e3)
+    assert torch.equal(occ_host, occ.cpu()), 'host-buffer path disagrees with the device path'
+
+    if world > 1:
+        t = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms, e2e_ms = float(t[0]), float(t[1])
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt[0])
+
+    if rank == 0:
+        peaks = measured_peaks()
+        ms_per_step = elapsed_ms / args.steps
+        value = total / (ms_per_step * 1e-3) / 1e6
+        e2e_value = total / (e2e_ms / args.steps * 1e-3) / 1e6
+        rows = count * 64.0 * args.steps  # (query, neighbour) rows this rank pushed through the dominant GEMMs
+        dom_flops = rows * GEMM_FLOP_PER_ROW
+        achieved = dom_flops / (dom_ms.value * 1e-3) / 1e12 if dom_ms.value > 0 else None
+        kernel = 'linear_kernel<128,true> x2 + linear_kernel<64,true> (fp32 SIMT fc2/fc3/fc_query)' if args.path == 0 else \
+            'projection_tc_kernel (tcgen05 split-fp16 fc2/fc3/fc_query + attention pooling)'
+        out = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+            'dtype': 'f32' if args.path == 0 else 'f32 via split-fp16 tensor cores (fp32 accumulate)', 'data': 'synthetic',
+            'config': {'workload': workload_name(args), 'parallelism': 'grid slabs x{}'.format(world), 'chunk': args.chunk,
+                       'decode_path': args.path, 'latents': args.latents,
+                       'l2': 'working set per step (fc1 table {} MB + >2 GB of chunk activations) exceeds the 126 MB L2'.format(
+                           args.points * 1024 // 2 ** 20),
+                       'seeded_weights': 'ppsurf_b200.synthetic.make_state_dict(seed=42)'},
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(total * 12), 'd2h_bytes_per_step': int(total * 4),
+                    'ms_per_step': e2e_ms / args.steps,
+                    'call': 'pps_decoder_decode_host: pinned host queries -> device -> pinned host occupancy, chunked copies overlapped'},
+            'gpu_launches': int(launches),
+            'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
+                         'frac': (achieved / peaks['bf16_tflops']) if achieved else None, 'traffic': None,
+                         'kernel': kernel, 'kernel_ms_per_step': dom_ms.value / args.steps,
+                         'kernel_share_of_step': dom_ms.value / elapsed_ms, 'brackets': int(brackets.value),
+                         'flop_per_row_executed': GEMM_FLOP_PER_ROW, 'peak_source': peaks['source'],
+                         'whole_decode_tflops_reference_formulation': value * 1e6 * FLOP_PER_QUERY_REFERENCE / 1e12},
+            'clocks': clocks.summary(),
+            'encoder_s': encoder_s, 'broadcast_ms': broadcast_ms,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            from oracle import ppsurf_oracle as oracle  # CPU baseline + checker leg only
+            weights = {k: v.numpy() for k, v in sd.items()}
+            rng = np.random.default_rng(7)
+            sel = np.sort(rng.choice(count, args.cpu_sample, replace=False))
+            q_np = queries[torch.from_numpy(sel).to(dev)].cpu().numpy()
+            lat_cn = latents[0].cpu().numpy()
+            cpu_decode(oracle, weights, pts_np, lat_cn, q_np[:256], args.num_pts_local)  # warm BLAS threads
+            t0 = time.perf_counter()
+            ref = cpu_decode(oracle, weights, pts_np, lat_cn, q_np, args.num_pts_local)
+            dt = time.perf_counter() - t0
+            out['cpu_baseline'] = {'value': args.cpu_sample / dt / 1e6, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
+                                   'sample': '{} random vertices of the same grid, torch-CPU oracle + scipy cKDTree (kd-tree rebuilt '
+                                             'per batch like the reference), {:.1f} s'.format(args.cpu_sample, dt)}
+            out['max_abs_err_vs_oracle'] = float(np.abs(occ[torch.from_numpy(sel).to(dev)].cpu().numpy() - ref).max())
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,240 @@
+/* ppsurf_b200 -- C ABI of the B200-native PPSurf occupancy hot path.
+ *
+ * The reference (cg-tuwien/ppsurf) is pure Python and has no FFI of its own, so every entry point
+ * below replaces a Python call site of the reference; the call site is cited as  file:line  relative to the
+ * reference root.  The Python side of this repo (ppsurf_b200/) binds these symbols with ctypes; INTEGRATION.md
+ * shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless the name ends in _host
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); every call is asynchronous on it
+ *     unless documented otherwise, never allocates device memory, and works only inside caller-owned buffers
+ *   - return value: 0 on success, negative pps_status on error; pps_last_error() returns a message for the
+ *     calling thread
+ *   - layouts are POINT-MAJOR (row = one point / query, channels contiguous): pts [N,3] f32, latents [N,C] f32,
+ *     indices int32.  The reference's [B,C,N] tensors are transposed once at the Python boundary.
+ */
+#ifndef PPSURF_B200_H
+#define PPSURF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum pps_status {
+    PPS_OK = 0,
+    PPS_ERR_INVALID = -1,   /* bad argument (null pointer, size out of range, k > supported ...) */
+    PPS_ERR_WORKSPACE = -2, /* caller-provided workspace too small                                 */
+    PPS_ERR_CUDA = -3,      /* a CUDA runtime call or kernel launch failed                         */
+    PPS_ERR_NO_DEVICE = -4  /* no sm_100 device: there is NO CPU fallback                          */
+} pps_status;
+
+const char* pps_last_error(void);
+/* library version and the SM architecture the kernels were compiled for (100 for sm_100a) */
+int pps_version(void);
+int pps_compiled_arch(void);
+/* 0 if the current device can run the kernels, PPS_ERR_NO_DEVICE otherwise */
+int pps_check_device(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+unsigned long long pps_launch_count(void);
+/* Measurement hooks: while enabled, the decoder brackets its dominant kernels (the fc2/fc3/fc_query GEMMs of the
+ * global branch) with CUDA events on the launching stream; pps_profile_read() synchronises, returns the summed
+ * device time and the number of brackets since the last read, and resets. */
+void pps_profile_enable(int on);
+int pps_profile_read(double* total_ms, long long* brackets);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * a6  exact k nearest neighbours
+ *     replaces  knn()                   source/poco_utils.py:257-273
+ *               make_kdtree/query_kdtree source/base/proximity.py:40-81  (pykdtree, CPU, rebuilt per call)
+ * Index = points sorted by 3-D Morton code + start offsets of the finest cells (an implicit octree).
+ * Distances are float32 ((dx*dx + dy*dy) + dz*dz, no FMA) like pykdtree's float path; results ascend by
+ * (dist2, index); k must be <= n (the reference clamps k to n before the query, poco_utils.py:259-260).
+ * ------------------------------------------------------------------------------------------------------------- */
+size_t pps_knn_index_bytes(int64_t n);
+int pps_knn_build(const float* pts, int64_t n, void* index, size_t index_bytes, void* stream);
+/* idx_out [q,k] int32 (original point numbering), dist2_out [q,k] f32 or NULL */
+int pps_knn_query(const void* index, int64_t n, const float* queries, int64_t q, int k, int32_t* idx_out,
+                  float* dist2_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * a7  local patches in patch space
+ *     replaces  _get_pts_local_ps                    source/poco_utils.py:67-72
+ *               PPSurfDataset.normalize_patches      source/ppsurf_data_loader.py:91-123
+ * idx [q,k_stride] are the (ascending) neighbours from pps_knn_query; the first p of each row form the patch;
+ * radius = sqrt(dist2[q,p-1]).  out [q,p,3] f32.
+ * ------------------------------------------------------------------------------------------------------------- */
+int pps_patch_normalize(const float* pts, const float* queries, const int32_t* idx, const float* dist2,
+                        int64_t q, int p, int k_stride, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * generic fused pointwise layer  Y = act( X[rows or gathered rows] . W^T + bias + residual )
+ *     replaces every 1x1 Conv1d/Conv2d/Linear (+ folded eval BatchNorm + ReLU) of
+ *     ResidualBlock / FKAConvNetwork decoder / STN / PointNetfeat / MLP
+ *     source/base/nn.py:162-190,305-373,415-417,438-450,530-548
+ * X [m or n_src, k] f32, W [n,k] f32 (row = output channel), Y [m,n].  gather (nullable) picks row gather[i] of X
+ * for output row i (the 1-NN `interpolate`, nn.py:684-697); residual (nullable, may alias Y) is added before the
+ * activation; act: 0 none, 1 ReLU.
+ * ------------------------------------------------------------------------------------------------------------- */
+int pps_linear(const float* x, const float* w, const float* bias, const float* residual, const int32_t* gather,
+               float* y, int64_t m, int n, int k, int ldx, int ldy, int act, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * a8-a11  occupancy decoder (global attention-interpolation branch + local PointNet branch + MLP + softmax)
+ *     replaces  PPSurfNetwork.from_latent             source/ppsurf_model.py:82-117
+ *               InterpAttentionKHeadsNet.forward      source/poco_model.py:381-419
+ *               PointNetfeat.forward / STN / AttentionPoco   source/base/nn.py:305-373,162-190,84-96
+ *               MLP.forward                           source/base/nn.py:415-417
+ *               _predict_from_latent                  source/poco_utils.py:74-82
+ * Weights are packed on the host by ppsurf_b200.packing (eval BatchNorm folded, algebraic merges listed in
+ * DESIGN.md); all matrices are [out,in] row-major f32.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct pps_decoder_weights {
+    int32_t latent;        /* C = 256 */
+    int32_t heads;         /* 64 (fc_query outputs) */
+    int32_t k;             /* 64 neighbours of the global branch */
+    int32_t num_pts_local; /* P = 50 / 200 */
+    /* global branch */
+    const float* w1_lat; /* [C,C]   fc1 weight, latent columns                     */
+    const float* w1_xyz; /* [C,3]   fc1 weight, xyz columns                        */
+    const float* b1;     /* [C]                                                    */
+    const float* w2;     /* [C,C] */
+    const float* b2;
+    const float* w3;     /* [C,C] */
+    const float* b3;
+    const float* wq;     /* [heads,C] */
+    const float* bq;
+    const float* wv8;    /* [C,C]   fc8 . fc_value                                 */
+    const float* bv8;    /* [C]     fc8 . b_value + b8                             */
+    /* local branch (BatchNorm folded) */
+    const float* pn0a_w; /* [64,3]  */
+    const float* pn0a_b;
+    const float* pn0b_w; /* [64,64] */
+    const float* pn0b_b;
+    const float* stn1_w; /* [64,64] */
+    const float* stn1_b;
+    const float* stn2_w; /* [128,64] */
+    const float* stn2_b;
+    const float* stn3_w; /* [S,128]  S = pointnet_latent_size */
+    const float* stn3_b;
+    const float* stnf1_w; /* [S/2,S] */
+    const float* stnf1_b;
+    const float* stnf2_w; /* [S/4,S/2] */
+    const float* stnf2_b;
+    const float* stnf3_w; /* [4096,S/4] */
+    const float* stnf3_b; /* [4096]  fc3 bias + identity                            */
+    const float* pn1_w;   /* [64,64] */
+    const float* pn1_b;
+    const float* pn2_w;   /* [128,64] */
+    const float* pn2_b;
+    const float* pnq_w;   /* [128]   att.fc_query . bn3 . conv3                     */
+    float pnq_b;
+    int32_t stn_size;     /* S */
+    const float* pnv_w;   /* [C,128] att.fc_value . bn3 . conv3                     */
+    const float* pnv_b;   /* [C]                                                    */
+    /* MLP (BatchNorm folded) */
+    const float* m0_w; /* [C,C] */
+    const float* m0_b;
+    const float* m1_w; /* [C,C] */
+    const float* m1_b;
+    const float* m2_w; /* [2,C] */
+    const float* m2_b; /* [2]   */
+} pps_decoder_weights;
+
+/* per-point table  U[n,:] = W1_lat . latent[n] - W1_xyz . pts[n] + b1   (fc1 hoisted out of the (query,neighbour)
+ * loop: fc1([latent_j, q - p_j]) = U_j + W1_xyz . q).  table [n,C] f32. */
+int pps_decoder_point_table(const pps_decoder_weights* w, const float* pts, const float* latents, int64_t n,
+                            float* table, void* stream);
+
+/* workspace bytes for decoding chunks of at most `chunk` queries */
+size_t pps_decoder_workspace_bytes(const pps_decoder_weights* w, int64_t chunk);
+
+/* Decode q queries: kNN (k = max(w->k, P)) -> both branches -> MLP.
+ *   logits_out [q,2] f32 or NULL;  occ_out [q] f32 (softmax(l)[0] - softmax(l)[1]) or NULL.
+ *   idx_out [q,kmax] int32 or NULL (the neighbour ids, = reference proj_ids for the first w->k columns).
+ *   path: 0 = fp32 SIMT kernels, 1 = tcgen05 split-fp16 tensor-core kernels (global branch GEMMs). */
+int pps_decoder_decode(const pps_decoder_weights* w, const void* knn_index, const float* pts, const float* table,
+                       int64_t n, const float* queries, int64_t q, int64_t chunk, void* workspace,
+                       size_t workspace_bytes, float* logits_out, float* occ_out, int32_t* idx_out, int path,
+                       void* stream);
+
+/* Same from HOST memory (the reference hands `pts_query` over as a CPU tensor, source/poco_utils.py:220 and
+ * source/poco_model.py:392, and reads the result back with .cpu(), poco_utils.py:81): queries_host [q,3] and
+ * occ_host [q] should be pinned; uploads/downloads are chunked on `copy_stream` and overlap the kernels.
+ * Synchronous: returns when occ_host is complete.  staging: device buffer of q*16 bytes. */
+int pps_decoder_decode_host(const pps_decoder_weights* w, const void* knn_index, const float* pts,
+                            const float* table, int64_t n, const float* queries_host, int64_t q, int64_t chunk,
+                            void* workspace, size_t workspace_bytes, void* staging, size_t staging_bytes,
+                            float* occ_host, int path, void* stream, void* copy_stream);
+
+/* stand-alone branches for the parity tests (same kernels as pps_decoder_decode) */
+int pps_decoder_projection(const pps_decoder_weights* w, const float* pts, const float* table, const float* queries,
+                           const int32_t* idx, int k_stride, int64_t q, void* workspace, size_t workspace_bytes,
+                           float* feat_out /* [q,C] */, int path, void* stream);
+int pps_decoder_pointnet(const pps_decoder_weights* w, const float* patches /* [q,P,3] */, int64_t q,
+                         void* workspace, size_t workspace_bytes, float* feat_out /* [q,C] */, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * a11  dense marching-cubes query grid
+ *     replaces  the coordinate expression of _create_volume   source/poco_utils.py:212-213
+ * out [(r^3),3] f32, C order, coordinate = idx * step + bmin_pad with separate multiply and add roundings.
+ * Only vertices [first, first+count) of the flattened grid are produced (multi-GPU slabs).
+ * ------------------------------------------------------------------------------------------------------------- */
+int pps_grid_queries(int r, float step, float bmin_pad, int64_t first, int64_t count, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * a3  FKAConv layer (point-major activations)
+ *     replaces  FKAConvLayer.forward   source/base/nn.py:592-652   (eval mode; InstanceNorm statistics are
+ *     per sample over (Ns,16), so the layer runs as stats1 -> stats2 -> fused gather/contract)
+ * x [b,n_in,cin], pts [b,n_in,3], support [b,n_s,3], ids [b,n_s,16] int32, out [b,n_s,cout].
+ * cv_w is [cout, 16*cin] with column = m*cin + c  (repacked from the reference [cout,cin,1,16]); the eval
+ * BatchNorm that always follows the layer (nn.py:441,519) is folded into cv_w / out_bias, out_relu applies its ReLU.
+ * act: 0 ReLU (POCO), 1 SiLU (PPSurf).
+ * Three launches of the kernel-weight MLP (InstanceNorm statistics 1, statistics 2, weights) and one fused
+ * gather * weights kernel produce the [b*n_s, 16*cin] operand of the final contraction.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct pps_fkaconv_weights {
+    int32_t cin, cout, act;
+    float alpha, beta, norm_radius;
+    const float* fc1;   /* [16,3]  */
+    const float* fc2;   /* [16,32] */
+    const float* fc3;   /* [16,32] */
+    const float* in1_w; /* [16] InstanceNorm affine */
+    const float* in1_b;
+    const float* in2_w;
+    const float* in2_b;
+    const float* cv_w;     /* [cout,16*cin] */
+    const float* out_bias; /* [cout], nullable */
+    int32_t out_relu;
+} pps_fkaconv_weights;
+
+size_t pps_fkaconv_workspace_bytes(int64_t b, int64_t n_s, int cin);
+int pps_fkaconv_forward(const pps_fkaconv_weights* w, const float* x, const float* pts, const float* support,
+                        const int32_t* ids, int64_t b, int64_t n_in, int64_t n_s, void* workspace,
+                        size_t workspace_bytes, float* out, void* stream);
+
+/* gather-max over the 16 neighbours (shortcut branch of a strided ResidualBlock)
+ *     replaces  max_pool   source/base/nn.py:677-680
+ * x [b,n_in,c], ids [b,n_s,16] -> out [b,n_s,c] */
+int pps_gather_max(const float* x, const int32_t* ids, int64_t b, int64_t n_in, int64_t n_s, int c, int kn,
+                   float* out, void* stream);
+/* max over all points of a sample: x [b,n,c] -> out [b,c]   (nn.py:531) */
+int pps_global_max(const float* x, int64_t b, int64_t n, int c, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * a1  latent accumulation of one encoder pass
+ *     replaces  latent[ids] += partial; counts[ids] += 1   source/poco_model.py:228-229
+ *     (torch advanced-index semantics: a duplicated id receives ONE of the duplicates' values, once)
+ * ids [n] int32 must already be de-duplicated by the caller when exact reference semantics are needed.
+ * ------------------------------------------------------------------------------------------------------------- */
+int pps_latent_accumulate(const float* partial, const int32_t* ids, int64_t n, int c, float* latent, float* counts,
+                          void* stream);
+int pps_latent_finalize(float* latent, const float* counts, int64_t n, int c, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPSURF_B200_H */

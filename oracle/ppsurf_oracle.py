@@ -235,7 +235,7 @@ def _pointwise(p: Params, name: str, x: np.ndarray, dtype) -> np.ndarray:
     """1x1 Conv1d / Conv2d / Linear over channel axis 1: ``x [B,Cin,...]`` -> ``[B,Cout,...]``."""
     w = _w(p, name + '.weight', dtype)
     w = w.reshape(w.shape[0], -1)
-    y = np.einsum('oc,bc...->bo...', w, x, optimize=True)
+    y = np.moveaxis(np.tensordot(w, x, axes=([1], [1])), 0, 1)  # BLAS gemm: [o,b,...] -> [b,o,...]
     if (name + '.bias') in p:
         bias = _w(p, name + '.bias', dtype)
         y = y + bias.reshape((1, -1) + (1,) * (x.ndim - 2))
@@ -308,6 +308,19 @@ def knn(points: np.ndarray, queries: np.ndarray, k: int, chunk: int = 2048) \
         idx[s:s + chunk] = order
         d2[s:s + chunk] = np.take_along_axis(dist, order, axis=1)
     return idx, d2
+
+
+def knn_kdtree(points: np.ndarray, queries: np.ndarray, k: int) -> typing.Tuple[np.ndarray, np.ndarray]:
+    """kd-tree search as the reference runs it (``make_kdtree`` + ``query_kdtree``, source/base/proximity.py:40-81) with
+    scipy's cKDTree(leafsize=10, all cores) standing in for pykdtree, which is not installable offline.  Used by the CPU
+    timing legs of bench.py (a brute-force search would misrepresent the reference's cost); the parity tests use the
+    exact float32 brute force above."""
+    from scipy.spatial import cKDTree
+    k = min(k, points.shape[0])
+    d, i = cKDTree(points, leafsize=10).query(queries, k=k, workers=-1)
+    if k == 1:
+        d, i = d[:, None], i[:, None]
+    return i.astype(np.int64), (d * d).astype(np.float32)
 
 
 def knn_batched(points: np.ndarray, support: np.ndarray, k: int) -> np.ndarray:

@@ -1,0 +1,404 @@
+// FKAConv encoder kernels, point-major activations.
+//
+// Replaces FKAConvLayer.forward (source/base/nn.py:592-652), max_pool (nn.py:677-680), the global max of
+// FKAConvNetwork.forward (nn.py:531) and the latent scatter of the predict loop (source/poco_model.py:228-234).
+//
+// FKAConv = (1) a tiny "kernel-weight" MLP on the 16 centred neighbour offsets of every support point that yields a
+// 16x16 matrix per point, with two InstanceNorm2d layers whose statistics run over ALL (point, neighbour) pairs of a
+// sample -> three launches of fka_weight_kernel (stats 1, stats 2, weights); (2) feat[n,m,c] = sum_j mat[n,j,m] *
+// x[ids[n,j],c]  (fused gather * weights, fka_feat_kernel); (3) a dense contraction with the [cout,16*cin] kernel
+// (linear_impl, BatchNorm/ReLU folded into its epilogue).
+#include "common.cuh"
+
+namespace pps {
+
+int linear_impl(const float* x, const float* w, const float* bias, const float* residual, const int32_t* gather,
+                float* y, int64_t m, int n, int k, int ldx, int ldy, int act, cudaStream_t st);
+
+constexpr int kNbr = 16;   // neighbours per support point == kernel size
+constexpr float kInEps = 1e-5f;
+
+struct FkaParams {
+    float alpha, beta, inv_radius;
+    int act;
+};
+
+__device__ __forceinline__ float fka_act(float v, int act) { return act == 1 ? v / (1.f + expf(-v)) : fmaxf(v, 0.f); }
+
+// PHASE 1: sum / sumsq of fc1 outputs; PHASE 2: sum / sumsq of fc2 outputs; PHASE 3: write mat [b,ns,16(j),16(m)]
+template <int PHASE>
+__global__ void __launch_bounds__(128) fka_weight_kernel(const float* __restrict__ pts, const float* __restrict__ support,
+                                                         const int32_t* __restrict__ ids, int n_in, int n_s, FkaParams prm,
+                                                         const float* __restrict__ fc1, const float* __restrict__ fc2,
+                                                         const float* __restrict__ fc3, const float* __restrict__ in1_w,
+                                                         const float* __restrict__ in1_b, const float* __restrict__ in2_w,
+                                                         const float* __restrict__ in2_b, double* stats, float* __restrict__ mat) {
+    __shared__ float W1[16 * 3], W2[16 * 32], W3[16 * 32];
+    __shared__ float A1[16], B1[16], A2[16], B2[16];
+    const int b = blockIdx.y;
+    const int tid = threadIdx.x;
+    double* st_b = stats + (size_t)b * 64;  // [phase(2)][sum16, sumsq16]
+    for (int e = tid; e < 48; e += 128) W1[e] = fc1[e];
+    for (int e = tid; e < 512; e += 128) {
+        W2[e] = fc2[e];
+        W3[e] = fc3[e];
+    }
+    const double cnt = double(n_s) * kNbr;
+    if (PHASE >= 2 && tid < 16) {
+        double mean = st_b[tid] / cnt;
+        double var = st_b[16 + tid] / cnt - mean * mean;
+        float rstd = float(1.0 / sqrt(fmax(var, 0.0) + double(kInEps)));
+        A1[tid] = rstd * in1_w[tid];
+        B1[tid] = in1_b[tid] - float(mean) * rstd * in1_w[tid];
+    }
+    if (PHASE >= 3 && tid < 16) {
+        double mean = st_b[32 + tid] / cnt;
+        double var = st_b[48 + tid] / cnt - mean * mean;
+        float rstd = float(1.0 / sqrt(fmax(var, 0.0) + double(kInEps)));
+        A2[tid] = rstd * in2_w[tid];
+        B2[tid] = in2_b[tid] - float(mean) * rstd * in2_w[tid];
+    }
+    __syncthreads();
+
+    const int n = blockIdx.x * 128 + tid;
+    const bool valid = n < n_s;
+    float s[16], ss[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) s[c] = ss[c] = 0.f;
+
+    if (valid) {
+        const size_t row = (size_t)b * n_s + n;
+        const float sx = support[3 * row], sy = support[3 * row + 1], sz = support[3 * row + 2];
+        float rel[kNbr][3];
+        float dw[kNbr];
+        float dsum = 0.f;
+#pragma unroll
+        for (int j = 0; j < kNbr; ++j) {
+            size_t src = (size_t)b * n_in + ids[row * kNbr + j];
+            float rx = pts[3 * src] - sx, ry = pts[3 * src + 1] - sy, rz = pts[3 * src + 2] - sz;
+            float dist = sqrtf(rx * rx + ry * ry + rz * rz);
+            rel[j][0] = rx * prm.inv_radius;
+            rel[j][1] = ry * prm.inv_radius;
+            rel[j][2] = rz * prm.inv_radius;
+            float wgt = 1.f / (1.f + expf(-(-prm.alpha * dist + prm.beta)));
+            dw[j] = wgt;
+            dsum += wgt;
+        }
+        dsum = dsum + (dsum == 0.f ? 1.f : 0.f) + 1e-6f;
+#pragma unroll
+        for (int j = 0; j < kNbr; ++j) dw[j] = dw[j] / dsum * float(kNbr);
+
+        if (PHASE == 1) {
+#pragma unroll
+            for (int j = 0; j < kNbr; ++j)
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    float y = W1[3 * c] * rel[j][0] + W1[3 * c + 1] * rel[j][1] + W1[3 * c + 2] * rel[j][2];
+                    s[c] += y;
+                    ss[c] += y * y;
+                }
+        } else {
+            // m1[c][j] = act(IN1(fc1 rel_j)); mp1[c] = max_j m1[c][j] * dw_j
+            float mp1[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) mp1[c] = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < kNbr; ++j)
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    float y = W1[3 * c] * rel[j][0] + W1[3 * c + 1] * rel[j][1] + W1[3 * c + 2] * rel[j][2];
+                    float m = fka_act(y * A1[c] + B1[c], prm.act);
+                    mp1[c] = fmaxf(mp1[c], m * dw[j]);
+                }
+            // fc2 on cat(m1[:,j], mp1): the mp1 half does not depend on j
+            float c2[16];
+#pragma unroll
+            for (int o = 0; o < 16; ++o) {
+                float a = 0.f;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) a = fmaf(W2[o * 32 + 16 + c], mp1[c], a);
+                c2[o] = a;
+            }
+            float mp2[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) mp2[c] = -INFINITY;
+            for (int j = 0; j < kNbr; ++j) {
+                float m1[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    float y = W1[3 * c] * rel[j][0] + W1[3 * c + 1] * rel[j][1] + W1[3 * c + 2] * rel[j][2];
+                    m1[c] = fka_act(y * A1[c] + B1[c], prm.act);
+                }
+#pragma unroll
+                for (int o = 0; o < 16; ++o) {
+                    float y = c2[o];
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) y = fmaf(W2[o * 32 + c], m1[c], y);
+                    if (PHASE == 2) {
+                        s[o] += y;
+                        ss[o] += y * y;
+                    } else {
+                        float m = fka_act(y * A2[o] + B2[o], prm.act);
+                        mp2[o] = fmaxf(mp2[o], m * dw[j]);
+                    }
+                }
+            }
+            if (PHASE == 3) {
+                float c3[16];
+#pragma unroll
+                for (int o = 0; o < 16; ++o) {
+                    float a = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) a = fmaf(W3[o * 32 + 16 + c], mp2[c], a);
+                    c3[o] = a;
+                }
+                for (int j = 0; j < kNbr; ++j) {
+                    float m1[16], m2[16];
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        float y = W1[3 * c] * rel[j][0] + W1[3 * c + 1] * rel[j][1] + W1[3 * c + 2] * rel[j][2];
+                        m1[c] = fka_act(y * A1[c] + B1[c], prm.act);
+                    }
+#pragma unroll
+                    for (int o = 0; o < 16; ++o) {
+                        float y = c2[o];
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) y = fmaf(W2[o * 32 + c], m1[c], y);
+                        m2[o] = fka_act(y * A2[o] + B2[o], prm.act);
+                    }
+                    float outv[16];
+#pragma unroll
+                    for (int o = 0; o < 16; ++o) {
+                        float y = c3[o];
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) y = fmaf(W3[o * 32 + c], m2[c], y);
+                        outv[o] = fka_act(y, prm.act) * dw[j];
+                    }
+                    float4* dst = reinterpret_cast<float4*>(mat + (row * kNbr + j) * 16);
+                    dst[0] = make_float4(outv[0], outv[1], outv[2], outv[3]);
+                    dst[1] = make_float4(outv[4], outv[5], outv[6], outv[7]);
+                    dst[2] = make_float4(outv[8], outv[9], outv[10], outv[11]);
+                    dst[3] = make_float4(outv[12], outv[13], outv[14], outv[15]);
+                }
+            }
+        }
+    }
+    if (PHASE <= 2) {
+        double* dst = st_b + (PHASE == 1 ? 0 : 32);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            float a = s[c], q = ss[c];
+            for (int o = 16; o > 0; o >>= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, o);
+                q += __shfl_xor_sync(0xffffffffu, q, o);
+            }
+            if ((tid & 31) == 0) {
+                atomicAdd(dst + c, double(a));
+                atomicAdd(dst + 16 + c, double(q));
+            }
+        }
+    }
+}
+
+// feat[row, m*cin + c] = sum_j mat[row,j,m] * x[b*n_in + ids[row,j], c];  16 support points per block
+constexpr int kFeatPts = 16;
+template <bool VEC>
+__global__ void __launch_bounds__(256) fka_feat_kernel(const float* __restrict__ x, const int32_t* __restrict__ ids,
+                                                       const float* __restrict__ mat, int n_in, int n_s, int cin,
+                                                       float* __restrict__ feat) {
+    __shared__ float smat[kFeatPts][kNbr][16];
+    __shared__ int sid[kFeatPts][kNbr];
+    const int b = blockIdx.y;
+    const int n0 = blockIdx.x * kFeatPts;
+    const int tid = threadIdx.x;
+    const int npts = min(kFeatPts, n_s - n0);
+    const size_t row0 = (size_t)b * n_s + n0;
+    for (int e = tid; e < npts * kNbr * 16; e += 256) (&smat[0][0][0])[e] = mat[row0 * kNbr * 16 + e];
+    for (int e = tid; e < npts * kNbr; e += 256) (&sid[0][0])[e] = ids[row0 * kNbr + e];
+    __syncthreads();
+    const int cw = VEC ? cin / 4 : cin;  // work items per point
+    for (int e = tid; e < npts * cw; e += 256) {
+        int pl = e / cw, cq = e % cw;
+        if (VEC) {
+            float4 acc[16];
+#pragma unroll
+            for (int m = 0; m < 16; ++m) acc[m] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+            for (int j = 0; j < kNbr; ++j) {
+                float4 xv = reinterpret_cast<const float4*>(x + ((size_t)b * n_in + sid[pl][j]) * cin)[cq];
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    float wgt = smat[pl][j][m];
+                    acc[m].x = fmaf(wgt, xv.x, acc[m].x);
+                    acc[m].y = fmaf(wgt, xv.y, acc[m].y);
+                    acc[m].z = fmaf(wgt, xv.z, acc[m].z);
+                    acc[m].w = fmaf(wgt, xv.w, acc[m].w);
+                }
+            }
+            float* dst = feat + (row0 + pl) * (size_t)(16 * cin);
+#pragma unroll
+            for (int m = 0; m < 16; ++m) reinterpret_cast<float4*>(dst + (size_t)m * cin)[cq] = acc[m];
+        } else {
+            float acc[16];
+#pragma unroll
+            for (int m = 0; m < 16; ++m) acc[m] = 0.f;
+            for (int j = 0; j < kNbr; ++j) {
+                float xv = x[((size_t)b * n_in + sid[pl][j]) * cin + cq];
+#pragma unroll
+                for (int m = 0; m < 16; ++m) acc[m] = fmaf(smat[pl][j][m], xv, acc[m]);
+            }
+            float* dst = feat + (row0 + pl) * (size_t)(16 * cin);
+#pragma unroll
+            for (int m = 0; m < 16; ++m) dst[(size_t)m * cin + cq] = acc[m];
+        }
+    }
+}
+
+__global__ void gather_max_kernel(const float* __restrict__ x, const int32_t* __restrict__ ids, int n_in, int n_s, int c,
+                                  int kn, float* __restrict__ out) {
+    const int b = blockIdx.y;
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)n_s * c) return;
+    int n = int(e / c), ch = int(e % c);
+    size_t row = (size_t)b * n_s + n;
+    float m = -INFINITY;
+    for (int j = 0; j < kn; ++j) m = fmaxf(m, x[((size_t)b * n_in + ids[row * kn + j]) * c + ch]);
+    out[row * c + ch] = m;
+}
+
+__global__ void __launch_bounds__(256) global_max_kernel(const float* __restrict__ x, int n, int c, float* __restrict__ out) {
+    __shared__ float red[8][33];
+    const int b = blockIdx.y;
+    const int ch = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int r = threadIdx.x >> 5;
+    float m = -INFINITY;
+    if (ch < c)
+        for (int i = r; i < n; i += 8) m = fmaxf(m, x[((size_t)b * n + i) * c + ch]);
+    red[r][threadIdx.x & 31] = m;
+    __syncthreads();
+    if (r == 0 && ch < c) {
+        for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i][threadIdx.x & 31]);
+        out[(size_t)b * c + ch] = m;
+    }
+}
+
+__global__ void latent_accumulate_kernel(const float* __restrict__ partial, const int32_t* __restrict__ ids, long long n, int c,
+                                         float* latent, float* counts) {
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n * c) return;
+    long long i = e / c;
+    int ch = int(e % c);
+    int dst = ids[i];
+    latent[(size_t)dst * c + ch] += partial[e];
+    if (ch == 0) counts[dst] += 1.f;
+}
+
+__global__ void latent_finalize_kernel(float* latent, const float* __restrict__ counts, long long n, int c) {
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n * c) return;
+    latent[e] = latent[e] / counts[e / c];
+}
+
+struct FkaLayout {
+    size_t stats, mat, feat, total;
+};
+static FkaLayout fka_layout(int64_t b, int64_t n_s, int cin) {
+    FkaLayout l;
+    size_t off = 0;
+    l.stats = off;
+    off = align_up(off + (size_t)b * 64 * sizeof(double), 256);
+    l.mat = off;
+    off = align_up(off + (size_t)b * n_s * kNbr * 16 * sizeof(float), 256);
+    l.feat = off;
+    off = align_up(off + (size_t)b * n_s * 16 * (size_t)cin * sizeof(float), 256);
+    l.total = off;
+    return l;
+}
+
+}  // namespace pps
+
+using namespace pps;
+
+extern "C" {
+
+size_t pps_fkaconv_workspace_bytes(int64_t b, int64_t n_s, int cin) {
+    if (b <= 0 || n_s <= 0 || cin <= 0) return 0;
+    return fka_layout(b, n_s, cin).total;
+}
+
+int pps_fkaconv_forward(const pps_fkaconv_weights* w, const float* x, const float* pts, const float* support,
+                        const int32_t* ids, int64_t b, int64_t n_in, int64_t n_s, void* workspace,
+                        size_t workspace_bytes, float* out, void* stream) {
+    PPS_CHECK_ARG(w && x && pts && support && ids && workspace && out, "pps_fkaconv_forward: null pointer");
+    PPS_CHECK_ARG(b >= 1 && b <= 65535 && n_in >= 1 && n_s >= 1 && n_in < (1ll << 31) && n_s < (1ll << 31),
+                  "pps_fkaconv_forward: bad sizes b=%lld n_in=%lld n_s=%lld", (long long)b, (long long)n_in, (long long)n_s);
+    PPS_CHECK_ARG(w->cin >= 1 && w->cout >= 1 && (w->act == 0 || w->act == 1), "pps_fkaconv_forward: bad weights");
+    FkaLayout l = fka_layout(b, n_s, w->cin);
+    if (workspace_bytes < l.total) {
+        set_error("pps_fkaconv_forward: workspace %zu < required %zu", workspace_bytes, l.total);
+        return PPS_ERR_WORKSPACE;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* base = static_cast<char*>(workspace);
+    double* stats = reinterpret_cast<double*>(base + l.stats);
+    float* mat = reinterpret_cast<float*>(base + l.mat);
+    float* feat = reinterpret_cast<float*>(base + l.feat);
+    PPS_CUDA(cudaMemsetAsync(stats, 0, (size_t)b * 64 * sizeof(double), st));
+    FkaParams prm{w->alpha, w->beta, 1.f / w->norm_radius, w->act};
+    dim3 grid((unsigned)ceil_div(n_s, 128), (unsigned)b);
+    fka_weight_kernel<1><<<grid, 128, 0, st>>>(pts, support, ids, (int)n_in, (int)n_s, prm, w->fc1, w->fc2, w->fc3, w->in1_w,
+                                               w->in1_b, w->in2_w, w->in2_b, stats, mat);
+    PPS_LAUNCH_CHECK();
+    fka_weight_kernel<2><<<grid, 128, 0, st>>>(pts, support, ids, (int)n_in, (int)n_s, prm, w->fc1, w->fc2, w->fc3, w->in1_w,
+                                               w->in1_b, w->in2_w, w->in2_b, stats, mat);
+    PPS_LAUNCH_CHECK();
+    fka_weight_kernel<3><<<grid, 128, 0, st>>>(pts, support, ids, (int)n_in, (int)n_s, prm, w->fc1, w->fc2, w->fc3, w->in1_w,
+                                               w->in1_b, w->in2_w, w->in2_b, stats, mat);
+    PPS_LAUNCH_CHECK();
+    dim3 fgrid((unsigned)ceil_div(n_s, kFeatPts), (unsigned)b);
+    bool vec = (w->cin % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    if (vec)
+        fka_feat_kernel<true><<<fgrid, 256, 0, st>>>(x, ids, mat, (int)n_in, (int)n_s, w->cin, feat);
+    else
+        fka_feat_kernel<false><<<fgrid, 256, 0, st>>>(x, ids, mat, (int)n_in, (int)n_s, w->cin, feat);
+    PPS_LAUNCH_CHECK();
+    int kdim = 16 * w->cin;
+    return linear_impl(feat, w->cv_w, w->out_bias, nullptr, nullptr, out, b * n_s, w->cout, kdim, kdim, w->cout,
+                       w->out_relu ? 1 : 0, st);
+}
+
+int pps_gather_max(const float* x, const int32_t* ids, int64_t b, int64_t n_in, int64_t n_s, int c, int kn, float* out,
+                   void* stream) {
+    PPS_CHECK_ARG(x && ids && out && b >= 1 && b <= 65535 && c >= 1 && kn >= 1, "pps_gather_max: bad arguments");
+    dim3 grid((unsigned)ceil_div(n_s * c, 256), (unsigned)b);
+    gather_max_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, ids, (int)n_in, (int)n_s, c, kn, out);
+    PPS_LAUNCH_CHECK();
+    return PPS_OK;
+}
+
+int pps_global_max(const float* x, int64_t b, int64_t n, int c, float* out, void* stream) {
+    PPS_CHECK_ARG(x && out && b >= 1 && b <= 65535 && n >= 1 && c >= 1, "pps_global_max: bad arguments");
+    dim3 grid((unsigned)ceil_div(c, 32), (unsigned)b);
+    global_max_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, (int)n, c, out);
+    PPS_LAUNCH_CHECK();
+    return PPS_OK;
+}
+
+int pps_latent_accumulate(const float* partial, const int32_t* ids, int64_t n, int c, float* latent, float* counts,
+                          void* stream) {
+    PPS_CHECK_ARG(partial && ids && latent && counts && n >= 0 && c >= 1, "pps_latent_accumulate: bad arguments");
+    if (n == 0) return PPS_OK;
+    latent_accumulate_kernel<<<(unsigned)ceil_div(n * c, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(partial, ids, n, c,
+                                                                                                           latent, counts);
+    PPS_LAUNCH_CHECK();
+    return PPS_OK;
+}
+
+int pps_latent_finalize(float* latent, const float* counts, int64_t n, int c, void* stream) {
+    PPS_CHECK_ARG(latent && counts && n >= 0 && c >= 1, "pps_latent_finalize: bad arguments");
+    if (n == 0) return PPS_OK;
+    latent_finalize_kernel<<<(unsigned)ceil_div(n * c, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(latent, counts, n, c);
+    PPS_LAUNCH_CHECK();
+    return PPS_OK;
+}
+}

@@ -1,0 +1,263 @@
+"""``PPSurfModel``: the reference LightningModule's constructor / ``predict_step`` surface
+(source/ppsurf_model.py:10-36, source/poco_model.py:183-273) on the B200 network, plus the reconstruction driver
+(source/poco_utils.py:26-254) with every per-query step on the device.  Selected from the reference CLI with
+``--model.class_path ppsurf_b200.PPSurfModel``; ``pps.py`` itself is not edited.
+
+What stays on the host, as in the reference: file I/O, the region-growing bookkeeping masks (numpy), marching cubes
+(scikit-image) and mesh cleaning (trimesh)  --  the rows SURVEY.md §8f ranks as "next".
+"""
+import os
+import typing
+
+import numpy as np
+import torch
+
+from . import ops
+from .network import PPSurfNetwork, _Base
+
+
+class _NullBar:
+    """stands in for Lightning's progress bar when the model is driven without a Trainer"""
+
+    class _Bar:
+        @staticmethod
+        def set_postfix_str(*_a, **_k):
+            pass
+
+    predict_progress_bar = _Bar()
+    test_progress_bar = _Bar()
+
+
+class PPSurfModel(_Base):
+
+    def __init__(self, pointnet_latent_size, output_names, in_channels, out_channels, k, lambda_l1, debug, in_file,
+                 results_dir, padding_factor, name, network_latent_size, gen_subsample_manifold_iter,
+                 gen_subsample_manifold, gen_resolution_global, num_pts_local, rec_batch_size, gen_refine_iter, workers):
+        super().__init__()
+        self.output_names = output_names
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.k = k
+        self.lambda_l1 = lambda_l1
+        self.network_latent_size = network_latent_size
+        self.gen_subsample_manifold_iter = gen_subsample_manifold_iter
+        self.gen_subsample_manifold = gen_subsample_manifold
+        self.gen_resolution_global = gen_resolution_global
+        self.rec_batch_size = rec_batch_size
+        self.gen_refine_iter = gen_refine_iter
+        self.workers = workers
+        self.in_file = in_file
+        self.results_dir = results_dir
+        self.padding_factor = padding_factor
+        self.debug = debug
+        self.name = name
+        self.num_pts_local = num_pts_local
+        self.pointnet_latent_size = pointnet_latent_size
+        self.network = PPSurfNetwork(in_channels=in_channels, latent_size=network_latent_size, out_channels=out_channels,
+                                     k=k, num_pts_local=num_pts_local, pointnet_latent_size=pointnet_latent_size,
+                                     decode_chunk=min(int(rec_batch_size), 16384))
+        self.test_step_outputs = []
+
+    # ---- a1: latent averaging loop (source/poco_model.py:200-237) ----------------------------------------------
+    def encode_cloud(self, pts_bcn: torch.Tensor, generator: typing.Optional[torch.Generator] = None,
+                     prog_bar=None) -> torch.Tensor:
+        """``pts_bcn [1,3,N]`` (device) -> latents ``[1,latent,N]``: every point is encoded at least
+        ``gen_subsample_manifold_iter`` times on random ``gen_subsample_manifold``-point subsets and averaged."""
+        pts = pts_bcn[0].transpose(0, 1).contiguous()  # [N,3]
+        n = pts.shape[0]
+        dev = pts.device
+        sub = self.gen_subsample_manifold
+        latent = torch.zeros((n, self.network_latent_size), dtype=torch.float32, device=dev)
+        counts = torch.zeros((n,), dtype=torch.float32, device=dev)
+        counts_host = np.zeros(n, dtype=np.int64)  # the schedule depends only on counts, keep it on the host: no syncs
+        iteration = 0
+        for current in range(self.gen_subsample_manifold_iter):
+            while counts_host.min() < current + 1:
+                valid = torch.from_numpy(np.nonzero(counts_host == current)[0])
+                if n >= sub:
+                    ids = valid[torch.randperm(valid.shape[0], generator=generator)[:sub]]
+                    if ids.shape[0] < sub:
+                        ids = torch.cat([ids, torch.randperm(n, generator=generator)[:sub - ids.shape[0]]])
+                else:
+                    ids = torch.arange(n)
+                ids_dev = ids.to(dev)
+                part = self.network.get_latent({'pts': pts[ids_dev].transpose(0, 1).unsqueeze(0).contiguous()})['latents']
+                # torch semantics of `latent[ids] += x` with repeated ids: one writer wins, counted once
+                uniq, first = np.unique(ids.numpy(), return_index=True)
+                sel = torch.from_numpy(first).to(dev)
+                ops.latent_accumulate(part[0].transpose(0, 1)[sel].contiguous(), ids_dev[sel].to(torch.int32).contiguous(),
+                                      latent, counts)
+                counts_host[uniq] += 1
+                iteration += 1
+                if prog_bar is not None:
+                    prog_bar.predict_progress_bar.set_postfix_str('get_latent iter: {}'.format(iteration), refresh=True)
+        ops.latent_finalize(latent, counts)
+        return latent.transpose(0, 1).unsqueeze(0)
+
+    # ---- a11: occupancy volume (source/poco_utils.py:52-61, 178-254) ------------------------------------------------
+    @staticmethod
+    def grid_definition(input_points: np.ndarray, resolution: int, padding: int = 1):
+        bmin, bmax = input_points.min(), input_points.max()
+        step = (bmax - bmin) / (resolution - 1)
+        bmin_pad = bmin - padding * step
+        pts_ids = ((input_points - bmin) / step + padding).astype(np.int32)
+        return np.float32(step), np.float32(bmin_pad), pts_ids
+
+    def occupancy(self, decoder: ops.Decoder, queries: torch.Tensor) -> torch.Tensor:
+        """softmax(logits)[0] - softmax(logits)[1] per query (source/poco_utils.py:74-82), on the device"""
+        return decoder.decode(queries.contiguous(), want_logits=False, want_occ=True)['occ']
+
+    def dense_volume(self, decoder: ops.Decoder, input_points: np.ndarray, resolution: int, padding: int = 1) -> torch.Tensor:
+        """all ``(resolution+2*padding)^3`` vertices (the benchmark workload) -> ``[r,r,r]`` fp32 device"""
+        step, bmin_pad, _ = self.grid_definition(input_points, resolution, padding)
+        r = resolution + 2 * padding
+        queries = ops.grid_queries(r, step, bmin_pad, device=decoder.pts.device)
+        return self.occupancy(decoder, queries).view(r, r, r)
+
+    def create_volume(self, decoder: ops.Decoder, input_points: np.ndarray, resolution: int, padding: int = 1,
+                      dilation_size: int = 2, out_value: float = 1.0, prog_bar=None, pc_file_in: str = 'unknown') -> np.ndarray:
+        """region-growing evaluation: only voxels within ``dilation_size`` of an input point, then of a sign change, are
+        decoded (source/poco_utils.py:178-254).  Masks live on the host like the reference's, the dilation is one
+        separable max-filter instead of the reference's per-point Python loop."""
+        step, bmin_pad, pts_ids = self.grid_definition(input_points, resolution, padding)
+        r = resolution + 2 * padding
+        shape = (r, r, r)
+        dev = decoder.pts.device
+
+        def dilate(ids: np.ndarray) -> np.ndarray:
+            m = np.zeros(shape, dtype=bool)
+            if ids.shape[0] == 0:
+                return m
+            m[ids[:, 0], ids[:, 1], ids[:, 2]] = True
+            for ax in range(3):  # box dilation [-d, +d] along each axis
+                acc = m.copy()
+                for s in range(1, dilation_size + 1):
+                    lo = [slice(None)] * 3
+                    hi = [slice(None)] * 3
+                    lo[ax], hi[ax] = slice(0, r - s), slice(s, r)
+                    acc[tuple(hi)] |= m[tuple(lo)]
+                    acc[tuple(lo)] |= m[tuple(hi)]
+                m = acc
+            return m
+
+        volume = np.full(shape, np.nan, dtype=np.float64)
+        to_see = np.ones(shape, dtype=bool)
+        pts_ids = pts_ids.astype(np.int64)
+        sweep = 0
+        while pts_ids.shape[0] > 0:
+            mask = dilate(pts_ids)
+            coord = torch.from_numpy(np.argwhere(mask).astype(np.float32)).to(dev)
+            queries = coord * float(step) + float(bmin_pad)  # same two fp32 roundings as poco_utils.py:213
+            z = self.occupancy(decoder, queries).cpu().numpy().astype(np.float64)
+            volume[mask] = z
+            to_see[pts_ids[:, 0], pts_ids[:, 1], pts_ids[:, 2]] = False
+            v = volume[pts_ids[:, 0], pts_ids[:, 1], pts_ids[:, 2]]
+            mask_neg, mask_pos = dilate(pts_ids[v <= 0]), dilate(pts_ids[v >= 0])
+            with np.errstate(invalid='ignore'):
+                new_mask = (mask_neg & (volume >= 0) & to_see) | (mask_pos & (volume <= 0) & to_see)
+            pts_ids = np.argwhere(new_mask).astype(np.int64)
+            sweep += 1
+            if prog_bar is not None:
+                prog_bar.predict_progress_bar.set_postfix_str(
+                    '{}, occ sweep {}'.format(os.path.basename(pc_file_in), sweep), refresh=True)
+        for ax in range(3):
+            sl = [slice(None)] * 3
+            sl[ax] = slice(0, padding)
+            volume[tuple(sl)] = out_value
+            sl[ax] = slice(-padding, None)
+            volume[tuple(sl)] = out_value
+        return volume
+
+    # ---- mesh extraction (host libraries, "next" rows of SURVEY.md §8f) --------------------------------------------
+    def extract_mesh(self, decoder: ops.Decoder, volume: np.ndarray, step, bmin_pad, refine_iter: int, prog_bar=None,
+                     pc_file_in: str = 'unknown'):
+        """marching cubes + bisection refinement of the vertices on grid edges (source/poco_utils.py:87-175); the
+        occupancy queries of the refinement run on the device.  Needs scikit-image and trimesh like the reference."""
+        try:
+            from skimage import measure
+            import trimesh
+        except ImportError as err:  # pragma: no cover - neither is installed in the build image
+            raise RuntimeError('mesh extraction needs scikit-image and trimesh (reference requirements.txt); '
+                               'the occupancy volume itself is available from create_volume()') from err
+        finite = volume[~np.isnan(volume)]
+        if not (finite.max() > 0 > finite.min()):
+            return None
+        verts, faces, _, _ = measure.marching_cubes(volume=volume.copy(), level=0)
+        mesh = trimesh.Trimesh(vertices=verts, faces=faces)
+        verts, faces = np.asarray(mesh.vertices), np.asarray(mesh.faces)
+        if refine_iter > 0:
+            frac = ((verts - np.floor(verts)) > 0).astype(verts.dtype)
+            on_edge = np.logical_and(frac.sum(axis=1) > 0, frac.sum(axis=1) < 2)
+            v = verts[on_edge]
+            a = np.floor(v).astype(int)
+            b = a + frac[on_edge].astype(int)
+            pa, pb = volume[a[:, 0], a[:, 1], a[:, 2]], volume[b[:, 0], b[:, 1], b[:, 2]]
+            ok = ~np.isnan(pa) & ~np.isnan(pb)
+            on_edge[on_edge] = ok
+            va = a[ok].astype(np.float32) * step + bmin_pad
+            vb = b[ok].astype(np.float32) * step + bmin_pad
+            pa, pb = pa[ok], pb[ok]
+            verts = verts * step + bmin_pad
+            v = v[ok] * step + bmin_pad
+            for it in range(refine_iter):
+                q = torch.tensor(v, dtype=torch.float32, device=decoder.pts.device)
+                pred = self.occupancy(decoder, q).cpu().numpy()
+                ma, mb = (pred * pa) > 0, (pred * pb) > 0
+                va[ma], pa[ma] = v[ma], pred[ma]
+                vb[mb], pb[mb] = v[mb], pred[mb]
+                v = (va + vb) / 2
+                verts[on_edge] = v
+                if prog_bar is not None:
+                    prog_bar.predict_progress_bar.set_postfix_str(
+                        '{}, refine iter {}'.format(os.path.basename(pc_file_in)[:16], it), refresh=True)
+        else:
+            verts = verts * step + bmin_pad
+        return trimesh.Trimesh(vertices=verts, faces=faces)
+
+    # ---- Lightning surface -----------------------------------------------------------------------------------------
+    def get_prog_bar(self):
+        trainer = getattr(self, '_trainer', None)
+        bar = getattr(trainer, 'progress_bar_callback', None) if trainer is not None else None
+        return bar if bar is not None else _NullBar()
+
+    def forward(self, batch):
+        return self.network.forward(batch)
+
+    def reconstruct(self, pts_ms: torch.Tensor, resolution: typing.Optional[int] = None, dense: bool = False,
+                    prog_bar=None, pc_file_in: str = 'unknown') -> dict:
+        """encoder + occupancy volume for one cloud ``pts_ms [1,N,3]`` on the device; returns the volume, the grid
+        definition and the decoder state (``predict_step`` adds meshing and export on top)."""
+        resolution = resolution or self.gen_resolution_global
+        pts_bcn = pts_ms.to(torch.float32).transpose(1, 2).contiguous()
+        latents = self.encode_cloud(pts_bcn, prog_bar=prog_bar)
+        decoder = self.network.decoder_for(pts_bcn, latents)
+        input_points = pts_ms[0].cpu().numpy()
+        step, bmin_pad, _ = self.grid_definition(input_points, resolution, 1)
+        if dense:
+            volume = self.dense_volume(decoder, input_points, resolution).cpu().numpy().astype(np.float64)
+        else:
+            volume = self.create_volume(decoder, input_points, resolution, prog_bar=prog_bar, pc_file_in=pc_file_in)
+        return {'volume': volume, 'step': step, 'bmin_pad': bmin_pad, 'decoder': decoder, 'latents': latents}
+
+    def predict_step(self, batch: dict, batch_idx, dataloader_idx=0):
+        """source/poco_model.py:183-273: one cloud per batch; writes ``<results_dir>/.../<name>.ply``"""
+        if batch['pts_ms'].shape[0] > 1:
+            raise NotImplementedError('batch size > 1 not supported')
+        prog_bar = self.get_prog_bar()
+        pc_file_in = batch['pc_file_in'][0] if 'pc_file_in' in batch else 'unknown'
+        rec = self.reconstruct(batch['pts_ms'], prog_bar=prog_bar, pc_file_in=pc_file_in)
+        mesh = self.extract_mesh(rec['decoder'], rec['volume'], rec['step'], rec['bmin_pad'], self.gen_refine_iter,
+                                 prog_bar=prog_bar, pc_file_in=pc_file_in)
+        if mesh is None:
+            print('No reconstruction for {}'.format(pc_file_in))
+            return 0
+        is_dataset = os.path.splitext(str(self.in_file))[1].lower() == '.txt'
+        base = os.path.basename(pc_file_in)
+        if is_dataset:
+            out_file = os.path.join(self.results_dir, self.name, os.path.basename(os.path.dirname(str(self.in_file))),
+                                    'meshes', base)
+        else:
+            out_file = os.path.join(self.results_dir, base, base + '.ply')
+        os.makedirs(os.path.dirname(out_file), exist_ok=True)
+        mesh.export(file_obj=out_file)
+        return 0

@@ -1,0 +1,323 @@
+"""``PPSurfNetwork`` on the B200 kernels: same constructor, ``forward`` / ``get_latent`` / ``from_latent`` surface, dict
+keys and ``state_dict`` layout as the reference network (source/ppsurf_model.py:39-117), so a reference checkpoint loads
+with ``strict=True`` and the reference's reconstruction driver can call it unchanged.
+
+The torch modules below are PARAMETER CONTAINERS ONLY (they give every tensor the reference's name and shape); their
+``forward`` is never used.  All math runs through the C ABI (``ppsurf_b200.ops``) on point-major fp32 tensors; there
+is no torch fallback  --  without the CUDA library or a device every entry point raises.
+"""
+import math
+import typing
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import ops, packing
+
+try:  # the reference derives everything from LightningModule; keep that when Lightning is installed
+    import pytorch_lightning as _pl
+
+    _Base = _pl.LightningModule
+except ImportError:  # not installed in the build image
+    _Base = nn.Module
+
+ENCODER_LEVELS = ((1, 1), (1, 2), (2, 2), (2, 4), (4, 4), (4, 8), (8, 8), (8, 16), (16, 16))
+
+
+def _bn(c):
+    return nn.BatchNorm1d(c)
+
+
+class FKAConvLayerParams(_Base):
+    """tensors of FKAConvLayer (source/base/nn.py:559-589)"""
+
+    def __init__(self, cin, cout, ks=16):
+        super().__init__()
+        self.cv = nn.Conv2d(cin, cout, (1, ks), bias=False)
+        self.register_buffer('norm_radius', torch.ones(1))
+        self.alpha = nn.Parameter(torch.ones(1))
+        self.beta = nn.Parameter(torch.ones(1))
+        self.fc1 = nn.Conv2d(3, ks, 1, bias=False)
+        self.fc2 = nn.Conv2d(2 * ks, ks, 1, bias=False)
+        self.fc3 = nn.Conv2d(2 * ks, ks, 1, bias=False)
+        self.bn1 = nn.InstanceNorm2d(ks, affine=True)
+        self.bn2 = nn.InstanceNorm2d(ks, affine=True)
+
+
+class ResidualBlockParams(_Base):
+    """tensors of ResidualBlock (source/base/nn.py:422-436)"""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        half = cin // 2
+        self.cv0, self.bn0 = nn.Conv1d(cin, half, 1), _bn(half)
+        self.cv1, self.bn1 = FKAConvLayerParams(half, half), _bn(half)
+        self.cv2, self.bn2 = nn.Conv1d(half, cout, 1), _bn(cout)
+        self.shortcut = nn.Conv1d(cin, cout, 1) if cin != cout else nn.Identity()
+        self.bn_shortcut = _bn(cout) if cin != cout else nn.Identity()
+
+
+class FKAConvNetworkParams(_Base):
+    """tensors of FKAConvNetwork(segmentation=True) (source/base/nn.py:455-506)"""
+
+    def __init__(self, in_channels, out_channels, hidden=64):
+        super().__init__()
+        h = hidden
+        self.cv0, self.bn0 = FKAConvLayerParams(in_channels, h), _bn(h)
+        for (a, b), name in zip(ENCODER_LEVELS, packing.RESBLOCKS):
+            setattr(self, name, ResidualBlockParams(a * h, b * h))
+        self.cv5, self.bn5 = nn.Conv1d(32 * h, 16 * h, 1), _bn(16 * h)
+        self.cv3d, self.bn3d = nn.Conv1d(24 * h, 8 * h, 1), _bn(8 * h)
+        self.cv2d, self.bn2d = nn.Conv1d(12 * h, 4 * h, 1), _bn(4 * h)
+        self.cv1d, self.bn1d = nn.Conv1d(6 * h, 2 * h, 1), _bn(2 * h)
+        self.cv0d, self.bn0d = nn.Conv1d(3 * h, h, 1), _bn(h)
+        self.fcout = nn.Conv1d(h, out_channels, 1)
+
+
+class InterpAttentionParams(nn.Module):
+    """tensors of InterpAttentionKHeadsNet (source/poco_model.py:364-379)"""
+
+    def __init__(self, latent, out_channels, k):
+        super().__init__()
+        self.fc1 = nn.Conv2d(latent + 3, latent, 1)
+        self.fc2 = nn.Conv2d(latent, latent, 1)
+        self.fc3 = nn.Conv2d(latent, latent, 1)
+        self.fc8 = nn.Conv1d(latent, out_channels, 1)
+        self.fc_query = nn.Conv2d(latent, 64, 1)
+        self.fc_value = nn.Conv2d(latent, latent, 1)
+        self.k = k
+
+
+class _AttentionParams(_Base):
+    def __init__(self, c):
+        super().__init__()
+        self.fc_query = nn.Conv2d(c, 1, 1)
+        self.fc_value = nn.Conv2d(c, c, 1)
+
+
+class _STNParams(_Base):
+    def __init__(self, size, dim=64):
+        super().__init__()
+        self.conv1, self.conv2, self.conv3 = nn.Conv1d(dim, 64, 1), nn.Conv1d(64, 128, 1), nn.Conv1d(128, size, 1)
+        self.fc1, self.fc2, self.fc3 = nn.Linear(size, size // 2), nn.Linear(size // 2, size // 4), nn.Linear(size // 4, dim * dim)
+        self.bn1, self.bn2, self.bn3, self.bn4, self.bn5 = _bn(64), _bn(128), _bn(size), _bn(size // 2), _bn(size // 4)
+
+
+class PointNetfeatParams(_Base):
+    """tensors of PointNetfeat(use_point_stn=False, use_feat_stn=True, sym_op='att') (source/base/nn.py:256-301)"""
+
+    def __init__(self, net_size_max, output_size):
+        super().__init__()
+        self.stn2 = _STNParams(net_size_max)
+        self.conv0a, self.conv0b = nn.Conv1d(3, 64, 1), nn.Conv1d(64, 64, 1)
+        self.bn0a, self.bn0b = _bn(64), _bn(64)
+        self.conv1, self.conv2, self.conv3 = nn.Conv1d(64, 64, 1), nn.Conv1d(64, 128, 1), nn.Conv1d(128, output_size, 1)
+        self.bn1, self.bn2, self.bn3 = _bn(64), _bn(128), _bn(output_size)
+        self.att = _AttentionParams(output_size)
+
+
+class MLPParams(_Base):
+    """tensors of MLP(num_layers=3, halving_size=False, dropout=0.3) (source/base/nn.py:377-413)"""
+
+    def __init__(self, size, out):
+        super().__init__()
+        blocks = [nn.Sequential(nn.Linear(size, size), _bn(size), nn.ReLU(), nn.Dropout(0.3)) for _ in range(2)]
+        self.layers = nn.Sequential(*blocks, nn.Sequential(nn.Linear(size, out)))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+
+
+def _pm(t: torch.Tensor) -> torch.Tensor:
+    """reference ``[B,C,N]`` -> point-major contiguous ``[B,N,C]`` fp32"""
+    return t.to(torch.float32).transpose(1, 2).contiguous()
+
+
+def _ids32(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.int32).contiguous()
+
+
+class PPSurfNetwork(_Base):
+
+    def __init__(self, in_channels, latent_size, out_channels, k, num_pts_local, pointnet_latent_size,
+                 decode_chunk=16384, decode_path=0):
+        super().__init__()
+        self.latent_size = latent_size
+        self.k = k
+        self.num_pts_local = num_pts_local
+        self.encoder = FKAConvNetworkParams(in_channels, latent_size)
+        self.projection = InterpAttentionParams(latent_size, latent_size, k)
+        self.point_net = PointNetfeatParams(pointnet_latent_size, latent_size)
+        self.mlp = MLPParams(latent_size, out_channels)
+        self.lcp_preprocess = True
+        self.decode_chunk = decode_chunk
+        self.decode_path = decode_path
+        self.sampling_seed = None  # set for reproducible support sampling
+        self._packed = None
+        self._decoder_cache = None
+        self.register_load_state_dict_post_hook(lambda module, _keys: module.invalidate())
+
+    # ---- packed weights ------------------------------------------------------------------------------------------
+    def invalidate(self):
+        self._packed = None
+        self._decoder_cache = None
+
+    def _apply(self, fn, *args, **kwargs):
+        self.invalidate()
+        return super()._apply(fn, *args, **kwargs)
+
+    def packed(self):
+        dev = self.mlp.layers[2][0].weight.device
+        if dev.type != 'cuda':
+            raise RuntimeError('PPSurfNetwork (ppsurf_b200) runs on a CUDA device only: move it with .cuda() first')
+        if self._packed is None or self._packed['device'] != dev:
+            ops.require_device()
+            sd = self.state_dict()
+            self._packed = {'device': dev,
+                            'decoder': packing.pack_decoder(sd, dev, self.k, self.num_pts_local),
+                            'encoder': packing.pack_encoder(sd, dev, act='silu')}
+        return self._packed
+
+    # ---- encoder ---------------------------------------------------------------------------------------------------
+    def _resblock(self, blk, x, pts, support, ids):
+        """x [B,Nin,C] -> [B,Ns,C'] (source/base/nn.py:438-450)"""
+        b, n_in, c = x.shape
+        n_s = support.shape[1]
+        y = ops.linear(x.view(b * n_in, c), blk['cv0'].w, blk['cv0'].b, relu=True).view(b, n_in, -1)
+        y = ops.fkaconv(blk['cv1'], y, pts, support, ids)  # bn1 + ReLU folded
+        short = x
+        if 'shortcut' in blk:
+            short = ops.linear(x.view(b * n_in, c), blk['shortcut'].w, blk['shortcut'].b).view(b, n_in, -1)
+        if n_s != n_in:
+            short = ops.gather_max(short, ids)
+        cout = blk['cv2'].w.shape[0]
+        out = ops.linear(y.view(b * n_s, -1), blk['cv2'].w, blk['cv2'].b, residual=short.reshape(b * n_s, cout), relu=True)
+        return out.view(b, n_s, cout)
+
+    def encode(self, data: dict) -> torch.Tensor:
+        """FKAConvNetwork.forward(spectral_only=True) (source/base/nn.py:508-548): needs ``pts``, ``support1-4`` and the
+        13 index tensors in ``data`` (reference layouts); returns point-major latents ``[B,N0,latent]``."""
+        enc = self.packed()['encoder']
+        pts = [_pm(data['pts'])] + [_pm(data['support%d' % i]) for i in (1, 2, 3, 4)]
+        ids = {key: _ids32(val) for key, val in data.items() if key.startswith('ids')}
+        b, n0, _ = pts[0].shape
+        x = torch.ones_like(pts[0])  # nn.py:517
+        x0 = ops.fkaconv(enc['cv0'], x, pts[0], pts[0], ids['ids00'])  # bn0 + ReLU folded (nn.py:519)
+        x0 = self._resblock(enc['resnetb01'], x0, pts[0], pts[0], ids['ids00'])
+        x1 = self._resblock(enc['resnetb10'], x0, pts[0], pts[1], ids['ids01'])
+        x1 = self._resblock(enc['resnetb11'], x1, pts[1], pts[1], ids['ids11'])
+        x2 = self._resblock(enc['resnetb20'], x1, pts[1], pts[2], ids['ids12'])
+        x2 = self._resblock(enc['resnetb21'], x2, pts[2], pts[2], ids['ids22'])
+        x3 = self._resblock(enc['resnetb30'], x2, pts[2], pts[3], ids['ids23'])
+        x3 = self._resblock(enc['resnetb31'], x3, pts[3], pts[3], ids['ids33'])
+        x4 = self._resblock(enc['resnetb40'], x3, pts[3], pts[4], ids['ids34'])
+        x4 = self._resblock(enc['resnetb41'], x4, pts[4], pts[4], ids['ids44'])
+
+        out = []
+        for s in range(b):  # the U-Net decoder gathers rows, so run it per sample
+            x4s, n4 = x4[s], x4.shape[1]
+            wa, wb = enc['cv5']
+            glob = ops.linear(ops.global_max(x4[s:s + 1]), wb.w, wb.b)  # [1,1024]: W5b . max + b  (x4d_bug_fixed=True)
+            deep = ops.linear(x4s, wa.w, glob.view(-1), relu=True)
+            for stage, skip, key in (('cv3d', x3, 'ids43'), ('cv2d', x2, 'ids32'), ('cv1d', x1, 'ids21'),
+                                     ('cv0d', x0, 'ids10')):
+                wa, wb = enc[stage]
+                up = ids[key][s].reshape(-1).clamp_min(0)  # interpolate(): ids < 0 -> 0, k=1 (nn.py:684-697)
+                t = ops.linear(deep, wa.w, gather=up)
+                deep = ops.linear(skip[s], wb.w, wb.b, residual=t, relu=True)
+            out.append(ops.linear(deep, enc['fcout'].w, enc['fcout'].b))
+        return torch.stack(out, dim=0)
+
+    def spatial_ids(self, pts_bcn: torch.Tensor) -> dict:
+        """get_fkaconv_ids on the device (source/poco_data_loader.py:137-209): four quantised support samplings at
+        ratio 1/4 and the 13 kNN index tensors, reference layouts (supports [B,3,Ns], ids int64)."""
+        from .sampling import sampling_quantized
+        gen = np.random.default_rng(self.sampling_seed)
+        pts = _pm(pts_bcn)
+        b = pts.shape[0]
+        levels = [pts]
+        for _ in range(4):
+            prev = levels[-1]
+            n_sup = max(1, int(prev.shape[1] * 0.25))
+            sel = [sampling_quantized(prev[i], n_sup, gen) for i in range(b)]
+            levels.append(torch.stack([prev[i][sel[i]] for i in range(b)], dim=0))
+        out = {'support%d' % i: levels[i].transpose(1, 2).contiguous() for i in (1, 2, 3, 4)}
+        pairs16 = ((0, 0), (0, 1), (1, 1), (1, 2), (2, 2), (2, 3), (3, 3), (3, 4), (4, 4))
+        pairs1 = ((4, 3), (3, 2), (2, 1), (1, 0))
+        res = {}
+        for i in range(b):
+            index = [ops.KnnIndex(levels[lv][i].contiguous()) for lv in range(5)]
+            for a, c in pairs16:
+                res.setdefault('ids%d%d' % (a, c), []).append(index[a].query(levels[c][i].contiguous(), 16))
+            for a, c in pairs1:
+                res.setdefault('ids%d%d' % (a, c), []).append(index[a].query(levels[c][i].contiguous(), 1))
+        for key, val in res.items():
+            out[key] = torch.stack(val, dim=0).long()
+        return out
+
+    # ---- reference surface -------------------------------------------------------------------------------------
+    def forward(self, data):
+        """train/test path (source/ppsurf_model.py:70-74): ids and ``proj_ids`` come with the batch"""
+        data['latents'] = self.encode(data).transpose(1, 2)
+        return self.from_latent(data, has_proj_ids='proj_ids' in data)
+
+    def get_latent(self, data):
+        """source/ppsurf_model.py:76-80; adds the supports / ids to ``data`` like the reference does"""
+        for key, val in self.spatial_ids(data['pts']).items():
+            data[key] = val
+        data['latents'] = self.encode(data).transpose(1, 2)  # [B,latent,N] view of the point-major result
+        data['proj_correction'] = None
+        return data
+
+    def decoder_for(self, pts_bcn: torch.Tensor, latents_bcn: torch.Tensor, sample: int = 0) -> ops.Decoder:
+        """per-cloud decoder state (kNN index + fc1 table), cached while the same tensors are passed again"""
+        key = (pts_bcn.data_ptr(), latents_bcn.data_ptr(), pts_bcn.shape, getattr(latents_bcn, '_version', 0), sample,
+               self.decode_chunk, self.decode_path)
+        if self._decoder_cache is None or self._decoder_cache[0] != key:
+            pts = pts_bcn[sample].to(torch.float32).transpose(0, 1).contiguous()
+            lat = latents_bcn[sample].to(torch.float32).transpose(0, 1).contiguous()
+            dec = ops.Decoder(self.packed()['decoder'], pts, lat, chunk=self.decode_chunk, path=self.decode_path)
+            self._decoder_cache = (key, dec)
+        return self._decoder_cache[1]
+
+    def from_latent(self, data: typing.Dict[str, torch.Tensor], has_proj_ids: bool = False) -> torch.Tensor:
+        """source/ppsurf_model.py:82-117.  ``data``: ``pts [B,3,N]``, ``latents [B,C,N]``, ``pts_query [B,Q,3]`` (CPU or
+        device), optional ``pts_local_ps [B,Q,P,3]`` / ``proj_ids [B,Q,k]``.  Returns logits ``[B,2,Q]`` and, like the
+        reference, stores ``proj_ids`` (int64) in ``data``.  When the caller supplies patches (the reference driver
+        computes them on the CPU) they are used as given; otherwise neighbours, patches and both branches come from
+        one fused ``pps_decoder_decode`` call."""
+        pts, latents = data['pts'], data['latents']
+        dev = pts.device
+        if pts.shape[1] != 3:
+            pts = pts.transpose(1, 2)
+        pts_query = data['pts_query'].to(dev, torch.float32)
+        if pts_query.dim() == 2:
+            pts_query = pts_query.unsqueeze(0)
+        if pts_query.shape[-1] != 3:
+            pts_query = pts_query.transpose(1, 2)
+        outs, proj_ids = [], []
+        for s in range(pts.shape[0]):
+            dec = self.decoder_for(pts, latents, s)
+            q = pts_query[s].contiguous()
+            if 'pts_local_ps' in data:
+                if has_proj_ids:
+                    idx = _ids32(data['proj_ids'][s])
+                else:
+                    idx = dec.index.query(q, self.k)
+                feat_proj = dec.projection(q, idx)
+                feat_pn = ops.pointnet(dec.packed, data['pts_local_ps'][s].to(dev, torch.float32).contiguous())
+                p = dec.packed.tensors
+                # mlp.layers.0 on (feat_proj + feat_pn): the sum of the branches rides on the layer's linearity
+                t = ops.linear(feat_proj, p['m0_w'])
+                h = ops.linear(feat_pn, p['m0_w'], p['m0_b'], residual=t, relu=True)
+                h = ops.linear(h, p['m1_w'], p['m1_b'], relu=True)
+                outs.append(ops.linear(h, p['m2_w'], p['m2_b']))
+                proj_ids.append(idx[:, :self.k])
+            else:
+                res = dec.decode(q, want_logits=True, want_idx=True)
+                outs.append(res['logits'])
+                proj_ids.append(res['idx'][:, :self.k])
+        if not has_proj_ids:
+            data['proj_ids'] = torch.stack(proj_ids, dim=0).long()
+        return torch.stack(outs, dim=0).transpose(1, 2)

@@ -1,0 +1,208 @@
+"""Tensor-level wrappers over the C ABI (``include/ppsurf_b200.h``).  torch supplies device memory and the current
+stream; every wrapper validates dtype / device / contiguity and raises ``PpsError`` on a non-zero status.  No wrapper
+falls back to torch math."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t, dtype=None):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise ValueError('expected a CUDA tensor')
+    if not t.is_contiguous():
+        raise ValueError('expected a contiguous tensor')
+    if dtype is not None and t.dtype != dtype:
+        raise ValueError('expected dtype {}, got {}'.format(dtype, t.dtype))
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def require_device():
+    """Raises unless the current CUDA device can run the sm_100a kernels (no CPU fallback exists)."""
+    if not torch.cuda.is_available():
+        raise _lib.PpsError('ppsurf_b200 needs a CUDA (sm_100a) device; there is no CPU fallback')
+    check(lib.pps_check_device())
+
+
+class KnnIndex:
+    """Morton-sorted implicit octree over ``pts [N,3]`` (replaces ``make_kdtree``, source/base/proximity.py:40-64)."""
+
+    def __init__(self, pts: torch.Tensor):
+        self.pts = pts
+        self.n = pts.shape[0]
+        self.buf = torch.empty(lib.pps_knn_index_bytes(self.n), dtype=torch.uint8, device=pts.device)
+        check(lib.pps_knn_build(_ptr(pts, torch.float32), self.n, _ptr(self.buf), self.buf.numel(), _stream()))
+
+    def query(self, queries: torch.Tensor, k: int, return_dist: bool = False):
+        """``queries [Q,3]`` -> ``idx [Q,k'] int32`` ascending by (dist2, index), ``k' = min(k, N)`` like the reference's
+        ``knn`` (source/poco_utils.py:259-260)."""
+        k = min(int(k), self.n)
+        q = queries.shape[0]
+        idx = torch.empty((q, k), dtype=torch.int32, device=queries.device)
+        d2 = torch.empty((q, k), dtype=torch.float32, device=queries.device) if return_dist else None
+        check(lib.pps_knn_query(_ptr(self.buf), self.n, _ptr(queries, torch.float32), q, k, _ptr(idx), _ptr(d2), _stream()))
+        return (idx, d2) if return_dist else idx
+
+
+def knn(points: torch.Tensor, queries: torch.Tensor, k: int, return_dist: bool = False):
+    """one-shot build + query, point-major ``[N,3]`` / ``[Q,3]``"""
+    return KnnIndex(points).query(queries, k, return_dist)
+
+
+def patch_normalize(pts, queries, idx, d2, p):
+    q = queries.shape[0]
+    out = torch.empty((q, p, 3), dtype=torch.float32, device=pts.device)
+    check(lib.pps_patch_normalize(_ptr(pts, torch.float32), _ptr(queries, torch.float32), _ptr(idx, torch.int32),
+                                  _ptr(d2, torch.float32), q, p, idx.shape[1], _ptr(out), _stream()))
+    return out
+
+
+def linear(x, w, bias=None, residual=None, gather=None, relu=False, out=None, rows=None):
+    """``act(x[gather] @ w.T + bias + residual)``; x ``[M,K]`` (or ``[Nsrc,K]`` with ``gather [M]`` int32), w ``[N,K]``."""
+    m = (gather.shape[0] if gather is not None else x.shape[0]) if rows is None else rows
+    n, k = w.shape
+    if x.shape[-1] != k:
+        raise ValueError('linear: x has {} columns, w expects {}'.format(x.shape[-1], k))
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float32, device=x.device)
+    check(lib.pps_linear(_ptr(x, torch.float32), _ptr(w, torch.float32), _ptr(bias), _ptr(residual),
+                         _ptr(gather, torch.int32) if gather is not None else None, _ptr(out), m, n, k, x.stride(-2)
+                         if x.dim() > 1 else k, n, 1 if relu else 0, _stream()))
+    return out
+
+
+def grid_queries(r, step, bmin_pad, first=0, count=None, device='cuda'):
+    count = r ** 3 - first if count is None else count
+    out = torch.empty((count, 3), dtype=torch.float32, device=device)
+    check(lib.pps_grid_queries(r, float(step), float(bmin_pad), first, count, _ptr(out), _stream()))
+    return out
+
+
+class Decoder:
+    """Per-cloud decoder state: kNN index + hoisted fc1 table; decodes query batches through ``pps_decoder_decode``."""
+
+    def __init__(self, packed, pts: torch.Tensor, latents: torch.Tensor, chunk: int = 16384, path: int = 0):
+        """``pts [N,3]``, ``latents [N,C]`` point-major fp32 on the device."""
+        self.packed = packed
+        self.pts = pts.contiguous()
+        self.latents = latents.contiguous()
+        self.n = pts.shape[0]
+        self.chunk = int(chunk)
+        self.path = int(path)
+        self.kmax = max(packed.struct.k, packed.struct.num_pts_local)
+        if self.n < self.kmax:
+            raise ValueError('cloud has {} points, the decoder needs at least {}'.format(self.n, self.kmax))
+        self.index = KnnIndex(self.pts)
+        self.table = torch.empty((self.n, packed.struct.latent), dtype=torch.float32, device=pts.device)
+        check(lib.pps_decoder_point_table(packed.ref, _ptr(self.pts, torch.float32), _ptr(self.latents, torch.float32),
+                                          self.n, _ptr(self.table), _stream()))
+        self._ws = None
+        self._ws_chunk = 0
+        self._staging = None
+        self._copy_stream = None
+
+    def workspace(self, chunk):
+        if self._ws is None or self._ws_chunk < chunk:
+            nbytes = lib.pps_decoder_workspace_bytes(self.packed.ref, chunk)
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.pts.device)
+            self._ws_chunk = chunk
+        return self._ws
+
+    def decode(self, queries: torch.Tensor, want_logits=True, want_occ=False, want_idx=False):
+        """``queries [Q,3]`` device -> dict(logits [Q,2], occ [Q], idx [Q,kmax])"""
+        q = queries.shape[0]
+        chunk = max(1, min(self.chunk, q))
+        ws = self.workspace(chunk)
+        dev = queries.device
+        logits = torch.empty((q, 2), dtype=torch.float32, device=dev) if want_logits else None
+        occ = torch.empty((q,), dtype=torch.float32, device=dev) if want_occ else None
+        idx = torch.empty((q, self.kmax), dtype=torch.int32, device=dev) if want_idx else None
+        check(lib.pps_decoder_decode(self.packed.ref, _ptr(self.index.buf), _ptr(self.pts), _ptr(self.table), self.n,
+                                     _ptr(queries, torch.float32), q, chunk, _ptr(ws), ws.numel(), _ptr(logits),
+                                     _ptr(occ), _ptr(idx), self.path, _stream()))
+        return {'logits': logits, 'occ': occ, 'idx': idx}
+
+    def decode_host(self, queries_host: torch.Tensor, occ_host: torch.Tensor = None):
+        """``queries_host [Q,3]`` pinned CPU tensor -> ``occ_host [Q]`` pinned CPU tensor (synchronous)."""
+        q = queries_host.shape[0]
+        if occ_host is None:
+            occ_host = torch.empty((q,), dtype=torch.float32).pin_memory()
+        chunk = max(1, min(self.chunk, q))
+        ws = self.workspace(chunk)
+        if self._staging is None or self._staging.numel() < q * 16:
+            self._staging = torch.empty(q * 16, dtype=torch.uint8, device=self.pts.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.pts.device)
+        assert queries_host.dtype == torch.float32 and queries_host.is_contiguous() and not queries_host.is_cuda
+        check(lib.pps_decoder_decode_host(self.packed.ref, _ptr(self.index.buf), _ptr(self.pts), _ptr(self.table), self.n,
+                                          ctypes.c_void_p(queries_host.data_ptr()), q, chunk, _ptr(ws), ws.numel(),
+                                          _ptr(self._staging), self._staging.numel(),
+                                          ctypes.c_void_p(occ_host.data_ptr()), self.path, _stream(),
+                                          ctypes.c_void_p(self._copy_stream.cuda_stream)))
+        return occ_host
+
+    def projection(self, queries, idx):
+        q = queries.shape[0]
+        ws = self.workspace(max(q, 1))
+        out = torch.empty((q, self.packed.struct.latent), dtype=torch.float32, device=queries.device)
+        check(lib.pps_decoder_projection(self.packed.ref, _ptr(self.pts), _ptr(self.table), _ptr(queries, torch.float32),
+                                         _ptr(idx, torch.int32), idx.shape[1], q, _ptr(ws), ws.numel(), _ptr(out),
+                                         self.path, _stream()))
+        return out
+
+
+def pointnet(packed, patches: torch.Tensor):
+    """``patches [Q,P,3]`` -> ``[Q,C]`` local-branch features"""
+    q = patches.shape[0]
+    nbytes = lib.pps_decoder_workspace_bytes(packed.ref, max(q, 1))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=patches.device)
+    out = torch.empty((q, packed.struct.latent), dtype=torch.float32, device=patches.device)
+    check(lib.pps_decoder_pointnet(packed.ref, _ptr(patches, torch.float32), q, _ptr(ws), ws.numel(), _ptr(out), _stream()))
+    return out
+
+
+def fkaconv(packed, x, pts, support, ids):
+    """``x [B,Nin,Cin]``, ``pts [B,Nin,3]``, ``support [B,Ns,3]``, ``ids [B,Ns,16] int32`` -> ``[B,Ns,Cout]``"""
+    b, n_in, cin = x.shape
+    n_s = support.shape[1]
+    if ids.shape[-1] != 16:
+        raise ValueError('FKAConv needs 16 neighbours per support point (kernel size 16), got {}'.format(ids.shape[-1]))
+    nbytes = lib.pps_fkaconv_workspace_bytes(b, n_s, cin)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    out = torch.empty((b, n_s, packed.struct.cout), dtype=torch.float32, device=x.device)
+    check(lib.pps_fkaconv_forward(packed.ref, _ptr(x, torch.float32), _ptr(pts, torch.float32), _ptr(support, torch.float32),
+                                  _ptr(ids, torch.int32), b, n_in, n_s, _ptr(ws), ws.numel(), _ptr(out), _stream()))
+    return out
+
+
+def gather_max(x, ids):
+    b, n_in, c = x.shape
+    n_s, kn = ids.shape[1], ids.shape[2]
+    out = torch.empty((b, n_s, c), dtype=torch.float32, device=x.device)
+    check(lib.pps_gather_max(_ptr(x, torch.float32), _ptr(ids, torch.int32), b, n_in, n_s, c, kn, _ptr(out), _stream()))
+    return out
+
+
+def global_max(x):
+    b, n, c = x.shape
+    out = torch.empty((b, c), dtype=torch.float32, device=x.device)
+    check(lib.pps_global_max(_ptr(x, torch.float32), b, n, c, _ptr(out), _stream()))
+    return out
+
+
+def latent_accumulate(partial, ids, latent, counts):
+    check(lib.pps_latent_accumulate(_ptr(partial, torch.float32), _ptr(ids, torch.int32), ids.shape[0], latent.shape[1],
+                                    _ptr(latent, torch.float32), _ptr(counts, torch.float32), _stream()))
+
+
+def latent_finalize(latent, counts):
+    check(lib.pps_latent_finalize(_ptr(latent, torch.float32), _ptr(counts, torch.float32), latent.shape[0],
+                                  latent.shape[1], _stream()))

@@ -1,0 +1,163 @@
+"""Host-side weight packing: reference ``state_dict`` tensors -> the flat fp32 matrices the C ABI consumes.
+
+Done once per ``load_state_dict`` in float64 on the CPU, then cast to fp32 and moved to the device:
+  * eval-mode BatchNorm folded into the preceding linear map,
+  * ``fc8 . fc_value`` and ``att.fc_value . bn3 . conv3`` merged (the attention weights sum to one, so the pooling
+    commutes with every affine map that follows it),
+  * FKAConv ``cv.weight [cout,cin,1,16]`` repacked to ``[cout, 16*cin]`` with column ``m*cin + c``.
+Names on the left are the reference's (source/ppsurf_model.py:39-68, source/base/nn.py, source/poco_model.py:364-379).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+BN_EPS = 1e-5
+
+
+def _f64(sd, name):
+    return sd[name].detach().to('cpu', torch.float64)
+
+
+def _mat(sd, name):
+    w = _f64(sd, name)
+    return w.reshape(w.shape[0], -1)
+
+
+def _fold_bn(sd, lin, bn, has_bias=True):
+    """(W, b) of ``bn(lin(x))`` in eval mode"""
+    w = _mat(sd, lin + '.weight')
+    b = _f64(sd, lin + '.bias') if has_bias else torch.zeros(w.shape[0], dtype=torch.float64)
+    s = _f64(sd, bn + '.weight') / torch.sqrt(_f64(sd, bn + '.running_var') + BN_EPS)
+    return w * s[:, None], (b - _f64(sd, bn + '.running_mean')) * s + _f64(sd, bn + '.bias')
+
+
+class Packed:
+    """A ctypes struct plus the device tensors that keep its pointers alive."""
+
+    def __init__(self, struct):
+        self.struct = struct
+        self.tensors = {}
+
+    def put(self, field, value, device):
+        t = value.to(torch.float32).contiguous().to(device)
+        self.tensors[field] = t
+        setattr(self.struct, field, t.data_ptr())
+        return t
+
+    @property
+    def ref(self):
+        return ctypes.byref(self.struct)
+
+
+def pack_decoder(sd, device, k, num_pts_local, prefix='') -> Packed:
+    p = Packed(_lib.DecoderWeights())
+    g = prefix + 'projection.'
+    w1 = _mat(sd, g + 'fc1.weight')
+    latent = w1.shape[0]
+    st = p.struct
+    st.latent, st.heads, st.k, st.num_pts_local = latent, _mat(sd, g + 'fc_query.weight').shape[0], int(k), int(num_pts_local)
+    p.put('w1_lat', w1[:, :latent], device)
+    p.put('w1_xyz', w1[:, latent:latent + 3], device)
+    p.put('b1', _f64(sd, g + 'fc1.bias'), device)
+    p.put('w2', _mat(sd, g + 'fc2.weight'), device)
+    p.put('b2', _f64(sd, g + 'fc2.bias'), device)
+    p.put('w3', _mat(sd, g + 'fc3.weight'), device)
+    p.put('b3', _f64(sd, g + 'fc3.bias'), device)
+    p.put('wq', _mat(sd, g + 'fc_query.weight'), device)
+    p.put('bq', _f64(sd, g + 'fc_query.bias'), device)
+    w8, wv = _mat(sd, g + 'fc8.weight'), _mat(sd, g + 'fc_value.weight')
+    p.put('wv8', w8 @ wv, device)
+    p.put('bv8', w8 @ _f64(sd, g + 'fc_value.bias') + _f64(sd, g + 'fc8.bias'), device)
+
+    n = prefix + 'point_net.'
+    for field, lin, bn in (('pn0a', 'conv0a', 'bn0a'), ('pn0b', 'conv0b', 'bn0b'), ('stn1', 'stn2.conv1', 'stn2.bn1'),
+                           ('stn2', 'stn2.conv2', 'stn2.bn2'), ('stn3', 'stn2.conv3', 'stn2.bn3'),
+                           ('stnf1', 'stn2.fc1', 'stn2.bn4'), ('stnf2', 'stn2.fc2', 'stn2.bn5'),
+                           ('pn1', 'conv1', 'bn1'), ('pn2', 'conv2', 'bn2')):
+        w, b = _fold_bn(sd, n + lin, n + bn)
+        p.put(field + '_w', w, device)
+        p.put(field + '_b', b, device)
+    st.stn_size = _mat(sd, n + 'stn2.conv3.weight').shape[0]
+    p.put('stnf3_w', _mat(sd, n + 'stn2.fc3.weight'), device)
+    p.put('stnf3_b', _f64(sd, n + 'stn2.fc3.bias') + torch.eye(64, dtype=torch.float64).reshape(-1), device)
+    a3, c3 = _fold_bn(sd, n + 'conv3', n + 'bn3')  # x3 = a3 h + c3 (no ReLU before the attention pooling)
+    wq = _mat(sd, n + 'att.fc_query.weight')  # [1,C]
+    p.put('pnq_w', (wq @ a3).reshape(-1), device)
+    st.pnq_b = float((wq @ c3).reshape(()) + _f64(sd, n + 'att.fc_query.bias').reshape(()))
+    wv_att = _mat(sd, n + 'att.fc_value.weight')
+    p.put('pnv_w', wv_att @ a3, device)
+    p.put('pnv_b', wv_att @ c3 + _f64(sd, n + 'att.fc_value.bias'), device)
+
+    m = prefix + 'mlp.layers.'
+    for i in (0, 1):
+        w, b = _fold_bn(sd, m + '{}.0'.format(i), m + '{}.1'.format(i))
+        p.put('m{}_w'.format(i), w, device)
+        p.put('m{}_b'.format(i), b, device)
+    p.put('m2_w', _mat(sd, m + '2.0.weight'), device)
+    p.put('m2_b', _f64(sd, m + '2.0.bias'), device)
+    return p
+
+
+def pack_fkaconv(sd, name, device, act, bn=None) -> Packed:
+    """``name`` = FKAConvLayer prefix; ``bn`` = the BatchNorm that follows it (folded, with its ReLU)."""
+    p = Packed(_lib.FKAConvWeights())
+    cv = _f64(sd, name + '.cv.weight')  # [cout,cin,1,16]
+    cout, cin = cv.shape[0], cv.shape[1]
+    w = cv[:, :, 0, :].permute(0, 2, 1).reshape(cout, 16 * cin)
+    st = p.struct
+    st.cin, st.cout, st.act = cin, cout, {'relu': 0, 'silu': 1}[act]
+    st.alpha = float(_f64(sd, name + '.alpha'))
+    st.beta = float(_f64(sd, name + '.beta'))
+    st.norm_radius = float(_f64(sd, name + '.norm_radius'))
+    if bn is not None:
+        s = _f64(sd, bn + '.weight') / torch.sqrt(_f64(sd, bn + '.running_var') + BN_EPS)
+        w = w * s[:, None]
+        p.put('out_bias', _f64(sd, bn + '.bias') - _f64(sd, bn + '.running_mean') * s, device)
+        st.out_relu = 1
+    else:
+        st.out_bias = None
+        st.out_relu = 0
+    p.put('cv_w', w, device)
+    p.put('fc1', _mat(sd, name + '.fc1.weight'), device)
+    p.put('fc2', _mat(sd, name + '.fc2.weight'), device)
+    p.put('fc3', _mat(sd, name + '.fc3.weight'), device)
+    p.put('in1_w', _f64(sd, name + '.bn1.weight'), device)
+    p.put('in1_b', _f64(sd, name + '.bn1.bias'), device)
+    p.put('in2_w', _f64(sd, name + '.bn2.weight'), device)
+    p.put('in2_b', _f64(sd, name + '.bn2.bias'), device)
+    return p
+
+
+class PackedLinear:
+    def __init__(self, w, b, device):
+        self.w = w.to(torch.float32).contiguous().to(device)
+        self.b = None if b is None else b.to(torch.float32).contiguous().to(device)
+
+
+RESBLOCKS = ('resnetb01', 'resnetb10', 'resnetb11', 'resnetb20', 'resnetb21', 'resnetb30', 'resnetb31', 'resnetb40',
+             'resnetb41')
+
+
+def pack_encoder(sd, device, act='silu', prefix='encoder.') -> dict:
+    """All encoder layers (source/base/nn.py:453-554).  Concat inputs of the U-Net decoder are split into one matrix
+    per source so that ``cat`` never materialises."""
+    e = prefix
+    out = {'cv0': pack_fkaconv(sd, e + 'cv0', device, act, bn=e + 'bn0')}
+    for rb in RESBLOCKS:
+        r = e + rb
+        blk = {'cv0': PackedLinear(*_fold_bn(sd, r + '.cv0', r + '.bn0'), device),
+               'cv1': pack_fkaconv(sd, r + '.cv1', device, act, bn=r + '.bn1'),
+               'cv2': PackedLinear(*_fold_bn(sd, r + '.cv2', r + '.bn2'), device)}
+        if (r + '.shortcut.weight') in sd:
+            blk['shortcut'] = PackedLinear(*_fold_bn(sd, r + '.shortcut', r + '.bn_shortcut'), device)
+        out[rb] = blk
+    for cv, bn in (('cv5', 'bn5'), ('cv3d', 'bn3d'), ('cv2d', 'bn2d'), ('cv1d', 'bn1d'), ('cv0d', 'bn0d')):
+        # input = cat([first, second]): cv5 sees [x4, global max]; cvXd sees [interpolate(deeper), skip] where the skip
+        # level has as many channels as the layer's output, so the first block is (in - out) columns wide
+        w, b = _fold_bn(sd, e + cv, e + bn)
+        c_first = w.shape[1] - w.shape[0]
+        out[cv] = (PackedLinear(w[:, :c_first], None, device), PackedLinear(w[:, c_first:], b, device))
+    out['fcout'] = PackedLinear(_mat(sd, e + 'fcout.weight'), _f64(sd, e + 'fcout.bias'), device)
+    return out

@@ -1,0 +1,383 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the golden vectors made by the reference.
+Run on the B200 box:  python -m pytest tests -m gpu"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 1e-4  # north-star tolerance: logits within 1e-4 abs of the reference's fp32 CPU path
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available(), 'the gpu tests need a CUDA device'
+    from ppsurf_b200 import ops
+    ops.require_device()
+    return torch.device('cuda:0')
+
+
+@pytest.fixture(scope='module')
+def net(dev, weights):
+    import ppsurf_b200
+    n = ppsurf_b200.PPSurfNetwork(3, 256, 2, 64, 50, 256)
+    n.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in weights.items()}, strict=True)
+    return n.to(dev).eval()
+
+
+def cu(a, dev, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(dev)
+
+
+def assert_knn_equal(oracle, pts, qry, idx, d2, ref_idx):
+    """identical distance multiset per query (bit exact), identical index set except inside exact ties"""
+    idx = idx.astype(np.int64)
+    got = oracle.sq_dist_f32(qry[:, None, :], pts[idx])
+    if d2 is not None:
+        np.testing.assert_array_equal(got, d2)  # the reported dist2 is the fp32 distance of the reported neighbour
+        assert np.all(np.diff(d2, axis=1) >= 0)
+    ref = oracle.sq_dist_f32(qry[:, None, :], pts[ref_idx])
+    np.testing.assert_array_equal(np.sort(got, axis=1), np.sort(ref, axis=1))
+    for r in np.nonzero(np.any(np.sort(idx, axis=1) != np.sort(ref_idx, axis=1), axis=1))[0]:
+        diff = list(set(idx[r]) ^ set(ref_idx[r]))
+        assert np.all(oracle.sq_dist_f32(qry[r][None], pts[diff]) == np.sort(ref[r])[-1]), 'row {}'.format(r)
+
+
+# ---- a6 kNN ---------------------------------------------------------------------------------------------------------
+
+def test_knn_golden(dev, oracle):
+    from ppsurf_b200 import ops
+    g = load_golden('knn')
+    index = ops.KnnIndex(cu(g['pts'], dev))
+    idx, d2 = index.query(cu(g['qry'], dev), 64, return_dist=True)
+    assert_knn_equal(oracle, g['pts'], g['qry'], idx.cpu().numpy(), d2.cpu().numpy(), g['idx64'].astype(np.int64))
+    idx1 = index.query(cu(g['qry'], dev), 1)
+    assert_knn_equal(oracle, g['pts'], g['qry'], idx1.cpu().numpy(), None, g['idx1'].astype(np.int64))
+    # k > N clamps to N like the reference (source/poco_utils.py:259-260)
+    small = ops.knn(cu(g['pts'][:10], dev), cu(g['qry'][:5], dev), 16)
+    assert tuple(small.shape) == (5, 10)
+    np.testing.assert_array_equal(small.cpu().numpy(), g['idx_small'])
+
+
+@pytest.mark.parametrize('n,q,k', [(20000, 3000, 64), (3000, 500, 200), (2500, 2500, 16), (39, 39, 16), (700, 100, 300)])
+def test_knn_vs_oracle(dev, oracle, n, q, k):
+    from ppsurf_b200 import ops
+    rng = np.random.default_rng(n + k)
+    pts = oracle.synthetic_cloud(n, seed=n)
+    qry = np.concatenate([pts[rng.integers(0, n, q // 2)] + 0.01 * rng.standard_normal((q // 2, 3)),
+                          rng.uniform(-0.6, 0.6, (q - q // 2, 3))]).astype(np.float32)
+    idx, d2 = ops.knn(cu(pts, dev), cu(qry, dev), k, return_dist=True)
+    ref_idx, _ = oracle.knn(pts, qry, k)
+    assert_knn_equal(oracle, pts, qry, idx.cpu().numpy(), d2.cpu().numpy(), ref_idx)
+
+
+def test_knn_edge_cases(dev, oracle):
+    from ppsurf_b200 import ops
+    rng = np.random.default_rng(5)
+    # duplicated points and exact ties: the (dist2, index) order makes the result unique -> equal to the oracle's
+    base = rng.uniform(-0.5, 0.5, (300, 3)).astype(np.float32)
+    pts = np.concatenate([base, base, base[:50]])
+    qry = base[:64].copy()
+    idx, d2 = ops.knn(cu(pts, dev), cu(qry, dev), 8, return_dist=True)
+    ref_idx, ref_d2 = oracle.knn(pts, qry, 8)
+    np.testing.assert_array_equal(idx.cpu().numpy(), ref_idx)
+    np.testing.assert_array_equal(d2.cpu().numpy(), ref_d2)
+    # all points identical (degenerate bounding box), queries far outside the box
+    same = np.tile(np.array([[0.1, -0.2, 0.3]], dtype=np.float32), (100, 1))
+    far = np.array([[10, 10, 10], [-7, 0, 3], [0.1, -0.2, 0.3]], dtype=np.float32)
+    idx = ops.knn(cu(same, dev), cu(far, dev), 5).cpu().numpy()
+    np.testing.assert_array_equal(idx, np.tile(np.arange(5), (3, 1)))
+    # empty query set
+    assert ops.knn(cu(base, dev), torch.empty((0, 3), device=dev), 4).shape == (0, 4)
+    # planar cloud (zero extent on one axis)
+    plane = base.copy()
+    plane[:, 2] = 0.25
+    q2 = rng.uniform(-0.5, 0.5, (200, 3)).astype(np.float32)
+    idx, d2 = ops.knn(cu(plane, dev), cu(q2, dev), 16, return_dist=True)
+    assert_knn_equal(oracle, plane, q2, idx.cpu().numpy(), d2.cpu().numpy(), oracle.knn(plane, q2, 16)[0])
+
+
+def test_knn_bad_arguments(dev):
+    from ppsurf_b200 import _lib, ops
+    pts = torch.zeros((10, 3), device=dev)
+    index = ops.KnnIndex(pts)
+    with pytest.raises(_lib.PpsError):
+        _lib.check(_lib.lib.pps_knn_query(index.buf.data_ptr(), 10, pts.data_ptr(), 10, 11, pts.data_ptr(), None, None))
+    with pytest.raises(_lib.PpsError):
+        _lib.check(_lib.lib.pps_knn_build(pts.data_ptr(), 10, index.buf.data_ptr(), 16, None))
+
+
+# ---- a7 patches -----------------------------------------------------------------------------------------------------
+
+def test_patches_golden(dev, oracle):
+    from ppsurf_b200 import ops
+    g = load_golden('patches')
+    pts, qry = cu(g['pts'], dev), cu(g['qry'], dev)
+    idx, d2 = ops.knn(pts, qry, 64, return_dist=True)
+    loc = ops.patch_normalize(pts, qry, idx, d2, 50).cpu().numpy()
+    # same neighbours, same fp32 expression: bit exact up to the order inside exact distance ties
+    np.testing.assert_array_equal(np.sort(loc, axis=1), np.sort(g['pts_local_ps'], axis=1))
+    same_order = np.all(loc == g['pts_local_ps'], axis=(1, 2))
+    assert same_order.mean() > 0.99
+
+
+# ---- generic linear ---------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize('m,n,k', [(1000, 256, 256), (333, 64, 64), (129, 2, 256), (77, 4096, 64), (500, 128, 3), (64, 70, 37)])
+def test_linear(dev, m, n, k):
+    from ppsurf_b200 import ops
+    gen = torch.Generator().manual_seed(m + n + k)
+    x = torch.randn((m, k), generator=gen)
+    w = torch.randn((n, k), generator=gen) / k ** 0.5
+    b = torch.randn((n,), generator=gen)
+    r = torch.randn((m, n), generator=gen)
+    ref = torch.relu(x.double() @ w.double().T + b.double() + r.double())
+    out = ops.linear(x.to(dev), w.to(dev), b.to(dev), residual=r.to(dev), relu=True).cpu().double()
+    assert (out - ref).abs().max() < 2e-5
+    src = torch.randn((50, k), generator=gen)
+    gi = torch.randint(0, 50, (m,), generator=gen)
+    ref = src.double()[gi] @ w.double().T
+    out = ops.linear(src.to(dev), w.to(dev), gather=gi.to(dev, torch.int32)).cpu().double()
+    assert (out - ref).abs().max() < 2e-5
+
+
+# ---- a3/a4/a5 encoder ---------------------------------------------------------------------------------------------------
+
+def test_fkaconv_and_resblock_golden(dev, net, weights_digest):
+    from ppsurf_b200 import ops
+    g = load_golden('fkaconv')
+    assert str(g['digest']) == weights_digest
+    enc = net.packed()['encoder']
+    pts, sup = cu(g['pts'][None], dev), cu(g['support'][None], dev)
+    ids = cu(g['ids'][None], dev, torch.int32)
+    # the packed layer includes bn1 + ReLU of the enclosing block: compare against the same composition of the golden
+    sd = net.state_dict()
+    s = (sd['encoder.resnetb01.bn1.weight'] / torch.sqrt(sd['encoder.resnetb01.bn1.running_var'] + 1e-5)).cpu().numpy()
+    sh = (sd['encoder.resnetb01.bn1.bias'].cpu().numpy() - sd['encoder.resnetb01.bn1.running_mean'].cpu().numpy() * s)
+    ref = np.maximum(g['y_fka'][0].T * s + sh, 0)
+    x32 = cu(g['x32'][0].T[None], dev)
+    y = ops.fkaconv(enc['resnetb01']['cv1'], x32, pts, sup, ids)[0].cpu().numpy()
+    assert np.abs(y - ref).max() < 2e-5 * max(1.0, np.abs(ref).max())
+    x64 = cu(g['x64'][0].T[None], dev)
+    y = net._resblock(enc['resnetb10'], x64, pts, sup, ids)[0].cpu().numpy()
+    assert np.abs(y - g['y_rb'][0].T).max() < 2e-5 * max(1.0, np.abs(g['y_rb']).max())
+    ids_same = cu(g['ids_same'][None], dev, torch.int32)
+    y = net._resblock(enc['resnetb01'], x64, pts, pts, ids_same)[0].cpu().numpy()
+    assert np.abs(y - g['y_rb_same'][0].T).max() < 2e-5 * max(1.0, np.abs(g['y_rb_same']).max())
+
+
+def test_encoder_golden(dev, net, oracle, weights):
+    g = load_golden('encoder')
+    data = {k: cu(v, dev, torch.int64 if k.startswith('ids') else None) for k, v in g.items() if k not in ('latents', 'digest')}
+    lat = net.encode(data)[0].cpu().numpy().T  # [C,N]
+    scale = np.abs(g['latents']).max()
+    assert np.abs(lat - g['latents'][0]).max() < 5e-5 * scale
+    # batch of two different clouds == two single runs (per-sample InstanceNorm statistics)
+    d2 = {k: torch.cat([v, v.flip(-1) if k in ('pts',) else v], dim=0) for k, v in data.items()}
+    d2['pts'] = torch.cat([data['pts'], data['pts'] * 0.9], dim=0)
+    for i in (1, 2, 3, 4):
+        d2['support%d' % i] = torch.cat([data['support%d' % i], data['support%d' % i] * 0.9], dim=0)
+    lat2 = net.encode(d2)
+    assert np.abs(lat2[0].cpu().numpy().T - g['latents'][0]).max() < 5e-5 * scale
+    ref1 = oracle.fkaconv_network(weights, {k: v[1:2].cpu().numpy() for k, v in d2.items()})
+    assert np.abs(lat2[1].cpu().numpy().T - ref1[0]).max() < 5e-5 * max(scale, np.abs(ref1).max())
+
+
+def test_get_latent_indices_and_latents(dev, net, oracle, weights):
+    """spatial_ids: supports are subsets of the right sizes, the 13 index tensors equal the oracle's kNN on those
+    supports, and get_latent's output equals the oracle encoder on the same supports/ids"""
+    pts = oracle.synthetic_cloud(1500, seed=21)
+    net.sampling_seed = 7
+    data = net.spatial_ids(cu(pts.T[None], dev))
+    sizes = [1500, 375, 93, 23, 5]
+    lv = [pts] + [data['support%d' % i][0].T.cpu().numpy() for i in (1, 2, 3, 4)]
+    for i in range(1, 5):
+        assert lv[i].shape == (sizes[i], 3)
+        prev = {tuple(r) for r in lv[i - 1].tolist()}
+        assert all(tuple(r) in prev for r in lv[i].tolist())
+    for a, c, k in ((0, 0, 16), (0, 1, 16), (1, 1, 16), (1, 2, 16), (2, 2, 16), (2, 3, 16), (3, 3, 16), (3, 4, 16), (4, 4, 16),
+                    (4, 3, 1), (3, 2, 1), (2, 1, 1), (1, 0, 1)):
+        got = data['ids%d%d' % (a, c)][0].cpu().numpy()
+        assert got.dtype == np.int64 and got.shape == (sizes[c], min(k, sizes[a]))
+        assert_knn_equal(oracle, lv[a], lv[c], got, None, oracle.knn(lv[a], lv[c], k)[0])
+    # with only 5 points in support4 the ids have 5 columns and the reference's 16-wide kernel cannot run either: use a
+    # cloud large enough (support4 = 16 points) for the comparison of values
+    pts = oracle.synthetic_cloud(4200, seed=22)
+    data = net.get_latent({'pts': cu(pts.T[None], dev)})
+    assert data['proj_correction'] is None and tuple(data['latents'].shape) == (1, 256, 4200)
+    ref = oracle.fkaconv_network(weights, {k: v.cpu().numpy() for k, v in data.items() if k.startswith(('pts', 'support', 'ids'))})
+    got = data['latents'].cpu().numpy()
+    assert np.abs(got - ref).max() < 5e-5 * max(1.0, np.abs(ref).max())
+
+
+# ---- a8-a11 decoder -------------------------------------------------------------------------------------------------------
+
+def _decode_inputs(g):
+    return np.random.default_rng(int(g['latents_seed'])).standard_normal((1, 256, g['pts'].shape[0])).astype(np.float32)
+
+
+@pytest.mark.parametrize('path', [0])
+def test_decode_golden(dev, net, oracle, weights, path):
+    from ppsurf_b200 import ops
+    g = load_golden('decode')
+    latents = _decode_inputs(g)
+    dec = ops.Decoder(net.packed()['decoder'], cu(g['pts'], dev), cu(latents[0].T, dev), chunk=100, path=path)
+    qry = cu(g['qry'], dev)
+    feat_proj = dec.projection(qry, cu(g['proj_ids'], dev, torch.int32)).cpu().numpy()
+    assert np.abs(feat_proj - g['feat_proj'][0].T).max() < 5e-5 * max(1.0, np.abs(g['feat_proj']).max())
+    feat_pn = ops.pointnet(dec.packed, cu(g['pts_local_ps'], dev)).cpu().numpy()
+    assert np.abs(feat_pn - g['feat_pn']).max() < 5e-5 * max(1.0, np.abs(g['feat_pn']).max())
+    res = dec.decode(qry, want_logits=True, want_occ=True, want_idx=True)  # 192 queries in chunks of 100: ragged tail
+    logits = res['logits'].cpu().numpy().T[None]
+    assert np.abs(logits - g['logits']).max() < LOGIT_TOL
+    assert np.abs(res['occ'].cpu().numpy() - g['occ'][0]).max() < LOGIT_TOL
+    assert_knn_equal(oracle, g['pts'], g['qry'], res['idx'].cpu().numpy(), None, g['proj_ids'].astype(np.int64))
+    # float64 oracle as the arbiter
+    data = {'pts': g['pts'].T[None], 'latents': latents, 'pts_query': g['qry'][None],
+            'pts_local_ps': g['pts_local_ps'][None], 'proj_ids': g['proj_ids'].astype(np.int64)[None]}
+    ref64 = oracle.from_latent(weights, data, dtype=np.float64)
+    assert np.abs(logits - ref64).max() < LOGIT_TOL
+    # host-buffer entry point == device entry point
+    occ_host = dec.decode_host(torch.from_numpy(g['qry']).pin_memory())
+    np.testing.assert_array_equal(occ_host.numpy(), res['occ'].cpu().numpy())
+
+
+def test_from_latent_reference_interface(dev, net):
+    """the dict the reference driver builds (source/poco_utils.py:220-223): CPU pts_query, device patches"""
+    g = load_golden('decode')
+    latents = _decode_inputs(g)
+    data = {'pts': cu(g['pts'].T[None], dev), 'latents': cu(latents, dev), 'pts_query': torch.from_numpy(g['qry'][None]),
+            'pts_local_ps': cu(g['pts_local_ps'][None], dev)}
+    out = net.from_latent(data)
+    assert tuple(out.shape) == (1, 2, g['qry'].shape[0]) and out.device.type == 'cuda'
+    assert np.abs(out.cpu().numpy() - g['logits']).max() < LOGIT_TOL
+    assert data['proj_ids'].dtype == torch.int64 and tuple(data['proj_ids'].shape) == (1, g['qry'].shape[0], 64)
+    # without caller-supplied patches everything comes from the fused call
+    data2 = {'pts': data['pts'], 'latents': data['latents'], 'pts_query': torch.from_numpy(g['qry'][None])}
+    out2 = net.from_latent(data2)
+    assert np.abs(out2.cpu().numpy() - g['logits']).max() < LOGIT_TOL
+    # supplied proj_ids (the train/test path)
+    data3 = dict(data)
+    data3['proj_ids'] = cu(g['proj_ids'][None], dev, torch.int64)
+    out3 = net.from_latent(data3, has_proj_ids=True)
+    assert np.abs(out3.cpu().numpy() - g['logits']).max() < LOGIT_TOL
+
+
+def test_decode_200nn(dev, oracle):
+    """P=200 (ppsurf_200nn): the kNN runs with k=200, the global branch uses the first 64"""
+    import ppsurf_b200
+    from ppsurf_b200 import ops
+    w = oracle.make_state_dict(43)
+    net = ppsurf_b200.PPSurfNetwork(3, 256, 2, 64, 200, 256)
+    net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in w.items()}, strict=True)
+    net = net.to(dev)
+    rng = np.random.default_rng(9)
+    pts = oracle.synthetic_cloud(3000, seed=31)
+    latents = rng.standard_normal((1, 256, 3000)).astype(np.float32)
+    qry = (pts[rng.integers(0, 3000, 40)] + 0.03 * rng.standard_normal((40, 3))).astype(np.float32)
+    out = net.from_latent({'pts': cu(pts.T[None], dev), 'latents': cu(latents, dev), 'pts_query': torch.from_numpy(qry[None])})
+    data = {'pts': pts.T[None], 'latents': latents, 'pts_query': qry[None],
+            'pts_local_ps': oracle.get_pts_local_ps(pts, qry, 200)[None]}
+    ref = oracle.from_latent(w, data, dtype=np.float64)
+    assert np.abs(out.cpu().numpy() - ref).max() < LOGIT_TOL
+
+
+def test_grid_queries_bit_exact(dev, oracle):
+    from ppsurf_b200 import ops
+    import ppsurf_b200
+    pts = oracle.synthetic_cloud(3000, seed=4)
+    step, bmin_pad, _ = ppsurf_b200.PPSurfModel.grid_definition(pts, 17, 1)
+    ref = oracle.dense_grid_queries(pts, 17, 1)
+    got = ops.grid_queries(19, step, bmin_pad, device=dev).cpu().numpy()
+    np.testing.assert_array_equal(got, ref)
+    part = ops.grid_queries(19, step, bmin_pad, first=1000, count=777, device=dev).cpu().numpy()
+    np.testing.assert_array_equal(part, ref[1000:1777])
+
+
+def test_region_growing_golden(dev, net):
+    """create_volume's bookkeeping against the reference's _create_volume on an analytic field"""
+    import ppsurf_b200
+    g = load_golden('volume')
+    model = ppsurf_b200.PPSurfModel(
+        pointnet_latent_size=256, output_names=['imp_surf_sign'], in_channels=3, out_channels=2, k=64, lambda_l1=0.0,
+        debug=False, in_file='x.txt', results_dir='results', padding_factor=0.05, name='t', network_latent_size=256,
+        gen_subsample_manifold_iter=1, gen_subsample_manifold=10000, gen_resolution_global=17, num_pts_local=50,
+        rec_batch_size=50000, gen_refine_iter=0, workers=1)
+
+    class FakeDecoder:
+        pts = torch.zeros((1, 3), device=dev)
+
+    model.occupancy = lambda dec, q: torch.tanh(20.0 * (q.double().norm(dim=1) - 0.4)).float()
+    vol = model.create_volume(FakeDecoder(), g['pts'], 17)
+    np.testing.assert_array_equal(np.isnan(vol), np.isnan(g['volume']))
+    assert np.nanmax(np.abs(vol - g['volume'])) < 1e-5
+
+
+def test_predict_pipeline_small(dev, net, oracle, weights):
+    """encode_cloud (latent loop) + region-grown volume on a small cloud; the decode inside the volume is checked
+    against the float64 oracle on the same latents"""
+    import ppsurf_b200
+    model = ppsurf_b200.PPSurfModel(
+        pointnet_latent_size=256, output_names=['imp_surf_sign'], in_channels=3, out_channels=2, k=64, lambda_l1=0.0,
+        debug=False, in_file='x.txt', results_dir='results', padding_factor=0.05, name='t', network_latent_size=256,
+        gen_subsample_manifold_iter=2, gen_subsample_manifold=4200, gen_resolution_global=17, num_pts_local=50,
+        rec_batch_size=5000, gen_refine_iter=0, workers=1)
+    model.network.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in weights.items()}, strict=True)
+    model = model.to(dev)
+    pts = oracle.synthetic_cloud(7000, seed=12)
+    rec = model.reconstruct(cu(pts[None], dev), resolution=17)
+    vol = rec['volume']
+    assert vol.shape == (19, 19, 19) and np.isfinite(vol[~np.isnan(vol)]).all() and (~np.isnan(vol)).sum() > 500
+    latents = rec['latents'].cpu().numpy()
+    assert np.isfinite(latents).all()
+    coords = np.argwhere(~np.isnan(vol))
+    coords = coords[np.all((coords > 0) & (coords < 18), axis=1)][::37][:40]
+    qry = (coords.astype(np.float32) * rec['step'] + rec['bmin_pad']).astype(np.float32)
+    data = {'pts': pts.T[None], 'latents': latents, 'pts_query': qry[None],
+            'pts_local_ps': oracle.get_pts_local_ps(pts, qry, 50)[None]}
+    ref = oracle.occupancy_from_logits(oracle.from_latent(weights, data, dtype=np.float64))[0]
+    got = vol[coords[:, 0], coords[:, 1], coords[:, 2]]
+    assert np.abs(got - ref).max() < 2e-4
+    dense = model.dense_volume(rec['decoder'], pts, 17).cpu().numpy()
+    assert np.abs(dense[coords[:, 0], coords[:, 1], coords[:, 2]] - ref).max() < 2e-4
+
+
+def test_full_size_properties(dev, net, oracle):
+    """BASELINE config 2 sizes (100k points, 131^3 grid): size-independent properties on a slab of the dense grid"""
+    import ppsurf_b200
+    from ppsurf_b200 import ops
+    pts = oracle.synthetic_cloud(100000, seed=42)
+    rng = np.random.default_rng(1)
+    latents = torch.from_numpy(rng.standard_normal((100000, 256)).astype(np.float32)).to(dev)
+    dec = ops.Decoder(net.packed()['decoder'], cu(pts, dev), latents, chunk=16384)
+    step, bmin_pad, _ = ppsurf_b200.PPSurfModel.grid_definition(pts, 129, 1)
+    first, count = 131 * 131 * 60, 131 * 131 * 3  # three z-slabs through the middle of the sphere: 51 483 queries
+    qry = ops.grid_queries(131, step, bmin_pad, first=first, count=count, device=dev)
+    res = dec.decode(qry, want_logits=True, want_occ=True, want_idx=True)
+    idx, occ, logits = res['idx'].cpu().numpy(), res['occ'].cpu().numpy(), res['logits'].cpu().numpy()
+    assert np.isfinite(logits).all() and np.all(np.abs(occ) <= 1.0)
+    assert np.all(np.sort(idx, axis=1)[:, 1:] != np.sort(idx, axis=1)[:, :-1])  # no duplicate neighbours
+    q = qry.cpu().numpy()
+    d2 = oracle.sq_dist_f32(q[:, None, :], pts[idx.astype(np.int64)])
+    assert np.all(np.diff(d2, axis=1) >= 0)  # ascending
+    sample = rng.integers(0, count, 64)  # brute-force check of a sample (includes queries deep inside the sphere)
+    ref_idx, _ = oracle.knn(pts, q[sample], 64)
+    assert_knn_equal(oracle, pts, q[sample], idx[sample], None, ref_idx)
+    # occupancy is a deterministic function of the query: decoding the same slab in other chunk sizes is bit identical
+    dec2 = ops.Decoder(net.packed()['decoder'], cu(pts, dev), latents, chunk=5000)
+    occ2 = dec2.decode(qry, want_logits=False, want_occ=True)['occ'].cpu().numpy()
+    np.testing.assert_array_equal(occ, occ2)
+    # logits of the sample against the float64 oracle
+    data = {'pts': pts.T[None], 'latents': latents.cpu().numpy().T[None], 'pts_query': q[sample][None],
+            'pts_local_ps': oracle.get_pts_local_ps(pts, q[sample], 50)[None], 'proj_ids': ref_idx[None]}
+    ref = oracle.from_latent(weights_for(net), data, dtype=np.float64)
+    assert np.abs(logits[sample].T[None] - ref).max() < LOGIT_TOL
+
+
+def weights_for(net):
+    return {k: v.detach().cpu().numpy() for k, v in net.state_dict().items()}

@@ -1,0 +1,145 @@
+"""CPU-only tests of the host side: the C-ABI library loads and exports every declared symbol, the weight packing is
+algebraically equal to the reference formulation, the module keeps the reference's state_dict layout, and the product
+path refuses to run without a device."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, 'include', 'ppsurf_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(pps_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ppsurf_b200 import _lib
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), '{} declared in include/ppsurf_b200.h but not exported'.format(name)
+        assert name in _lib.SIGNATURES, '{} has no ctypes signature'.format(name)
+    assert sorted(_lib.SIGNATURES) == declared
+    assert _lib.lib.pps_compiled_arch() == 100
+    assert _lib.lib.pps_knn_index_bytes(100000) > 100000 * 16  # pure size arithmetic, no device needed
+
+
+def test_struct_layouts_match_header():
+    """field order of the ctypes mirrors == field order of the C structs"""
+    from ppsurf_b200 import _lib
+    text = open(os.path.join(ROOT, 'include', 'ppsurf_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    for cname, mirror in (('pps_decoder_weights', _lib.DecoderWeights), ('pps_fkaconv_weights', _lib.FKAConvWeights)):
+        body = re.search(r'typedef struct ' + cname + r' \{(.*?)\} ' + cname, text, flags=re.S).group(1)
+        fields = []
+        for decl in body.split(';'):
+            decl = decl.strip()
+            if not decl:
+                continue
+            names = decl.split(None, 1)[1] if not decl.startswith('const') else decl.split('*', 1)[1]
+            fields += [n.strip().lstrip('*') for n in names.split(',')]
+        assert fields == [f[0] for f in mirror._fields_], cname
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-device behaviour')
+def test_no_cpu_fallback(weights):
+    import ppsurf_b200
+    net = ppsurf_b200.PPSurfNetwork(3, 256, 2, 64, 50, 256)
+    data = {'pts': torch.zeros(1, 3, 100), 'latents': torch.zeros(1, 256, 100), 'pts_query': torch.zeros(1, 4, 3)}
+    with pytest.raises(RuntimeError):
+        net.from_latent(data)
+    with pytest.raises(Exception):
+        ppsurf_b200.ops.require_device()
+
+
+def test_state_dict_layout_matches_reference(oracle, weights):
+    import ppsurf_b200
+    net = ppsurf_b200.PPSurfNetwork(3, 256, 2, 64, 50, 256)
+    sd = net.state_dict()
+    spec = oracle.param_spec()
+    assert list(sd.keys()) == list(spec.keys())
+    for k, v in sd.items():
+        assert tuple(v.shape) == tuple(spec[k]), k
+    net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in weights.items()}, strict=True)
+    model = ppsurf_b200.PPSurfModel(
+        pointnet_latent_size=256, output_names=['imp_surf_sign'], in_channels=3, out_channels=2, k=64, lambda_l1=0.0,
+        debug=False, in_file='x.txt', results_dir='results', padding_factor=0.05, name='ppsurf_50nn',
+        network_latent_size=256, gen_subsample_manifold_iter=10, gen_subsample_manifold=10000,
+        gen_resolution_global=129, num_pts_local=50, rec_batch_size=50000, gen_refine_iter=10, workers=8)
+    assert [k for k in model.state_dict()] == ['network.' + k for k in spec]
+
+
+def test_packed_decoder_equals_reference_formulation(oracle, weights):
+    from ppsurf_b200 import packing
+    from packed_math import decode_packed
+    g = load_golden('decode')
+    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in weights.items()}
+    p = packing.pack_decoder(sd, 'cpu', k=64, num_pts_local=50)
+    latents = np.random.default_rng(int(g['latents_seed'])).standard_normal((1, 256, g['pts'].shape[0])).astype(np.float32)
+    fp, fn, logits = decode_packed(p, torch.from_numpy(g['pts']), torch.from_numpy(latents[0].T.copy()),
+                                   torch.from_numpy(g['qry']), torch.from_numpy(g['proj_ids'].astype(np.int64)),
+                                   torch.from_numpy(g['pts_local_ps']))
+    assert np.abs(fp.numpy() - g['feat_proj'][0].T).max() < 5e-5
+    assert np.abs(fn.numpy() - g['feat_pn']).max() < 5e-5
+    assert np.abs(logits.numpy().T[None] - g['logits']).max() < 1e-4
+
+
+def test_packed_fkaconv_kernel_layout(weights):
+    """cv_w column m*cin + c holds cv.weight[o,c,0,m] scaled by the folded BatchNorm"""
+    from ppsurf_b200 import packing
+    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in weights.items()}
+    p = packing.pack_fkaconv(sd, 'encoder.resnetb01.cv1', 'cpu', 'silu', bn='encoder.resnetb01.bn1')
+    cv = sd['encoder.resnetb01.cv1.cv.weight'].double()
+    s = sd['encoder.resnetb01.bn1.weight'].double() / torch.sqrt(sd['encoder.resnetb01.bn1.running_var'].double() + 1e-5)
+    w = p.tensors['cv_w'].double().view(32, 16, 32)
+    for o, m, c in ((0, 0, 0), (3, 5, 7), (31, 15, 31)):
+        assert abs(float(w[o, m, c]) - float(cv[o, c, 0, m] * s[o])) < 1e-6
+    assert p.struct.cin == 32 and p.struct.cout == 32 and p.struct.act == 1 and p.struct.out_relu == 1
+    enc = packing.pack_encoder(sd, 'cpu')
+    assert enc['cv3d'][0].w.shape == (512, 1024) and enc['cv3d'][1].w.shape == (512, 512)
+    assert enc['cv5'][0].w.shape == (1024, 1024) and enc['cv0d'][0].w.shape == (64, 128)
+
+
+def test_grid_definition_matches_oracle(oracle):
+    import ppsurf_b200
+    pts = oracle.synthetic_cloud(5000, 3)
+    step, bmin_pad, ids = ppsurf_b200.PPSurfModel.grid_definition(pts, 129, 1)
+    s2, b2, i2 = oracle.grid_definition(pts, 129, 1)
+    assert step == np.float32(s2) and bmin_pad == np.float32(b2)
+    np.testing.assert_array_equal(ids, i2)
+
+
+def test_sampling_quantized_host_properties(oracle):
+    """the device sampler (torch ops) run on the CPU: right count, unique ids, well spread like the oracle's"""
+    from ppsurf_b200.sampling import sampling_quantized
+    pts = oracle.synthetic_cloud(4000, 5)
+    gen = np.random.default_rng(1)
+    sel = sampling_quantized(torch.from_numpy(pts), 1000, gen).numpy()
+    assert sel.shape == (1000,) and np.unique(sel).shape[0] == 1000
+    ref = oracle.sampling_quantized(pts, 1000, np.random.default_rng(1))
+    assert ref.shape == (1000,) and np.unique(ref).shape[0] == 1000
+
+    def spread(ids):  # mean nearest-neighbour distance inside the sample: blue-noise-like samples score high
+        _, d2 = oracle.knn(pts[ids], pts[ids], 2)
+        return float(np.sqrt(d2[:, 1]).mean())
+
+    rnd = spread(np.random.default_rng(2).permutation(4000)[:1000])
+    assert spread(sel) > 1.15 * rnd and abs(spread(sel) - spread(ref)) < 0.15 * spread(ref)
+
+
+def test_synthetic_generators_match_oracle(oracle, weights):
+    import ppsurf_b200
+    from ppsurf_b200 import synthetic
+    net = ppsurf_b200.PPSurfNetwork(3, 256, 2, 64, 50, 256)
+    sd = synthetic.make_state_dict(net, 42)
+    assert list(sd) == list(weights)
+    for k in sd:
+        np.testing.assert_array_equal(sd[k].numpy(), np.asarray(weights[k]), err_msg=k)
+    np.testing.assert_array_equal(synthetic.synthetic_cloud(1000, 3), oracle.synthetic_cloud(1000, 3))

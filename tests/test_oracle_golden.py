@@ -116,3 +116,16 @@ def test_latent_schedule(oracle):
     assert counts.min() >= 3
     small = oracle.latent_loop_schedule(500, 10000, 2, rng)
     assert len(small) == 2 and all(np.array_equal(s, np.arange(500)) for s in small)
+
+
+def test_torch_timing_twin_matches(oracle, weights):
+    """the multi-threaded torch restatement used for CPU timing gives the numpy oracle's / the reference's numbers"""
+    import torch
+    from oracle import ppsurf_oracle_torch as OT
+    g = load_golden('decode')
+    latents = np.random.default_rng(int(g['latents_seed'])).standard_normal((1, 256, g['pts'].shape[0])).astype(np.float32)
+    occ, logits = OT.from_latent(weights, torch.from_numpy(g['pts']), torch.from_numpy(latents[0].T.copy()),
+                                 torch.from_numpy(g['qry']), torch.from_numpy(g['proj_ids'].astype(np.int64)),
+                                 torch.from_numpy(g['pts_local_ps']))
+    assert np.abs(logits.numpy().T[None] - g['logits']).max() < 1e-4
+    assert np.abs(occ.numpy() - g['occ'][0]).max() < 1e-4
