@@ -142,7 +142,12 @@ typedef struct pps_decoder_weights {
     const float* m1_b;
     const float* m2_w; /* [2,C] */
     const float* m2_b; /* [2]   */
+    /* tensor-core pack of fc2 / fc3 / fc_query for path 1 (pps_decoder_tc_pack_bytes() bytes, nullable): per layer 16
+     * k16 stages, each [W_hi k8-block 0 | W_hi k8-block 1 | W_lo block 0 | W_lo block 1], a block = N rows x 8 fp16 */
+    const void* tc_wpack;
 } pps_decoder_weights;
+
+size_t pps_decoder_tc_pack_bytes(void);
 
 /* per-point table  U[n,:] = W1_lat . latent[n] - W1_xyz . pts[n] + b1   (fc1 hoisted out of the (query,neighbour)
  * loop: fc1([latent_j, q - p_j]) = U_j + W1_xyz . q).  table [n,C] f32. */
@@ -189,7 +194,8 @@ int pps_grid_queries(int r, float step, float bmin_pad, int64_t first, int64_t c
  * a3  FKAConv layer (point-major activations)
  *     replaces  FKAConvLayer.forward   source/base/nn.py:592-652   (eval mode; InstanceNorm statistics are
  *     per sample over (Ns,16), so the layer runs as stats1 -> stats2 -> fused gather/contract)
- * x [b,n_in,cin], pts [b,n_in,3], support [b,n_s,3], ids [b,n_s,16] int32, out [b,n_s,cout].
+ * x [b,n_in,cin], pts [b,n_in,3], support [b,n_s,3], ids [b,n_s,kn] int32 with 1 <= kn <= 16 (the reference asks for
+ * 16 neighbours and clamps to n_in; kn == 1 skips both InstanceNorms like nn.py:627-636), out [b,n_s,cout].
  * cv_w is [cout, 16*cin] with column = m*cin + c  (repacked from the reference [cout,cin,1,16]); the eval
  * BatchNorm that always follows the layer (nn.py:441,519) is folded into cv_w / out_bias, out_relu applies its ReLU.
  * act: 0 ReLU (POCO), 1 SiLU (PPSurf).
@@ -213,7 +219,7 @@ typedef struct pps_fkaconv_weights {
 
 size_t pps_fkaconv_workspace_bytes(int64_t b, int64_t n_s, int cin);
 int pps_fkaconv_forward(const pps_fkaconv_weights* w, const float* x, const float* pts, const float* support,
-                        const int32_t* ids, int64_t b, int64_t n_in, int64_t n_s, void* workspace,
+                        const int32_t* ids, int kn, int64_t b, int64_t n_in, int64_t n_s, void* workspace,
                         size_t workspace_bytes, float* out, void* stream);
 
 /* gather-max over the 16 neighbours (shortcut branch of a strided ResidualBlock)

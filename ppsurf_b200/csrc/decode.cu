@@ -259,6 +259,8 @@ __global__ void grid_queries_kernel(int r, float step, float bmin_pad, long long
 // host-side pipeline
 // ---------------------------------------------------------------------------------------------------------------
 static inline int kmax_of(const pps_decoder_weights* w) { return w->k > w->num_pts_local ? w->k : w->num_pts_local; }
+// the neighbour search runs over kKnnSuper decode chunks at once: a 16k-query launch cannot fill 148 SMs
+constexpr int kKnnSuper = 16;
 
 struct DecodeBuffers {
     int32_t* idx;
@@ -288,8 +290,8 @@ static bool carve(const pps_decoder_weights* w, int64_t chunk, void* ws, size_t 
     const int kmax = kmax_of(w);
     size_t rows = (size_t)chunk * (size_t)(K > P ? K : P);
     size_t wide = C > S ? C : S;
-    b.idx = a.take<int32_t>((size_t)chunk * kmax);
-    b.d2 = a.take<float>((size_t)chunk * kmax);
+    b.idx = a.take<int32_t>((size_t)chunk * kKnnSuper * kmax);
+    b.d2 = a.take<float>((size_t)chunk * kKnnSuper * kmax);
     b.bufA = a.take<float>(rows * wide);
     b.bufB = a.take<float>(rows * wide);
     b.score = a.take<float>((size_t)chunk * K * w->heads);
@@ -369,21 +371,35 @@ static int pointnet_run(const pps_decoder_weights* w, const float* patches, int6
     return PPS_OK;
 }
 
-static int decode_chunk(const pps_decoder_weights* w, const void* knn_index, const float* pts, const float* table,
-                        int64_t n, const float* queries, int64_t q, DecodeBuffers& b, float* logits_out, float* occ_out,
-                        int32_t* idx_out, int path, cudaStream_t st) {
+// one decode chunk; `idx`/`d2` [q,kmax] are this chunk's rows of the neighbour search
+static int decode_chunk(const pps_decoder_weights* w, const float* pts, const float* table, const float* queries, int64_t q,
+                        const int32_t* idx, const float* d2, DecodeBuffers& b, float* logits_out, float* occ_out, int path,
+                        cudaStream_t st) {
     const int C = w->latent, P = w->num_pts_local;
     const int kmax = kmax_of(w);
-    PPS_TRY(knn_query_impl(knn_index, n, queries, q, kmax, b.idx, b.d2, st));
-    if (idx_out) PPS_CUDA(cudaMemcpyAsync(idx_out, b.idx, (size_t)q * kmax * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
-    patch_normalize_kernel<<<(unsigned)ceil_div(q * P, 256), 256, 0, st>>>(pts, queries, b.idx, b.d2, q, P, kmax, b.patches);
+    patch_normalize_kernel<<<(unsigned)ceil_div(q * P, 256), 256, 0, st>>>(pts, queries, idx, d2, q, P, kmax, b.patches);
     PPS_LAUNCH_CHECK();
-    PPS_TRY(projection_run(w, table, queries, b.idx, kmax, q, b, b.feat_proj, path, st));
+    PPS_TRY(projection_run(w, table, queries, idx, kmax, q, b, b.feat_proj, path, st));
     PPS_TRY(pointnet_run(w, b.patches, q, b, b.feat_proj, b.feat, st));
     PPS_TRY(linear_impl(b.feat, w->m0_w, w->m0_b, nullptr, nullptr, b.m0, q, C, C, C, C, 1, st));
     PPS_TRY(linear_impl(b.m0, w->m1_w, w->m1_b, nullptr, nullptr, b.m1, q, C, C, C, C, 1, st));
     mlp_head_kernel<<<(unsigned)ceil_div(q * 32, 256), 256, 0, st>>>(b.m1, w->m2_w, w->m2_b, q, C, logits_out, occ_out);
     PPS_LAUNCH_CHECK();
+    return PPS_OK;
+}
+
+// neighbour search for up to kKnnSuper chunks, then the chunks one after the other
+static int decode_super(const pps_decoder_weights* w, const void* knn_index, const float* pts, const float* table, int64_t n,
+                        const float* queries, int64_t q, int64_t chunk, DecodeBuffers& b, float* logits_out, float* occ_out,
+                        int32_t* idx_out, int path, cudaStream_t st) {
+    const int kmax = kmax_of(w);
+    PPS_TRY(knn_query_impl(knn_index, n, queries, q, kmax, b.idx, b.d2, st));
+    if (idx_out) PPS_CUDA(cudaMemcpyAsync(idx_out, b.idx, (size_t)q * kmax * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    for (int64_t s = 0; s < q; s += chunk) {
+        int64_t c = q - s < chunk ? q - s : chunk;
+        PPS_TRY(decode_chunk(w, pts, table, queries + 3 * s, c, b.idx + s * kmax, b.d2 + s * kmax, b,
+                             logits_out ? logits_out + 2 * s : nullptr, occ_out ? occ_out + s : nullptr, path, st));
+    }
     return PPS_OK;
 }
 
@@ -450,9 +466,10 @@ int pps_decoder_decode(const pps_decoder_weights* w, const void* knn_index, cons
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int kmax = kmax_of(w);
-    for (int64_t s = 0; s < q; s += chunk) {
-        int64_t c = q - s < chunk ? q - s : chunk;
-        PPS_TRY(decode_chunk(w, knn_index, pts, table, n, queries + 3 * s, c, b, logits_out ? logits_out + 2 * s : nullptr,
+    const int64_t super = chunk * kKnnSuper;
+    for (int64_t s = 0; s < q; s += super) {
+        int64_t c = q - s < super ? q - s : super;
+        PPS_TRY(decode_super(w, knn_index, pts, table, n, queries + 3 * s, c, chunk, b, logits_out ? logits_out + 2 * s : nullptr,
                              occ_out ? occ_out + s : nullptr, idx_out ? idx_out + s * kmax : nullptr, path, st));
     }
     return PPS_OK;
@@ -479,8 +496,9 @@ int pps_decoder_decode_host(const pps_decoder_weights* w, const void* knn_index,
     cudaStream_t st = static_cast<cudaStream_t>(stream), cs = static_cast<cudaStream_t>(copy_stream);
     float* dq = static_cast<float*>(staging);
     float* docc = dq + 3 * q;
-    int64_t nchunks = ceil_div(q, chunk);
-    // one event pair per chunk: upload on the copy stream, compute on `stream`, download on the copy stream
+    const int64_t super = chunk * kKnnSuper;
+    int64_t nchunks = ceil_div(q, super);
+    // one event pair per super-chunk: upload on the copy stream, compute on `stream`, download on the copy stream
     cudaEvent_t* up = new cudaEvent_t[nchunks];
     cudaEvent_t* done = new cudaEvent_t[nchunks];
     int rc = PPS_OK;
@@ -489,14 +507,14 @@ int pps_decoder_decode_host(const pps_decoder_weights* w, const void* knn_index,
         cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming);
     }
     for (int64_t i = 0; i < nchunks && rc == PPS_OK; ++i) {
-        int64_t s = i * chunk, c = q - s < chunk ? q - s : chunk;
+        int64_t s = i * super, c = q - s < super ? q - s : super;
         cudaMemcpyAsync(dq + 3 * s, queries_host + 3 * s, (size_t)c * 12, cudaMemcpyHostToDevice, cs);
         cudaEventRecord(up[i], cs);
     }
     for (int64_t i = 0; i < nchunks && rc == PPS_OK; ++i) {
-        int64_t s = i * chunk, c = q - s < chunk ? q - s : chunk;
+        int64_t s = i * super, c = q - s < super ? q - s : super;
         cudaStreamWaitEvent(st, up[i], 0);
-        rc = decode_chunk(w, knn_index, pts, table, n, dq + 3 * s, c, b, nullptr, docc + s, nullptr, path, st);
+        rc = decode_super(w, knn_index, pts, table, n, dq + 3 * s, c, chunk, b, nullptr, docc + s, nullptr, path, st);
         cudaEventRecord(done[i], st);
         cudaStreamWaitEvent(cs, done[i], 0);
         cudaMemcpyAsync(occ_host + s, docc + s, (size_t)c * 4, cudaMemcpyDeviceToHost, cs);

@@ -1,12 +1,434 @@
-// Tensor-core path of the decoder's global branch (path 1).  Placeholder until the tcgen05 kernel lands: it reports an
-// error instead of silently falling back.
+// Tensor-core path of the decoder's global branch (path 1): ONE persistent, warp-specialised tcgen05 kernel per chunk.
+//
+// Replaces the per-(query,neighbour) part of InterpAttentionKHeadsNet.forward (source/poco_model.py:400-414): gather of
+// the hoisted fc1 table, fc2, fc3, fc_query, softmax over the 64 neighbours, mean over the 64 heads and the
+// attention-weighted pooling, for tiles of 128 rows = 2 queries x 64 neighbours.  Nothing but the pooled [q,256] vectors
+// leaves the SM (the unfused path moves ~0.5 MB per query through HBM).
+//
+// Precision: the reference is fp32 and the contract is 1e-4 abs on the logits, so every GEMM runs as a split-fp16
+// product on the 5th-gen tensor cores:  x = x_hi + x_lo (two fp16, 22 mantissa bits), W = W_hi + W_lo,
+//   x.W ~= x_hi.W_hi + x_lo.W_hi + x_hi.W_lo   (fp32 accumulation in TMEM),
+// i.e. three tcgen05.mma per k-step; the dropped x_lo.W_lo term is O(2^-22) relative.
+//
+// Roles (320 threads, one CTA per SM, persistent over tiles):
+//   warp 0      weight producer: cp.async.bulk (TMA bulk copy, UBLKCP) of pre-packed k16 weight stages into a 3-slot ring
+//   warp 1      MMA issuer: tcgen05.mma (SS, M=128, N=256/64, K=16) + tcgen05.commit onto mbarriers; owns the TMEM allocation
+//   warps 2..9  gather + epilogues: table rows -> fp16 hi/lo operand tiles in shared memory (UMMA canonical K-major layout,
+//               no swizzle, k8-blocks padded by 16 B so that row-wise AND k-wise accesses are bank-conflict free),
+//               tcgen05.ld of the accumulators, bias + ReLU + re-split, softmax / pooling
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace pps {
-size_t projection_tc_workspace(const pps_decoder_weights*, int64_t) { return 256; }
-int projection_tc_impl(const pps_decoder_weights*, const float*, const float*, const int32_t*, int, int64_t, void*, size_t,
-                       float*, cudaStream_t) {
-    set_error("decoder path 1 (tcgen05) is not built into this library yet");
-    return PPS_ERR_INVALID;
+namespace tc {
+
+constexpr int kRows = 128;                  // rows per tile
+constexpr int kC = 256;                     // latent width
+constexpr int kHeads = 64;
+constexpr int kNbrs = 64;                   // neighbours per query
+constexpr int kKB = kC / 8;                 // k8 blocks per row
+constexpr int kALbo = kRows * 16 + 16;      // bytes between k8 blocks of an activation tile (padded)
+constexpr int kABytes = kKB * kALbo;        // 66048
+constexpr int kStageBytes = 16384;          // one k16 step of a 256-wide layer: W_hi 8 KB + W_lo 8 KB
+constexpr int kStageBytesQ = 4096;          // same for the 64-wide fc_query
+constexpr int kStages = 3;
+constexpr int kKSteps = kC / 16;            // 16 k16 steps per layer
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = 64 + kEpiThreads;  // 320
+constexpr long long kSpinLimit = 4000000000ll;  // ~2 s of SM clocks: turns a protocol bug into a trap instead of a hang
+
+// shared memory map (bytes from the 1024-aligned base)
+constexpr int kOffAhi = 0;
+constexpr int kOffAlo = kOffAhi + kABytes;
+constexpr int kOffRing = kOffAlo + kABytes;                  // 132096
+constexpr int kOffScore = kOffRing + kStages * kStageBytes;  // 181248
+constexpr int kOffBias = kOffScore + kRows * kHeads * 4;     // 214016: b2[256] b3[256] bq[64]
+constexpr int kOffAtt = kOffBias + (256 + 256 + 64) * 4;     // 216320: att[128]
+constexpr int kOffBar = kOffAtt + kRows * 4;                 // 216832: full[3] empty[3] accum a_ready
+constexpr int kOffTmem = kOffBar + 8 * 8;
+constexpr int kSmemBytes = kOffTmem + 16 + 1024;             // + alignment slack
+
+// packed weights in global memory: [fc2: 16 stages][fc3: 16 stages][fc_query: 16 stages]
+constexpr size_t kPackBytes = size_t(2) * kKSteps * kStageBytes + size_t(kKSteps) * kStageBytesQ;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (clock64() - t0 > kSpinLimit) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_copy(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// UMMA shared-memory descriptor, K-major, no swizzle: core matrix = 8 rows x 16 B (128 contiguous bytes);
+// LBO = byte distance between the two k8 halves of a k16 step, SBO = byte distance between 8-row groups; version 1 (sm_100)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) |
+           (1ull << 46);
+}
+// instruction descriptor kind::f16: D fp32, A/B fp16, both K-major, M=128
+__host__ __device__ constexpr uint32_t umma_idesc(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
+
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// x (>= 0 after ReLU) -> fp16 hi + fp16 lo, 8 values -> two 16-byte vectors
+__device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float a = fminf(x[2 * i], 65000.f), b = fminf(x[2 * i + 1], 65000.f);
+        __half ha = __float2half_rn(a), hb = __float2half_rn(b);
+        __half la = __float2half_rn(a - __half2float(ha)), lb = __float2half_rn(b - __half2float(hb));
+        h[i] = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
+        l[i] = (uint32_t)__half_as_ushort(la) | ((uint32_t)__half_as_ushort(lb) << 16);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+
+__global__ void __launch_bounds__(kThreads, 1)
+    projection_tc_kernel(const float* __restrict__ table, const float* __restrict__ queries, const int32_t* __restrict__ idx, int ks,
+                         long long nq, const uint8_t* __restrict__ wpack, const float* __restrict__ b2, const float* __restrict__ b3,
+                         const float* __restrict__ bq, const float* __restrict__ w1_xyz, float* __restrict__ pooled) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t sbase = smem_u32(smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float* s_bias = reinterpret_cast<float*>(smem + kOffBias);
+    float* s_att = reinterpret_cast<float*>(smem + kOffAtt);
+    float* s_score = reinterpret_cast<float*>(smem + kOffScore);
+    volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + kOffTmem);
+    const uint32_t bar_full = sbase + kOffBar, bar_empty = bar_full + 8 * kStages, bar_accum = bar_empty + 8 * kStages,
+                   bar_aready = bar_accum + 8;
+
+    for (int e = tid; e < 256; e += kThreads) {
+        s_bias[e] = b2[e];
+        s_bias[256 + e] = b3[e];
+        if (e < 64) s_bias[512 + e] = bq[e];
+    }
+    if (tid == 0) {
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(bar_full + 8 * i, 1);
+            mbar_init(bar_empty + 8 * i, 1);
+        }
+        mbar_init(bar_accum, 1);
+        mbar_init(bar_aready, kEpiThreads);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kOffTmem), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+
+    const long long ntiles = (nq + 1) / 2;
+
+    if (warp == 0) {
+        // ---------------------------------------------------------------- weight producer
+        if (lane == 0) {
+            uint32_t slot = 0, phase = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const uint8_t* src = wpack;
+                for (int layer = 0; layer < 3; ++layer) {
+                    const uint32_t bytes = layer < 2 ? kStageBytes : kStageBytesQ;
+                    for (int s = 0; s < kKSteps; ++s) {
+                        mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+                        mbar_expect_tx(bar_full + 8 * slot, bytes);
+                        bulk_copy(sbase + kOffRing + slot * kStageBytes, src, bytes, bar_full + 8 * slot);
+                        src += bytes;
+                        if (++slot == kStages) {
+                            slot = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------------------------------------------------------- MMA issuer
+        if (lane == 0) {
+            uint32_t slot = 0, phase = 0, ready_phase = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int layer = 0; layer < 3; ++layer) {
+                    const int n = layer < 2 ? 256 : 64;
+                    const uint32_t idesc = umma_idesc(n);
+                    const uint32_t b_lbo = n * 16, b_lo_off = n * 32;
+                    mbar_wait(bar_aready, ready_phase);
+                    ready_phase ^= 1;
+                    tc_fence_after();
+                    for (int s = 0; s < kKSteps; ++s) {
+                        mbar_wait(bar_full + 8 * slot, phase);
+                        tc_fence_after();
+                        const uint32_t a_off = 2 * s * kALbo;
+                        const uint64_t a_hi = umma_desc(sbase + kOffAhi + a_off, kALbo, 128);
+                        const uint64_t a_lo = umma_desc(sbase + kOffAlo + a_off, kALbo, 128);
+                        const uint32_t bst = sbase + kOffRing + slot * kStageBytes;
+                        const uint64_t w_hi = umma_desc(bst, b_lbo, 128);
+                        const uint64_t w_lo = umma_desc(bst + b_lo_off, b_lbo, 128);
+                        umma(tmem, a_hi, w_hi, idesc, s > 0 ? 1u : 0u);
+                        umma(tmem, a_lo, w_hi, idesc, 1u);
+                        umma(tmem, a_hi, w_lo, idesc, 1u);
+                        tc_commit(bar_empty + 8 * slot);  // frees the ring slot when these MMAs have read it
+                        if (++slot == kStages) {
+                            slot = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    tc_commit(bar_accum);  // accumulator of this layer complete
+                }
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- gather + epilogue warps
+        const int ew = warp - 2;               // 0..7
+        const int et = tid - 64;               // 0..255
+        const int lane_grp = warp & 3;         // TMEM lanes this warp may touch: 32*lane_grp .. +31
+        const int half = ew >> 2;              // which half of the columns this warp owns
+        const int row = lane_grp * 32 + lane;  // accumulator row (= TMEM lane) of this thread
+        float w1[8][3];                        // fc1 xyz weights of the 8 channels this lane gathers
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) w1[c][d] = w1_xyz[(8 * lane + c) * 3 + d];
+        uint32_t accum_phase = 0;
+
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            // ---- gather: h1 = relu(U[idx] + W1_xyz.q) -> A_hi/A_lo; warp ew owns rows 16*ew .. +15, lane owns k8 block `lane`
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {
+                const int r = ew * 16 + i;
+                long long q = 2 * tile + (r >> 6);
+                q = q < nq ? q : nq - 1;
+                const int src = idx[q * ks + (r & 63)];
+                const float qx = queries[3 * q], qy = queries[3 * q + 1], qz = queries[3 * q + 2];
+                const float4* urow = reinterpret_cast<const float4*>(table + (size_t)src * kC) + 2 * lane;
+                const float4 u0 = urow[0], u1 = urow[1];
+                float x[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+                for (int c = 0; c < 8; ++c) x[c] = fmaxf(x[c] + (w1[c][0] * qx + w1[c][1] * qy + w1[c][2] * qz), 0.f);
+                uint4 hi, lo;
+                split8(x, hi, lo);
+                *reinterpret_cast<uint4*>(smem + kOffAhi + lane * kALbo + r * 16) = hi;
+                *reinterpret_cast<uint4*>(smem + kOffAlo + lane * kALbo + r * 16) = lo;
+            }
+            fence_async_smem();
+            tc_fence_before();
+            mbar_arrive(bar_aready);
+
+            // ---- fc2 / fc3 epilogues: D -> +bias, ReLU, split -> A (in place: the layer's MMAs are complete)
+            for (int layer = 0; layer < 2; ++layer) {
+                mbar_wait(bar_accum, accum_phase);
+                accum_phase ^= 1;
+                tc_fence_after();
+                const float* bias = s_bias + layer * 256;
+#pragma unroll 1
+                for (int cb = 0; cb < 4; ++cb) {
+                    const int col0 = half * 128 + cb * 32;
+                    float v[32];
+                    tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + col0, v);
+#pragma unroll
+                    for (int kb = 0; kb < 4; ++kb) {
+                        float x[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) x[c] = fmaxf(v[kb * 8 + c] + bias[col0 + kb * 8 + c], 0.f);
+                        uint4 hi, lo;
+                        split8(x, hi, lo);
+                        const int kblk = (col0 >> 3) + kb;
+                        *reinterpret_cast<uint4*>(smem + kOffAhi + kblk * kALbo + row * 16) = hi;
+                        *reinterpret_cast<uint4*>(smem + kOffAlo + kblk * kALbo + row * 16) = lo;
+                    }
+                }
+                fence_async_smem();
+                tc_fence_before();
+                mbar_arrive(bar_aready);
+            }
+
+            // ---- fc_query epilogue: scores -> shared (16-byte chunks XOR-swizzled by the row)
+            mbar_wait(bar_accum, accum_phase);
+            accum_phase ^= 1;
+            tc_fence_after();
+            {
+                float v[32];
+                tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + half * 32, v);
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const int chunk = half * 8 + c4;
+                    float4 o = make_float4(v[4 * c4] + s_bias[512 + 4 * chunk], v[4 * c4 + 1] + s_bias[512 + 4 * chunk + 1],
+                                           v[4 * c4 + 2] + s_bias[512 + 4 * chunk + 2], v[4 * c4 + 3] + s_bias[512 + 4 * chunk + 3]);
+                    *reinterpret_cast<float4*>(s_score + row * 64 + ((chunk ^ (row & 15)) << 2)) = o;
+                }
+            }
+            tc_fence_before();
+            epi_barrier();
+            // softmax over the 64 neighbours for each (query, head): threads 0..127
+            if (et < 128) {
+                const int ql = et >> 6, h = et & 63;
+                const int c4 = h >> 2, w = h & 3;
+                float m = -INFINITY;
+                for (int j = 0; j < kNbrs; ++j) {
+                    const int r = ql * 64 + j;
+                    m = fmaxf(m, s_score[r * 64 + ((c4 ^ (r & 15)) << 2) + w]);
+                }
+                float sum = 0.f;
+                for (int j = 0; j < kNbrs; ++j) {
+                    const int r = ql * 64 + j;
+                    float* p = s_score + r * 64 + ((c4 ^ (r & 15)) << 2) + w;
+                    const float ev = expf(*p - m);
+                    *p = ev;
+                    sum += ev;
+                }
+                const float inv = 1.f / sum;
+                for (int j = 0; j < kNbrs; ++j) {
+                    const int r = ql * 64 + j;
+                    s_score[r * 64 + ((c4 ^ (r & 15)) << 2) + w] *= inv;
+                }
+            }
+            epi_barrier();
+            // attention of a neighbour = mean over the heads: thread per row
+            if (et < 128) {
+                float a = 0.f;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float4 p = *reinterpret_cast<const float4*>(s_score + et * 64 + (((i + et) & 15) << 2));
+                    a += (p.x + p.y) + (p.z + p.w);
+                }
+                s_att[et] = a * (1.f / kHeads);
+            }
+            epi_barrier();
+            // pooled[q, 8kb..8kb+7] = sum_j att_j * h3[j, .]: warp ew owns k8 blocks ew, ew+8, ew+16, ew+24
+#pragma unroll 1
+            for (int t = 0; t < 4; ++t) {
+                const int kb = ew + 8 * t;
+#pragma unroll
+                for (int ql = 0; ql < 2; ++ql) {
+                    float acc[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int r = ql * 64 + hh * 32 + lane;
+                        const float a = s_att[r];
+                        const uint4 hi = *reinterpret_cast<const uint4*>(smem + kOffAhi + kb * kALbo + r * 16);
+                        const uint4 lo = *reinterpret_cast<const uint4*>(smem + kOffAlo + kb * kALbo + r * 16);
+                        const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
+                            const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&lw[i]));
+                            acc[2 * i] = fmaf(a, fh.x + fl.x, acc[2 * i]);
+                            acc[2 * i + 1] = fmaf(a, fh.y + fl.y, acc[2 * i + 1]);
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+                    const long long q = 2 * tile + ql;
+                    if (lane == 0 && q < nq) {
+                        float4* dst = reinterpret_cast<float4*>(pooled + q * kC + kb * 8);
+                        dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                        dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+                    }
+                }
+            }
+            epi_barrier();  // every warp is done with A and the scores before the next tile's gather overwrites them
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
+}  // namespace tc
+
+size_t projection_tc_workspace(const pps_decoder_weights*, int64_t) { return 256; }
+
+int projection_tc_impl(const pps_decoder_weights* w, const float* table, const float* queries, const int32_t* idx, int k_stride,
+                       int64_t q, void*, size_t, float* pooled, cudaStream_t st) {
+    PPS_CHECK_ARG(w->tc_wpack != nullptr, "decoder path 1: the weights carry no tensor-core pack (tc_wpack is null)");
+    PPS_CHECK_ARG(w->k == tc::kNbrs && w->latent == tc::kC && w->heads == tc::kHeads,
+                  "decoder path 1 is built for k=64, latent=256, heads=64 (got %d, %d, %d)", w->k, w->latent, w->heads);
+    if (q == 0) return PPS_OK;
+    static bool configured = false;
+    if (!configured) {
+        PPS_CUDA(cudaFuncSetAttribute(tc::projection_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+        configured = true;
+    }
+    long long ntiles = (q + 1) / 2;
+    int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
+    profile_begin(st);
+    tc::projection_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, st>>>(table, queries, idx, k_stride, q,
+                                                                         static_cast<const uint8_t*>(w->tc_wpack), w->b2, w->b3, w->bq,
+                                                                         w->w1_xyz, pooled);
+    PPS_LAUNCH_CHECK();
+    profile_end(st);
+    return PPS_OK;
+}
+
 }  // namespace pps
+
+extern "C" size_t pps_decoder_tc_pack_bytes(void) { return pps::tc::kPackBytes; }

@@ -15,7 +15,7 @@ namespace pps {
 int linear_impl(const float* x, const float* w, const float* bias, const float* residual, const int32_t* gather,
                 float* y, int64_t m, int n, int k, int ldx, int ldy, int act, cudaStream_t st);
 
-constexpr int kNbr = 16;   // neighbours per support point == kernel size
+constexpr int kNbr = 16;   // max neighbours per support point (the reference always asks for 16, clamped to n_in)
 constexpr float kInEps = 1e-5f;
 
 struct FkaParams {
@@ -28,7 +28,7 @@ __device__ __forceinline__ float fka_act(float v, int act) { return act == 1 ? v
 // PHASE 1: sum / sumsq of fc1 outputs; PHASE 2: sum / sumsq of fc2 outputs; PHASE 3: write mat [b,ns,16(j),16(m)]
 template <int PHASE>
 __global__ void __launch_bounds__(128) fka_weight_kernel(const float* __restrict__ pts, const float* __restrict__ support,
-                                                         const int32_t* __restrict__ ids, int n_in, int n_s, FkaParams prm,
+                                                         const int32_t* __restrict__ ids, int n_in, int n_s, int kn, FkaParams prm,
                                                          const float* __restrict__ fc1, const float* __restrict__ fc2,
                                                          const float* __restrict__ fc3, const float* __restrict__ in1_w,
                                                          const float* __restrict__ in1_b, const float* __restrict__ in2_w,
@@ -43,20 +43,21 @@ __global__ void __launch_bounds__(128) fka_weight_kernel(const float* __restrict
         W2[e] = fc2[e];
         W3[e] = fc3[e];
     }
-    const double cnt = double(n_s) * kNbr;
+    const double cnt = double(n_s) * kn;
+    // with a single neighbour the reference skips both InstanceNorms (nn.py:627-628,635-636)
     if (PHASE >= 2 && tid < 16) {
         double mean = st_b[tid] / cnt;
         double var = st_b[16 + tid] / cnt - mean * mean;
         float rstd = float(1.0 / sqrt(fmax(var, 0.0) + double(kInEps)));
-        A1[tid] = rstd * in1_w[tid];
-        B1[tid] = in1_b[tid] - float(mean) * rstd * in1_w[tid];
+        A1[tid] = kn == 1 ? 1.f : rstd * in1_w[tid];
+        B1[tid] = kn == 1 ? 0.f : in1_b[tid] - float(mean) * rstd * in1_w[tid];
     }
     if (PHASE >= 3 && tid < 16) {
         double mean = st_b[32 + tid] / cnt;
         double var = st_b[48 + tid] / cnt - mean * mean;
         float rstd = float(1.0 / sqrt(fmax(var, 0.0) + double(kInEps)));
-        A2[tid] = rstd * in2_w[tid];
-        B2[tid] = in2_b[tid] - float(mean) * rstd * in2_w[tid];
+        A2[tid] = kn == 1 ? 1.f : rstd * in2_w[tid];
+        B2[tid] = kn == 1 ? 0.f : in2_b[tid] - float(mean) * rstd * in2_w[tid];
     }
     __syncthreads();
 
@@ -74,7 +75,12 @@ __global__ void __launch_bounds__(128) fka_weight_kernel(const float* __restrict
         float dsum = 0.f;
 #pragma unroll
         for (int j = 0; j < kNbr; ++j) {
-            size_t src = (size_t)b * n_in + ids[row * kNbr + j];
+            if (j >= kn) {
+                rel[j][0] = rel[j][1] = rel[j][2] = 0.f;
+                dw[j] = 0.f;
+                continue;
+            }
+            size_t src = (size_t)b * n_in + ids[row * kn + j];
             float rx = pts[3 * src] - sx, ry = pts[3 * src + 1] - sy, rz = pts[3 * src + 2] - sz;
             float dist = sqrtf(rx * rx + ry * ry + rz * rz);
             rel[j][0] = rx * prm.inv_radius;
@@ -86,16 +92,18 @@ __global__ void __launch_bounds__(128) fka_weight_kernel(const float* __restrict
         }
         dsum = dsum + (dsum == 0.f ? 1.f : 0.f) + 1e-6f;
 #pragma unroll
-        for (int j = 0; j < kNbr; ++j) dw[j] = dw[j] / dsum * float(kNbr);
+        for (int j = 0; j < kNbr; ++j) dw[j] = dw[j] / dsum * float(kn);
 
         if (PHASE == 1) {
 #pragma unroll
             for (int j = 0; j < kNbr; ++j)
+                if (j < kn) {
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    float y = W1[3 * c] * rel[j][0] + W1[3 * c + 1] * rel[j][1] + W1[3 * c + 2] * rel[j][2];
-                    s[c] += y;
-                    ss[c] += y * y;
+                    for (int c = 0; c < 16; ++c) {
+                        float y = W1[3 * c] * rel[j][0] + W1[3 * c + 1] * rel[j][1] + W1[3 * c + 2] * rel[j][2];
+                        s[c] += y;
+                        ss[c] += y * y;
+                    }
                 }
         } else {
             // m1[c][j] = act(IN1(fc1 rel_j)); mp1[c] = max_j m1[c][j] * dw_j
@@ -104,11 +112,13 @@ __global__ void __launch_bounds__(128) fka_weight_kernel(const float* __restrict
             for (int c = 0; c < 16; ++c) mp1[c] = -INFINITY;
 #pragma unroll
             for (int j = 0; j < kNbr; ++j)
+                if (j < kn) {
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    float y = W1[3 * c] * rel[j][0] + W1[3 * c + 1] * rel[j][1] + W1[3 * c + 2] * rel[j][2];
-                    float m = fka_act(y * A1[c] + B1[c], prm.act);
-                    mp1[c] = fmaxf(mp1[c], m * dw[j]);
+                    for (int c = 0; c < 16; ++c) {
+                        float y = W1[3 * c] * rel[j][0] + W1[3 * c + 1] * rel[j][1] + W1[3 * c + 2] * rel[j][2];
+                        float m = fka_act(y * A1[c] + B1[c], prm.act);
+                        mp1[c] = fmaxf(mp1[c], m * dw[j]);
+                    }
                 }
             // fc2 on cat(m1[:,j], mp1): the mp1 half does not depend on j
             float c2[16];
@@ -122,7 +132,7 @@ __global__ void __launch_bounds__(128) fka_weight_kernel(const float* __restrict
             float mp2[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) mp2[c] = -INFINITY;
-            for (int j = 0; j < kNbr; ++j) {
+            for (int j = 0; j < kn; ++j) {
                 float m1[16];
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
@@ -152,7 +162,7 @@ __global__ void __launch_bounds__(128) fka_weight_kernel(const float* __restrict
                     for (int c = 0; c < 16; ++c) a = fmaf(W3[o * 32 + 16 + c], mp2[c], a);
                     c3[o] = a;
                 }
-                for (int j = 0; j < kNbr; ++j) {
+                for (int j = 0; j < kn; ++j) {
                     float m1[16], m2[16];
 #pragma unroll
                     for (int c = 0; c < 16; ++c) {
@@ -174,7 +184,7 @@ __global__ void __launch_bounds__(128) fka_weight_kernel(const float* __restrict
                         for (int c = 0; c < 16; ++c) y = fmaf(W3[o * 32 + c], m2[c], y);
                         outv[o] = fka_act(y, prm.act) * dw[j];
                     }
-                    float4* dst = reinterpret_cast<float4*>(mat + (row * kNbr + j) * 16);
+                    float4* dst = reinterpret_cast<float4*>(mat + (row * kn + j) * 16);
                     dst[0] = make_float4(outv[0], outv[1], outv[2], outv[3]);
                     dst[1] = make_float4(outv[4], outv[5], outv[6], outv[7]);
                     dst[2] = make_float4(outv[8], outv[9], outv[10], outv[11]);
@@ -204,7 +214,7 @@ __global__ void __launch_bounds__(128) fka_weight_kernel(const float* __restrict
 constexpr int kFeatPts = 16;
 template <bool VEC>
 __global__ void __launch_bounds__(256) fka_feat_kernel(const float* __restrict__ x, const int32_t* __restrict__ ids,
-                                                       const float* __restrict__ mat, int n_in, int n_s, int cin,
+                                                       const float* __restrict__ mat, int n_in, int n_s, int kn, int cin,
                                                        float* __restrict__ feat) {
     __shared__ float smat[kFeatPts][kNbr][16];
     __shared__ int sid[kFeatPts][kNbr];
@@ -213,8 +223,8 @@ __global__ void __launch_bounds__(256) fka_feat_kernel(const float* __restrict__
     const int tid = threadIdx.x;
     const int npts = min(kFeatPts, n_s - n0);
     const size_t row0 = (size_t)b * n_s + n0;
-    for (int e = tid; e < npts * kNbr * 16; e += 256) (&smat[0][0][0])[e] = mat[row0 * kNbr * 16 + e];
-    for (int e = tid; e < npts * kNbr; e += 256) (&sid[0][0])[e] = ids[row0 * kNbr + e];
+    for (int e = tid; e < npts * kn * 16; e += 256) smat[e / (kn * 16)][(e / 16) % kn][e % 16] = mat[row0 * kn * 16 + e];
+    for (int e = tid; e < npts * kn; e += 256) sid[e / kn][e % kn] = ids[row0 * kn + e];
     __syncthreads();
     const int cw = VEC ? cin / 4 : cin;  // work items per point
     for (int e = tid; e < npts * cw; e += 256) {
@@ -224,7 +234,7 @@ __global__ void __launch_bounds__(256) fka_feat_kernel(const float* __restrict__
 #pragma unroll
             for (int m = 0; m < 16; ++m) acc[m] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
-            for (int j = 0; j < kNbr; ++j) {
+            for (int j = 0; j < kn; ++j) {
                 float4 xv = reinterpret_cast<const float4*>(x + ((size_t)b * n_in + sid[pl][j]) * cin)[cq];
 #pragma unroll
                 for (int m = 0; m < 16; ++m) {
@@ -242,7 +252,7 @@ __global__ void __launch_bounds__(256) fka_feat_kernel(const float* __restrict__
             float acc[16];
 #pragma unroll
             for (int m = 0; m < 16; ++m) acc[m] = 0.f;
-            for (int j = 0; j < kNbr; ++j) {
+            for (int j = 0; j < kn; ++j) {
                 float xv = x[((size_t)b * n_in + sid[pl][j]) * cin + cq];
 #pragma unroll
                 for (int m = 0; m < 16; ++m) acc[m] = fmaf(smat[pl][j][m], xv, acc[m]);
@@ -302,7 +312,7 @@ __global__ void latent_finalize_kernel(float* latent, const float* __restrict__ 
 struct FkaLayout {
     size_t stats, mat, feat, total;
 };
-static FkaLayout fka_layout(int64_t b, int64_t n_s, int cin) {
+static FkaLayout fka_layout(int64_t b, int64_t n_s, int cin) {  // sized for kn = 16
     FkaLayout l;
     size_t off = 0;
     l.stats = off;
@@ -327,9 +337,10 @@ size_t pps_fkaconv_workspace_bytes(int64_t b, int64_t n_s, int cin) {
 }
 
 int pps_fkaconv_forward(const pps_fkaconv_weights* w, const float* x, const float* pts, const float* support,
-                        const int32_t* ids, int64_t b, int64_t n_in, int64_t n_s, void* workspace,
+                        const int32_t* ids, int kn, int64_t b, int64_t n_in, int64_t n_s, void* workspace,
                         size_t workspace_bytes, float* out, void* stream) {
     PPS_CHECK_ARG(w && x && pts && support && ids && workspace && out, "pps_fkaconv_forward: null pointer");
+    PPS_CHECK_ARG(kn >= 1 && kn <= kNbr, "pps_fkaconv_forward: %d neighbours per support point, supported 1..16", kn);
     PPS_CHECK_ARG(b >= 1 && b <= 65535 && n_in >= 1 && n_s >= 1 && n_in < (1ll << 31) && n_s < (1ll << 31),
                   "pps_fkaconv_forward: bad sizes b=%lld n_in=%lld n_s=%lld", (long long)b, (long long)n_in, (long long)n_s);
     PPS_CHECK_ARG(w->cin >= 1 && w->cout >= 1 && (w->act == 0 || w->act == 1), "pps_fkaconv_forward: bad weights");
@@ -346,21 +357,21 @@ int pps_fkaconv_forward(const pps_fkaconv_weights* w, const float* x, const floa
     PPS_CUDA(cudaMemsetAsync(stats, 0, (size_t)b * 64 * sizeof(double), st));
     FkaParams prm{w->alpha, w->beta, 1.f / w->norm_radius, w->act};
     dim3 grid((unsigned)ceil_div(n_s, 128), (unsigned)b);
-    fka_weight_kernel<1><<<grid, 128, 0, st>>>(pts, support, ids, (int)n_in, (int)n_s, prm, w->fc1, w->fc2, w->fc3, w->in1_w,
+    fka_weight_kernel<1><<<grid, 128, 0, st>>>(pts, support, ids, (int)n_in, (int)n_s, kn, prm, w->fc1, w->fc2, w->fc3, w->in1_w,
                                                w->in1_b, w->in2_w, w->in2_b, stats, mat);
     PPS_LAUNCH_CHECK();
-    fka_weight_kernel<2><<<grid, 128, 0, st>>>(pts, support, ids, (int)n_in, (int)n_s, prm, w->fc1, w->fc2, w->fc3, w->in1_w,
+    fka_weight_kernel<2><<<grid, 128, 0, st>>>(pts, support, ids, (int)n_in, (int)n_s, kn, prm, w->fc1, w->fc2, w->fc3, w->in1_w,
                                                w->in1_b, w->in2_w, w->in2_b, stats, mat);
     PPS_LAUNCH_CHECK();
-    fka_weight_kernel<3><<<grid, 128, 0, st>>>(pts, support, ids, (int)n_in, (int)n_s, prm, w->fc1, w->fc2, w->fc3, w->in1_w,
+    fka_weight_kernel<3><<<grid, 128, 0, st>>>(pts, support, ids, (int)n_in, (int)n_s, kn, prm, w->fc1, w->fc2, w->fc3, w->in1_w,
                                                w->in1_b, w->in2_w, w->in2_b, stats, mat);
     PPS_LAUNCH_CHECK();
     dim3 fgrid((unsigned)ceil_div(n_s, kFeatPts), (unsigned)b);
     bool vec = (w->cin % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     if (vec)
-        fka_feat_kernel<true><<<fgrid, 256, 0, st>>>(x, ids, mat, (int)n_in, (int)n_s, w->cin, feat);
+        fka_feat_kernel<true><<<fgrid, 256, 0, st>>>(x, ids, mat, (int)n_in, (int)n_s, kn, w->cin, feat);
     else
-        fka_feat_kernel<false><<<fgrid, 256, 0, st>>>(x, ids, mat, (int)n_in, (int)n_s, w->cin, feat);
+        fka_feat_kernel<false><<<fgrid, 256, 0, st>>>(x, ids, mat, (int)n_in, (int)n_s, kn, w->cin, feat);
     PPS_LAUNCH_CHECK();
     int kdim = 16 * w->cin;
     return linear_impl(feat, w->cv_w, w->out_bias, nullptr, nullptr, out, b * n_s, w->cout, kdim, kdim, w->cout,

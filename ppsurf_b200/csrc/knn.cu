@@ -304,10 +304,10 @@ static int launch_query(const KnnHeader* hdr, const float4* sorted, const int* c
 
 int knn_query_impl(const void* index, int64_t n, const float* queries, int64_t q, int k, int32_t* idx_out,
                    float* d2_out, cudaStream_t st) {
+    if (q == 0) return PPS_OK;
     PPS_CHECK_ARG(index && queries && idx_out, "pps_knn_query: null pointer");
     PPS_CHECK_ARG(n > 0 && n < (int64_t(1) << 31), "pps_knn_query: n=%lld out of range", (long long)n);
     PPS_CHECK_ARG(k >= 1 && k <= n && k <= 512, "pps_knn_query: k=%d must be in [1, min(n,512)] (n=%lld)", k, (long long)n);
-    if (q == 0) return PPS_OK;
     KnnLayout l = knn_layout(n);
     const char* base = static_cast<const char*>(index);
     const KnnHeader* hdr = reinterpret_cast<const KnnHeader*>(base + l.header);

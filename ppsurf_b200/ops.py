@@ -170,16 +170,15 @@ def pointnet(packed, patches: torch.Tensor):
 
 
 def fkaconv(packed, x, pts, support, ids):
-    """``x [B,Nin,Cin]``, ``pts [B,Nin,3]``, ``support [B,Ns,3]``, ``ids [B,Ns,16] int32`` -> ``[B,Ns,Cout]``"""
+    """``x [B,Nin,Cin]``, ``pts [B,Nin,3]``, ``support [B,Ns,3]``, ``ids [B,Ns,kn<=16] int32`` -> ``[B,Ns,Cout]``"""
     b, n_in, cin = x.shape
     n_s = support.shape[1]
-    if ids.shape[-1] != 16:
-        raise ValueError('FKAConv needs 16 neighbours per support point (kernel size 16), got {}'.format(ids.shape[-1]))
+    kn = ids.shape[-1]
     nbytes = lib.pps_fkaconv_workspace_bytes(b, n_s, cin)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
     out = torch.empty((b, n_s, packed.struct.cout), dtype=torch.float32, device=x.device)
     check(lib.pps_fkaconv_forward(packed.ref, _ptr(x, torch.float32), _ptr(pts, torch.float32), _ptr(support, torch.float32),
-                                  _ptr(ids, torch.int32), b, n_in, n_s, _ptr(ws), ws.numel(), _ptr(out), _stream()))
+                                  _ptr(ids, torch.int32), kn, b, n_in, n_s, _ptr(ws), ws.numel(), _ptr(out), _stream()))
     return out
 
 

@@ -97,7 +97,32 @@ def pack_decoder(sd, device, k, num_pts_local, prefix='') -> Packed:
         p.put('m{}_b'.format(i), b, device)
     p.put('m2_w', _mat(sd, m + '2.0.weight'), device)
     p.put('m2_b', _f64(sd, m + '2.0.bias'), device)
+    if latent == 256 and st.heads == 64:
+        pack = torch.cat([tc_pack_matrix(_mat(sd, g + name + '.weight')) for name in ('fc2', 'fc3', 'fc_query')])
+        assert pack.numel() == _lib.lib.pps_decoder_tc_pack_bytes()
+        p.tensors['tc_wpack'] = pack.to(device)
+        st.tc_wpack = p.tensors['tc_wpack'].data_ptr()
+    else:
+        st.tc_wpack = None
     return p
+
+
+def tc_split(w: torch.Tensor):
+    """fp32 value -> (fp16 hi, fp16 lo) with hi + lo carrying 22 mantissa bits"""
+    w32 = w.to(torch.float32)
+    hi = w32.to(torch.float16)
+    lo = (w32 - hi.to(torch.float32)).to(torch.float16)
+    return hi, lo
+
+
+def tc_pack_matrix(w: torch.Tensor) -> torch.Tensor:
+    """``w [N,256]`` -> uint8 tensor: 16 k16 stages of [hi block 0 | hi block 1 | lo block 0 | lo block 1], block = [N rows, 8
+    fp16] (the UMMA canonical K-major no-swizzle layout the kernel copies verbatim into shared memory)"""
+    n, k = w.shape
+    assert k % 16 == 0
+    hi, lo = tc_split(w)
+    both = torch.stack([hi, lo], dim=0).view(2, n, k // 16, 2, 8)  # [hl, n, stage, kb, 8]
+    return both.permute(2, 0, 3, 1, 4).contiguous().view(torch.uint8).reshape(-1)
 
 
 def pack_fkaconv(sd, name, device, act, bn=None) -> Packed:

@@ -221,7 +221,7 @@ def _decode_inputs(g):
     return np.random.default_rng(int(g['latents_seed'])).standard_normal((1, 256, g['pts'].shape[0])).astype(np.float32)
 
 
-@pytest.mark.parametrize('path', [0])
+@pytest.mark.parametrize('path', [0, 1])
 def test_decode_golden(dev, net, oracle, weights, path):
     from ppsurf_b200 import ops
     g = load_golden('decode')
@@ -377,6 +377,35 @@ def test_full_size_properties(dev, net, oracle):
             'pts_local_ps': oracle.get_pts_local_ps(pts, q[sample], 50)[None], 'proj_ids': ref_idx[None]}
     ref = oracle.from_latent(weights_for(net), data, dtype=np.float64)
     assert np.abs(logits[sample].T[None] - ref).max() < LOGIT_TOL
+
+
+def test_tensor_core_path_matches_fp32_path(dev, net, oracle):
+    """path 1 (tcgen05 split-fp16) against path 0 (fp32 SIMT) and the float64 oracle on 3001 queries: odd count (half-filled
+    last tile), more tiles than SMs (persistent loop + ring wrap-around), far-away queries"""
+    from ppsurf_b200 import ops
+    rng = np.random.default_rng(77)
+    pts = oracle.synthetic_cloud(6000, seed=5)
+    latents = torch.from_numpy(rng.standard_normal((6000, 256)).astype(np.float32)).to(dev)
+    qry = np.concatenate([pts[rng.integers(0, 6000, 2000)] + 0.02 * rng.standard_normal((2000, 3)),
+                          rng.uniform(-0.6, 0.6, (1001, 3))]).astype(np.float32)
+    out = []
+    for path in (0, 1):
+        dec = ops.Decoder(net.packed()['decoder'], cu(pts, dev), latents, chunk=1024, path=path)
+        out.append(dec.decode(cu(qry, dev), want_logits=True, want_idx=True))
+    l0, l1 = out[0]['logits'].cpu().numpy(), out[1]['logits'].cpu().numpy()
+    assert np.isfinite(l1).all()
+    assert np.abs(l0 - l1).max() < LOGIT_TOL
+    sel = rng.integers(0, 3001, 48)
+    data = {'pts': pts.T[None], 'latents': latents.cpu().numpy().T[None], 'pts_query': qry[sel][None],
+            'pts_local_ps': oracle.get_pts_local_ps(pts, qry[sel], 50)[None]}
+    ref = oracle.from_latent(weights_for(net), data, dtype=np.float64)
+    assert np.abs(l1[sel].T[None] - ref).max() < LOGIT_TOL
+    # the projection alone, so that a tensor-core error is not hidden behind the MLP
+    dec0 = ops.Decoder(net.packed()['decoder'], cu(pts, dev), latents, path=0)
+    dec1 = ops.Decoder(net.packed()['decoder'], cu(pts, dev), latents, path=1)
+    idx = out[0]['idx'][:, :64].contiguous()
+    f0, f1 = dec0.projection(cu(qry, dev), idx).cpu().numpy(), dec1.projection(cu(qry, dev), idx).cpu().numpy()
+    assert np.abs(f0 - f1).max() < 2e-5 * max(1.0, np.abs(f0).max())
 
 
 def weights_for(net):
