@@ -4,10 +4,10 @@
 // source/base/proximity.py:40-89).  Index: the points sorted by a 3-D Morton code of a 2^L grid over their bounding
 // cube, plus the start offset of every finest cell.  Because Morton order nests, the points of ANY octree node
 // (level l, code c) are the contiguous range [start[c << 3(L-l)], start[(c+1) << 3(L-l)]), so one array is a whole
-// implicit octree.  A query is one thread doing a depth-first, near-child-first traversal with box pruning against
-// the current k-th distance; the k candidates live in a per-thread max-heap in shared memory ([slot][thread]
-// layout, conflict free).  Results are exact under the total order (dist2, index) with float32 distances computed
-// like pykdtree's float path: (dx*dx + dy*dy) + dz*dz, every operation rounded, no FMA.
+// implicit octree.  A query is one WARP doing a depth-first, near-child-first traversal with box pruning against the
+// current k-th distance; the k candidates live in registers as a sorted list spread over the lanes.  Results are exact
+// under the total order (dist2, index) with float32 distances computed like pykdtree's float path:
+// (dx*dx + dy*dy) + dz*dz, every operation rounded, no FMA.
 #include <cub/device/device_radix_sort.cuh>
 
 #include "common.cuh"
@@ -15,7 +15,6 @@
 namespace pps {
 
 constexpr int kMaxLevels = 7;  // 128^3 finest cells, 21-bit codes
-constexpr int kLeafCount = 16;
 
 struct KnnHeader {
     unsigned int min_enc[3];
@@ -151,153 +150,150 @@ __global__ void knn_finalize(const float* __restrict__ pts, int n, const unsigne
 }
 
 // ---- query -------------------------------------------------------------------------------------------------------
+// One WARP per query.  The k best candidates live in registers as a sorted list distributed over the lanes (element
+// g = slot*32 + lane), the traversal stack is per warp in shared memory, and control flow is warp-uniform:
+//   * a leaf (<= 32 points, or the finest level) is scanned 32 points at a time with one coalesced float4 load per
+//     lane; survivors of the (dist2, index) < worst test are inserted one by one (ballot + shuffle-up);
+//   * at an inner node lanes 0..7 fetch the ranges and box distances of the 8 children and push the non-empty,
+//     non-pruned ones far-to-near (rank by shuffles), so the nearest child is popped first.
 
-struct HeapRef {
-    float* d;
-    int* id;
-    int stride;  // BS + 1
-    int k;
-    __device__ __forceinline__ float& dist(int s) { return d[s * stride]; }
-    __device__ __forceinline__ int& idx(int s) { return id[s * stride]; }
-};
+__device__ __forceinline__ bool cand_less(float da, int ia, float db, int ib) { return da < db || (da == db && ia < ib); }
 
-__device__ __forceinline__ bool heap_greater(float da, int ia, float db, int ib) {
-    return da > db || (da == db && ia > ib);
-}
-
-// place (nd, ni) at the root of a max-heap of size n (root is being replaced) and restore the heap property
-__device__ __forceinline__ void heap_sift_root(HeapRef& h, int n, float nd, int ni) {
-    int pos = 0;
-    while (true) {
-        int l = 2 * pos + 1;
-        if (l >= n) break;
-        int r = l + 1;
-        float dl = h.dist(l);
-        int il = h.idx(l);
-        int c = l;
-        float dc = dl;
-        int ic = il;
-        if (r < n) {
-            float dr = h.dist(r);
-            int ir = h.idx(r);
-            if (heap_greater(dr, ir, dl, il)) {
-                c = r;
-                dc = dr;
-                ic = ir;
-            }
-        }
-        if (!heap_greater(dc, ic, nd, ni)) break;
-        h.dist(pos) = dc;
-        h.idx(pos) = ic;
-        pos = c;
-    }
-    h.dist(pos) = nd;
-    h.idx(pos) = ni;
-}
-
-template <int BS>
-__global__ void __launch_bounds__(BS) knn_query_kernel(const KnnHeader* __restrict__ hdr, const float4* __restrict__ sorted,
+template <int SLOTS>
+__global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restrict__ hdr, const float4* __restrict__ sorted,
                                                        const int* __restrict__ cell_start, const float* __restrict__ queries,
                                                        long long nq, int k, int32_t* __restrict__ idx_out,
                                                        float* __restrict__ d2_out) {
-    extern __shared__ float smem[];
-    const int stride = BS + 1;
-    float* hd = smem;
-    int* hi = reinterpret_cast<int*>(smem + (size_t)k * stride);
-    const int tid = threadIdx.x;
-    const long long q0 = (long long)blockIdx.x * BS;
-    const long long qi = q0 + tid;
-    HeapRef heap{hd + tid, hi + tid, stride, k};
-    for (int s = 0; s < k; ++s) {
-        heap.dist(s) = INFINITY;
-        heap.idx(s) = 0x7fffffff;
+    __shared__ unsigned int stack_s[8][8 * kMaxLevels + 8];
+    const unsigned int full = 0xffffffffu;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long qi = (long long)blockIdx.x * 8 + warp;
+    if (qi >= nq) return;
+    unsigned int* stack = stack_s[warp];
+    float ld[SLOTS];
+    int li[SLOTS];
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+        ld[s] = INFINITY;
+        li[s] = 0x7fffffff;
     }
-    if (qi < nq) {
-        const int L = hdr->levels;
-        const float ox = hdr->origin[0], oy = hdr->origin[1], oz = hdr->origin[2];
-        const float cell = hdr->cell;
-        const float pad = cell * 1e-3f;
-        const float qx = queries[3 * qi], qy = queries[3 * qi + 1], qz = queries[3 * qi + 2];
-        float worst = INFINITY;
-        int worst_i = 0x7fffffff;
+    const int L = hdr->levels;
+    const float ox = hdr->origin[0], oy = hdr->origin[1], oz = hdr->origin[2];
+    const float cell = hdr->cell;
+    const float pad = cell * 1e-3f;
+    const float qx = queries[3 * qi], qy = queries[3 * qi + 1], qz = queries[3 * qi + 2];
+    float worst = INFINITY;
+    int worst_i = 0x7fffffff;
+    const int wslot = (k - 1) >> 5, wlane = (k - 1) & 31;  // where the k-th best lives
 
-        auto box_dist = [&](int level, int cx, int cy, int cz) -> float {
-            float size = cell * float(1 << (L - level));
-            float lx = ox + cx * size - pad, ly = oy + cy * size - pad, lz = oz + cz * size - pad;
-            float hx = lx + size + 2 * pad, hy = ly + size + 2 * pad, hz = lz + size + 2 * pad;
-            float dx = fmaxf(fmaxf(lx - qx, qx - hx), 0.f);
-            float dy = fmaxf(fmaxf(ly - qy, qy - hy), 0.f);
-            float dz = fmaxf(fmaxf(lz - qz, qz - hz), 0.f);
-            return (dx * dx + dy * dy + dz * dz) * 0.99999f;  // conservative lower bound
-        };
+    auto box_dist = [&](int level, int cx, int cy, int cz) -> float {
+        float size = cell * float(1 << (L - level));
+        float lx = ox + cx * size - pad, ly = oy + cy * size - pad, lz = oz + cz * size - pad;
+        float hx = lx + size + 2 * pad, hy = ly + size + 2 * pad, hz = lz + size + 2 * pad;
+        float dx = fmaxf(fmaxf(lx - qx, qx - hx), 0.f);
+        float dy = fmaxf(fmaxf(ly - qy, qy - hy), 0.f);
+        float dz = fmaxf(fmaxf(lz - qz, qz - hz), 0.f);
+        return (dx * dx + dy * dy + dz * dz) * 0.99999f;  // conservative lower bound
+    };
 
-        unsigned int stack[8 * kMaxLevels + 8];
-        int sp = 0;
-        stack[sp++] = 0u;  // root: level 0, cell (0,0,0)
-        const unsigned char order[8] = {0, 1, 2, 4, 3, 5, 6, 7};
-        while (sp > 0) {
-            unsigned int nd = stack[--sp];
-            int level = nd >> 21, cx = nd & 127, cy = (nd >> 7) & 127, cz = (nd >> 14) & 127;
-            if (box_dist(level, cx, cy, cz) > worst) continue;
-            unsigned int code = morton3(cx, cy, cz);
-            int sh = 3 * (L - level);
-            int lo = cell_start[code << sh], hi_ = cell_start[(code + 1u) << sh];
-            int cnt = hi_ - lo;
-            if (cnt == 0) continue;
-            if (cnt <= kLeafCount || level == L) {
-                for (int i = lo; i < hi_; ++i) {
-                    float4 p = sorted[i];
-                    float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
-                    float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                    int pi = __float_as_int(p.w);
-                    if (heap_greater(worst, worst_i, d2, pi)) {
-                        heap_sift_root(heap, k, d2, pi);
-                        worst = heap.dist(0);
-                        worst_i = heap.idx(0);
-                    }
+    int sp = 1;
+    if (lane == 0) stack[0] = 0u;  // root: level 0, cell (0,0,0)
+    __syncwarp();
+    while (sp > 0) {
+        const unsigned int nd = stack[--sp];
+        const int level = nd >> 21, cx = nd & 127, cy = (nd >> 7) & 127, cz = (nd >> 14) & 127;
+        if (box_dist(level, cx, cy, cz) > worst) continue;
+        const unsigned int code = morton3(cx, cy, cz);
+        const int sh = 3 * (L - level);
+        const int lo = cell_start[code << sh], hi = cell_start[(code + 1u) << sh];
+        const int cnt = hi - lo;
+        if (cnt == 0) continue;
+        if (cnt <= 32 || level == L) {
+            for (int base = lo; base < hi; base += 32) {
+                const int i = base + lane;
+                float d2 = INFINITY;
+                int pi = 0x7fffffff;
+                if (i < hi) {
+                    const float4 p = sorted[i];
+                    const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+                    d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                    pi = __float_as_int(p.w);
                 }
-            } else {
-                float size = cell * float(1 << (L - level));
-                int o = (qx >= ox + (cx + 0.5f) * size ? 1 : 0) | (qy >= oy + (cy + 0.5f) * size ? 2 : 0) |
-                        (qz >= oz + (cz + 0.5f) * size ? 4 : 0);
-                int sh2 = sh - 3;
-                unsigned int base = code * 8u;
-                for (int t = 7; t >= 0; --t) {  // far children first so that the nearest is popped first
-                    int ch = o ^ order[t];
-                    int clo = cell_start[(base + ch) << sh2], chi = cell_start[(base + ch + 1u) << sh2];
-                    if (chi == clo) continue;
-                    int ccx = cx * 2 + (ch & 1), ccy = cy * 2 + ((ch >> 1) & 1), ccz = cz * 2 + (ch >> 2);
-                    if (box_dist(level + 1, ccx, ccy, ccz) > worst) continue;
-                    stack[sp++] = ((unsigned int)(level + 1) << 21) | ccx | (ccy << 7) | (ccz << 14);
+                unsigned int mask = __ballot_sync(full, i < hi && cand_less(d2, pi, worst, worst_i));
+                while (mask) {
+                    const int src = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const float vd = __shfl_sync(full, d2, src);
+                    const int vi = __shfl_sync(full, pi, src);
+                    if (!cand_less(vd, vi, worst, worst_i)) continue;  // the bound may have tightened meanwhile
+                    int pos = 0;  // number of list elements smaller than the candidate
+#pragma unroll
+                    for (int s = 0; s < SLOTS; ++s) pos += __popc(__ballot_sync(full, cand_less(ld[s], li[s], vd, vi)));
+#pragma unroll
+                    for (int s = SLOTS - 1; s >= 0; --s) {
+                        float pd = __shfl_up_sync(full, ld[s], 1);
+                        int pj = __shfl_up_sync(full, li[s], 1);
+                        if (s > 0) {
+                            const float cd = __shfl_sync(full, ld[s - 1], 31);
+                            const int cj = __shfl_sync(full, li[s - 1], 31);
+                            if (lane == 0) {
+                                pd = cd;
+                                pj = cj;
+                            }
+                        }
+                        const int g = s * 32 + lane;
+                        if (g == pos) {
+                            ld[s] = vd;
+                            li[s] = vi;
+                        } else if (g > pos) {
+                            ld[s] = pd;
+                            li[s] = pj;
+                        }
+                    }
+                    worst = __shfl_sync(full, ld[wslot < SLOTS ? wslot : SLOTS - 1], wlane);
+                    worst_i = __shfl_sync(full, li[wslot < SLOTS ? wslot : SLOTS - 1], wlane);
                 }
             }
-        }
-        // in-place heapsort -> ascending (dist2, index)
-        for (int end = k - 1; end > 0; --end) {
-            float td = heap.dist(end);
-            int ti = heap.idx(end);
-            heap.dist(end) = heap.dist(0);
-            heap.idx(end) = heap.idx(0);
-            heap_sift_root(heap, end, td, ti);
+        } else {
+            const int sh2 = sh - 3;
+            const unsigned int cbase = code * 8u;
+            bool ok = false;
+            float d = INFINITY;
+            unsigned int child = 0;
+            if (lane < 8) {
+                const int clo = cell_start[(cbase + lane) << sh2], chi = cell_start[(cbase + lane + 1u) << sh2];
+                const int ccx = cx * 2 + (lane & 1), ccy = cy * 2 + ((lane >> 1) & 1), ccz = cz * 2 + (lane >> 2);
+                d = box_dist(level + 1, ccx, ccy, ccz);
+                ok = chi > clo && d <= worst;
+                child = ((unsigned int)(level + 1) << 21) | ccx | (ccy << 7) | (ccz << 14);
+            }
+            const unsigned int m = __ballot_sync(full, ok);
+            int rank = 0;  // far children first -> the nearest one ends on top of the stack
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const float dt = __shfl_sync(full, d, t);
+                if (((m >> t) & 1u) && (dt > d || (dt == d && t < lane))) ++rank;
+            }
+            if (ok) stack[sp + rank] = child;
+            sp += __popc(m);
+            __syncwarp();
         }
     }
-    __syncthreads();
-    // transposed, coalesced write-out of the block's [BS,k] results
-    long long rows = nq - q0 < BS ? nq - q0 : BS;
-    long long total = rows * k;
-    for (long long e = tid; e < total; e += BS) {
-        int r = int(e / k), s = int(e % k);
-        idx_out[q0 * k + e] = hi[s * stride + r];
-        if (d2_out) d2_out[q0 * k + e] = hd[s * stride + r];
+    // the list is sorted ascending by (dist2, index): element g = slot*32 + lane
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+        const int g = s * 32 + lane;
+        if (g < k) {
+            idx_out[qi * k + g] = li[s];
+            if (d2_out) d2_out[qi * k + g] = ld[s];
+        }
     }
 }
 
-template <int BS>
+template <int SLOTS>
 static int launch_query(const KnnHeader* hdr, const float4* sorted, const int* cell_start, const float* queries,
                         int64_t q, int k, int32_t* idx_out, float* d2_out, cudaStream_t st) {
-    size_t smem = size_t(k) * (BS + 1) * 8;
-    PPS_CUDA(cudaFuncSetAttribute(knn_query_kernel<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    knn_query_kernel<BS><<<(unsigned)ceil_div(q, BS), BS, smem, st>>>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out);
+    knn_warp_kernel<SLOTS><<<(unsigned)ceil_div(q, 8), 256, 0, st>>>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out);
     PPS_LAUNCH_CHECK();
     return PPS_OK;
 }
@@ -313,9 +309,11 @@ int knn_query_impl(const void* index, int64_t n, const float* queries, int64_t q
     const KnnHeader* hdr = reinterpret_cast<const KnnHeader*>(base + l.header);
     const float4* sorted = reinterpret_cast<const float4*>(base + l.sorted);
     const int* cell_start = reinterpret_cast<const int*>(base + l.cell_start);
-    if (k <= 64) return launch_query<128>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out, st);
-    if (k <= 200) return launch_query<64>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out, st);
-    return launch_query<32>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out, st);
+    if (k <= 32) return launch_query<1>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out, st);
+    if (k <= 64) return launch_query<2>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out, st);
+    if (k <= 128) return launch_query<4>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out, st);
+    if (k <= 224) return launch_query<7>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out, st);
+    return launch_query<16>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out, st);
 }
 
 int knn_build_impl(const float* pts, int64_t n, void* index, size_t index_bytes, cudaStream_t st) {
