@@ -145,9 +145,15 @@ typedef struct pps_decoder_weights {
     /* tensor-core pack of fc2 / fc3 / fc_query for path 1 (pps_decoder_tc_pack_bytes() bytes, nullable): per layer 16
      * k16 stages, each [W_hi k8-block 0 | W_hi k8-block 1 | W_lo block 0 | W_lo block 1], a block = N rows x 8 fp16 */
     const void* tc_wpack;
+    /* same stage format for the local branch (P <= 64): [conv0b | stn.conv1 | stn.conv2 | stn.conv3 rows 0-127 | rows
+     * 128-255] and [conv1 | conv2]; pps_decoder_tc_pn_stn_bytes() / pps_decoder_tc_pn_feat_bytes() bytes, nullable */
+    const void* tc_pn_stn;
+    const void* tc_pn_feat;
 } pps_decoder_weights;
 
 size_t pps_decoder_tc_pack_bytes(void);
+size_t pps_decoder_tc_pn_stn_bytes(void);
+size_t pps_decoder_tc_pn_feat_bytes(void);
 
 /* per-point table  U[n,:] = W1_lat . latent[n] - W1_xyz . pts[n] + b1   (fc1 hoisted out of the (query,neighbour)
  * loop: fc1([latent_j, q - p_j]) = U_j + W1_xyz . q).  table [n,C] f32. */
@@ -160,7 +166,8 @@ size_t pps_decoder_workspace_bytes(const pps_decoder_weights* w, int64_t chunk);
 /* Decode q queries: kNN (k = max(w->k, P)) -> both branches -> MLP.
  *   logits_out [q,2] f32 or NULL;  occ_out [q] f32 (softmax(l)[0] - softmax(l)[1]) or NULL.
  *   idx_out [q,kmax] int32 or NULL (the neighbour ids, = reference proj_ids for the first w->k columns).
- *   path: 0 = fp32 SIMT kernels, 1 = tcgen05 split-fp16 tensor-core kernels (global branch GEMMs). */
+ *   path: 0 = fp32 SIMT kernels, 1 = tcgen05 split-fp16 tensor-core kernels (both branches; the local branch needs
+ *   P <= 64 and otherwise stays on the fp32 kernels). */
 int pps_decoder_decode(const pps_decoder_weights* w, const void* knn_index, const float* pts, const float* table,
                        int64_t n, const float* queries, int64_t q, int64_t chunk, void* workspace,
                        size_t workspace_bytes, float* logits_out, float* occ_out, int32_t* idx_out, int path,
@@ -180,7 +187,7 @@ int pps_decoder_projection(const pps_decoder_weights* w, const float* pts, const
                            const int32_t* idx, int k_stride, int64_t q, void* workspace, size_t workspace_bytes,
                            float* feat_out /* [q,C] */, int path, void* stream);
 int pps_decoder_pointnet(const pps_decoder_weights* w, const float* patches /* [q,P,3] */, int64_t q,
-                         void* workspace, size_t workspace_bytes, float* feat_out /* [q,C] */, void* stream);
+                         void* workspace, size_t workspace_bytes, float* feat_out /* [q,C] */, int path, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * a11  dense marching-cubes query grid

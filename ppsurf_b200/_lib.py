@@ -31,7 +31,7 @@ class DecoderWeights(ctypes.Structure):
         ('pn2_b', c_f32p), ('pnq_w', c_f32p), ('pnq_b', ctypes.c_float), ('stn_size', ctypes.c_int32),
         ('pnv_w', c_f32p), ('pnv_b', c_f32p),
         ('m0_w', c_f32p), ('m0_b', c_f32p), ('m1_w', c_f32p), ('m1_b', c_f32p), ('m2_w', c_f32p), ('m2_b', c_f32p),
-        ('tc_wpack', c_voidp),
+        ('tc_wpack', c_voidp), ('tc_pn_stn', c_voidp), ('tc_pn_feat', c_voidp),
     ]
 
 
@@ -61,6 +61,8 @@ SIGNATURES = {
     'pps_linear': (i32, [c_f32p, c_f32p, c_f32p, c_f32p, c_i32p, c_f32p, i64, i32, i32, i32, i32, i32, c_voidp]),
     'pps_decoder_point_table': (i32, [ctypes.POINTER(DecoderWeights), c_f32p, c_f32p, i64, c_f32p, c_voidp]),
     'pps_decoder_tc_pack_bytes': (size_t, []),
+    'pps_decoder_tc_pn_stn_bytes': (size_t, []),
+    'pps_decoder_tc_pn_feat_bytes': (size_t, []),
     'pps_decoder_workspace_bytes': (size_t, [ctypes.POINTER(DecoderWeights), i64]),
     'pps_decoder_decode': (i32, [ctypes.POINTER(DecoderWeights), c_voidp, c_f32p, c_f32p, i64, c_f32p, i64, i64, c_voidp,
                                  size_t, c_f32p, c_f32p, c_i32p, i32, c_voidp]),
@@ -68,7 +70,7 @@ SIGNATURES = {
                                       c_voidp, size_t, c_voidp, size_t, c_voidp, i32, c_voidp, c_voidp]),
     'pps_decoder_projection': (i32, [ctypes.POINTER(DecoderWeights), c_f32p, c_f32p, c_f32p, c_i32p, i32, i64, c_voidp,
                                      size_t, c_f32p, i32, c_voidp]),
-    'pps_decoder_pointnet': (i32, [ctypes.POINTER(DecoderWeights), c_f32p, i64, c_voidp, size_t, c_f32p, c_voidp]),
+    'pps_decoder_pointnet': (i32, [ctypes.POINTER(DecoderWeights), c_f32p, i64, c_voidp, size_t, c_f32p, i32, c_voidp]),
     'pps_grid_queries': (i32, [i32, ctypes.c_float, ctypes.c_float, i64, i64, c_f32p, c_voidp]),
     'pps_fkaconv_workspace_bytes': (size_t, [i64, i64, i32]),
     'pps_fkaconv_forward': (i32, [ctypes.POINTER(FKAConvWeights), c_f32p, c_f32p, c_f32p, c_i32p, i32, i64, i64, i64, c_voidp,

@@ -21,6 +21,9 @@ int knn_query_impl(const void* index, int64_t n, const float* queries, int64_t q
 int projection_tc_impl(const pps_decoder_weights* w, const float* table, const float* queries, const int32_t* idx,
                        int k_stride, int64_t q, void* ws, size_t ws_bytes, float* pooled, cudaStream_t st);
 size_t projection_tc_workspace(const pps_decoder_weights* w, int64_t chunk);
+bool pointnet_tc_supported(const pps_decoder_weights* w);
+int pointnet_tc_impl(const pps_decoder_weights* w, const float* patches, int64_t q, float* a1, float* g, float* f1, float* f2,
+                     float* tmat, float* pooled128, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------------------------
 // patches (a7)
@@ -347,8 +350,12 @@ static int projection_run(const pps_decoder_weights* w, const float* table, cons
 
 // local branch for q patches [q,P,3] -> feat_out [q,C]; `residual` (nullable) is added (sum of the branches)
 static int pointnet_run(const pps_decoder_weights* w, const float* patches, int64_t q, DecodeBuffers& b,
-                        const float* residual, float* feat_out, cudaStream_t st) {
+                        const float* residual, float* feat_out, int path, cudaStream_t st) {
     const int C = w->latent, P = w->num_pts_local, S = w->stn_size;
+    if (path == 1 && pointnet_tc_supported(w)) {
+        PPS_TRY(pointnet_tc_impl(w, patches, q, b.a1, b.g, b.f1, b.f2, b.tmat, b.pooled128, st));
+        return linear_impl(b.pooled128, w->pnv_w, w->pnv_b, residual, nullptr, feat_out, q, C, 128, 128, C, 0, st);
+    }
     int64_t m = q * P;
     pn_conv0a_kernel<<<(unsigned)ceil_div(m * 16, 256), 256, 0, st>>>(patches, w->pn0a_w, w->pn0a_b, m, b.bufA);
     PPS_LAUNCH_CHECK();
@@ -380,7 +387,7 @@ static int decode_chunk(const pps_decoder_weights* w, const float* pts, const fl
     patch_normalize_kernel<<<(unsigned)ceil_div(q * P, 256), 256, 0, st>>>(pts, queries, idx, d2, q, P, kmax, b.patches);
     PPS_LAUNCH_CHECK();
     PPS_TRY(projection_run(w, table, queries, idx, kmax, q, b, b.feat_proj, path, st));
-    PPS_TRY(pointnet_run(w, b.patches, q, b, b.feat_proj, b.feat, st));
+    PPS_TRY(pointnet_run(w, b.patches, q, b, b.feat_proj, b.feat, path, st));
     PPS_TRY(linear_impl(b.feat, w->m0_w, w->m0_b, nullptr, nullptr, b.m0, q, C, C, C, C, 1, st));
     PPS_TRY(linear_impl(b.m0, w->m1_w, w->m1_b, nullptr, nullptr, b.m1, q, C, C, C, C, 1, st));
     mlp_head_kernel<<<(unsigned)ceil_div(q * 32, 256), 256, 0, st>>>(b.m1, w->m2_w, w->m2_b, q, C, logits_out, occ_out);
@@ -552,7 +559,7 @@ int pps_decoder_projection(const pps_decoder_weights* w, const float* pts, const
 }
 
 int pps_decoder_pointnet(const pps_decoder_weights* w, const float* patches, int64_t q, void* workspace,
-                         size_t workspace_bytes, float* feat_out, void* stream) {
+                         size_t workspace_bytes, float* feat_out, int path, void* stream) {
     PPS_TRY(check_weights(w));
     PPS_CHECK_ARG(patches && workspace && feat_out, "pps_decoder_pointnet: null pointer");
     if (q == 0) return PPS_OK;
@@ -562,6 +569,7 @@ int pps_decoder_pointnet(const pps_decoder_weights* w, const float* patches, int
         set_error("pps_decoder_pointnet: workspace %zu < required %zu", workspace_bytes, need);
         return PPS_ERR_WORKSPACE;
     }
-    return pointnet_run(w, patches, q, b, nullptr, feat_out, static_cast<cudaStream_t>(stream));
+    PPS_CHECK_ARG(path == 0 || path == 1, "pps_decoder_pointnet: unknown path %d", path);
+    return pointnet_run(w, patches, q, b, nullptr, feat_out, path, static_cast<cudaStream_t>(stream));
 }
 }

@@ -1,0 +1,629 @@
+// Tensor-core path of the decoder's local branch (PointNetfeat with feature-STN and attention pooling,
+// source/base/nn.py:305-373,162-190,84-96) for patches of P <= 64 points: two persistent warp-specialised tcgen05 kernels
+// on tiles of 128 rows = 2 queries x 64 point slots (rows >= P are zero padding), same split-fp16 scheme and roles as
+// decode_tc.cu.
+//
+//   pn_stn_kernel   patches -> conv0a (SIMT, K=3) -> conv0b -> [a1 to global] -> stn.conv1 -> stn.conv2 -> stn.conv3
+//                   computed TRANSPOSED (weights as the M=128 operand, the activation tile as the N=128 operand) so that
+//                   the max over a patch's points is a max over accumulator COLUMNS inside one thread -> g [q,S]
+//   (SIMT linears)  g -> stn.fc1 -> stn.fc2 -> stn.fc3 (+I) = T [q,64,64]          (M = queries: batched over the chunk)
+//   pn_feat_kernel  a1, T -> x' = T_q . a1 (per-query operand built in shared memory) -> conv1 -> conv2 -> attention
+//                   logits, softmax over the patch, pooled [q,128]
+// The pooled vector then goes through the merged (att.fc_value . bn3 . conv3) matrix in linear_impl.
+#include "tc_common.cuh"
+
+namespace pps {
+namespace tc {
+
+constexpr int kPnRows = 128;
+constexpr int kPnLbo = kPnRows * 16 + 16;  // 2064: padded k8-block pitch of an activation tile
+constexpr int kPnSlot = 8192;              // ring slot: one k16 step of the widest weight stage
+constexpr int kPnStages = 4;
+constexpr int kPnThreads = 320;
+constexpr int kPnEpiThreads = 256;
+
+__device__ __forceinline__ void pn_epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kPnEpiThreads) : "memory"); }
+
+// bytes of the packed weights
+constexpr size_t kPackStnBytes = size_t(4) * 4096 * 2 + size_t(4) * 8192 + size_t(16) * 8192;  // conv0b, stn1, stn2, stn3
+constexpr size_t kPackFeatBytes = size_t(4) * 4096 + size_t(4) * 8192;                         // conv1, conv2
+
+// ---------------------------------------------------------------------------------------------------------------------
+// kernel A: conv0a .. stn.conv3 + max
+// ---------------------------------------------------------------------------------------------------------------------
+namespace stn {
+constexpr int kOffAhi = 0;
+constexpr int kABytes = 16 * kPnLbo;                 // up to 128 columns
+constexpr int kOffAlo = kOffAhi + kABytes;           // 33024
+constexpr int kOffRing = kOffAlo + kABytes;          // 66048
+constexpr int kOffPar = kOffRing + kPnStages * kPnSlot;  // 98816: w0a[192] b0a[64] b0b[64] bs1[64] bs2[128] bs3[256]
+constexpr int kParFloats = 192 + 64 + 64 + 64 + 128 + 256;
+constexpr int kOffBar = kOffPar + kParFloats * 4;    // full[4] empty[4] accum aready
+constexpr int kOffTmem = kOffBar + 10 * 8;
+constexpr int kSmemBytes = kOffTmem + 16 + 1024;     // ~103 KB -> two CTAs per SM
+constexpr int kTmemCols = 256;
+}  // namespace stn
+
+__global__ void __launch_bounds__(kPnThreads, 2)
+    pn_stn_kernel(const float* __restrict__ patches, long long nq, int P, const uint8_t* __restrict__ wpack,
+                  const float* __restrict__ w0a, const float* __restrict__ b0a, const float* __restrict__ b0b,
+                  const float* __restrict__ bs1, const float* __restrict__ bs2, const float* __restrict__ bs3,
+                  float* __restrict__ a1_out, float* __restrict__ g_out) {
+    using namespace stn;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t sbase = smem_u32(smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float* s_par = reinterpret_cast<float*>(smem + kOffPar);
+    float* s_w0a = s_par;
+    float* s_b0a = s_par + 192;
+    float* s_b0b = s_b0a + 64;
+    float* s_bs1 = s_b0b + 64;
+    float* s_bs2 = s_bs1 + 64;
+    float* s_bs3 = s_bs2 + 128;
+    volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + kOffTmem);
+    const uint32_t bar_full = sbase + kOffBar, bar_empty = bar_full + 8 * kPnStages, bar_accum = bar_empty + 8 * kPnStages,
+                   bar_aready = bar_accum + 8;
+
+    for (int e = tid; e < 256; e += kPnThreads) {
+        if (e < 192) s_w0a[e] = w0a[e];
+        if (e < 64) {
+            s_b0a[e] = b0a[e];
+            s_b0b[e] = b0b[e];
+            s_bs1[e] = bs1[e];
+        }
+        if (e < 128) s_bs2[e] = bs2[e];
+        s_bs3[e] = bs3[e];
+    }
+    if (tid == 0) {
+        for (int i = 0; i < kPnStages; ++i) {
+            mbar_init(bar_full + 8 * i, 1);
+            mbar_init(bar_empty + 8 * i, 1);
+        }
+        mbar_init(bar_accum, 1);
+        mbar_init(bar_aready, kPnEpiThreads);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kOffTmem), "r"((uint32_t)kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    const long long ntiles = (nq + 1) / 2;
+
+    // weight stages of one tile, in issue order: (bytes per stage, number of stages)
+    // conv0b 4x4096, stn1 4x4096, stn2 4x8192, stn3 16x8192
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t slot = 0, phase = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const uint8_t* src = wpack;
+                for (int s = 0; s < 28; ++s) {
+                    const uint32_t bytes = s < 8 ? 4096u : 8192u;
+                    mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+                    mbar_expect_tx(bar_full + 8 * slot, bytes);
+                    bulk_copy(sbase + kOffRing + slot * kPnSlot, src, bytes, bar_full + 8 * slot);
+                    src += bytes;
+                    if (++slot == kPnStages) {
+                        slot = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t slot = 0, phase = 0, ready_phase = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int layer = 0; layer < 4; ++layer) {
+                    mbar_wait(bar_aready, ready_phase);
+                    ready_phase ^= 1;
+                    tc_fence_after();
+                    if (layer < 3) {
+                        // D[rows, n] = X[rows, 64] . W[n, 64]^T
+                        const int n = layer < 2 ? 64 : 128;
+                        const uint32_t idesc = umma_idesc(n);
+                        for (int s = 0; s < 4; ++s) {
+                            mbar_wait(bar_full + 8 * slot, phase);
+                            tc_fence_after();
+                            const uint64_t x_hi = umma_desc(sbase + kOffAhi + 2 * s * kPnLbo, kPnLbo, 128);
+                            const uint64_t x_lo = umma_desc(sbase + kOffAlo + 2 * s * kPnLbo, kPnLbo, 128);
+                            const uint32_t bst = sbase + kOffRing + slot * kPnSlot;
+                            const uint64_t w_hi = umma_desc(bst, n * 16, 128);
+                            const uint64_t w_lo = umma_desc(bst + n * 32, n * 16, 128);
+                            umma(tmem, x_hi, w_hi, idesc, s > 0 ? 1u : 0u);
+                            umma(tmem, x_lo, w_hi, idesc, 1u);
+                            umma(tmem, x_hi, w_lo, idesc, 1u);
+                            tc_commit(bar_empty + 8 * slot);
+                            if (++slot == kPnStages) {
+                                slot = 0;
+                                phase ^= 1;
+                            }
+                        }
+                    } else {
+                        // transposed: D^T[features(128 per block), rows(128)] = W[features, 128] . X[rows, 128]^T
+                        const uint32_t idesc = umma_idesc(128);
+                        for (int fb = 0; fb < 2; ++fb) {
+                            for (int s = 0; s < 8; ++s) {
+                                mbar_wait(bar_full + 8 * slot, phase);
+                                tc_fence_after();
+                                const uint64_t x_hi = umma_desc(sbase + kOffAhi + 2 * s * kPnLbo, kPnLbo, 128);
+                                const uint64_t x_lo = umma_desc(sbase + kOffAlo + 2 * s * kPnLbo, kPnLbo, 128);
+                                const uint32_t wst = sbase + kOffRing + slot * kPnSlot;
+                                const uint64_t w_hi = umma_desc(wst, 128 * 16, 128);
+                                const uint64_t w_lo = umma_desc(wst + 4096, 128 * 16, 128);
+                                umma(tmem + fb * 128, w_hi, x_hi, idesc, s > 0 ? 1u : 0u);
+                                umma(tmem + fb * 128, w_hi, x_lo, idesc, 1u);
+                                umma(tmem + fb * 128, w_lo, x_hi, idesc, 1u);
+                                tc_commit(bar_empty + 8 * slot);
+                                if (++slot == kPnStages) {
+                                    slot = 0;
+                                    phase ^= 1;
+                                }
+                            }
+                        }
+                    }
+                    tc_commit(bar_accum);
+                }
+            }
+        }
+    } else {
+        const int ew = warp - 2, et = tid - 64;
+        const int lane_grp = warp & 3, half = ew >> 2;
+        const int row = lane_grp * 32 + lane;  // TMEM lane of this thread
+        uint32_t accum_phase = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            // ---- gather + conv0a (SIMT, K=3): thread = (row, half of the 64 channels)
+            {
+                const int r = et & 127, hf = et >> 7;
+                const long long q = 2 * tile + (r >> 6);
+                const int p = r & 63;
+                const bool valid = q < nq && p < P;
+                float x = 0.f, y = 0.f, z = 0.f;
+                if (valid) {
+                    const float* src = patches + (q * P + p) * 3;
+                    x = src[0];
+                    y = src[1];
+                    z = src[2];
+                }
+#pragma unroll
+                for (int kb = 0; kb < 4; ++kb) {
+                    float v[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const int ch = hf * 32 + kb * 8 + c;
+                        v[c] = valid ? fmaxf(s_w0a[3 * ch] * x + s_w0a[3 * ch + 1] * y + s_w0a[3 * ch + 2] * z + s_b0a[ch], 0.f) : 0.f;
+                    }
+                    uint4 hi, lo;
+                    split8(v, hi, lo);
+                    *reinterpret_cast<uint4*>(smem + kOffAhi + (hf * 4 + kb) * kPnLbo + r * 16) = hi;
+                    *reinterpret_cast<uint4*>(smem + kOffAlo + (hf * 4 + kb) * kPnLbo + r * 16) = lo;
+                }
+            }
+            fence_async_smem();
+            tc_fence_before();
+            mbar_arrive(bar_aready);
+
+            const long long q_row = 2 * tile + (row >> 6);
+            const int p_row = row & 63;
+            const bool row_valid = q_row < nq && p_row < P;
+            // ---- conv0b / stn.conv1 (64 wide) and stn.conv2 (128 wide): bias + ReLU -> operand tile (in place)
+            for (int layer = 0; layer < 3; ++layer) {
+                mbar_wait(bar_accum, accum_phase);
+                accum_phase ^= 1;
+                tc_fence_after();
+                const float* bias = layer == 0 ? s_b0b : (layer == 1 ? s_bs1 : s_bs2);
+                const int nload = layer < 2 ? 1 : 2;  // 32 or 64 columns per thread
+                for (int cb = 0; cb < nload; ++cb) {
+                    const int col0 = (layer < 2 ? half * 32 : half * 64) + cb * 32;
+                    float v[32];
+                    tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + col0, v);
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) v[c] = row_valid ? fmaxf(v[c] + bias[col0 + c], 0.f) : 0.f;
+                    if (layer == 0 && row_valid) {  // a1 feeds the feature transform of pn_feat_kernel
+                        float4* dst = reinterpret_cast<float4*>(a1_out + (q_row * P + p_row) * 64 + col0);
+#pragma unroll
+                        for (int c4 = 0; c4 < 8; ++c4) dst[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+                    }
+#pragma unroll
+                    for (int kb = 0; kb < 4; ++kb) {
+                        float x8[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) x8[c] = v[kb * 8 + c];
+                        uint4 hi, lo;
+                        split8(x8, hi, lo);
+                        const int kblk = (col0 >> 3) + kb;
+                        *reinterpret_cast<uint4*>(smem + kOffAhi + kblk * kPnLbo + row * 16) = hi;
+                        *reinterpret_cast<uint4*>(smem + kOffAlo + kblk * kPnLbo + row * 16) = lo;
+                    }
+                }
+                fence_async_smem();
+                tc_fence_before();
+                mbar_arrive(bar_aready);
+            }
+            // ---- stn.conv3 transposed: TMEM lane = feature, columns = rows of the tile; max over the patch's points
+            mbar_wait(bar_accum, accum_phase);
+            accum_phase ^= 1;
+            tc_fence_after();
+            {
+                const long long q = 2 * tile + half;  // this warp's column half = one query
+                for (int fb = 0; fb < 2; ++fb) {
+                    float m = -INFINITY;
+                    for (int cb = 0; cb < 2; ++cb) {
+                        float v[32];
+                        tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + fb * 128 + half * 64 + cb * 32, v);
+#pragma unroll
+                        for (int c = 0; c < 32; ++c)
+                            if (cb * 32 + c < P) m = fmaxf(m, v[c]);
+                    }
+                    const int f = fb * 128 + row;
+                    if (q < nq) g_out[q * 256 + f] = fmaxf(m + s_bs3[f], 0.f);  // ReLU and max commute
+                }
+            }
+            tc_fence_before();
+            // the next tile's gather overwrites the operand tile: the MMAs that read it are complete (accum barrier)
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)kTmemCols) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// kernel C: feature transform, conv1, conv2, attention pooling
+// ---------------------------------------------------------------------------------------------------------------------
+namespace feat {
+constexpr int kOffAhi = 0;
+constexpr int kABytes = 16 * kPnLbo;
+constexpr int kOffAlo = kOffAhi + kABytes;                // 33024
+constexpr int kTLbo = 64 * 16 + 16;                       // 1040: k8-block pitch of a per-query 64x64 transform
+constexpr int kTBytes = 8 * kTLbo;                        // 8320 per (query, hi/lo)
+constexpr int kOffT = kOffAlo + kABytes;                  // 66048: [query][hi,lo]
+constexpr int kOffRing = kOffT + 4 * kTBytes;             // 99328
+constexpr int kOffPar = kOffRing + kPnStages * kPnSlot;   // 132096: b1[64] b2[128] wq[128] part[2][128] att[128]
+constexpr int kParFloats = 64 + 128 + 128 + 256 + 128;
+constexpr int kOffBar = kOffPar + kParFloats * 4;
+constexpr int kOffTmem = kOffBar + 10 * 8;
+constexpr int kSmemBytes = kOffTmem + 16 + 1024;          // ~136 KB
+constexpr int kTmemCols = 128;
+}  // namespace feat
+
+__global__ void __launch_bounds__(kPnThreads, 1)
+    pn_feat_kernel(const float* __restrict__ a1, const float* __restrict__ tmat, long long nq, int P,
+                   const uint8_t* __restrict__ wpack, const float* __restrict__ b1, const float* __restrict__ b2,
+                   const float* __restrict__ wq, float* __restrict__ pooled) {
+    using namespace feat;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t sbase = smem_u32(smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float* s_b1 = reinterpret_cast<float*>(smem + kOffPar);
+    float* s_b2 = s_b1 + 64;
+    float* s_wq = s_b2 + 128;
+    float* s_part = s_wq + 128;  // [2][128] partial attention logits of the two column halves
+    float* s_att = s_part + 256;
+    volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + kOffTmem);
+    const uint32_t bar_full = sbase + kOffBar, bar_empty = bar_full + 8 * kPnStages, bar_accum = bar_empty + 8 * kPnStages,
+                   bar_aready = bar_accum + 8;
+
+    for (int e = tid; e < 128; e += kPnThreads) {
+        if (e < 64) s_b1[e] = b1[e];
+        s_b2[e] = b2[e];
+        s_wq[e] = wq[e];
+    }
+    if (tid == 0) {
+        for (int i = 0; i < kPnStages; ++i) {
+            mbar_init(bar_full + 8 * i, 1);
+            mbar_init(bar_empty + 8 * i, 1);
+        }
+        mbar_init(bar_accum, 1);
+        mbar_init(bar_aready, kPnEpiThreads);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kOffTmem), "r"((uint32_t)kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    const long long ntiles = (nq + 1) / 2;
+
+    if (warp == 0) {
+        if (lane == 0) {  // conv1 4x4096, conv2 4x8192 per tile
+            uint32_t slot = 0, phase = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const uint8_t* src = wpack;
+                for (int s = 0; s < 8; ++s) {
+                    const uint32_t bytes = s < 4 ? 4096u : 8192u;
+                    mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+                    mbar_expect_tx(bar_full + 8 * slot, bytes);
+                    bulk_copy(sbase + kOffRing + slot * kPnSlot, src, bytes, bar_full + 8 * slot);
+                    src += bytes;
+                    if (++slot == kPnStages) {
+                        slot = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t slot = 0, phase = 0, ready_phase = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                // feature transform: D[rows, ql*64 + i] = a1[rows, :] . T_ql[i, :]   (operand built by the epilogue warps)
+                mbar_wait(bar_aready, ready_phase);
+                ready_phase ^= 1;
+                tc_fence_after();
+                {
+                    const uint32_t idesc = umma_idesc(64);
+                    for (int ql = 0; ql < 2; ++ql) {
+                        const uint32_t t_hi = sbase + kOffT + (2 * ql) * kTBytes, t_lo = t_hi + kTBytes;
+                        for (int s = 0; s < 4; ++s) {
+                            const uint64_t x_hi = umma_desc(sbase + kOffAhi + 2 * s * kPnLbo, kPnLbo, 128);
+                            const uint64_t x_lo = umma_desc(sbase + kOffAlo + 2 * s * kPnLbo, kPnLbo, 128);
+                            const uint64_t w_hi = umma_desc(t_hi + 2 * s * kTLbo, kTLbo, 128);
+                            const uint64_t w_lo = umma_desc(t_lo + 2 * s * kTLbo, kTLbo, 128);
+                            umma(tmem + ql * 64, x_hi, w_hi, idesc, s > 0 ? 1u : 0u);
+                            umma(tmem + ql * 64, x_lo, w_hi, idesc, 1u);
+                            umma(tmem + ql * 64, x_hi, w_lo, idesc, 1u);
+                        }
+                    }
+                    tc_commit(bar_accum);
+                }
+                for (int layer = 0; layer < 2; ++layer) {  // conv1 (64 wide), conv2 (128 wide)
+                    const int n = layer == 0 ? 64 : 128;
+                    const uint32_t idesc = umma_idesc(n);
+                    mbar_wait(bar_aready, ready_phase);
+                    ready_phase ^= 1;
+                    tc_fence_after();
+                    for (int s = 0; s < 4; ++s) {
+                        mbar_wait(bar_full + 8 * slot, phase);
+                        tc_fence_after();
+                        const uint64_t x_hi = umma_desc(sbase + kOffAhi + 2 * s * kPnLbo, kPnLbo, 128);
+                        const uint64_t x_lo = umma_desc(sbase + kOffAlo + 2 * s * kPnLbo, kPnLbo, 128);
+                        const uint32_t bst = sbase + kOffRing + slot * kPnSlot;
+                        const uint64_t w_hi = umma_desc(bst, n * 16, 128);
+                        const uint64_t w_lo = umma_desc(bst + n * 32, n * 16, 128);
+                        umma(tmem, x_hi, w_hi, idesc, s > 0 ? 1u : 0u);
+                        umma(tmem, x_lo, w_hi, idesc, 1u);
+                        umma(tmem, x_hi, w_lo, idesc, 1u);
+                        tc_commit(bar_empty + 8 * slot);
+                        if (++slot == kPnStages) {
+                            slot = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    tc_commit(bar_accum);
+                }
+            }
+        }
+    } else {
+        const int ew = warp - 2, et = tid - 64;
+        const int lane_grp = warp & 3, half = ew >> 2;
+        const int row = lane_grp * 32 + lane;
+        uint32_t accum_phase = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            // ---- load a1 rows (coalesced: 8 lanes x 32 B per row, 4 rows per warp instruction) and split
+#pragma unroll 2
+            for (int i = 0; i < 4; ++i) {
+                const int r = ew * 16 + i * 4 + (lane >> 3), kb = lane & 7;
+                const long long q = 2 * tile + (r >> 6);
+                const int p = r & 63;
+                float v[8];
+                if (q < nq && p < P) {
+                    const float4* src = reinterpret_cast<const float4*>(a1 + (q * P + p) * 64) + 2 * kb;
+                    const float4 u0 = src[0], u1 = src[1];
+                    v[0] = u0.x; v[1] = u0.y; v[2] = u0.z; v[3] = u0.w;
+                    v[4] = u1.x; v[5] = u1.y; v[6] = u1.z; v[7] = u1.w;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) v[c] = 0.f;
+                }
+                uint4 hi, lo;
+                split8(v, hi, lo);
+                *reinterpret_cast<uint4*>(smem + kOffAhi + kb * kPnLbo + r * 16) = hi;
+                *reinterpret_cast<uint4*>(smem + kOffAlo + kb * kPnLbo + r * 16) = lo;
+            }
+            // ---- per-query transforms T_q [i][j] -> K-major operand (row i, k = j), values may be negative: plain split
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int e = et + 256 * t;
+                const int ql = e >> 9, i = (e >> 3) & 63, kb = e & 7;
+                long long q = 2 * tile + ql;
+                q = q < nq ? q : nq - 1;
+                const float4* src = reinterpret_cast<const float4*>(tmat + q * 4096 + i * 64) + 2 * kb;
+                const float4 u0 = src[0], u1 = src[1];
+                const float v[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+                uint4 hi, lo;
+                split8_signed(v, hi, lo);
+                *reinterpret_cast<uint4*>(smem + kOffT + (2 * ql) * kTBytes + kb * kTLbo + i * 16) = hi;
+                *reinterpret_cast<uint4*>(smem + kOffT + (2 * ql + 1) * kTBytes + kb * kTLbo + i * 16) = lo;
+            }
+            fence_async_smem();
+            tc_fence_before();
+            mbar_arrive(bar_aready);
+
+            const long long q_row = 2 * tile + (row >> 6);
+            const bool row_valid = q_row < nq && (row & 63) < P;
+            // ---- x' = T . a1 (no bias, no activation; may be negative) -> operand tile
+            mbar_wait(bar_accum, accum_phase);
+            accum_phase ^= 1;
+            tc_fence_after();
+            {
+                float v[32];
+                tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + (row >> 6) * 64 + half * 32, v);
+#pragma unroll
+                for (int kb = 0; kb < 4; ++kb) {
+                    float x8[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) x8[c] = row_valid ? v[kb * 8 + c] : 0.f;
+                    uint4 hi, lo;
+                    split8_signed(x8, hi, lo);
+                    *reinterpret_cast<uint4*>(smem + kOffAhi + (half * 4 + kb) * kPnLbo + row * 16) = hi;
+                    *reinterpret_cast<uint4*>(smem + kOffAlo + (half * 4 + kb) * kPnLbo + row * 16) = lo;
+                }
+            }
+            fence_async_smem();
+            tc_fence_before();
+            mbar_arrive(bar_aready);
+            // ---- conv1: bias + ReLU -> operand tile
+            mbar_wait(bar_accum, accum_phase);
+            accum_phase ^= 1;
+            tc_fence_after();
+            {
+                float v[32];
+                tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + half * 32, v);
+#pragma unroll
+                for (int kb = 0; kb < 4; ++kb) {
+                    float x8[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) x8[c] = row_valid ? fmaxf(v[kb * 8 + c] + s_b1[half * 32 + kb * 8 + c], 0.f) : 0.f;
+                    uint4 hi, lo;
+                    split8(x8, hi, lo);
+                    *reinterpret_cast<uint4*>(smem + kOffAhi + (half * 4 + kb) * kPnLbo + row * 16) = hi;
+                    *reinterpret_cast<uint4*>(smem + kOffAlo + (half * 4 + kb) * kPnLbo + row * 16) = lo;
+                }
+            }
+            fence_async_smem();
+            tc_fence_before();
+            mbar_arrive(bar_aready);
+            // ---- conv2: bias + ReLU -> c2 (hi/lo tile for the pooling) and this thread's share of the attention logit
+            mbar_wait(bar_accum, accum_phase);
+            accum_phase ^= 1;
+            tc_fence_after();
+            {
+                float logit = 0.f;
+                for (int cb = 0; cb < 2; ++cb) {
+                    const int col0 = half * 64 + cb * 32;
+                    float v[32];
+                    tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + col0, v);
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        v[c] = row_valid ? fmaxf(v[c] + s_b2[col0 + c], 0.f) : 0.f;
+                        logit = fmaf(v[c], s_wq[col0 + c], logit);
+                    }
+#pragma unroll
+                    for (int kb = 0; kb < 4; ++kb) {
+                        float x8[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) x8[c] = v[kb * 8 + c];
+                        uint4 hi, lo;
+                        split8(x8, hi, lo);
+                        const int kblk = (col0 >> 3) + kb;
+                        *reinterpret_cast<uint4*>(smem + kOffAhi + kblk * kPnLbo + row * 16) = hi;
+                        *reinterpret_cast<uint4*>(smem + kOffAlo + kblk * kPnLbo + row * 16) = lo;
+                    }
+                }
+                s_part[half * 128 + row] = logit;
+            }
+            tc_fence_before();
+            pn_epi_barrier();
+            // ---- softmax over the patch's points: thread per row
+            if (et < 128) {
+                const int r0 = (et >> 6) * 64, p = et & 63;
+                float m = -INFINITY;
+                for (int j = 0; j < P; ++j) m = fmaxf(m, s_part[r0 + j] + s_part[128 + r0 + j]);
+                float sum = 0.f;
+                for (int j = 0; j < P; ++j) sum += expf(s_part[r0 + j] + s_part[128 + r0 + j] - m);
+                s_att[et] = p < P ? expf(s_part[et] + s_part[128 + et] - m) / sum : 0.f;  // the query bias cancels in the softmax
+            }
+            pn_epi_barrier();
+            // ---- pooled[q, 8kb..] = sum_p att_p c2[p, .]: warp ew owns k8 blocks ew and ew + 8
+#pragma unroll 1
+            for (int t = 0; t < 2; ++t) {
+                const int kb = ew + 8 * t;
+#pragma unroll
+                for (int ql = 0; ql < 2; ++ql) {
+                    float acc[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int r = ql * 64 + hh * 32 + lane;
+                        const float a = s_att[r];
+                        const uint4 hi = *reinterpret_cast<const uint4*>(smem + kOffAhi + kb * kPnLbo + r * 16);
+                        const uint4 lo = *reinterpret_cast<const uint4*>(smem + kOffAlo + kb * kPnLbo + r * 16);
+                        const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
+                            const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&lw[i]));
+                            acc[2 * i] = fmaf(a, fh.x + fl.x, acc[2 * i]);
+                            acc[2 * i + 1] = fmaf(a, fh.y + fl.y, acc[2 * i + 1]);
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+                    const long long q = 2 * tile + ql;
+                    if (lane == 0 && q < nq) {
+                        float4* dst = reinterpret_cast<float4*>(pooled + q * 128 + kb * 8);
+                        dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                        dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+                    }
+                }
+            }
+            pn_epi_barrier();  // all warps are done with the tile before the next gather overwrites it
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)kTmemCols) : "memory");
+    }
+}
+
+}  // namespace tc
+
+int linear_impl(const float* x, const float* w, const float* bias, const float* residual, const int32_t* gather,
+                float* y, int64_t m, int n, int k, int ldx, int ldy, int act, cudaStream_t st);
+
+bool pointnet_tc_supported(const pps_decoder_weights* w) {
+    return w->tc_pn_stn != nullptr && w->tc_pn_feat != nullptr && w->num_pts_local <= 64 && w->stn_size == 256 && w->latent == 256;
+}
+
+// local branch on the tensor cores: patches [q,P,3] -> pooled128 [q,128]; scratch: a1 [q*P,64], g [q,256], f1 [q,128],
+// f2 [q,64], tmat [q,4096]
+int pointnet_tc_impl(const pps_decoder_weights* w, const float* patches, int64_t q, float* a1, float* g, float* f1, float* f2,
+                     float* tmat, float* pooled128, cudaStream_t st) {
+    if (q == 0) return PPS_OK;
+    static bool configured = false;
+    if (!configured) {
+        PPS_CUDA(cudaFuncSetAttribute(tc::pn_stn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::stn::kSmemBytes));
+        PPS_CUDA(cudaFuncSetAttribute(tc::pn_feat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::feat::kSmemBytes));
+        configured = true;
+    }
+    const int P = w->num_pts_local, S = w->stn_size;
+    const long long ntiles = (q + 1) / 2;
+    const int grid_a = (int)(ntiles < 2 * kNumSMs ? ntiles : 2 * kNumSMs);
+    const int grid_c = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
+    tc::pn_stn_kernel<<<grid_a, tc::kPnThreads, tc::stn::kSmemBytes, st>>>(patches, q, P, static_cast<const uint8_t*>(w->tc_pn_stn),
+                                                                          w->pn0a_w, w->pn0a_b, w->pn0b_b, w->stn1_b, w->stn2_b,
+                                                                          w->stn3_b, a1, g);
+    PPS_LAUNCH_CHECK();
+    PPS_TRY(linear_impl(g, w->stnf1_w, w->stnf1_b, nullptr, nullptr, f1, q, S / 2, S, S, S / 2, 1, st));
+    PPS_TRY(linear_impl(f1, w->stnf2_w, w->stnf2_b, nullptr, nullptr, f2, q, S / 4, S / 2, S / 2, S / 4, 1, st));
+    PPS_TRY(linear_impl(f2, w->stnf3_w, w->stnf3_b, nullptr, nullptr, tmat, q, 4096, S / 4, S / 4, 4096, 0, st));
+    tc::pn_feat_kernel<<<grid_c, tc::kPnThreads, tc::feat::kSmemBytes, st>>>(a1, tmat, q, P, static_cast<const uint8_t*>(w->tc_pn_feat),
+                                                                            w->pn1_b, w->pn2_b, w->pnq_w, pooled128);
+    PPS_LAUNCH_CHECK();
+    return PPS_OK;
+}
+
+}  // namespace pps
+
+extern "C" size_t pps_decoder_tc_pn_stn_bytes(void) { return pps::tc::kPackStnBytes; }
+extern "C" size_t pps_decoder_tc_pn_feat_bytes(void) { return pps::tc::kPackFeatBytes; }

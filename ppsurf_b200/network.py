@@ -306,7 +306,7 @@ class PPSurfNetwork(_Base):
                 else:
                     idx = dec.index.query(q, self.k)
                 feat_proj = dec.projection(q, idx)
-                feat_pn = ops.pointnet(dec.packed, data['pts_local_ps'][s].to(dev, torch.float32).contiguous())
+                feat_pn = ops.pointnet(dec.packed, data['pts_local_ps'][s].to(dev, torch.float32).contiguous(), self.decode_path)
                 p = dec.packed.tensors
                 # mlp.layers.0 on (feat_proj + feat_pn): the sum of the branches rides on the layer's linearity
                 t = ops.linear(feat_proj, p['m0_w'])

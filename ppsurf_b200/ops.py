@@ -159,13 +159,14 @@ class Decoder:
         return out
 
 
-def pointnet(packed, patches: torch.Tensor):
+def pointnet(packed, patches: torch.Tensor, path: int = 0):
     """``patches [Q,P,3]`` -> ``[Q,C]`` local-branch features"""
     q = patches.shape[0]
     nbytes = lib.pps_decoder_workspace_bytes(packed.ref, max(q, 1))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=patches.device)
     out = torch.empty((q, packed.struct.latent), dtype=torch.float32, device=patches.device)
-    check(lib.pps_decoder_pointnet(packed.ref, _ptr(patches, torch.float32), q, _ptr(ws), ws.numel(), _ptr(out), _stream()))
+    check(lib.pps_decoder_pointnet(packed.ref, _ptr(patches, torch.float32), q, _ptr(ws), ws.numel(), _ptr(out), int(path),
+                                   _stream()))
     return out
 
 

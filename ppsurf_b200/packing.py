@@ -104,6 +104,17 @@ def pack_decoder(sd, device, k, num_pts_local, prefix='') -> Packed:
         st.tc_wpack = p.tensors['tc_wpack'].data_ptr()
     else:
         st.tc_wpack = None
+    if latent == 256 and st.stn_size == 256 and num_pts_local <= 64:
+        t = p.tensors
+        w3 = t['stn3_w'].to('cpu', torch.float64)
+        stn = torch.cat([tc_pack_matrix(t['pn0b_w'].cpu()), tc_pack_matrix(t['stn1_w'].cpu()), tc_pack_matrix(t['stn2_w'].cpu()),
+                         tc_pack_matrix(w3[:128]), tc_pack_matrix(w3[128:])])
+        feat = torch.cat([tc_pack_matrix(t['pn1_w'].cpu()), tc_pack_matrix(t['pn2_w'].cpu())])
+        assert stn.numel() == _lib.lib.pps_decoder_tc_pn_stn_bytes() and feat.numel() == _lib.lib.pps_decoder_tc_pn_feat_bytes()
+        t['tc_pn_stn'], t['tc_pn_feat'] = stn.to(device), feat.to(device)
+        st.tc_pn_stn, st.tc_pn_feat = t['tc_pn_stn'].data_ptr(), t['tc_pn_feat'].data_ptr()
+    else:
+        st.tc_pn_stn = st.tc_pn_feat = None
     return p
 
 

@@ -230,7 +230,7 @@ def test_decode_golden(dev, net, oracle, weights, path):
     qry = cu(g['qry'], dev)
     feat_proj = dec.projection(qry, cu(g['proj_ids'], dev, torch.int32)).cpu().numpy()
     assert np.abs(feat_proj - g['feat_proj'][0].T).max() < 5e-5 * max(1.0, np.abs(g['feat_proj']).max())
-    feat_pn = ops.pointnet(dec.packed, cu(g['pts_local_ps'], dev)).cpu().numpy()
+    feat_pn = ops.pointnet(dec.packed, cu(g['pts_local_ps'], dev), path).cpu().numpy()
     assert np.abs(feat_pn - g['feat_pn']).max() < 5e-5 * max(1.0, np.abs(g['feat_pn']).max())
     res = dec.decode(qry, want_logits=True, want_occ=True, want_idx=True)  # 192 queries in chunks of 100: ragged tail
     logits = res['logits'].cpu().numpy().T[None]
