@@ -29,9 +29,10 @@ constexpr int kKB = kC / 8;                 // k8 blocks per row
 constexpr int kALbo = kRows * 16 + 16;      // bytes between k8 blocks of an activation tile (padded)
 constexpr int kABytes = kKB * kALbo;        // 66048
 constexpr int kStageBytes = 16384;          // one k16 step of a 256-wide layer: W_hi 8 KB + W_lo 8 KB
-constexpr int kStageBytesQ = 4096;          // same for the 64-wide fc_query
-constexpr int kStages = 3;
+constexpr int kStageBytesQ = 8192;          // fc_query as the M operand: 128 rows (64 heads + 64 zero rows) x k16, hi + lo
+constexpr int kStages = 5;
 constexpr int kKSteps = kC / 16;            // 16 k16 steps per layer
+constexpr int kChunks = 4;                  // a layer's K range is released to the MMA warp in 4 chunks of 64 columns
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = 64 + kEpiThreads;  // 320
@@ -40,11 +41,10 @@ constexpr int kThreads = 64 + kEpiThreads;  // 320
 constexpr int kOffAhi = 0;
 constexpr int kOffAlo = kOffAhi + kABytes;
 constexpr int kOffRing = kOffAlo + kABytes;                  // 132096
-constexpr int kOffScore = kOffRing + kStages * kStageBytes;  // 181248
-constexpr int kOffBias = kOffScore + kRows * kHeads * 4;     // 214016: b2[256] b3[256] bq[64]
-constexpr int kOffAtt = kOffBias + (256 + 256 + 64) * 4;     // 216320: att[128]
-constexpr int kOffBar = kOffAtt + kRows * 4;                 // 216832: full[3] empty[3] accum a_ready
-constexpr int kOffTmem = kOffBar + 8 * 8;
+constexpr int kOffBias = kOffRing + kStages * kStageBytes;   // 214016: b2[256] b3[256] bq[64]
+constexpr int kOffAttp = kOffBias + (256 + 256 + 64) * 4;    // 216320: [head half][query][64] partial head sums
+constexpr int kOffBar = kOffAttp + 2 * 2 * 64 * 4;           // 217344: full[5] empty[5] accum chunk[4]
+constexpr int kOffTmem = kOffBar + (2 * kStages + 1 + kChunks) * 8;
 constexpr int kSmemBytes = kOffTmem + 16 + 1024;             // + alignment slack
 
 // packed weights in global memory: [fc2: 16 stages][fc3: 16 stages][fc_query: 16 stages]
@@ -52,6 +52,12 @@ constexpr size_t kPackBytes = size_t(2) * kKSteps * kStageBytes + size_t(kKSteps
 
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 
+// Pipeline of one tile (2 queries x 64 neighbours):
+//   gather -> fc2 (D0) -> E2 -> fc3 (D1) -> E3 -> fc_query^T (D0) -> softmax / head mean / pooling
+// The epilogue E_l rewrites the operand tile in place 64 columns at a time and releases each chunk through its own
+// mbarrier, so layer l+1's MMAs (other accumulator) start after the first quarter of E_l and overlap the rest.
+// fc_query is computed TRANSPOSED (heads on the TMEM lanes, the tile's rows on the columns): the softmax over a
+// query's 64 neighbours is then a reduction inside one thread; the mean over heads is a butterfly across lanes.
 __global__ void __launch_bounds__(kThreads, 1)
     projection_tc_kernel(const float* __restrict__ table, const float* __restrict__ queries, const int32_t* __restrict__ idx, int ks,
                          long long nq, const uint8_t* __restrict__ wpack, const float* __restrict__ b2, const float* __restrict__ b3,
@@ -61,11 +67,10 @@ __global__ void __launch_bounds__(kThreads, 1)
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float* s_bias = reinterpret_cast<float*>(smem + kOffBias);
-    float* s_att = reinterpret_cast<float*>(smem + kOffAtt);
-    float* s_score = reinterpret_cast<float*>(smem + kOffScore);
+    float* s_attp = reinterpret_cast<float*>(smem + kOffAttp);
     volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + kOffTmem);
     const uint32_t bar_full = sbase + kOffBar, bar_empty = bar_full + 8 * kStages, bar_accum = bar_empty + 8 * kStages,
-                   bar_aready = bar_accum + 8;
+                   bar_chunk = bar_accum + 8;
 
     for (int e = tid; e < 256; e += kThreads) {
         s_bias[e] = b2[e];
@@ -78,7 +83,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             mbar_init(bar_empty + 8 * i, 1);
         }
         mbar_init(bar_accum, 1);
-        mbar_init(bar_aready, kEpiThreads);
+        for (int i = 0; i < kChunks; ++i) mbar_init(bar_chunk + 8 * i, kEpiThreads);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -116,27 +121,35 @@ __global__ void __launch_bounds__(kThreads, 1)
     } else if (warp == 1) {
         // ---------------------------------------------------------------- MMA issuer
         if (lane == 0) {
-            uint32_t slot = 0, phase = 0, ready_phase = 0;
+            uint32_t slot = 0, phase = 0, chunk_phase = 0;
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 for (int layer = 0; layer < 3; ++layer) {
-                    const int n = layer < 2 ? 256 : 64;
-                    const uint32_t idesc = umma_idesc(n);
-                    const uint32_t b_lbo = n * 16, b_lo_off = n * 32;
-                    mbar_wait(bar_aready, ready_phase);
-                    ready_phase ^= 1;
-                    tc_fence_after();
+                    const uint32_t idesc = umma_idesc(layer < 2 ? 256 : 128);
+                    const uint32_t dcol = layer == 1 ? 256u : 0u;
                     for (int s = 0; s < kKSteps; ++s) {
+                        if ((s & 3) == 0) {  // operand columns [64c, 64c+64) written by the previous stage of the pipeline
+                            mbar_wait(bar_chunk + 8 * (s >> 2), chunk_phase);
+                            tc_fence_after();
+                        }
                         mbar_wait(bar_full + 8 * slot, phase);
                         tc_fence_after();
                         const uint32_t a_off = 2 * s * kALbo;
-                        const uint64_t a_hi = umma_desc(sbase + kOffAhi + a_off, kALbo, 128);
-                        const uint64_t a_lo = umma_desc(sbase + kOffAlo + a_off, kALbo, 128);
-                        const uint32_t bst = sbase + kOffRing + slot * kStageBytes;
-                        const uint64_t w_hi = umma_desc(bst, b_lbo, 128);
-                        const uint64_t w_lo = umma_desc(bst + b_lo_off, b_lbo, 128);
-                        umma(tmem, a_hi, w_hi, idesc, s > 0 ? 1u : 0u);
-                        umma(tmem, a_lo, w_hi, idesc, 1u);
-                        umma(tmem, a_hi, w_lo, idesc, 1u);
+                        const uint64_t x_hi = umma_desc(sbase + kOffAhi + a_off, kALbo, 128);
+                        const uint64_t x_lo = umma_desc(sbase + kOffAlo + a_off, kALbo, 128);
+                        const uint32_t wst = sbase + kOffRing + slot * kStageBytes;
+                        if (layer < 2) {
+                            const uint64_t w_hi = umma_desc(wst, 256 * 16, 128);
+                            const uint64_t w_lo = umma_desc(wst + 8192, 256 * 16, 128);
+                            umma(tmem + dcol, x_hi, w_hi, idesc, s > 0 ? 1u : 0u);
+                            umma(tmem + dcol, x_lo, w_hi, idesc, 1u);
+                            umma(tmem + dcol, x_hi, w_lo, idesc, 1u);
+                        } else {  // scores^T[head, row] = Wq[head, :] . h3[row, :]
+                            const uint64_t w_hi = umma_desc(wst, 128 * 16, 128);
+                            const uint64_t w_lo = umma_desc(wst + 4096, 128 * 16, 128);
+                            umma(tmem, w_hi, x_hi, idesc, s > 0 ? 1u : 0u);
+                            umma(tmem, w_hi, x_lo, idesc, 1u);
+                            umma(tmem, w_lo, x_hi, idesc, 1u);
+                        }
                         tc_commit(bar_empty + 8 * slot);  // frees the ring slot when these MMAs have read it
                         if (++slot == kStages) {
                             slot = 0;
@@ -144,15 +157,15 @@ __global__ void __launch_bounds__(kThreads, 1)
                         }
                     }
                     tc_commit(bar_accum);  // accumulator of this layer complete
+                    chunk_phase ^= 1;
                 }
             }
         }
     } else {
         // ---------------------------------------------------------------- gather + epilogue warps
         const int ew = warp - 2;               // 0..7
-        const int et = tid - 64;               // 0..255
         const int lane_grp = warp & 3;         // TMEM lanes this warp may touch: 32*lane_grp .. +31
-        const int half = ew >> 2;              // which half of the columns this warp owns
+        const int half = ew >> 2;              // which half of every 64-column chunk (E2/E3) / which query (scores)
         const int row = lane_grp * 32 + lane;  // accumulator row (= TMEM lane) of this thread
         float w1[8][3];                        // fc1 xyz weights of the 8 channels this lane gathers
 #pragma unroll
@@ -182,19 +195,21 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
             fence_async_smem();
             tc_fence_before();
-            mbar_arrive(bar_aready);
+#pragma unroll
+            for (int c = 0; c < kChunks; ++c) mbar_arrive(bar_chunk + 8 * c);
 
-            // ---- fc2 / fc3 epilogues: D -> +bias, ReLU, split -> A (in place: the layer's MMAs are complete)
+            // ---- fc2 / fc3 epilogues: D -> +bias, ReLU, split -> A in place, released chunk by chunk
             for (int layer = 0; layer < 2; ++layer) {
                 mbar_wait(bar_accum, accum_phase);
                 accum_phase ^= 1;
                 tc_fence_after();
                 const float* bias = s_bias + layer * 256;
+                const uint32_t dcol = layer == 1 ? 256u : 0u;
 #pragma unroll 1
-                for (int cb = 0; cb < 4; ++cb) {
-                    const int col0 = half * 128 + cb * 32;
+                for (int cb = 0; cb < kChunks; ++cb) {
+                    const int col0 = cb * 64 + half * 32;
                     float v[32];
-                    tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + col0, v);
+                    tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + dcol + col0, v);
 #pragma unroll
                     for (int kb = 0; kb < 4; ++kb) {
                         float x[8];
@@ -206,63 +221,54 @@ __global__ void __launch_bounds__(kThreads, 1)
                         *reinterpret_cast<uint4*>(smem + kOffAhi + kblk * kALbo + row * 16) = hi;
                         *reinterpret_cast<uint4*>(smem + kOffAlo + kblk * kALbo + row * 16) = lo;
                     }
+                    fence_async_smem();
+                    tc_fence_before();
+                    mbar_arrive(bar_chunk + 8 * cb);
                 }
-                fence_async_smem();
-                tc_fence_before();
-                mbar_arrive(bar_aready);
             }
 
-            // ---- fc_query epilogue: scores -> shared (16-byte chunks XOR-swizzled by the row)
+            // ---- scores^T: TMEM lane = head (lanes 0..63 are real), columns = rows of the tile; this warp's query = half
             mbar_wait(bar_accum, accum_phase);
             accum_phase ^= 1;
             tc_fence_after();
-            {
-                float v[32];
-                tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + half * 32, v);
+            if (lane_grp < 2) {
+                float e[64];
+                {
+                    float v[32];
+                    tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + half * 64, v);
 #pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) {
-                    const int chunk = half * 8 + c4;
-                    float4 o = make_float4(v[4 * c4] + s_bias[512 + 4 * chunk], v[4 * c4 + 1] + s_bias[512 + 4 * chunk + 1],
-                                           v[4 * c4 + 2] + s_bias[512 + 4 * chunk + 2], v[4 * c4 + 3] + s_bias[512 + 4 * chunk + 3]);
-                    *reinterpret_cast<float4*>(s_score + row * 64 + ((chunk ^ (row & 15)) << 2)) = o;
+                    for (int j = 0; j < 32; ++j) e[j] = v[j];
+                    tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + half * 64 + 32, v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) e[32 + j] = v[j];
                 }
-            }
-            tc_fence_before();
-            epi_barrier();
-            // softmax over the 64 neighbours for each (query, head): threads 0..127
-            if (et < 128) {
-                const int ql = et >> 6, h = et & 63;
-                const int c4 = h >> 2, w = h & 3;
-                float m = -INFINITY;
-                for (int j = 0; j < kNbrs; ++j) {
-                    const int r = ql * 64 + j;
-                    m = fmaxf(m, s_score[r * 64 + ((c4 ^ (r & 15)) << 2) + w]);
-                }
+                // softmax over the 64 neighbours (the head's bias shifts every score alike and cancels)
+                float m = e[0];
+#pragma unroll
+                for (int j = 1; j < 64; ++j) m = fmaxf(m, e[j]);
                 float sum = 0.f;
-                for (int j = 0; j < kNbrs; ++j) {
-                    const int r = ql * 64 + j;
-                    float* p = s_score + r * 64 + ((c4 ^ (r & 15)) << 2) + w;
-                    const float ev = expf(*p - m);
-                    *p = ev;
-                    sum += ev;
+#pragma unroll
+                for (int j = 0; j < 64; ++j) {
+                    e[j] = expf(e[j] - m);
+                    sum += e[j];
                 }
                 const float inv = 1.f / sum;
-                for (int j = 0; j < kNbrs; ++j) {
-                    const int r = ql * 64 + j;
-                    s_score[r * 64 + ((c4 ^ (r & 15)) << 2) + w] *= inv;
-                }
-            }
-            epi_barrier();
-            // attention of a neighbour = mean over the heads: thread per row
-            if (et < 128) {
-                float a = 0.f;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float4 p = *reinterpret_cast<const float4*>(s_score + et * 64 + (((i + et) & 15) << 2));
-                    a += (p.x + p.y) + (p.z + p.w);
+                for (int j = 0; j < 64; ++j) e[j] *= inv;
+                // sum over this warp's 32 heads: recursive halving, lane l ends with neighbours 2l and 2l+1
+#pragma unroll
+                for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+                    const bool upper = (lane & off) != 0;
+#pragma unroll
+                    for (int i = 0; i < n; ++i) {
+                        const float send = upper ? e[i] : e[i + n];
+                        const float keep = upper ? e[i + n] : e[i];
+                        e[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                    }
                 }
-                s_att[et] = a * (1.f / kHeads);
+                *reinterpret_cast<float2*>(s_attp + (lane_grp * 2 + half) * 64 + 2 * lane) = make_float2(e[0], e[1]);
             }
+            tc_fence_before();
             epi_barrier();
             // pooled[q, 8kb..8kb+7] = sum_j att_j * h3[j, .]: warp ew owns k8 blocks ew, ew+8, ew+16, ew+24
 #pragma unroll 1
@@ -275,8 +281,9 @@ __global__ void __launch_bounds__(kThreads, 1)
                     for (int c = 0; c < 8; ++c) acc[c] = 0.f;
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
-                        const int r = ql * 64 + hh * 32 + lane;
-                        const float a = s_att[r];
+                        const int jj = hh * 32 + lane;
+                        const int r = ql * 64 + jj;
+                        const float a = (s_attp[ql * 64 + jj] + s_attp[(2 + ql) * 64 + jj]) * (1.f / kHeads);
                         const uint4 hi = *reinterpret_cast<const uint4*>(smem + kOffAhi + kb * kALbo + r * 16);
                         const uint4 lo = *reinterpret_cast<const uint4*>(smem + kOffAlo + kb * kALbo + r * 16);
                         const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
@@ -299,7 +306,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                     }
                 }
             }
-            epi_barrier();  // every warp is done with A and the scores before the next tile's gather overwrites them
+            epi_barrier();  // every warp is done with A and the head sums before the next tile's gather overwrites them
         }
     }
 

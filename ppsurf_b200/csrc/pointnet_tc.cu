@@ -282,21 +282,26 @@ __global__ void __launch_bounds__(kPnThreads, 2)
 // ---------------------------------------------------------------------------------------------------------------------
 namespace feat {
 constexpr int kOffAhi = 0;
-constexpr int kABytes = 16 * kPnLbo;
-constexpr int kOffAlo = kOffAhi + kABytes;                // 33024
+constexpr int kABytes = 8 * kPnLbo;                       // 64-column operand tile (a1, x', conv1 output)
+constexpr int kOffAlo = kOffAhi + kABytes;                // 16512
 constexpr int kTLbo = 64 * 16 + 16;                       // 1040: k8-block pitch of a per-query 64x64 transform
 constexpr int kTBytes = 8 * kTLbo;                        // 8320 per (query, hi/lo)
-constexpr int kOffT = kOffAlo + kABytes;                  // 66048: [query][hi,lo]
-constexpr int kOffRing = kOffT + 4 * kTBytes;             // 99328
-constexpr int kOffPar = kOffRing + kPnStages * kPnSlot;   // 132096: b1[64] b2[128] wq[128] part[2][128] att[128]
+constexpr int kOffT = kOffAlo + kABytes;                  // 33024: [query][hi,lo]; dead after the transform MMAs, so
+                                                          // the upper 64 columns of conv2's output are parked here
+constexpr int kOffRing = kOffT + 4 * kTBytes;             // 66304
+constexpr int kOffPar = kOffRing + kPnStages * kPnSlot;   // 99072: b1[64] b2[128] wq[128] part[2][128] att[128]
 constexpr int kParFloats = 64 + 128 + 128 + 256 + 128;
 constexpr int kOffBar = kOffPar + kParFloats * 4;
 constexpr int kOffTmem = kOffBar + 10 * 8;
-constexpr int kSmemBytes = kOffTmem + 16 + 1024;          // ~136 KB
+constexpr int kSmemBytes = kOffTmem + 16 + 1024;          // ~103 KB -> two CTAs per SM
 constexpr int kTmemCols = 128;
+static_assert(2 * kABytes <= 4 * kTBytes, "conv2's upper half must fit into the transform buffers");
+// byte offset of k8 block `kblk` (0..15) of the 128-column conv2 output
+__device__ __forceinline__ int c2_hi(int kblk) { return kblk < 8 ? kOffAhi + kblk * kPnLbo : kOffT + (kblk - 8) * kPnLbo; }
+__device__ __forceinline__ int c2_lo(int kblk) { return kblk < 8 ? kOffAlo + kblk * kPnLbo : kOffT + kABytes + (kblk - 8) * kPnLbo; }
 }  // namespace feat
 
-__global__ void __launch_bounds__(kPnThreads, 1)
+__global__ void __launch_bounds__(kPnThreads, 2)
     pn_feat_kernel(const float* __restrict__ a1, const float* __restrict__ tmat, long long nq, int P,
                    const uint8_t* __restrict__ wpack, const float* __restrict__ b1, const float* __restrict__ b2,
                    const float* __restrict__ wq, float* __restrict__ pooled) {
@@ -521,8 +526,8 @@ __global__ void __launch_bounds__(kPnThreads, 1)
                         uint4 hi, lo;
                         split8(x8, hi, lo);
                         const int kblk = (col0 >> 3) + kb;
-                        *reinterpret_cast<uint4*>(smem + kOffAhi + kblk * kPnLbo + row * 16) = hi;
-                        *reinterpret_cast<uint4*>(smem + kOffAlo + kblk * kPnLbo + row * 16) = lo;
+                        *reinterpret_cast<uint4*>(smem + c2_hi(kblk) + row * 16) = hi;
+                        *reinterpret_cast<uint4*>(smem + c2_lo(kblk) + row * 16) = lo;
                     }
                 }
                 s_part[half * 128 + row] = logit;
@@ -552,8 +557,8 @@ __global__ void __launch_bounds__(kPnThreads, 1)
                     for (int hh = 0; hh < 2; ++hh) {
                         const int r = ql * 64 + hh * 32 + lane;
                         const float a = s_att[r];
-                        const uint4 hi = *reinterpret_cast<const uint4*>(smem + kOffAhi + kb * kPnLbo + r * 16);
-                        const uint4 lo = *reinterpret_cast<const uint4*>(smem + kOffAlo + kb * kPnLbo + r * 16);
+                        const uint4 hi = *reinterpret_cast<const uint4*>(smem + c2_hi(kb) + r * 16);
+                        const uint4 lo = *reinterpret_cast<const uint4*>(smem + c2_lo(kb) + r * 16);
                         const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
@@ -609,7 +614,7 @@ int pointnet_tc_impl(const pps_decoder_weights* w, const float* patches, int64_t
     const int P = w->num_pts_local, S = w->stn_size;
     const long long ntiles = (q + 1) / 2;
     const int grid_a = (int)(ntiles < 2 * kNumSMs ? ntiles : 2 * kNumSMs);
-    const int grid_c = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
+    const int grid_c = (int)(ntiles < 2 * kNumSMs ? ntiles : 2 * kNumSMs);
     tc::pn_stn_kernel<<<grid_a, tc::kPnThreads, tc::stn::kSmemBytes, st>>>(patches, q, P, static_cast<const uint8_t*>(w->tc_pn_stn),
                                                                           w->pn0a_w, w->pn0a_b, w->pn0b_b, w->stn1_b, w->stn2_b,
                                                                           w->stn3_b, a1, g);
