@@ -43,7 +43,8 @@ constexpr int kOffAlo = kOffAhi + kABytes;
 constexpr int kOffRing = kOffAlo + kABytes;                  // 132096
 constexpr int kOffBias = kOffRing + kStages * kStageBytes;   // 214016: b2[256] b3[256] bq[64]
 constexpr int kOffAttp = kOffBias + (256 + 256 + 64) * 4;    // 216320: [head half][query][64] partial head sums
-constexpr int kOffBar = kOffAttp + 2 * 2 * 64 * 4;           // 217344: full[5] empty[5] accum chunk[4]
+constexpr int kOffPool = kOffAttp + 2 * 2 * 64 * 4;          // 217344: [lane group][256] partial pooled sums
+constexpr int kOffBar = kOffPool + 4 * 256 * 4;              // 221440: full[5] empty[5] accum chunk[4]
 constexpr int kOffTmem = kOffBar + (2 * kStages + 1 + kChunks) * 8;
 constexpr int kSmemBytes = kOffTmem + 16 + 1024;             // + alignment slack
 
@@ -61,13 +62,14 @@ __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" :
 __global__ void __launch_bounds__(kThreads, 1)
     projection_tc_kernel(const float* __restrict__ table, const float* __restrict__ queries, const int32_t* __restrict__ idx, int ks,
                          long long nq, const uint8_t* __restrict__ wpack, const float* __restrict__ b2, const float* __restrict__ b3,
-                         const float* __restrict__ bq, const float* __restrict__ w1_xyz, float* __restrict__ pooled) {
+                         const float* __restrict__ bq, const float* __restrict__ w1_xyz, float* __restrict__ pooled, long long* prof) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float* s_bias = reinterpret_cast<float*>(smem + kOffBias);
     float* s_attp = reinterpret_cast<float*>(smem + kOffAttp);
+    float* s_pool = reinterpret_cast<float*>(smem + kOffPool);
     volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + kOffTmem);
     const uint32_t bar_full = sbase + kOffBar, bar_empty = bar_full + 8 * kStages, bar_accum = bar_empty + 8 * kStages,
                    bar_chunk = bar_accum + 8;
@@ -122,17 +124,22 @@ __global__ void __launch_bounds__(kThreads, 1)
         // ---------------------------------------------------------------- MMA issuer
         if (lane == 0) {
             uint32_t slot = 0, phase = 0, chunk_phase = 0;
+            long long t_chunk = 0, t_full = 0, t_total = clock64();
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 for (int layer = 0; layer < 3; ++layer) {
                     const uint32_t idesc = umma_idesc(layer < 2 ? 256 : 128);
                     const uint32_t dcol = layer == 1 ? 256u : 0u;
                     for (int s = 0; s < kKSteps; ++s) {
+                        long long t0 = clock64();
                         if ((s & 3) == 0) {  // operand columns [64c, 64c+64) written by the previous stage of the pipeline
                             mbar_wait(bar_chunk + 8 * (s >> 2), chunk_phase);
                             tc_fence_after();
                         }
+                        long long t1 = clock64();
                         mbar_wait(bar_full + 8 * slot, phase);
                         tc_fence_after();
+                        t_chunk += t1 - t0;
+                        t_full += clock64() - t1;
                         const uint32_t a_off = 2 * s * kALbo;
                         const uint64_t x_hi = umma_desc(sbase + kOffAhi + a_off, kALbo, 128);
                         const uint64_t x_lo = umma_desc(sbase + kOffAlo + a_off, kALbo, 128);
@@ -160,6 +167,11 @@ __global__ void __launch_bounds__(kThreads, 1)
                     chunk_phase ^= 1;
                 }
             }
+            if (prof && blockIdx.x == 0) {  // cycles: [0] MMA warp total, [1] waiting for operand chunks, [2] waiting for weights
+                prof[0] = clock64() - t_total;
+                prof[1] = t_chunk;
+                prof[2] = t_full;
+            }
         }
     } else {
         // ---------------------------------------------------------------- gather + epilogue warps
@@ -173,10 +185,11 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
             for (int d = 0; d < 3; ++d) w1[c][d] = w1_xyz[(8 * lane + c) * 3 + d];
         uint32_t accum_phase = 0;
+        long long t_gather = 0, t_wait = 0, t_epi = 0, t_att = 0, t_mark = clock64();
 
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             // ---- gather: h1 = relu(U[idx] + W1_xyz.q) -> A_hi/A_lo; warp ew owns rows 16*ew .. +15, lane owns k8 block `lane`
-#pragma unroll 4
+#pragma unroll 8
             for (int i = 0; i < 16; ++i) {
                 const int r = ew * 16 + i;
                 long long q = 2 * tile + (r >> 6);
@@ -197,12 +210,22 @@ __global__ void __launch_bounds__(kThreads, 1)
             tc_fence_before();
 #pragma unroll
             for (int c = 0; c < kChunks; ++c) mbar_arrive(bar_chunk + 8 * c);
+            {
+                const long long now = clock64();
+                t_gather += now - t_mark;
+                t_mark = now;
+            }
 
             // ---- fc2 / fc3 epilogues: D -> +bias, ReLU, split -> A in place, released chunk by chunk
             for (int layer = 0; layer < 2; ++layer) {
                 mbar_wait(bar_accum, accum_phase);
                 accum_phase ^= 1;
                 tc_fence_after();
+                {
+                    const long long now = clock64();
+                    t_wait += now - t_mark;
+                    t_mark = now;
+                }
                 const float* bias = s_bias + layer * 256;
                 const uint32_t dcol = layer == 1 ? 256u : 0u;
 #pragma unroll 1
@@ -225,12 +248,22 @@ __global__ void __launch_bounds__(kThreads, 1)
                     tc_fence_before();
                     mbar_arrive(bar_chunk + 8 * cb);
                 }
+                {
+                    const long long now = clock64();
+                    t_epi += now - t_mark;
+                    t_mark = now;
+                }
             }
 
             // ---- scores^T: TMEM lane = head (lanes 0..63 are real), columns = rows of the tile; this warp's query = half
             mbar_wait(bar_accum, accum_phase);
             accum_phase ^= 1;
             tc_fence_after();
+            {
+                const long long now = clock64();
+                t_wait += now - t_mark;
+                t_mark = now;
+            }
             if (lane_grp < 2) {
                 float e[64];
                 {
@@ -270,43 +303,54 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
             tc_fence_before();
             epi_barrier();
-            // pooled[q, 8kb..8kb+7] = sum_j att_j * h3[j, .]: warp ew owns k8 blocks ew, ew+8, ew+16, ew+24
+            // pooled[q, :] = sum_j att_j * h3[j, :] straight from the fp32 accumulator of fc3 (still in TMEM): every thread
+            // scales its row, the 32 rows of a warp are summed by recursive halving (lane l ends with column l of the block)
+            {
+                const float a = (s_attp[(row >> 6) * 64 + (row & 63)] + s_attp[(2 + (row >> 6)) * 64 + (row & 63)]) * (1.f / kHeads);
+                const float* bias = s_bias + 256;
 #pragma unroll 1
-            for (int t = 0; t < 4; ++t) {
-                const int kb = ew + 8 * t;
+                for (int cb = 0; cb < kChunks; ++cb) {
+                    const int col0 = cb * 64 + half * 32;
+                    float v[32];
+                    tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + 256u + col0, v);
 #pragma unroll
-                for (int ql = 0; ql < 2; ++ql) {
-                    float acc[8];
+                    for (int c = 0; c < 32; ++c) v[c] = a * fmaxf(v[c] + bias[col0 + c], 0.f);
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+                    for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
+                        const bool upper = (lane & off) != 0;
 #pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        const int jj = hh * 32 + lane;
-                        const int r = ql * 64 + jj;
-                        const float a = (s_attp[ql * 64 + jj] + s_attp[(2 + ql) * 64 + jj]) * (1.f / kHeads);
-                        const uint4 hi = *reinterpret_cast<const uint4*>(smem + kOffAhi + kb * kALbo + r * 16);
-                        const uint4 lo = *reinterpret_cast<const uint4*>(smem + kOffAlo + kb * kALbo + r * 16);
-                        const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
-                            const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&lw[i]));
-                            acc[2 * i] = fmaf(a, fh.x + fl.x, acc[2 * i]);
-                            acc[2 * i + 1] = fmaf(a, fh.y + fl.y, acc[2 * i + 1]);
+                        for (int i = 0; i < n; ++i) {
+                            const float send = upper ? v[i] : v[i + n];
+                            const float keep = upper ? v[i + n] : v[i];
+                            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
                         }
                     }
+                    s_pool[lane_grp * 256 + col0 + lane] = v[0];
+                }
+            }
+            tc_fence_before();
+            epi_barrier();
+            {
+                const int et = tid - 64;
 #pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+                for (int t = 0; t < 2; ++t) {
+                    const int ql = t, c = et;
                     const long long q = 2 * tile + ql;
-                    if (lane == 0 && q < nq) {
-                        float4* dst = reinterpret_cast<float4*>(pooled + q * kC + kb * 8);
-                        dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                        dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-                    }
+                    if (q < nq) pooled[q * kC + c] = s_pool[(2 * ql) * 256 + c] + s_pool[(2 * ql + 1) * 256 + c];
                 }
             }
             epi_barrier();  // every warp is done with A and the head sums before the next tile's gather overwrites them
+            {
+                const long long now = clock64();
+                t_att += now - t_mark;
+                t_mark = now;
+            }
+        }
+        if (prof && blockIdx.x == 0 && tid == 64) {  // cycles of epilogue warp 0: gather, waiting for MMAs, E2+E3, softmax+pooling
+            prof[3] = t_gather;
+            prof[4] = t_wait;
+            prof[5] = t_epi;
+            prof[6] = t_att;
         }
     }
 
@@ -320,6 +364,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 }
 
 }  // namespace tc
+
+static long long* g_tc_prof = nullptr;  // device buffer of 8 counters, set by pps_debug_tc_profile
 
 size_t projection_tc_workspace(const pps_decoder_weights*, int64_t) { return 256; }
 
@@ -339,7 +385,7 @@ int projection_tc_impl(const pps_decoder_weights* w, const float* table, const f
     profile_begin(st);
     tc::projection_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, st>>>(table, queries, idx, k_stride, q,
                                                                          static_cast<const uint8_t*>(w->tc_wpack), w->b2, w->b3, w->bq,
-                                                                         w->w1_xyz, pooled);
+                                                                         w->w1_xyz, pooled, g_tc_prof);
     PPS_LAUNCH_CHECK();
     profile_end(st);
     return PPS_OK;
@@ -348,3 +394,6 @@ int projection_tc_impl(const pps_decoder_weights* w, const float* table, const f
 }  // namespace pps
 
 extern "C" size_t pps_decoder_tc_pack_bytes(void) { return pps::tc::kPackBytes; }
+// debug: CTA 0 of projection_tc_kernel writes its per-phase cycle counters into `counters` (8 x int64, device memory);
+// pass NULL to switch the instrumentation output off
+extern "C" void pps_debug_tc_profile(long long* counters) { pps::g_tc_prof = counters; }

@@ -83,32 +83,31 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// x (>= 0 after ReLU) -> fp16 hi + fp16 lo, 8 values -> two 16-byte vectors
+// fp32 -> fp16 hi + fp16 lo, 8 values -> two 16-byte vectors.  hi is the value TRUNCATED to fp16's 10 explicit mantissa
+// bits (a mask, so hi converts exactly and x - hi is exact), lo = fp16(x - hi): hi + lo carries 21 mantissa bits.  Both
+// conversions are the packed 2-in-1 cvt.rn.f16x2.f32, i.e. one conversion instruction per element instead of three
+// (the conversion pipe, not the FMA pipe, bounds the epilogues).  Inputs are clamped to the fp16 range.
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const float ah = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u), bh = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
+    const __half2 h = __floats2half2_rn(ah, bh);
+    const __half2 l = __floats2half2_rn(a - ah, b - bh);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// non-negative inputs (after ReLU)
 __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
     uint32_t h[4], l[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        float a = fminf(x[2 * i], 65000.f), b = fminf(x[2 * i + 1], 65000.f);
-        __half ha = __float2half_rn(a), hb = __float2half_rn(b);
-        __half la = __float2half_rn(a - __half2float(ha)), lb = __float2half_rn(b - __half2float(hb));
-        h[i] = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
-        l[i] = (uint32_t)__half_as_ushort(la) | ((uint32_t)__half_as_ushort(lb) << 16);
-    }
+    for (int i = 0; i < 4; ++i) split_pair(fminf(x[2 * i], 65000.f), fminf(x[2 * i + 1], 65000.f), h[i], l[i]);
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
-
-// same for values of either sign (pre-activation quantities, transform matrices)
+// inputs of either sign (pre-activation quantities, transform matrices)
 __device__ __forceinline__ void split8_signed(const float (&x)[8], uint4& hi, uint4& lo) {
     uint32_t h[4], l[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        float a = fminf(fmaxf(x[2 * i], -65000.f), 65000.f), b = fminf(fmaxf(x[2 * i + 1], -65000.f), 65000.f);
-        __half ha = __float2half_rn(a), hb = __float2half_rn(b);
-        __half la = __float2half_rn(a - __half2float(ha)), lb = __float2half_rn(b - __half2float(hb));
-        h[i] = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
-        l[i] = (uint32_t)__half_as_ushort(la) | ((uint32_t)__half_as_ushort(lb) << 16);
-    }
+    for (int i = 0; i < 4; ++i)
+        split_pair(fminf(fmaxf(x[2 * i], -65000.f), 65000.f), fminf(fmaxf(x[2 * i + 1], -65000.f), 65000.f), h[i], l[i]);
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }

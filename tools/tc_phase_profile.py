@@ -1,0 +1,34 @@
+"""Per-phase cycle counters of CTA 0 of projection_tc_kernel on one chunk of the bench workload (debug aid)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ppsurf_b200
+from ppsurf_b200 import _lib, ops, synthetic
+
+dev = torch.device('cuda:0')
+net = ppsurf_b200.PPSurfNetwork(3, 256, 2, 64, 50, 256)
+net.load_state_dict(synthetic.make_state_dict(net, 42))
+net = net.to(dev)
+n = 100000
+pts = torch.from_numpy(synthetic.synthetic_cloud(n, 42)).to(dev)
+lat = torch.from_numpy(np.random.default_rng(7).standard_normal((n, 256)).astype(np.float32)).to(dev)
+dec = ops.Decoder(net.packed()['decoder'], pts, lat, chunk=16384, path=1)
+step, bmin_pad, _ = ppsurf_b200.PPSurfModel.grid_definition(pts.cpu().numpy(), 129, 1)
+qry = ops.grid_queries(131, step, bmin_pad, first=131 * 131 * 60, count=16384, device=dev)
+idx = dec.index.query(qry, 64)
+counters = torch.zeros(8, dtype=torch.int64, device=dev)
+for it in range(3):
+    _lib.lib.pps_debug_tc_profile(counters.data_ptr())
+    dec.projection(qry, idx)
+    torch.cuda.synchronize()
+c = counters.cpu().numpy()
+tiles = (16384 // 2 + 147) // 148
+names = ['mma_total', 'mma_wait_chunk', 'mma_wait_weights', 'epi_gather', 'epi_wait_mma', 'epi_E2E3', 'epi_softmax_pool']
+print('tiles per CTA', tiles)
+for k, v in zip(names, c):
+    print('{:18s} {:10d} cycles  {:8.0f} per tile'.format(k, int(v), v / tiles))
+_lib.lib.pps_debug_tc_profile(None)
