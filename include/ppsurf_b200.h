@@ -149,6 +149,11 @@ typedef struct pps_decoder_weights {
      * 128-255] and [conv1 | conv2]; pps_decoder_tc_pn_stn_bytes() / pps_decoder_tc_pn_feat_bytes() bytes, nullable */
     const void* tc_pn_stn;
     const void* tc_pn_feat;
+    /* per-query chains: [stn.fc1 | stn.fc2 | stn.fc3 in 16 blocks of 256 rows] and [(W8 Wv) | (Wv_att A3) | mlp.0 | mlp.1];
+     * tc_bias_feat [C] = bv8 + pnv_b (bias of the summed branches); nullable */
+    const void* tc_stn_fc;
+    const void* tc_mlp;
+    const float* tc_bias_feat;
 } pps_decoder_weights;
 
 size_t pps_decoder_tc_pack_bytes(void);
@@ -156,6 +161,8 @@ size_t pps_decoder_tc_pack_bytes(void);
 void pps_debug_tc_profile(long long* counters);
 size_t pps_decoder_tc_pn_stn_bytes(void);
 size_t pps_decoder_tc_pn_feat_bytes(void);
+size_t pps_decoder_tc_stn_fc_bytes(void);
+size_t pps_decoder_tc_mlp_bytes(void);
 
 /* per-point table  U[n,:] = W1_lat . latent[n] - W1_xyz . pts[n] + b1   (fc1 hoisted out of the (query,neighbour)
  * loop: fc1([latent_j, q - p_j]) = U_j + W1_xyz . q).  table [n,C] f32. */

@@ -31,7 +31,8 @@ class DecoderWeights(ctypes.Structure):
         ('pn2_b', c_f32p), ('pnq_w', c_f32p), ('pnq_b', ctypes.c_float), ('stn_size', ctypes.c_int32),
         ('pnv_w', c_f32p), ('pnv_b', c_f32p),
         ('m0_w', c_f32p), ('m0_b', c_f32p), ('m1_w', c_f32p), ('m1_b', c_f32p), ('m2_w', c_f32p), ('m2_b', c_f32p),
-        ('tc_wpack', c_voidp), ('tc_pn_stn', c_voidp), ('tc_pn_feat', c_voidp),
+        ('tc_wpack', c_voidp), ('tc_pn_stn', c_voidp), ('tc_pn_feat', c_voidp), ('tc_stn_fc', c_voidp), ('tc_mlp', c_voidp),
+        ('tc_bias_feat', c_f32p),
     ]
 
 
@@ -64,6 +65,8 @@ SIGNATURES = {
     'pps_debug_tc_profile': (None, [c_voidp]),
     'pps_decoder_tc_pn_stn_bytes': (size_t, []),
     'pps_decoder_tc_pn_feat_bytes': (size_t, []),
+    'pps_decoder_tc_stn_fc_bytes': (size_t, []),
+    'pps_decoder_tc_mlp_bytes': (size_t, []),
     'pps_decoder_workspace_bytes': (size_t, [ctypes.POINTER(DecoderWeights), i64]),
     'pps_decoder_decode': (i32, [ctypes.POINTER(DecoderWeights), c_voidp, c_f32p, c_f32p, i64, c_f32p, i64, i64, c_voidp,
                                  size_t, c_f32p, c_f32p, c_i32p, i32, c_voidp]),

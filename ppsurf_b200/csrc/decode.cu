@@ -22,6 +22,9 @@ int projection_tc_impl(const pps_decoder_weights* w, const float* table, const f
                        int k_stride, int64_t q, void* ws, size_t ws_bytes, float* pooled, cudaStream_t st);
 size_t projection_tc_workspace(const pps_decoder_weights* w, int64_t chunk);
 bool pointnet_tc_supported(const pps_decoder_weights* w);
+bool chain_tc_supported(const pps_decoder_weights* w);
+int mlp_tc_impl(const pps_decoder_weights* w, const float* pooled_proj, const float* pooled_pn, int64_t q, float* logits_out,
+                float* occ_out, cudaStream_t st);
 int pointnet_tc_impl(const pps_decoder_weights* w, const float* patches, int64_t q, float* a1, float* g, float* f1, float* f2,
                      float* tmat, float* pooled128, cudaStream_t st);
 
@@ -386,6 +389,12 @@ static int decode_chunk(const pps_decoder_weights* w, const float* pts, const fl
     const int kmax = kmax_of(w);
     patch_normalize_kernel<<<(unsigned)ceil_div(q * P, 256), 256, 0, st>>>(pts, queries, idx, d2, q, P, kmax, b.patches);
     PPS_LAUNCH_CHECK();
+    if (path == 1 && pointnet_tc_supported(w) && chain_tc_supported(w)) {
+        // all-tensor-core tail: both pooled vectors go straight into the chain kernel (merged value matrices + MLP + head)
+        PPS_TRY(projection_tc_impl(w, table, queries, idx, kmax, q, b.tc_ws, b.tc_ws_bytes, b.pooled, st));
+        PPS_TRY(pointnet_tc_impl(w, b.patches, q, b.a1, b.g, b.f1, b.f2, b.tmat, b.pooled128, st));
+        return mlp_tc_impl(w, b.pooled, b.pooled128, q, logits_out, occ_out, st);
+    }
     PPS_TRY(projection_run(w, table, queries, idx, kmax, q, b, b.feat_proj, path, st));
     PPS_TRY(pointnet_run(w, b.patches, q, b, b.feat_proj, b.feat, path, st));
     PPS_TRY(linear_impl(b.feat, w->m0_w, w->m0_b, nullptr, nullptr, b.m0, q, C, C, C, C, 1, st));

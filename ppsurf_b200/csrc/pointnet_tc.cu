@@ -595,6 +595,8 @@ __global__ void __launch_bounds__(kPnThreads, 2)
 
 int linear_impl(const float* x, const float* w, const float* bias, const float* residual, const int32_t* gather,
                 float* y, int64_t m, int n, int k, int ldx, int ldy, int act, cudaStream_t st);
+bool chain_tc_supported(const pps_decoder_weights* w);
+int stn_fc_tc_impl(const pps_decoder_weights* w, const float* g, int64_t q, float* tmat, cudaStream_t st);
 
 bool pointnet_tc_supported(const pps_decoder_weights* w) {
     return w->tc_pn_stn != nullptr && w->tc_pn_feat != nullptr && w->num_pts_local <= 64 && w->stn_size == 256 && w->latent == 256;
@@ -619,9 +621,13 @@ int pointnet_tc_impl(const pps_decoder_weights* w, const float* patches, int64_t
                                                                           w->pn0a_w, w->pn0a_b, w->pn0b_b, w->stn1_b, w->stn2_b,
                                                                           w->stn3_b, a1, g);
     PPS_LAUNCH_CHECK();
-    PPS_TRY(linear_impl(g, w->stnf1_w, w->stnf1_b, nullptr, nullptr, f1, q, S / 2, S, S, S / 2, 1, st));
-    PPS_TRY(linear_impl(f1, w->stnf2_w, w->stnf2_b, nullptr, nullptr, f2, q, S / 4, S / 2, S / 2, S / 4, 1, st));
-    PPS_TRY(linear_impl(f2, w->stnf3_w, w->stnf3_b, nullptr, nullptr, tmat, q, 4096, S / 4, S / 4, 4096, 0, st));
+    if (chain_tc_supported(w)) {
+        PPS_TRY(stn_fc_tc_impl(w, g, q, tmat, st));
+    } else {
+        PPS_TRY(linear_impl(g, w->stnf1_w, w->stnf1_b, nullptr, nullptr, f1, q, S / 2, S, S, S / 2, 1, st));
+        PPS_TRY(linear_impl(f1, w->stnf2_w, w->stnf2_b, nullptr, nullptr, f2, q, S / 4, S / 2, S / 2, S / 4, 1, st));
+        PPS_TRY(linear_impl(f2, w->stnf3_w, w->stnf3_b, nullptr, nullptr, tmat, q, 4096, S / 4, S / 4, 4096, 0, st));
+    }
     tc::pn_feat_kernel<<<grid_c, tc::kPnThreads, tc::feat::kSmemBytes, st>>>(a1, tmat, q, P, static_cast<const uint8_t*>(w->tc_pn_feat),
                                                                             w->pn1_b, w->pn2_b, w->pnq_w, pooled128);
     PPS_LAUNCH_CHECK();

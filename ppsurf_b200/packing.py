@@ -117,6 +117,18 @@ def pack_decoder(sd, device, k, num_pts_local, prefix='') -> Packed:
         st.tc_pn_stn, st.tc_pn_feat = t['tc_pn_stn'].data_ptr(), t['tc_pn_feat'].data_ptr()
     else:
         st.tc_pn_stn = st.tc_pn_feat = None
+    if latent == 256 and st.stn_size == 256:
+        t = p.tensors
+        f3 = t['stnf3_w'].cpu()
+        stn_fc = torch.cat([tc_pack_matrix(t['stnf1_w'].cpu()), tc_pack_matrix(t['stnf2_w'].cpu())] +
+                           [tc_pack_matrix(f3[nb * 256:(nb + 1) * 256]) for nb in range(16)])
+        mlp = torch.cat([tc_pack_matrix(t[name].cpu()) for name in ('wv8', 'pnv_w', 'm0_w', 'm1_w')])
+        assert stn_fc.numel() == _lib.lib.pps_decoder_tc_stn_fc_bytes() and mlp.numel() == _lib.lib.pps_decoder_tc_mlp_bytes()
+        t['tc_stn_fc'], t['tc_mlp'] = stn_fc.to(device), mlp.to(device)
+        st.tc_stn_fc, st.tc_mlp = t['tc_stn_fc'].data_ptr(), t['tc_mlp'].data_ptr()
+        p.put('tc_bias_feat', t['bv8'].cpu().double() + t['pnv_b'].cpu().double(), device)
+    else:
+        st.tc_stn_fc = st.tc_mlp = st.tc_bias_feat = None
     return p
 
 
