@@ -33,7 +33,7 @@ constexpr int kSmemBytes = kOffTmem + 16 + 1024;      // ~224 KB
 struct Ctx {
     uint8_t* smem;
     uint32_t sbase, tmem;
-    uint32_t bar_full, bar_empty, bar_accum, bar_ready, bar_afree, bar_tfree;
+    uint32_t bar_full, bar_empty, bar_accum, bar_ready, bar_afree, bar_tfree, bar_accum2;
 };
 
 struct Ring {
@@ -147,6 +147,7 @@ __device__ __forceinline__ void setup(Ctx& c, uint8_t* smem_raw, int tid, int wa
     c.bar_ready = c.bar_accum + 8;
     c.bar_afree = c.bar_ready + 8;
     c.bar_tfree = c.bar_afree + 8;  // two barriers
+    c.bar_accum2 = c.bar_tfree + 16;  // accumulator-complete barrier of the second TMEM buffer
     if (tid == 0) {
         for (int i = 0; i < kStages; ++i) {
             mbar_init(c.bar_full + 8 * i, 1);
@@ -157,6 +158,7 @@ __device__ __forceinline__ void setup(Ctx& c, uint8_t* smem_raw, int tid, int wa
         mbar_init(c.bar_afree, 1);
         mbar_init(c.bar_tfree, kEpiThreads);
         mbar_init(c.bar_tfree + 8, kEpiThreads);
+        mbar_init(c.bar_accum2, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -234,14 +236,16 @@ __global__ void __launch_bounds__(kThreads, 1)
                     tfree_phase[buf] ^= 1;
                     tc_fence_after();
                     mma_layer(c, r, buf * 256, 256, 4, false);
-                    tc_commit(c.bar_accum);
+                    // one completion barrier PER accumulator: the issuer can run a block ahead of the epilogue, and a single
+                    // barrier advancing two phases would alias in the parity wait
+                    tc_commit(buf ? c.bar_accum2 : c.bar_accum);
                 }
             }
         }
     } else {
         const int ew = warp - 2, lane_grp = warp & 3, half = ew >> 2;
         const int row = lane_grp * 32 + lane;
-        uint32_t accum_phase = 0;
+        uint32_t accum_phase = 0, accum2_phase = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const long long row0 = tile * 128;
             load_rows(c, g, row0, nq, 256, 256, ew, lane);
@@ -259,8 +263,13 @@ __global__ void __launch_bounds__(kThreads, 1)
             const long long q = row0 + row;
             for (int nb = 0; nb < 16; ++nb) {
                 const int buf = nb & 1;
-                mbar_wait(c.bar_accum, accum_phase);
-                accum_phase ^= 1;
+                if (buf) {
+                    mbar_wait(c.bar_accum2, accum2_phase);
+                    accum2_phase ^= 1;
+                } else {
+                    mbar_wait(c.bar_accum, accum_phase);
+                    accum_phase ^= 1;
+                }
                 tc_fence_after();
 #pragma unroll 1
                 for (int cb = 0; cb < 4; ++cb) {

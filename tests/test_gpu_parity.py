@@ -372,6 +372,11 @@ def test_full_size_properties(dev, net, oracle):
     dec2 = ops.Decoder(net.packed()['decoder'], cu(pts, dev), latents, chunk=5000)
     occ2 = dec2.decode(qry, want_logits=False, want_occ=True)['occ'].cpu().numpy()
     np.testing.assert_array_equal(occ, occ2)
+    # the tensor-core path at full chunk size (128 tiles per launch, every SM busy) agrees with the fp32 path
+    dec_tc = ops.Decoder(net.packed()['decoder'], cu(pts, dev), latents, chunk=16384, path=1)
+    res_tc = dec_tc.decode(qry, want_logits=True, want_occ=True)
+    assert np.abs(res_tc['logits'].cpu().numpy() - logits).max() < LOGIT_TOL
+    assert np.abs(res_tc['occ'].cpu().numpy() - occ).max() < LOGIT_TOL
     # logits of the sample against the float64 oracle
     data = {'pts': pts.T[None], 'latents': latents.cpu().numpy().T[None], 'pts_query': q[sample][None],
             'pts_local_ps': oracle.get_pts_local_ps(pts, q[sample], 50)[None], 'proj_ids': ref_idx[None]}
