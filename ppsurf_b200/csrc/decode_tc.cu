@@ -10,10 +10,10 @@
 //   x.W ~= x_hi.W_hi + x_lo.W_hi + x_hi.W_lo   (fp32 accumulation in TMEM),
 // i.e. three tcgen05.mma per k-step; the dropped x_lo.W_lo term is O(2^-22) relative.
 //
-// Roles (576 threads, one CTA per SM, persistent over tiles):
-//   warp 0       weight producer: cp.async.bulk (TMA bulk copy, UBLKCP) of pre-packed k16 weight stages into a 5-slot ring
-//   warp 1       MMA issuer: tcgen05.mma (SS, M=128, N=256/128, K=16) + tcgen05.commit onto mbarriers; owns the TMEM allocation
-//   warps 2..17  gather + epilogues: table rows -> fp16 hi/lo operand tiles in shared memory (UMMA canonical K-major layout,
+// Roles (320 threads, one CTA per SM, persistent over tiles):
+//   warp 0      weight producer: cp.async.bulk (TMA bulk copy, UBLKCP) of pre-packed k16 weight stages into a 3-slot ring
+//   warp 1      MMA issuer: tcgen05.mma (SS, M=128, N=256/64, K=16) + tcgen05.commit onto mbarriers; owns the TMEM allocation
+//   warps 2..9  gather + epilogues: table rows -> fp16 hi/lo operand tiles in shared memory (UMMA canonical K-major layout,
 //               no swizzle, k8-blocks padded by 16 B so that row-wise AND k-wise accesses are bank-conflict free),
 //               tcgen05.ld of the accumulators, bias + ReLU + re-split, softmax / pooling
 #include "tc_common.cuh"
@@ -33,9 +33,9 @@ constexpr int kStageBytesQ = 8192;          // fc_query as the M operand: 128 ro
 constexpr int kStages = 5;
 constexpr int kKSteps = kC / 16;            // 16 k16 steps per layer
 constexpr int kChunks = 4;                  // a layer's K range is released to the MMA warp in 4 chunks of 64 columns
-constexpr int kEpiWarps = 16;                // 4 warps per TMEM lane quadrant, each owning a quarter of the columns
+constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kThreads = 64 + kEpiThreads;  // 576
+constexpr int kThreads = 64 + kEpiThreads;  // 320
 
 // shared memory map (bytes from the 1024-aligned base)
 constexpr int kOffAhi = 0;
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             mbar_init(bar_empty + 8 * i, 1);
         }
         mbar_init(bar_accum, 1);
-        for (int i = 0; i < kChunks; ++i) mbar_init(bar_chunk + 8 * i, kEpiThreads / 2);  // 8 of the 16 warps per chunk
+        for (int i = 0; i < kChunks; ++i) mbar_init(bar_chunk + 8 * i, kEpiThreads);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -175,12 +175,10 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
     } else {
         // ---------------------------------------------------------------- gather + epilogue warps
-        const int ew = warp - 2;               // 0..15
-        const int et = tid - 64;               // 0..511
+        const int ew = warp - 2;               // 0..7
         const int lane_grp = warp & 3;         // TMEM lanes this warp may touch: 32*lane_grp .. +31
-        const int cq = ew >> 2;                // column quarter: every (lane_grp, cq) pair is exactly one warp
+        const int half = ew >> 2;              // which half of every 64-column chunk (E2/E3) / which query (scores)
         const int row = lane_grp * 32 + lane;  // accumulator row (= TMEM lane) of this thread
-        const int my_chunk = cq >> 1;          // this warp releases chunks my_chunk (round 0) and 2 + my_chunk (round 1)
         float w1[8][3];                        // fc1 xyz weights of the 8 channels this lane gathers
 #pragma unroll
         for (int c = 0; c < 8; ++c)
@@ -190,10 +188,10 @@ __global__ void __launch_bounds__(kThreads, 1)
         long long t_gather = 0, t_wait = 0, t_epi = 0, t_att = 0, t_mark = clock64();
 
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            // ---- gather: h1 = relu(U[idx] + W1_xyz.q) -> A_hi/A_lo; warp ew owns rows 8*ew .. +7, lane owns k8 block `lane`
-#pragma unroll 4
-            for (int i = 0; i < 8; ++i) {
-                const int r = ew * 8 + i;
+            // ---- gather: h1 = relu(U[idx] + W1_xyz.q) -> A_hi/A_lo; warp ew owns rows 16*ew .. +15, lane owns k8 block `lane`
+#pragma unroll 8
+            for (int i = 0; i < 16; ++i) {
+                const int r = ew * 16 + i;
                 long long q = 2 * tile + (r >> 6);
                 q = q < nq ? q : nq - 1;
                 const int src = idx[q * ks + (r & 63)];
@@ -209,10 +207,9 @@ __global__ void __launch_bounds__(kThreads, 1)
                 *reinterpret_cast<uint4*>(smem + kOffAlo + lane * kALbo + r * 16) = lo;
             }
             fence_async_smem();
-            epi_barrier();  // the gather is row-wise: every k-chunk is complete only when ALL warps are done
             tc_fence_before();
-            mbar_arrive(bar_chunk + 8 * my_chunk);
-            mbar_arrive(bar_chunk + 8 * (2 + my_chunk));
+#pragma unroll
+            for (int c = 0; c < kChunks; ++c) mbar_arrive(bar_chunk + 8 * c);
             {
                 const long long now = clock64();
                 t_gather += now - t_mark;
@@ -232,8 +229,8 @@ __global__ void __launch_bounds__(kThreads, 1)
                 const float* bias = s_bias + layer * 256;
                 const uint32_t dcol = layer == 1 ? 256u : 0u;
 #pragma unroll 1
-                for (int rd = 0; rd < 2; ++rd) {
-                    const int col0 = rd * 128 + cq * 32;
+                for (int cb = 0; cb < kChunks; ++cb) {
+                    const int col0 = cb * 64 + half * 32;
                     float v[32];
                     tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + dcol + col0, v);
 #pragma unroll
@@ -249,7 +246,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                     }
                     fence_async_smem();
                     tc_fence_before();
-                    mbar_arrive(bar_chunk + 8 * (rd * 2 + my_chunk));
+                    mbar_arrive(bar_chunk + 8 * cb);
                 }
                 {
                     const long long now = clock64();
@@ -258,7 +255,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                 }
             }
 
-            // ---- scores^T: TMEM lane = head (lanes 0..63 are real), columns = rows of the tile; 4 warps: (head half, query)
+            // ---- scores^T: TMEM lane = head (lanes 0..63 are real), columns = rows of the tile; this warp's query = half
             mbar_wait(bar_accum, accum_phase);
             accum_phase ^= 1;
             tc_fence_after();
@@ -267,43 +264,42 @@ __global__ void __launch_bounds__(kThreads, 1)
                 t_wait += now - t_mark;
                 t_mark = now;
             }
-            if (lane_grp < 2 && cq < 2) {
-                const uint32_t taddr = tmem + ((uint32_t)(lane_grp * 32) << 16) + cq * 64;
-                float v[32];
-                // softmax over the 64 neighbours in three passes over TMEM (the head's bias shifts every score alike and cancels)
-                float m = -INFINITY;
-#pragma unroll 1
-                for (int blk = 0; blk < 2; ++blk) {
-                    tmem_ld32(taddr + blk * 32, v);
+            if (lane_grp < 2) {
+                float e[64];
+                {
+                    float v[32];
+                    tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + half * 64, v);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) m = fmaxf(m, v[j]);
+                    for (int j = 0; j < 32; ++j) e[j] = v[j];
+                    tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + half * 64 + 32, v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) e[32 + j] = v[j];
                 }
-                float sum = 0.f;
-#pragma unroll 1
-                for (int blk = 0; blk < 2; ++blk) {
-                    tmem_ld32(taddr + blk * 32, v);
+                // softmax over the 64 neighbours (the head's bias shifts every score alike and cancels)
+                float m = e[0];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) sum += expf(v[j] - m);
+                for (int j = 1; j < 64; ++j) m = fmaxf(m, e[j]);
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < 64; ++j) {
+                    e[j] = expf(e[j] - m);
+                    sum += e[j];
                 }
                 const float inv = 1.f / sum;
-#pragma unroll 1
-                for (int blk = 0; blk < 2; ++blk) {
-                    tmem_ld32(taddr + blk * 32, v);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = expf(v[j] - m) * inv;
-                    // sum over this warp's 32 heads: recursive halving, lane l ends with neighbour blk*32 + l
+                for (int j = 0; j < 64; ++j) e[j] *= inv;
+                // sum over this warp's 32 heads: recursive halving, lane l ends with neighbours 2l and 2l+1
 #pragma unroll
-                    for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
-                        const bool upper = (lane & off) != 0;
+                for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+                    const bool upper = (lane & off) != 0;
 #pragma unroll
-                        for (int i = 0; i < n; ++i) {
-                            const float send = upper ? v[i] : v[i + n];
-                            const float keep = upper ? v[i + n] : v[i];
-                            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                        }
+                    for (int i = 0; i < n; ++i) {
+                        const float send = upper ? e[i] : e[i + n];
+                        const float keep = upper ? e[i + n] : e[i];
+                        e[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
                     }
-                    s_attp[(lane_grp * 2 + cq) * 64 + blk * 32 + lane] = v[0];
                 }
+                *reinterpret_cast<float2*>(s_attp + (lane_grp * 2 + half) * 64 + 2 * lane) = make_float2(e[0], e[1]);
             }
             tc_fence_before();
             epi_barrier();
@@ -313,8 +309,8 @@ __global__ void __launch_bounds__(kThreads, 1)
                 const float a = (s_attp[(row >> 6) * 64 + (row & 63)] + s_attp[(2 + (row >> 6)) * 64 + (row & 63)]) * (1.f / kHeads);
                 const float* bias = s_bias + 256;
 #pragma unroll 1
-                for (int rd = 0; rd < 2; ++rd) {
-                    const int col0 = rd * 128 + cq * 32;
+                for (int cb = 0; cb < kChunks; ++cb) {
+                    const int col0 = cb * 64 + half * 32;
                     float v[32];
                     tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + 256u + col0, v);
 #pragma unroll
@@ -335,11 +331,15 @@ __global__ void __launch_bounds__(kThreads, 1)
             tc_fence_before();
             epi_barrier();
             {
-                const int ql = et >> 8, c = et & 255;
-                const long long q = 2 * tile + ql;
-                if (q < nq) pooled[q * kC + c] = s_pool[(2 * ql) * 256 + c] + s_pool[(2 * ql + 1) * 256 + c];
+                const int et = tid - 64;
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const int ql = t, c = et;
+                    const long long q = 2 * tile + ql;
+                    if (q < nq) pooled[q * kC + c] = s_pool[(2 * ql) * 256 + c] + s_pool[(2 * ql + 1) * 256 + c];
+                }
             }
-            epi_barrier();  // every warp is done with the head sums / pooled partials before the next tile reuses them
+            epi_barrier();  // every warp is done with A and the head sums before the next tile's gather overwrites them
             {
                 const long long now = clock64();
                 t_att += now - t_mark;
