@@ -15,6 +15,7 @@
 namespace pps {
 
 constexpr int kMaxLevels = 7;  // 128^3 finest cells, 21-bit codes
+constexpr int kRun = 8;        // consecutive queries handled by one warp (each seeds the next one's pruning bound)
 
 struct KnnHeader {
     unsigned int min_enc[3];
@@ -155,7 +156,9 @@ __global__ void knn_finalize(const float* __restrict__ pts, int n, const unsigne
 //   * a leaf (<= 32 points, or the finest level) is scanned 32 points at a time with one coalesced float4 load per
 //     lane; survivors of the (dist2, index) < worst test are inserted one by one (ballot + shuffle-up);
 //   * at an inner node lanes 0..7 fetch the ranges and box distances of the 8 children and push the non-empty,
-//     non-pruned ones far-to-near (rank by shuffles), so the nearest child is popped first.
+//     non-pruned ones far-to-near (rank by shuffles), so the nearest child is popped first;
+//   * a warp handles kRun consecutive queries: by the triangle inequality sqrt(kth_prev) + |q - q_prev| bounds the k-th
+//     distance of the next query, so its traversal prunes from the first node on (grid-ordered queries: tight bound).
 
 __device__ __forceinline__ bool cand_less(float da, int ia, float db, int ib) { return da < db || (da == db && ia < ib); }
 
@@ -167,133 +170,151 @@ __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restri
     __shared__ unsigned int stack_s[8][8 * kMaxLevels + 8];
     const unsigned int full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long qi = (long long)blockIdx.x * 8 + warp;
-    if (qi >= nq) return;
+    const long long q_first = ((long long)blockIdx.x * 8 + warp) * kRun;
+    if (q_first >= nq) return;
     unsigned int* stack = stack_s[warp];
-    float ld[SLOTS];
-    int li[SLOTS];
-#pragma unroll
-    for (int s = 0; s < SLOTS; ++s) {
-        ld[s] = INFINITY;
-        li[s] = 0x7fffffff;
-    }
     const int L = hdr->levels;
     const float ox = hdr->origin[0], oy = hdr->origin[1], oz = hdr->origin[2];
     const float cell = hdr->cell;
     const float pad = cell * 1e-3f;
-    const float qx = queries[3 * qi], qy = queries[3 * qi + 1], qz = queries[3 * qi + 2];
-    float worst = INFINITY;
-    int worst_i = 0x7fffffff;
     const int wslot = (k - 1) >> 5, wlane = (k - 1) & 31;  // where the k-th best lives
+    float bound = INFINITY;  // upper bound of this query's k-th distance, seeded from the previous query of the run
+    float pqx = 0.f, pqy = 0.f, pqz = 0.f;
 
-    auto box_dist = [&](int level, int cx, int cy, int cz) -> float {
-        float size = cell * float(1 << (L - level));
-        float lx = ox + cx * size - pad, ly = oy + cy * size - pad, lz = oz + cz * size - pad;
-        float hx = lx + size + 2 * pad, hy = ly + size + 2 * pad, hz = lz + size + 2 * pad;
-        float dx = fmaxf(fmaxf(lx - qx, qx - hx), 0.f);
-        float dy = fmaxf(fmaxf(ly - qy, qy - hy), 0.f);
-        float dz = fmaxf(fmaxf(lz - qz, qz - hz), 0.f);
-        return (dx * dx + dy * dy + dz * dz) * 0.99999f;  // conservative lower bound
-    };
+    for (int rq = 0; rq < kRun; ++rq) {
+        const long long qi = q_first + rq;
+        if (qi >= nq) break;
+        float ld[SLOTS];
+        int li[SLOTS];
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+            ld[s] = INFINITY;
+            li[s] = 0x7fffffff;
+        }
+        const float qx = queries[3 * qi], qy = queries[3 * qi + 1], qz = queries[3 * qi + 2];
+        if (rq > 0) {
+            // triangle inequality: the k neighbours of the previous query lie within sqrt(kth_prev) + |q - q_prev| of q
+            const float dx = qx - pqx, dy = qy - pqy, dz = qz - pqz;
+            const float r = sqrtf(bound) + sqrtf(dx * dx + dy * dy + dz * dz);
+            bound = r * r * 1.0001f + 1e-30f;
+        }
+        float worst = INFINITY;
+        int worst_i = 0x7fffffff;
 
-    int sp = 1;
-    if (lane == 0) stack[0] = 0u;  // root: level 0, cell (0,0,0)
-    __syncwarp();
-    while (sp > 0) {
-        const unsigned int nd = stack[--sp];
-        const int level = nd >> 21, cx = nd & 127, cy = (nd >> 7) & 127, cz = (nd >> 14) & 127;
-        if (box_dist(level, cx, cy, cz) > worst) continue;
-        const unsigned int code = morton3(cx, cy, cz);
-        const int sh = 3 * (L - level);
-        const int lo = cell_start[code << sh], hi = cell_start[(code + 1u) << sh];
-        const int cnt = hi - lo;
-        if (cnt == 0) continue;
-        if (cnt <= 32 || level == L) {
-            for (int base = lo; base < hi; base += 32) {
-                const int i = base + lane;
-                float d2 = INFINITY;
-                int pi = 0x7fffffff;
-                if (i < hi) {
-                    const float4 p = sorted[i];
-                    const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
-                    d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                    pi = __float_as_int(p.w);
-                }
-                unsigned int mask = __ballot_sync(full, i < hi && cand_less(d2, pi, worst, worst_i));
-                while (mask) {
-                    const int src = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    const float vd = __shfl_sync(full, d2, src);
-                    const int vi = __shfl_sync(full, pi, src);
-                    if (!cand_less(vd, vi, worst, worst_i)) continue;  // the bound may have tightened meanwhile
-                    int pos = 0;  // number of list elements smaller than the candidate
+        auto box_dist = [&](int level, int cx, int cy, int cz) -> float {
+            float size = cell * float(1 << (L - level));
+            float lx = ox + cx * size - pad, ly = oy + cy * size - pad, lz = oz + cz * size - pad;
+            float hx = lx + size + 2 * pad, hy = ly + size + 2 * pad, hz = lz + size + 2 * pad;
+            float dx = fmaxf(fmaxf(lx - qx, qx - hx), 0.f);
+            float dy = fmaxf(fmaxf(ly - qy, qy - hy), 0.f);
+            float dz = fmaxf(fmaxf(lz - qz, qz - hz), 0.f);
+            return (dx * dx + dy * dy + dz * dz) * 0.99999f;  // conservative lower bound
+        };
+
+        int sp = 1;
+        if (lane == 0) stack[0] = 0u;  // root: level 0, cell (0,0,0)
+        __syncwarp();
+        while (sp > 0) {
+            const unsigned int nd = stack[--sp];
+            const int level = nd >> 21, cx = nd & 127, cy = (nd >> 7) & 127, cz = (nd >> 14) & 127;
+            if (box_dist(level, cx, cy, cz) > fminf(worst, bound)) continue;
+            const unsigned int code = morton3(cx, cy, cz);
+            const int sh = 3 * (L - level);
+            const int lo = cell_start[code << sh], hi = cell_start[(code + 1u) << sh];
+            const int cnt = hi - lo;
+            if (cnt == 0) continue;
+            if (cnt <= 32 || level == L) {
+                for (int base = lo; base < hi; base += 32) {
+                    const int i = base + lane;
+                    float d2 = INFINITY;
+                    int pi = 0x7fffffff;
+                    if (i < hi) {
+                        const float4 p = sorted[i];
+                        const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+                        d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                        pi = __float_as_int(p.w);
+                    }
+                    unsigned int mask = __ballot_sync(full, i < hi && d2 <= bound && cand_less(d2, pi, worst, worst_i));
+                    while (mask) {
+                        const int src = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const float vd = __shfl_sync(full, d2, src);
+                        const int vi = __shfl_sync(full, pi, src);
+                        if (!cand_less(vd, vi, worst, worst_i)) continue;  // the bound may have tightened meanwhile
+                        int pos = 0;  // number of list elements smaller than the candidate
 #pragma unroll
-                    for (int s = 0; s < SLOTS; ++s) pos += __popc(__ballot_sync(full, cand_less(ld[s], li[s], vd, vi)));
+                        for (int s = 0; s < SLOTS; ++s) pos += __popc(__ballot_sync(full, cand_less(ld[s], li[s], vd, vi)));
 #pragma unroll
-                    for (int s = SLOTS - 1; s >= 0; --s) {
-                        float pd = __shfl_up_sync(full, ld[s], 1);
-                        int pj = __shfl_up_sync(full, li[s], 1);
-                        if (s > 0) {
-                            const float cd = __shfl_sync(full, ld[s - 1], 31);
-                            const int cj = __shfl_sync(full, li[s - 1], 31);
-                            if (lane == 0) {
-                                pd = cd;
-                                pj = cj;
+                        for (int s = SLOTS - 1; s >= 0; --s) {
+                            float pd = __shfl_up_sync(full, ld[s], 1);
+                            int pj = __shfl_up_sync(full, li[s], 1);
+                            if (s > 0) {
+                                const float cd = __shfl_sync(full, ld[s - 1], 31);
+                                const int cj = __shfl_sync(full, li[s - 1], 31);
+                                if (lane == 0) {
+                                    pd = cd;
+                                    pj = cj;
+                                }
+                            }
+                            const int g = s * 32 + lane;
+                            if (g == pos) {
+                                ld[s] = vd;
+                                li[s] = vi;
+                            } else if (g > pos) {
+                                ld[s] = pd;
+                                li[s] = pj;
                             }
                         }
-                        const int g = s * 32 + lane;
-                        if (g == pos) {
-                            ld[s] = vd;
-                            li[s] = vi;
-                        } else if (g > pos) {
-                            ld[s] = pd;
-                            li[s] = pj;
-                        }
+                        worst = __shfl_sync(full, ld[wslot < SLOTS ? wslot : SLOTS - 1], wlane);
+                        worst_i = __shfl_sync(full, li[wslot < SLOTS ? wslot : SLOTS - 1], wlane);
                     }
-                    worst = __shfl_sync(full, ld[wslot < SLOTS ? wslot : SLOTS - 1], wlane);
-                    worst_i = __shfl_sync(full, li[wslot < SLOTS ? wslot : SLOTS - 1], wlane);
                 }
-            }
-        } else {
-            const int sh2 = sh - 3;
-            const unsigned int cbase = code * 8u;
-            bool ok = false;
-            float d = INFINITY;
-            unsigned int child = 0;
-            if (lane < 8) {
-                const int clo = cell_start[(cbase + lane) << sh2], chi = cell_start[(cbase + lane + 1u) << sh2];
-                const int ccx = cx * 2 + (lane & 1), ccy = cy * 2 + ((lane >> 1) & 1), ccz = cz * 2 + (lane >> 2);
-                d = box_dist(level + 1, ccx, ccy, ccz);
-                ok = chi > clo && d <= worst;
-                child = ((unsigned int)(level + 1) << 21) | ccx | (ccy << 7) | (ccz << 14);
-            }
-            const unsigned int m = __ballot_sync(full, ok);
-            int rank = 0;  // far children first -> the nearest one ends on top of the stack
+            } else {
+                const int sh2 = sh - 3;
+                const unsigned int cbase = code * 8u;
+                const float prune = fminf(worst, bound);
+                bool ok = false;
+                float d = INFINITY;
+                unsigned int child = 0;
+                if (lane < 8) {
+                    const int clo = cell_start[(cbase + lane) << sh2], chi = cell_start[(cbase + lane + 1u) << sh2];
+                    const int ccx = cx * 2 + (lane & 1), ccy = cy * 2 + ((lane >> 1) & 1), ccz = cz * 2 + (lane >> 2);
+                    d = box_dist(level + 1, ccx, ccy, ccz);
+                    ok = chi > clo && d <= prune;
+                    child = ((unsigned int)(level + 1) << 21) | ccx | (ccy << 7) | (ccz << 14);
+                }
+                const unsigned int m = __ballot_sync(full, ok);
+                int rank = 0;  // far children first -> the nearest one ends on top of the stack
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                const float dt = __shfl_sync(full, d, t);
-                if (((m >> t) & 1u) && (dt > d || (dt == d && t < lane))) ++rank;
+                for (int t = 0; t < 8; ++t) {
+                    const float dt = __shfl_sync(full, d, t);
+                    if (((m >> t) & 1u) && (dt > d || (dt == d && t < lane))) ++rank;
+                }
+                if (ok) stack[sp + rank] = child;
+                sp += __popc(m);
+                __syncwarp();
             }
-            if (ok) stack[sp + rank] = child;
-            sp += __popc(m);
-            __syncwarp();
         }
-    }
-    // the list is sorted ascending by (dist2, index): element g = slot*32 + lane
+        // the list is sorted ascending by (dist2, index): element g = slot*32 + lane
 #pragma unroll
-    for (int s = 0; s < SLOTS; ++s) {
-        const int g = s * 32 + lane;
-        if (g < k) {
-            idx_out[qi * k + g] = li[s];
-            if (d2_out) d2_out[qi * k + g] = ld[s];
+        for (int s = 0; s < SLOTS; ++s) {
+            const int g = s * 32 + lane;
+            if (g < k) {
+                idx_out[qi * k + g] = li[s];
+                if (d2_out) d2_out[qi * k + g] = ld[s];
+            }
         }
+        bound = worst;  // k-th distance of this query (the list is full: k <= n)
+        pqx = qx;
+        pqy = qy;
+        pqz = qz;
     }
 }
 
 template <int SLOTS>
 static int launch_query(const KnnHeader* hdr, const float4* sorted, const int* cell_start, const float* queries,
                         int64_t q, int k, int32_t* idx_out, float* d2_out, cudaStream_t st) {
-    knn_warp_kernel<SLOTS><<<(unsigned)ceil_div(q, 8), 256, 0, st>>>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out);
+    knn_warp_kernel<SLOTS><<<(unsigned)ceil_div(q, 8 * kRun), 256, 0, st>>>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out);
     PPS_LAUNCH_CHECK();
     return PPS_OK;
 }
