@@ -15,6 +15,7 @@
 namespace pps {
 
 constexpr int kMaxLevels = 7;  // 128^3 finest cells, 21-bit codes
+constexpr int kScanMax = 1024;  // an unprunable node with at most this many points is scanned as one contiguous range
 constexpr int kRun = 8;        // consecutive queries handled by one warp (each seeds the next one's pruning bound)
 
 struct KnnHeader {
@@ -223,7 +224,41 @@ __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restri
             const int lo = cell_start[code << sh], hi = cell_start[(code + 1u) << sh];
             const int cnt = hi - lo;
             if (cnt == 0) continue;
-            if (cnt <= 32 || level == L) {
+            bool scan = cnt <= 32 || level == L;
+            if (!scan) {
+                const int sh2 = sh - 3;
+                const unsigned int cbase = code * 8u;
+                const float prune = fminf(worst, bound);
+                bool ok = false, nonempty = false;
+                float d = INFINITY;
+                unsigned int child = 0;
+                if (lane < 8) {
+                    const int clo = cell_start[(cbase + lane) << sh2], chi = cell_start[(cbase + lane + 1u) << sh2];
+                    const int ccx = cx * 2 + (lane & 1), ccy = cy * 2 + ((lane >> 1) & 1), ccz = cz * 2 + (lane >> 2);
+                    d = box_dist(level + 1, ccx, ccy, ccz);
+                    nonempty = chi > clo;
+                    ok = nonempty && d <= prune;
+                    child = ((unsigned int)(level + 1) << 21) | ccx | (ccy << 7) | (ccz << 14);
+                }
+                const unsigned int m = __ballot_sync(full, ok);
+                // no child can be pruned and the node is small: its points are one contiguous range, stream through it
+                // instead of paying the traversal for every grandchild (queries far from the surface see all points at
+                // nearly the same distance and cannot prune)
+                if (cnt <= kScanMax && m == __ballot_sync(full, nonempty)) {
+                    scan = true;
+                } else {
+                    int rank = 0;  // far children first -> the nearest one ends on top of the stack
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        const float dt = __shfl_sync(full, d, t);
+                        if (((m >> t) & 1u) && (dt > d || (dt == d && t < lane))) ++rank;
+                    }
+                    if (ok) stack[sp + rank] = child;
+                    sp += __popc(m);
+                    __syncwarp();
+                }
+            }
+            if (scan) {
                 for (int base = lo; base < hi; base += 32) {
                     const int i = base + lane;
                     float d2 = INFINITY;
@@ -269,30 +304,6 @@ __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restri
                         worst_i = __shfl_sync(full, li[wslot < SLOTS ? wslot : SLOTS - 1], wlane);
                     }
                 }
-            } else {
-                const int sh2 = sh - 3;
-                const unsigned int cbase = code * 8u;
-                const float prune = fminf(worst, bound);
-                bool ok = false;
-                float d = INFINITY;
-                unsigned int child = 0;
-                if (lane < 8) {
-                    const int clo = cell_start[(cbase + lane) << sh2], chi = cell_start[(cbase + lane + 1u) << sh2];
-                    const int ccx = cx * 2 + (lane & 1), ccy = cy * 2 + ((lane >> 1) & 1), ccz = cz * 2 + (lane >> 2);
-                    d = box_dist(level + 1, ccx, ccy, ccz);
-                    ok = chi > clo && d <= prune;
-                    child = ((unsigned int)(level + 1) << 21) | ccx | (ccy << 7) | (ccz << 14);
-                }
-                const unsigned int m = __ballot_sync(full, ok);
-                int rank = 0;  // far children first -> the nearest one ends on top of the stack
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    const float dt = __shfl_sync(full, d, t);
-                    if (((m >> t) & 1u) && (dt > d || (dt == d && t < lane))) ++rank;
-                }
-                if (ok) stack[sp + rank] = child;
-                sp += __popc(m);
-                __syncwarp();
             }
         }
         // the list is sorted ascending by (dist2, index): element g = slot*32 + lane
