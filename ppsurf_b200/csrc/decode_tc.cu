@@ -59,6 +59,9 @@ __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" :
 // mbarrier, so layer l+1's MMAs (other accumulator) start after the first quarter of E_l and overlap the rest.
 // fc_query is computed TRANSPOSED (heads on the TMEM lanes, the tile's rows on the columns): the softmax over a
 // query's 64 neighbours is then a reduction inside one thread; the mean over heads is a butterfly across lanes.
+// CS = CTAs per cluster: the CTAs of a cluster consume the same weight stages in lockstep, each fetches 1/CS of a stage and
+// multicasts it into every member's ring slot (the weight stream is L2-bandwidth bound: 16 KB per 384 tensor cycles and SM)
+template <int CS>
 __global__ void __launch_bounds__(kThreads, 1)
     projection_tc_kernel(const float* __restrict__ table, const float* __restrict__ queries, const int32_t* __restrict__ idx, int ks,
                          long long nq, const uint8_t* __restrict__ wpack, const float* __restrict__ b2, const float* __restrict__ b3,
@@ -82,7 +85,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (tid == 0) {
         for (int i = 0; i < kStages; ++i) {
             mbar_init(bar_full + 8 * i, 1);
-            mbar_init(bar_empty + 8 * i, 1);
+            mbar_init(bar_empty + 8 * i, CS);  // every CTA of the cluster releases the slot in every member
         }
         mbar_init(bar_accum, 1);
         for (int i = 0; i < kChunks; ++i) mbar_init(bar_chunk + 8 * i, kEpiThreads);
@@ -94,23 +97,34 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     tc_fence_before();
     __syncthreads();
+    if (CS > 1) cluster_sync_all();  // barriers of every member are initialised before any remote arrive / multicast
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
 
     const long long ntiles = (nq + 1) / 2;
+    // every CTA runs the same number of iterations (lockstep weight ring); surplus iterations redo the last tile silently
+    const long long iters = (ntiles + gridDim.x - 1) / gridDim.x;
+    constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1u);
+    const uint32_t crank = CS > 1 ? cluster_ctarank() : 0u;
 
     if (warp == 0) {
         // ---------------------------------------------------------------- weight producer
         if (lane == 0) {
             uint32_t slot = 0, phase = 0;
-            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (long long it = 0; it < iters; ++it) {
                 const uint8_t* src = wpack;
                 for (int layer = 0; layer < 3; ++layer) {
                     const uint32_t bytes = layer < 2 ? kStageBytes : kStageBytesQ;
                     for (int s = 0; s < kKSteps; ++s) {
                         mbar_wait(bar_empty + 8 * slot, phase ^ 1);
                         mbar_expect_tx(bar_full + 8 * slot, bytes);
-                        bulk_copy(sbase + kOffRing + slot * kStageBytes, src, bytes, bar_full + 8 * slot);
+                        if (CS == 1) {
+                            bulk_copy(sbase + kOffRing + slot * kStageBytes, src, bytes, bar_full + 8 * slot);
+                        } else {
+                            const uint32_t part = bytes / CS;
+                            bulk_copy_multicast(sbase + kOffRing + slot * kStageBytes + crank * part, src + crank * part, part,
+                                                bar_full + 8 * slot, kMask);
+                        }
                         src += bytes;
                         if (++slot == kStages) {
                             slot = 0;
@@ -125,7 +139,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (lane == 0) {
             uint32_t slot = 0, phase = 0, chunk_phase = 0;
             long long t_chunk = 0, t_full = 0, t_total = clock64();
-            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (long long it = 0; it < iters; ++it) {
                 for (int layer = 0; layer < 3; ++layer) {
                     const uint32_t idesc = umma_idesc(layer < 2 ? 256 : 128);
                     const uint32_t dcol = layer == 1 ? 256u : 0u;
@@ -157,7 +171,10 @@ __global__ void __launch_bounds__(kThreads, 1)
                             umma(tmem, w_hi, x_lo, idesc, 1u);
                             umma(tmem, w_lo, x_hi, idesc, 1u);
                         }
-                        tc_commit(bar_empty + 8 * slot);  // frees the ring slot when these MMAs have read it
+                        if (CS == 1)
+                            tc_commit(bar_empty + 8 * slot);  // frees the ring slot when these MMAs have read it
+                        else
+                            tc_commit_multicast(bar_empty + 8 * slot, kMask);  // ... in every member of the cluster
                         if (++slot == kStages) {
                             slot = 0;
                             phase ^= 1;
@@ -187,7 +204,10 @@ __global__ void __launch_bounds__(kThreads, 1)
         uint32_t accum_phase = 0;
         long long t_gather = 0, t_wait = 0, t_epi = 0, t_att = 0, t_mark = clock64();
 
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (long long it = 0; it < iters; ++it) {
+            long long tile = blockIdx.x + it * gridDim.x;
+            const bool live = tile < ntiles;  // surplus iteration: same work on the last tile, nothing is written
+            tile = live ? tile : ntiles - 1;
             // ---- gather: h1 = relu(U[idx] + W1_xyz.q) -> A_hi/A_lo; warp ew owns rows 16*ew .. +15, lane owns k8 block `lane`
 #pragma unroll 8
             for (int i = 0; i < 16; ++i) {
@@ -336,7 +356,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                 for (int t = 0; t < 2; ++t) {
                     const int ql = t, c = et;
                     const long long q = 2 * tile + ql;
-                    if (q < nq) pooled[q * kC + c] = s_pool[(2 * ql) * 256 + c] + s_pool[(2 * ql + 1) * 256 + c];
+                    if (q < nq && live) pooled[q * kC + c] = s_pool[(2 * ql) * 256 + c] + s_pool[(2 * ql + 1) * 256 + c];
                 }
             }
             epi_barrier();  // every warp is done with A and the head sums before the next tile's gather overwrites them
@@ -356,6 +376,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 
     tc_fence_before();
     __syncthreads();
+    if (CS > 1) cluster_sync_all();  // no member exits while a peer may still multicast into it or arrive on its barriers
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
@@ -365,6 +386,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 
 }  // namespace tc
 
+static int g_tc_cluster = 2;             // CTAs per cluster of the tensor-core kernels (1, 2 or 4): multicast weight stages
 static long long* g_tc_prof = nullptr;  // device buffer of 8 counters, set by pps_debug_tc_profile
 
 size_t projection_tc_workspace(const pps_decoder_weights*, int64_t) { return 256; }
@@ -377,15 +399,40 @@ int projection_tc_impl(const pps_decoder_weights* w, const float* table, const f
     if (q == 0) return PPS_OK;
     static bool configured = false;
     if (!configured) {
-        PPS_CUDA(cudaFuncSetAttribute(tc::projection_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+        PPS_CUDA(cudaFuncSetAttribute(tc::projection_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+        PPS_CUDA(cudaFuncSetAttribute(tc::projection_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+        PPS_CUDA(cudaFuncSetAttribute(tc::projection_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
         configured = true;
     }
     long long ntiles = (q + 1) / 2;
+    int cs = g_tc_cluster;
+    if (ntiles < 2 * cs) cs = 1;
     int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
+    grid -= grid % cs;  // whole clusters only; 148 = 4 * 37
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(tc::kThreads);
+    cfg.dynamicSmemBytes = tc::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const uint8_t* wp = static_cast<const uint8_t*>(w->tc_wpack);
+    long long nq = q;
     profile_begin(st);
-    tc::projection_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, st>>>(table, queries, idx, k_stride, q,
-                                                                         static_cast<const uint8_t*>(w->tc_wpack), w->b2, w->b3, w->bq,
-                                                                         w->w1_xyz, pooled, g_tc_prof);
+    if (cs == 4)
+        PPS_CUDA(cudaLaunchKernelEx(&cfg, tc::projection_tc_kernel<4>, table, queries, idx, k_stride, nq, wp, w->b2, w->b3, w->bq,
+                                    w->w1_xyz, pooled, g_tc_prof));
+    else if (cs == 2)
+        PPS_CUDA(cudaLaunchKernelEx(&cfg, tc::projection_tc_kernel<2>, table, queries, idx, k_stride, nq, wp, w->b2, w->b3, w->bq,
+                                    w->w1_xyz, pooled, g_tc_prof));
+    else
+        PPS_CUDA(cudaLaunchKernelEx(&cfg, tc::projection_tc_kernel<1>, table, queries, idx, k_stride, nq, wp, w->b2, w->b3, w->bq,
+                                    w->w1_xyz, pooled, g_tc_prof));
     PPS_LAUNCH_CHECK();
     profile_end(st);
     return PPS_OK;
@@ -397,3 +444,5 @@ extern "C" size_t pps_decoder_tc_pack_bytes(void) { return pps::tc::kPackBytes; 
 // debug: CTA 0 of projection_tc_kernel writes its per-phase cycle counters into `counters` (8 x int64, device memory);
 // pass NULL to switch the instrumentation output off
 extern "C" void pps_debug_tc_profile(long long* counters) { pps::g_tc_prof = counters; }
+// tuning knob: CTAs per cluster (1, 2, 4) sharing multicast weight stages in the tensor-core projection kernel
+extern "C" void pps_debug_tc_cluster(int cs) { pps::g_tc_cluster = (cs == 4 || cs == 2) ? cs : 1; }

@@ -21,14 +21,25 @@ step, bmin_pad, _ = ppsurf_b200.PPSurfModel.grid_definition(pts.cpu().numpy(), 1
 qry = ops.grid_queries(131, step, bmin_pad, first=131 * 131 * 60, count=16384, device=dev)
 idx = dec.index.query(qry, 64)
 counters = torch.zeros(8, dtype=torch.int64, device=dev)
-for it in range(3):
-    _lib.lib.pps_debug_tc_profile(counters.data_ptr())
-    dec.projection(qry, idx)
-    torch.cuda.synchronize()
-c = counters.cpu().numpy()
 tiles = (16384 // 2 + 147) // 148
 names = ['mma_total', 'mma_wait_chunk', 'mma_wait_weights', 'epi_gather', 'epi_wait_mma', 'epi_E2E3', 'epi_softmax_pool']
-print('tiles per CTA', tiles)
-for k, v in zip(names, c):
-    print('{:18s} {:10d} cycles  {:8.0f} per tile'.format(k, int(v), v / tiles))
+ref = None
+for cs in (1, 2, 4):
+    _lib.lib.pps_debug_tc_cluster(cs)
+    for it in range(3):
+        _lib.lib.pps_debug_tc_profile(counters.data_ptr())
+        out = dec.projection(qry, idx)
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for it in range(5):
+        dec.projection(qry, idx)
+    e1.record()
+    torch.cuda.synchronize()
+    c = counters.cpu().numpy()
+    ref = out if ref is None else ref
+    print('cluster size {}: {:.1f} us per chunk (incl. value matrix), max |diff| vs cs=1 {:.2e}'.format(
+        cs, e0.elapsed_time(e1) * 200, float((out - ref).abs().max())))
+    print('   ' + '  '.join('{}={:.0f}'.format(k, v / tiles) for k, v in zip(names, c)))
 _lib.lib.pps_debug_tc_profile(None)
+_lib.lib.pps_debug_tc_cluster(2)
