@@ -159,7 +159,7 @@ typedef struct pps_decoder_weights {
 size_t pps_decoder_tc_pack_bytes(void);
 /* debug aid: CTA 0 of the tensor-core projection kernel writes per-phase cycle counters (8 x int64, device memory) */
 void pps_debug_tc_profile(long long* counters);
-/* tuning knob: CTAs per cluster (1, 2 or 4) that share multicast weight stages in the projection kernel (default 2) */
+/* tuning knob: CTAs per cluster (1, 2 or 4) that share multicast weight stages in the projection kernel (default 1) */
 void pps_debug_tc_cluster(int cs);
 size_t pps_decoder_tc_pn_stn_bytes(void);
 size_t pps_decoder_tc_pn_feat_bytes(void);

@@ -386,7 +386,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 
 }  // namespace tc
 
-static int g_tc_cluster = 2;             // CTAs per cluster of the tensor-core kernels (1, 2 or 4): multicast weight stages
+static int g_tc_cluster = 1;             // CTAs per cluster (1, 2 or 4) sharing multicast weight stages.  Measured on B200:
+                                         // 2 = no gain (the ring refill is latency-, not L2-bandwidth-bound), 4 strands 16 SMs
 static long long* g_tc_prof = nullptr;  // device buffer of 8 counters, set by pps_debug_tc_profile
 
 size_t projection_tc_workspace(const pps_decoder_weights*, int64_t) { return 256; }

@@ -42,4 +42,4 @@ for cs in (1, 2, 4):
         cs, e0.elapsed_time(e1) * 200, float((out - ref).abs().max())))
     print('   ' + '  '.join('{}={:.0f}'.format(k, v / tiles) for k, v in zip(names, c)))
 _lib.lib.pps_debug_tc_profile(None)
-_lib.lib.pps_debug_tc_cluster(2)
+_lib.lib.pps_debug_tc_cluster(1)
