@@ -38,7 +38,8 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--path', type=int, default=int(os.environ.get('PPS_DECODE_PATH', '0')))
+    ap.add_argument('--path', type=int, default=int(os.environ.get('PPS_DECODE_PATH', '1')),
+                    help='1 = tcgen05 split-fp16 kernels (default), 0 = fp32 SIMT kernels')
     ap.add_argument('--points', type=int, default=100000)
     ap.add_argument('--resolution', type=int, default=129)
     ap.add_argument('--num-pts-local', type=int, default=50)
@@ -298,7 +299,7 @@ def run_b200(args):
         dom_flops = rows * GEMM_FLOP_PER_ROW
         achieved = dom_flops / (dom_ms.value * 1e-3) / 1e12 if dom_ms.value > 0 else None
         kernel = 'linear_kernel<128,true> x2 + linear_kernel<64,true> (fp32 SIMT fc2/fc3/fc_query)' if args.path == 0 else \
-            'projection_tc_kernel (tcgen05 split-fp16 fc2/fc3/fc_query + attention pooling)'
+            'projection_tc_kernel (tcgen05 split-fp16: gather + fc2/fc3/fc_query + softmax + attention pooling)'
         out = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': warmup,
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,

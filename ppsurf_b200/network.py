@@ -141,7 +141,7 @@ def _ids32(t: torch.Tensor) -> torch.Tensor:
 class PPSurfNetwork(_Base):
 
     def __init__(self, in_channels, latent_size, out_channels, k, num_pts_local, pointnet_latent_size,
-                 decode_chunk=16384, decode_path=0):
+                 decode_chunk=16384, decode_path=None):
         super().__init__()
         self.latent_size = latent_size
         self.k = k
@@ -152,7 +152,8 @@ class PPSurfNetwork(_Base):
         self.mlp = MLPParams(latent_size, out_channels)
         self.lcp_preprocess = True
         self.decode_chunk = decode_chunk
-        self.decode_path = decode_path
+        # 1 = tcgen05 split-fp16 kernels (built for latent 256 / k 64 / 64 heads), 0 = fp32 SIMT kernels for every other shape
+        self.decode_path = (1 if (latent_size == 256 and k == 64) else 0) if decode_path is None else decode_path
         self.sampling_seed = None  # set for reproducible support sampling
         self._packed = None
         self._decoder_cache = None
