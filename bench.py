@@ -314,7 +314,10 @@ def run_b200(args):
                     'call': 'pps_decoder_decode_host: pinned host queries -> device -> pinned host occupancy, chunked copies overlapped'},
             'gpu_launches': int(launches),
             'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
-                         'frac': (achieved / peaks['bf16_tflops']) if achieved else None, 'traffic': None,
+                         'frac': (achieved / peaks['bf16_tflops']) if achieved else None,
+                         # DRAM bytes per launch (16384-query chunk) from the ncu --set full capture under profiles/
+                         'traffic': 26.70e6 if args.path == 1 else None,
+                         'traffic_source': 'profiles/r01_projection_tc_full_summary.csv' if args.path == 1 else None,
                          'kernel': kernel, 'kernel_ms_per_step': dom_ms.value / args.steps,
                          'kernel_share_of_step': dom_ms.value / elapsed_ms, 'brackets': int(brackets.value),
                          'flop_per_row_executed': GEMM_FLOP_PER_ROW, 'peak_source': peaks['source'],
