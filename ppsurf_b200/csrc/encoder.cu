@@ -25,9 +25,13 @@ struct FkaParams {
 
 __device__ __forceinline__ float fka_act(float v, int act) { return act == 1 ? v / (1.f + expf(-v)) : fmaxf(v, 0.f); }
 
-// PHASE 1: sum / sumsq of fc1 outputs; PHASE 2: sum / sumsq of fc2 outputs; PHASE 3: write mat [b,ns,16(j),16(m)]
+// PHASE 1: sum / sumsq of fc1 outputs; PHASE 2: sum / sumsq of fc2 outputs; PHASE 3: write mat [b,ns,kn(j),16(m)]
+// 16 lanes per support point (one per neighbour), 16 points per block of 256 threads: the max over the neighbourhood and
+// the distance-weight normalisation are half-warp shuffles, the j-independent halves of fc2 / fc3 (the pooled maxima)
+// are computed once per point (lane o owns output o) and shared by shuffles.
+constexpr int kFkaPts = 16;
 template <int PHASE>
-__global__ void __launch_bounds__(128) fka_weight_kernel(const float* __restrict__ pts, const float* __restrict__ support,
+__global__ void __launch_bounds__(256) fka_weight_kernel(const float* __restrict__ pts, const float* __restrict__ support,
                                                          const int32_t* __restrict__ ids, int n_in, int n_s, int kn, FkaParams prm,
                                                          const float* __restrict__ fc1, const float* __restrict__ fc2,
                                                          const float* __restrict__ fc3, const float* __restrict__ in1_w,
@@ -35,11 +39,14 @@ __global__ void __launch_bounds__(128) fka_weight_kernel(const float* __restrict
                                                          const float* __restrict__ in2_b, double* stats, float* __restrict__ mat) {
     __shared__ float W1[16 * 3], W2[16 * 32], W3[16 * 32];
     __shared__ float A1[16], B1[16], A2[16], B2[16];
+    __shared__ float red[8][32];
+    const unsigned int full = 0xffffffffu;
     const int b = blockIdx.y;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int j = tid & 15;  // neighbour slot of this lane
     double* st_b = stats + (size_t)b * 64;  // [phase(2)][sum16, sumsq16]
-    for (int e = tid; e < 48; e += 128) W1[e] = fc1[e];
-    for (int e = tid; e < 512; e += 128) {
+    for (int e = tid; e < 48; e += 256) W1[e] = fc1[e];
+    for (int e = tid; e < 512; e += 256) {
         W2[e] = fc2[e];
         W3[e] = fc3[e];
     }
@@ -61,151 +68,123 @@ __global__ void __launch_bounds__(128) fka_weight_kernel(const float* __restrict
     }
     __syncthreads();
 
-    const int n = blockIdx.x * 128 + tid;
-    const bool valid = n < n_s;
-    float s[16], ss[16];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) s[c] = ss[c] = 0.f;
-
+    const int n = blockIdx.x * kFkaPts + (tid >> 4);
+    const bool valid = n < n_s && j < kn;
+    const size_t row = (size_t)b * n_s + (n < n_s ? n : 0);
+    float rx = 0.f, ry = 0.f, rz = 0.f, wgt = 0.f;
     if (valid) {
-        const size_t row = (size_t)b * n_s + n;
-        const float sx = support[3 * row], sy = support[3 * row + 1], sz = support[3 * row + 2];
-        float rel[kNbr][3];
-        float dw[kNbr];
-        float dsum = 0.f;
+        const size_t src = (size_t)b * n_in + ids[row * kn + j];
+        rx = pts[3 * src] - support[3 * row];
+        ry = pts[3 * src + 1] - support[3 * row + 1];
+        rz = pts[3 * src + 2] - support[3 * row + 2];
+        const float dist = sqrtf(rx * rx + ry * ry + rz * rz);
+        rx *= prm.inv_radius;
+        ry *= prm.inv_radius;
+        rz *= prm.inv_radius;
+        wgt = 1.f / (1.f + expf(-(-prm.alpha * dist + prm.beta)));
+    }
+    float dsum = wgt;
 #pragma unroll
-        for (int j = 0; j < kNbr; ++j) {
-            if (j >= kn) {
-                rel[j][0] = rel[j][1] = rel[j][2] = 0.f;
-                dw[j] = 0.f;
-                continue;
-            }
-            size_t src = (size_t)b * n_in + ids[row * kn + j];
-            float rx = pts[3 * src] - sx, ry = pts[3 * src + 1] - sy, rz = pts[3 * src + 2] - sz;
-            float dist = sqrtf(rx * rx + ry * ry + rz * rz);
-            rel[j][0] = rx * prm.inv_radius;
-            rel[j][1] = ry * prm.inv_radius;
-            rel[j][2] = rz * prm.inv_radius;
-            float wgt = 1.f / (1.f + expf(-(-prm.alpha * dist + prm.beta)));
-            dw[j] = wgt;
-            dsum += wgt;
-        }
-        dsum = dsum + (dsum == 0.f ? 1.f : 0.f) + 1e-6f;
-#pragma unroll
-        for (int j = 0; j < kNbr; ++j) dw[j] = dw[j] / dsum * float(kn);
+    for (int o = 8; o > 0; o >>= 1) dsum += __shfl_xor_sync(full, dsum, o, 16);
+    dsum = dsum + (dsum == 0.f ? 1.f : 0.f) + 1e-6f;
+    const float dw = wgt / dsum * float(kn);
 
-        if (PHASE == 1) {
+    float y1[16];
 #pragma unroll
-            for (int j = 0; j < kNbr; ++j)
-                if (j < kn) {
+    for (int c = 0; c < 16; ++c) y1[c] = W1[3 * c] * rx + W1[3 * c + 1] * ry + W1[3 * c + 2] * rz;
+
+    float s[16], ss[16];  // statistics of this lane (PHASE 1, 2)
+    if (PHASE == 1) {
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) {
-                        float y = W1[3 * c] * rel[j][0] + W1[3 * c + 1] * rel[j][1] + W1[3 * c + 2] * rel[j][2];
-                        s[c] += y;
-                        ss[c] += y * y;
-                    }
-                }
+        for (int c = 0; c < 16; ++c) {
+            s[c] = valid ? y1[c] : 0.f;
+            ss[c] = valid ? y1[c] * y1[c] : 0.f;
+        }
+    } else {
+        // m1 = act(IN1(fc1 rel)); mp1 = max over the neighbourhood of m1 * dw
+        float m1[16], mp[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            m1[c] = fka_act(y1[c] * A1[c] + B1[c], prm.act);
+            float v = valid ? m1[c] * dw : -INFINITY;
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(full, v, o, 16));
+            mp[c] = v;
+        }
+        // fc2 on cat(m1, mp1): lane o owns the j-independent half of output o
+        float cown = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) cown = fmaf(W2[j * 32 + 16 + c], mp[c], cown);
+        float y2[16];
+#pragma unroll
+        for (int o = 0; o < 16; ++o) {
+            float y = __shfl_sync(full, cown, o, 16);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) y = fmaf(W2[o * 32 + c], m1[c], y);
+            y2[o] = y;
+        }
+        if (PHASE == 2) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                s[c] = valid ? y2[c] : 0.f;
+                ss[c] = valid ? y2[c] * y2[c] : 0.f;
+            }
         } else {
-            // m1[c][j] = act(IN1(fc1 rel_j)); mp1[c] = max_j m1[c][j] * dw_j
-            float mp1[16];
+            float m2[16];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) mp1[c] = -INFINITY;
+            for (int c = 0; c < 16; ++c) {
+                m2[c] = fka_act(y2[c] * A2[c] + B2[c], prm.act);
+                float v = valid ? m2[c] * dw : -INFINITY;
 #pragma unroll
-            for (int j = 0; j < kNbr; ++j)
-                if (j < kn) {
+                for (int o = 8; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(full, v, o, 16));
+                mp[c] = v;
+            }
+            cown = 0.f;
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) {
-                        float y = W1[3 * c] * rel[j][0] + W1[3 * c + 1] * rel[j][1] + W1[3 * c + 2] * rel[j][2];
-                        float m = fka_act(y * A1[c] + B1[c], prm.act);
-                        mp1[c] = fmaxf(mp1[c], m * dw[j]);
-                    }
-                }
-            // fc2 on cat(m1[:,j], mp1): the mp1 half does not depend on j
-            float c2[16];
+            for (int c = 0; c < 16; ++c) cown = fmaf(W3[j * 32 + 16 + c], mp[c], cown);
+            float outv[16];
 #pragma unroll
             for (int o = 0; o < 16; ++o) {
-                float a = 0.f;
+                float y = __shfl_sync(full, cown, o, 16);
 #pragma unroll
-                for (int c = 0; c < 16; ++c) a = fmaf(W2[o * 32 + 16 + c], mp1[c], a);
-                c2[o] = a;
+                for (int c = 0; c < 16; ++c) y = fmaf(W3[o * 32 + c], m2[c], y);
+                outv[o] = fka_act(y, prm.act) * dw;
             }
-            float mp2[16];
-#pragma unroll
-            for (int c = 0; c < 16; ++c) mp2[c] = -INFINITY;
-            for (int j = 0; j < kn; ++j) {
-                float m1[16];
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    float y = W1[3 * c] * rel[j][0] + W1[3 * c + 1] * rel[j][1] + W1[3 * c + 2] * rel[j][2];
-                    m1[c] = fka_act(y * A1[c] + B1[c], prm.act);
-                }
-#pragma unroll
-                for (int o = 0; o < 16; ++o) {
-                    float y = c2[o];
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) y = fmaf(W2[o * 32 + c], m1[c], y);
-                    if (PHASE == 2) {
-                        s[o] += y;
-                        ss[o] += y * y;
-                    } else {
-                        float m = fka_act(y * A2[o] + B2[o], prm.act);
-                        mp2[o] = fmaxf(mp2[o], m * dw[j]);
-                    }
-                }
-            }
-            if (PHASE == 3) {
-                float c3[16];
-#pragma unroll
-                for (int o = 0; o < 16; ++o) {
-                    float a = 0.f;
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) a = fmaf(W3[o * 32 + 16 + c], mp2[c], a);
-                    c3[o] = a;
-                }
-                for (int j = 0; j < kn; ++j) {
-                    float m1[16], m2[16];
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) {
-                        float y = W1[3 * c] * rel[j][0] + W1[3 * c + 1] * rel[j][1] + W1[3 * c + 2] * rel[j][2];
-                        m1[c] = fka_act(y * A1[c] + B1[c], prm.act);
-                    }
-#pragma unroll
-                    for (int o = 0; o < 16; ++o) {
-                        float y = c2[o];
-#pragma unroll
-                        for (int c = 0; c < 16; ++c) y = fmaf(W2[o * 32 + c], m1[c], y);
-                        m2[o] = fka_act(y * A2[o] + B2[o], prm.act);
-                    }
-                    float outv[16];
-#pragma unroll
-                    for (int o = 0; o < 16; ++o) {
-                        float y = c3[o];
-#pragma unroll
-                        for (int c = 0; c < 16; ++c) y = fmaf(W3[o * 32 + c], m2[c], y);
-                        outv[o] = fka_act(y, prm.act) * dw[j];
-                    }
-                    float4* dst = reinterpret_cast<float4*>(mat + (row * kn + j) * 16);
-                    dst[0] = make_float4(outv[0], outv[1], outv[2], outv[3]);
-                    dst[1] = make_float4(outv[4], outv[5], outv[6], outv[7]);
-                    dst[2] = make_float4(outv[8], outv[9], outv[10], outv[11]);
-                    dst[3] = make_float4(outv[12], outv[13], outv[14], outv[15]);
-                }
+            if (valid) {
+                float4* dst = reinterpret_cast<float4*>(mat + (row * kn + j) * 16);
+                dst[0] = make_float4(outv[0], outv[1], outv[2], outv[3]);
+                dst[1] = make_float4(outv[4], outv[5], outv[6], outv[7]);
+                dst[2] = make_float4(outv[8], outv[9], outv[10], outv[11]);
+                dst[3] = make_float4(outv[12], outv[13], outv[14], outv[15]);
             }
         }
     }
     if (PHASE <= 2) {
-        double* dst = st_b + (PHASE == 1 ? 0 : 32);
+        // block reduction of the 32 statistics: lanes -> warp sums (recursive halving: lane l ends with statistic l),
+        // warps -> shared memory, then one double atomic per statistic and block
+        float v[32];
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
-            float a = s[c], q = ss[c];
-            for (int o = 16; o > 0; o >>= 1) {
-                a += __shfl_xor_sync(0xffffffffu, a, o);
-                q += __shfl_xor_sync(0xffffffffu, q, o);
+            v[c] = s[c];
+            v[16 + c] = ss[c];
+        }
+#pragma unroll
+        for (int off = 16, nn = 16; off >= 1; off >>= 1, nn >>= 1) {
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < nn; ++i) {
+                const float send = upper ? v[i] : v[i + nn];
+                const float keep = upper ? v[i + nn] : v[i];
+                v[i] = keep + __shfl_xor_sync(full, send, off);
             }
-            if ((tid & 31) == 0) {
-                atomicAdd(dst + c, double(a));
-                atomicAdd(dst + 16 + c, double(q));
-            }
+        }
+        red[warp][lane] = v[0];
+        __syncthreads();
+        if (warp == 0) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) t += red[w][lane];
+            atomicAdd(st_b + (PHASE == 1 ? 0 : 32) + lane, double(t));
         }
     }
 }
@@ -356,14 +335,14 @@ int pps_fkaconv_forward(const pps_fkaconv_weights* w, const float* x, const floa
     float* feat = reinterpret_cast<float*>(base + l.feat);
     PPS_CUDA(cudaMemsetAsync(stats, 0, (size_t)b * 64 * sizeof(double), st));
     FkaParams prm{w->alpha, w->beta, 1.f / w->norm_radius, w->act};
-    dim3 grid((unsigned)ceil_div(n_s, 128), (unsigned)b);
-    fka_weight_kernel<1><<<grid, 128, 0, st>>>(pts, support, ids, (int)n_in, (int)n_s, kn, prm, w->fc1, w->fc2, w->fc3, w->in1_w,
+    dim3 grid((unsigned)ceil_div(n_s, kFkaPts), (unsigned)b);
+    fka_weight_kernel<1><<<grid, 256, 0, st>>>(pts, support, ids, (int)n_in, (int)n_s, kn, prm, w->fc1, w->fc2, w->fc3, w->in1_w,
                                                w->in1_b, w->in2_w, w->in2_b, stats, mat);
     PPS_LAUNCH_CHECK();
-    fka_weight_kernel<2><<<grid, 128, 0, st>>>(pts, support, ids, (int)n_in, (int)n_s, kn, prm, w->fc1, w->fc2, w->fc3, w->in1_w,
+    fka_weight_kernel<2><<<grid, 256, 0, st>>>(pts, support, ids, (int)n_in, (int)n_s, kn, prm, w->fc1, w->fc2, w->fc3, w->in1_w,
                                                w->in1_b, w->in2_w, w->in2_b, stats, mat);
     PPS_LAUNCH_CHECK();
-    fka_weight_kernel<3><<<grid, 128, 0, st>>>(pts, support, ids, (int)n_in, (int)n_s, kn, prm, w->fc1, w->fc2, w->fc3, w->in1_w,
+    fka_weight_kernel<3><<<grid, 256, 0, st>>>(pts, support, ids, (int)n_in, (int)n_s, kn, prm, w->fc1, w->fc2, w->fc3, w->in1_w,
                                                w->in1_b, w->in2_w, w->in2_b, stats, mat);
     PPS_LAUNCH_CHECK();
     dim3 fgrid((unsigned)ceil_div(n_s, kFeatPts), (unsigned)b);

@@ -59,38 +59,52 @@ class PPSurfModel(_Base):
         self.test_step_outputs = []
 
     # ---- a1: latent averaging loop (source/poco_model.py:200-237) ----------------------------------------------
-    def encode_cloud(self, pts_bcn: torch.Tensor, generator: typing.Optional[torch.Generator] = None,
-                     prog_bar=None) -> torch.Tensor:
-        """``pts_bcn [1,3,N]`` (device) -> latents ``[1,latent,N]``: every point is encoded at least
-        ``gen_subsample_manifold_iter`` times on random ``gen_subsample_manifold``-point subsets and averaged."""
-        pts = pts_bcn[0].transpose(0, 1).contiguous()  # [N,3]
-        n = pts.shape[0]
-        dev = pts.device
+    def latent_schedule(self, n: int, generator: typing.Optional[torch.Generator] = None) -> typing.List[torch.Tensor]:
+        """index sets of the latent loop (source/poco_model.py:207-224).  They depend only on the visit counts, never on
+        network output, so the whole schedule is drawn on the host before any pass runs."""
         sub = self.gen_subsample_manifold
-        latent = torch.zeros((n, self.network_latent_size), dtype=torch.float32, device=dev)
-        counts = torch.zeros((n,), dtype=torch.float32, device=dev)
-        counts_host = np.zeros(n, dtype=np.int64)  # the schedule depends only on counts, keep it on the host: no syncs
-        iteration = 0
+        counts = np.zeros(n, dtype=np.int64)
+        passes = []
         for current in range(self.gen_subsample_manifold_iter):
-            while counts_host.min() < current + 1:
-                valid = torch.from_numpy(np.nonzero(counts_host == current)[0])
+            while counts.min() < current + 1:
+                valid = torch.from_numpy(np.nonzero(counts == current)[0])
                 if n >= sub:
                     ids = valid[torch.randperm(valid.shape[0], generator=generator)[:sub]]
                     if ids.shape[0] < sub:
                         ids = torch.cat([ids, torch.randperm(n, generator=generator)[:sub - ids.shape[0]]])
                 else:
                     ids = torch.arange(n)
-                ids_dev = ids.to(dev)
-                part = self.network.get_latent({'pts': pts[ids_dev].transpose(0, 1).unsqueeze(0).contiguous()})['latents']
+                counts[np.unique(ids.numpy())] += 1  # `counts[ids] += 1` counts a repeated id once
+                passes.append(ids)
+        return passes
+
+    def encode_cloud(self, pts_bcn: torch.Tensor, generator: typing.Optional[torch.Generator] = None,
+                     prog_bar=None, batch_passes: int = 8) -> torch.Tensor:
+        """``pts_bcn [1,3,N]`` (device) -> latents ``[1,latent,N]``: every point is encoded at least
+        ``gen_subsample_manifold_iter`` times on random ``gen_subsample_manifold``-point subsets and averaged
+        (source/poco_model.py:200-237).  The passes are independent given the schedule, so ``batch_passes`` of them go
+        through the encoder as one batch (InstanceNorm statistics are per sample); the accumulation keeps pass order."""
+        pts = pts_bcn[0].transpose(0, 1).contiguous()  # [N,3]
+        n = pts.shape[0]
+        dev = pts.device
+        latent = torch.zeros((n, self.network_latent_size), dtype=torch.float32, device=dev)
+        counts = torch.zeros((n,), dtype=torch.float32, device=dev)
+        passes = self.latent_schedule(n, generator)
+        iteration = 0
+        for b0 in range(0, len(passes), batch_passes):
+            group = passes[b0:b0 + batch_passes]
+            ids_dev = [ids.to(dev) for ids in group]
+            batch = torch.stack([pts[i] for i in ids_dev], dim=0).transpose(1, 2).contiguous()  # [B,3,sub]
+            part = self.network.get_latent({'pts': batch})['latents']  # [B,latent,sub]
+            for k, ids in enumerate(group):
                 # torch semantics of `latent[ids] += x` with repeated ids: one writer wins, counted once
-                uniq, first = np.unique(ids.numpy(), return_index=True)
+                _, first = np.unique(ids.numpy(), return_index=True)
                 sel = torch.from_numpy(first).to(dev)
-                ops.latent_accumulate(part[0].transpose(0, 1)[sel].contiguous(), ids_dev[sel].to(torch.int32).contiguous(),
+                ops.latent_accumulate(part[k].transpose(0, 1)[sel].contiguous(), ids_dev[k][sel].to(torch.int32).contiguous(),
                                       latent, counts)
-                counts_host[uniq] += 1
                 iteration += 1
-                if prog_bar is not None:
-                    prog_bar.predict_progress_bar.set_postfix_str('get_latent iter: {}'.format(iteration), refresh=True)
+            if prog_bar is not None:
+                prog_bar.predict_progress_bar.set_postfix_str('get_latent iter: {}'.format(iteration), refresh=True)
         ops.latent_finalize(latent, counts)
         return latent.transpose(0, 1).unsqueeze(0)
 

@@ -128,7 +128,8 @@ def test_patches_golden(dev, oracle):
 
 # ---- generic linear ---------------------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize('m,n,k', [(1000, 256, 256), (333, 64, 64), (129, 2, 256), (77, 4096, 64), (500, 128, 3), (64, 70, 37)])
+@pytest.mark.parametrize('m,n,k', [(1000, 256, 256), (333, 64, 64), (129, 2, 256), (77, 4096, 64), (500, 128, 3), (64, 70, 37),
+                                   (39, 512, 8192), (156, 256, 4096), (625, 40, 2048)])  # the last three take the split-K route
 def test_linear(dev, m, n, k):
     from ppsurf_b200 import ops
     gen = torch.Generator().manual_seed(m + n + k)
