@@ -204,12 +204,13 @@ def run_b200(args):
     if rank == 0:
         if args.latents == 'encoder':
             net.sampling_seed = 42
+            model.encode_cloud(pts_bcn[:, :, :20000].contiguous(), generator=torch.Generator().manual_seed(1))  # warm-up
             gen = torch.Generator().manual_seed(42)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             latents = model.encode_cloud(pts_bcn, generator=gen).contiguous()
             torch.cuda.synchronize()
-            encoder_s = time.perf_counter() - t0
+            encoder_s = time.perf_counter() - t0  # 10 encodings per point on random 10k-point subsets = ~100 passes
         else:
             latents = torch.from_numpy(np.random.default_rng(7).standard_normal((1, 256, args.points)).astype(np.float32)).to(dev)
     broadcast_ms = None

@@ -79,7 +79,7 @@ class PPSurfModel(_Base):
         return passes
 
     def encode_cloud(self, pts_bcn: torch.Tensor, generator: typing.Optional[torch.Generator] = None,
-                     prog_bar=None, batch_passes: int = 8) -> torch.Tensor:
+                     prog_bar=None, batch_passes: int = 16) -> torch.Tensor:
         """``pts_bcn [1,3,N]`` (device) -> latents ``[1,latent,N]``: every point is encoded at least
         ``gen_subsample_manifold_iter`` times on random ``gen_subsample_manifold``-point subsets and averaged
         (source/poco_model.py:200-237).  The passes are independent given the schedule, so ``batch_passes`` of them go
