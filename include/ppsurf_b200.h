@@ -209,6 +209,32 @@ int pps_decoder_pointnet(const pps_decoder_weights* w, const float* patches /* [
 int pps_grid_queries(int r, float step, float bmin_pad, int64_t first, int64_t count, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * a2  quantised support sampling and the encoder's index tensors
+ *     replaces  sampling_quantized   source/poco_data_loader.py:59-134   (torch_geometric voxel_grid + host loop)
+ *               get_fkaconv_ids      source/poco_data_loader.py:137-209  (4 samplings at ratio 1/4, 13 kNN tensors)
+ * pps_sample_quantized picks n_support of the n points: one representative per voxel of a randomly rotated grid, voxel
+ * edge ||bbox||_2 / sqrt(n_support), halved until enough points are found, random trim of the last round.  rotations
+ * [n_rot,9] are row-major 3x3 matrices in DEVICE memory (the caller draws the random angles), one per round (n_rot >= 6
+ * recommended).  No host synchronisation.  sel_out [n_support] int32.  Random by construction in the reference too:
+ * parity is distributional.
+ * pps_encoder_ids runs the whole get_fkaconv_ids for a batch of clouds pts [b,n0,3]: level sizes n_{l+1} =
+ * max(1, n_l / 4); rotations [b,4,n_rot,9]; outputs (caller-allocated, device): support[l-1] [b,n_l,3];
+ * ids16[p] [b,n_c,min(16,n_a)] for (a,c) = (0,0),(0,1),(1,1),(1,2),(2,2),(2,3),(3,3),(3,4),(4,4);
+ * ids1[p] [b,n_c,1] for (a,c) = (4,3),(3,2),(2,1),(1,0).
+ * ------------------------------------------------------------------------------------------------------------- */
+size_t pps_sample_workspace_bytes(int64_t n);
+int pps_sample_quantized(const float* pts, int64_t n, int64_t n_support, const float* rotations, int n_rot, uint32_t seed,
+                         void* workspace, size_t workspace_bytes, int32_t* sel_out, void* stream);
+typedef struct pps_encoder_ids_out {
+    float* support[4];
+    int32_t* ids16[9];
+    int32_t* ids1[4];
+} pps_encoder_ids_out;
+size_t pps_encoder_ids_workspace_bytes(int64_t n0);
+int pps_encoder_ids(const float* pts, int64_t b, int64_t n0, const float* rotations, int n_rot, uint32_t seed, void* workspace,
+                    size_t workspace_bytes, const pps_encoder_ids_out* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * a3  FKAConv layer (point-major activations)
  *     replaces  FKAConvLayer.forward   source/base/nn.py:592-652   (eval mode; InstanceNorm statistics are
  *     per sample over (Ns,16), so the layer runs as stats1 -> stats2 -> fused gather/contract)

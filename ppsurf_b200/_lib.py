@@ -46,6 +46,11 @@ class FKAConvWeights(ctypes.Structure):
     ]
 
 
+class EncoderIdsOut(ctypes.Structure):
+    """mirror of ``pps_encoder_ids_out``"""
+    _fields_ = [('support', c_f32p * 4), ('ids16', c_i32p * 9), ('ids1', c_i32p * 4)]
+
+
 # name -> (restype, argtypes); every symbol include/ppsurf_b200.h declares
 SIGNATURES = {
     'pps_last_error': (ctypes.c_char_p, []),
@@ -77,6 +82,10 @@ SIGNATURES = {
                                      size_t, c_f32p, i32, c_voidp]),
     'pps_decoder_pointnet': (i32, [ctypes.POINTER(DecoderWeights), c_f32p, i64, c_voidp, size_t, c_f32p, i32, c_voidp]),
     'pps_grid_queries': (i32, [i32, ctypes.c_float, ctypes.c_float, i64, i64, c_f32p, c_voidp]),
+    'pps_sample_workspace_bytes': (size_t, [i64]),
+    'pps_sample_quantized': (i32, [c_f32p, i64, i64, c_f32p, i32, ctypes.c_uint32, c_voidp, size_t, c_i32p, c_voidp]),
+    'pps_encoder_ids_workspace_bytes': (size_t, [i64]),
+    'pps_encoder_ids': (i32, [c_f32p, i64, i64, c_f32p, i32, ctypes.c_uint32, c_voidp, size_t, ctypes.POINTER(EncoderIdsOut), c_voidp]),
     'pps_fkaconv_workspace_bytes': (size_t, [i64, i64, i32]),
     'pps_fkaconv_forward': (i32, [ctypes.POINTER(FKAConvWeights), c_f32p, c_f32p, c_f32p, c_i32p, i32, i64, i64, i64, c_voidp,
                                   size_t, c_f32p, c_voidp]),

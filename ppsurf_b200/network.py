@@ -232,29 +232,17 @@ class PPSurfNetwork(_Base):
 
     def spatial_ids(self, pts_bcn: torch.Tensor) -> dict:
         """get_fkaconv_ids on the device (source/poco_data_loader.py:137-209): four quantised support samplings at
-        ratio 1/4 and the 13 kNN index tensors, reference layouts (supports [B,3,Ns], ids int64)."""
-        from .sampling import sampling_quantized
+        ratio 1/4 and the 13 kNN index tensors in ONE C-ABI call per batch; reference layouts on return (supports
+        [B,3,Ns], ids int64)."""
+        from .sampling import ROUNDS, random_rotations
         gen = np.random.default_rng(self.sampling_seed)
         pts = _pm(pts_bcn)
         b = pts.shape[0]
-        levels = [pts]
-        for _ in range(4):
-            prev = levels[-1]
-            n_sup = max(1, int(prev.shape[1] * 0.25))
-            sel = [sampling_quantized(prev[i], n_sup, gen) for i in range(b)]
-            levels.append(torch.stack([prev[i][sel[i]] for i in range(b)], dim=0))
-        out = {'support%d' % i: levels[i].transpose(1, 2).contiguous() for i in (1, 2, 3, 4)}
-        pairs16 = ((0, 0), (0, 1), (1, 1), (1, 2), (2, 2), (2, 3), (3, 3), (3, 4), (4, 4))
-        pairs1 = ((4, 3), (3, 2), (2, 1), (1, 0))
-        res = {}
-        for i in range(b):
-            index = [ops.KnnIndex(levels[lv][i].contiguous()) for lv in range(5)]
-            for a, c in pairs16:
-                res.setdefault('ids%d%d' % (a, c), []).append(index[a].query(levels[c][i].contiguous(), 16))
-            for a, c in pairs1:
-                res.setdefault('ids%d%d' % (a, c), []).append(index[a].query(levels[c][i].contiguous(), 1))
+        rot = torch.from_numpy(random_rotations(gen, b * 4 * ROUNDS).reshape(b, 4, ROUNDS, 9)).to(pts.device)
+        res = ops.encoder_ids(pts, rot, int(gen.integers(0, 2 ** 31)))
+        out = {}
         for key, val in res.items():
-            out[key] = torch.stack(val, dim=0).long()
+            out[key] = val.transpose(1, 2).contiguous() if key.startswith('support') else val.long()
         return out
 
     # ---- reference surface -------------------------------------------------------------------------------------

@@ -170,6 +170,43 @@ def pointnet(packed, patches: torch.Tensor, path: int = 0):
     return out
 
 
+def sample_quantized(pts: torch.Tensor, n_support: int, rotations: torch.Tensor, seed: int) -> torch.Tensor:
+    """``pts [N,3]`` -> indices ``[n_support]`` int32 of the quantised support sampling; ``rotations [R,9]`` on the device"""
+    n = pts.shape[0]
+    ws = torch.empty(lib.pps_sample_workspace_bytes(n), dtype=torch.uint8, device=pts.device)
+    sel = torch.empty((n_support,), dtype=torch.int32, device=pts.device)
+    check(lib.pps_sample_quantized(_ptr(pts, torch.float32), n, n_support, _ptr(rotations, torch.float32), rotations.shape[0],
+                                   int(seed) & 0xFFFFFFFF, _ptr(ws), ws.numel(), _ptr(sel), _stream()))
+    return sel
+
+
+def encoder_ids(pts: torch.Tensor, rotations: torch.Tensor, seed: int) -> dict:
+    """get_fkaconv_ids for a batch: ``pts [B,N0,3]``, ``rotations [B,4,R,9]`` -> point-major supports ``support1..4 [B,Nl,3]``
+    and int32 index tensors ``ids00 ... ids10``"""
+    b, n0, _ = pts.shape
+    dev = pts.device
+    sizes = [n0]
+    for _ in range(4):
+        sizes.append(max(1, sizes[-1] // 4))
+    out = {}
+    st = _lib.EncoderIdsOut()
+    for lv in range(1, 5):
+        out['support%d' % lv] = torch.empty((b, sizes[lv], 3), dtype=torch.float32, device=dev)
+        st.support[lv - 1] = out['support%d' % lv].data_ptr()
+    for p, (a, c) in enumerate(((0, 0), (0, 1), (1, 1), (1, 2), (2, 2), (2, 3), (3, 3), (3, 4), (4, 4))):
+        t = torch.empty((b, sizes[c], min(16, sizes[a])), dtype=torch.int32, device=dev)
+        out['ids%d%d' % (a, c)] = t
+        st.ids16[p] = t.data_ptr()
+    for p, (a, c) in enumerate(((4, 3), (3, 2), (2, 1), (1, 0))):
+        t = torch.empty((b, sizes[c], 1), dtype=torch.int32, device=dev)
+        out['ids%d%d' % (a, c)] = t
+        st.ids1[p] = t.data_ptr()
+    ws = torch.empty(lib.pps_encoder_ids_workspace_bytes(n0), dtype=torch.uint8, device=dev)
+    check(lib.pps_encoder_ids(_ptr(pts, torch.float32), b, n0, _ptr(rotations, torch.float32), rotations.shape[2],
+                              int(seed) & 0xFFFFFFFF, _ptr(ws), ws.numel(), ctypes.byref(st), _stream()))
+    return out
+
+
 def fkaconv(packed, x, pts, support, ids):
     """``x [B,Nin,Cin]``, ``pts [B,Nin,3]``, ``support [B,Ns,3]``, ``ids [B,Ns,kn<=16] int32`` -> ``[B,Ns,Cout]``"""
     b, n_in, cin = x.shape

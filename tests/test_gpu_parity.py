@@ -216,6 +216,36 @@ def test_get_latent_indices_and_latents(dev, net, oracle, weights):
     assert np.abs(got - ref).max() < 5e-5 * max(1.0, np.abs(ref).max())
 
 
+def test_device_support_sampling(dev, oracle):
+    """quantised support sampling on the device: right count, unique ids, reproducible, blue-noise-like spread comparable
+    to the oracle's restatement of the reference algorithm (the reference is random by construction: distributional parity)"""
+    from ppsurf_b200 import ops
+    from ppsurf_b200.sampling import ROUNDS, random_rotations
+    pts = oracle.synthetic_cloud(4000, 5)
+    rot = torch.from_numpy(random_rotations(np.random.default_rng(1), ROUNDS)).to(dev)
+    sel = ops.sample_quantized(cu(pts, dev), 1000, rot, seed=7).cpu().numpy()
+    assert sel.shape == (1000,) and np.unique(sel).shape[0] == 1000 and sel.min() >= 0 and sel.max() < 4000
+    again = ops.sample_quantized(cu(pts, dev), 1000, rot, seed=7).cpu().numpy()
+    np.testing.assert_array_equal(sel, again)
+    other = ops.sample_quantized(cu(pts, dev), 1000, rot, seed=8).cpu().numpy()
+    assert not np.array_equal(np.sort(sel), np.sort(other))
+
+    def spread(ids):  # mean nearest-neighbour distance inside the sample
+        _, d2 = oracle.knn(pts[ids], pts[ids], 2)
+        return float(np.sqrt(d2[:, 1]).mean())
+
+    ref = oracle.sampling_quantized(pts, 1000, np.random.default_rng(1))
+    rnd = spread(np.random.default_rng(2).permutation(4000)[:1000])
+    assert spread(sel) > 1.15 * rnd and abs(spread(sel) - spread(ref)) < 0.15 * spread(ref)
+    # edge cases: tiny clouds, n_support == n, heavy duplication (hash table / voxel halving cannot separate the points)
+    tiny = cu(pts[:7], dev)
+    assert sorted(ops.sample_quantized(tiny, 1, rot, 1).cpu().tolist())[0] in range(7)
+    np.testing.assert_array_equal(np.sort(ops.sample_quantized(tiny, 7, rot, 1).cpu().numpy()), np.arange(7))
+    dup = cu(np.repeat(pts[:10], 40, axis=0), dev)
+    s = ops.sample_quantized(dup, 100, rot, 3).cpu().numpy()
+    assert np.unique(s).shape[0] == 100
+
+
 # ---- a8-a11 decoder -------------------------------------------------------------------------------------------------------
 
 def _decode_inputs(g):

@@ -116,22 +116,14 @@ def test_grid_definition_matches_oracle(oracle):
     np.testing.assert_array_equal(ids, i2)
 
 
-def test_sampling_quantized_host_properties(oracle):
-    """the device sampler (torch ops) run on the CPU: right count, unique ids, well spread like the oracle's"""
-    from ppsurf_b200.sampling import sampling_quantized
-    pts = oracle.synthetic_cloud(4000, 5)
-    gen = np.random.default_rng(1)
-    sel = sampling_quantized(torch.from_numpy(pts), 1000, gen).numpy()
-    assert sel.shape == (1000,) and np.unique(sel).shape[0] == 1000
-    ref = oracle.sampling_quantized(pts, 1000, np.random.default_rng(1))
-    assert ref.shape == (1000,) and np.unique(ref).shape[0] == 1000
-
-    def spread(ids):  # mean nearest-neighbour distance inside the sample: blue-noise-like samples score high
-        _, d2 = oracle.knn(pts[ids], pts[ids], 2)
-        return float(np.sqrt(d2[:, 1]).mean())
-
-    rnd = spread(np.random.default_rng(2).permutation(4000)[:1000])
-    assert spread(sel) > 1.15 * rnd and abs(spread(sel) - spread(ref)) < 0.15 * spread(ref)
+def test_sampling_rotations():
+    """host side of the support sampling: proper rotations, reproducible from the seed"""
+    from ppsurf_b200.sampling import random_rotations
+    r = random_rotations(np.random.default_rng(3), 12).reshape(12, 3, 3).astype(np.float64)
+    for m in r:
+        assert np.abs(m @ m.T - np.eye(3)).max() < 1e-6 and abs(np.linalg.det(m) - 1) < 1e-6
+    np.testing.assert_array_equal(random_rotations(np.random.default_rng(3), 12).reshape(12, 3, 3), r.astype(np.float32))
+    assert np.abs(r[0] - r[1]).max() > 1e-3
 
 
 def test_synthetic_generators_match_oracle(oracle, weights):
