@@ -19,6 +19,7 @@ int knn_query_impl(const void* index, int64_t n, const float* queries, int64_t q
                    cudaStream_t st);
 
 constexpr int kSampleRounds = 6;
+constexpr int kIdStreams = 4;  // clouds of a batch are independent chains of small kernels: run them on side streams
 constexpr unsigned long long kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
 
 struct SampleState {
@@ -329,8 +330,7 @@ static void level_sizes(int64_t n0, int64_t (&n)[5]) {
     for (int l = 1; l < 5; ++l) n[l] = n[l - 1] / 4 > 1 ? n[l - 1] / 4 : 1;
 }
 
-size_t pps_encoder_ids_workspace_bytes(int64_t n0) {
-    if (n0 <= 0) return 0;
+static size_t encoder_ids_slice_bytes(int64_t n0) {
     int64_t n[5];
     level_sizes(n0, n);
     size_t bytes = align_up(pps_sample_workspace_bytes(n0), 256);
@@ -338,6 +338,8 @@ size_t pps_encoder_ids_workspace_bytes(int64_t n0) {
     bytes += align_up(size_t(n[1]) * 4, 256);  // selection scratch
     return bytes;
 }
+
+size_t pps_encoder_ids_workspace_bytes(int64_t n0) { return n0 > 0 ? kIdStreams * encoder_ids_slice_bytes(n0) : 0; }
 
 int pps_encoder_ids(const float* pts, int64_t b, int64_t n0, const float* rotations, int n_rot, uint32_t seed, void* workspace,
                     size_t workspace_bytes, const pps_encoder_ids_out* out, void* stream) {
@@ -347,25 +349,40 @@ int pps_encoder_ids(const float* pts, int64_t b, int64_t n0, const float* rotati
         set_error("pps_encoder_ids: workspace %zu < required %zu", workspace_bytes, pps_encoder_ids_workspace_bytes(n0));
         return PPS_ERR_WORKSPACE;
     }
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaStream_t user = static_cast<cudaStream_t>(stream);
+    // fork: side streams (created once per process) wait for the caller's stream, each owns one workspace slice
+    static cudaStream_t side[kIdStreams] = {};
+    static cudaEvent_t ev_fork = nullptr, ev_join[kIdStreams] = {};
+    if (!ev_fork) {
+        PPS_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        for (int i = 0; i < kIdStreams; ++i) {
+            PPS_CUDA(cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking));
+            PPS_CUDA(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming));
+        }
+    }
+    const int nstreams = b < kIdStreams ? (int)b : kIdStreams;
+    PPS_CUDA(cudaEventRecord(ev_fork, user));
+    for (int i = 0; i < nstreams; ++i) PPS_CUDA(cudaStreamWaitEvent(side[i], ev_fork, 0));
     int64_t n[5];
     level_sizes(n0, n);
-    char* base = static_cast<char*>(workspace);
-    size_t off = 0;
-    void* sample_ws = base;
-    const size_t sample_bytes = align_up(pps_sample_workspace_bytes(n0), 256);
-    off += sample_bytes;
-    void* index[5];
-    size_t index_bytes[5];
-    for (int l = 0; l < 5; ++l) {
-        index[l] = base + off;
-        index_bytes[l] = pps_knn_index_bytes(n[l]);
-        off += align_up(index_bytes[l], 256);
-    }
-    int32_t* sel = reinterpret_cast<int32_t*>(base + off);
+    const size_t slice = encoder_ids_slice_bytes(n0);
     static const int pair16[9][2] = {{0, 0}, {0, 1}, {1, 1}, {1, 2}, {2, 2}, {2, 3}, {3, 3}, {3, 4}, {4, 4}};
     static const int pair1[4][2] = {{4, 3}, {3, 2}, {2, 1}, {1, 0}};
     for (int64_t s = 0; s < b; ++s) {
+        cudaStream_t st = side[s % nstreams];
+        char* base = static_cast<char*>(workspace) + (s % nstreams) * slice;
+        size_t off = 0;
+        void* sample_ws = base;
+        const size_t sample_bytes = align_up(pps_sample_workspace_bytes(n0), 256);
+        off += sample_bytes;
+        void* index[5];
+        size_t index_bytes[5];
+        for (int l = 0; l < 5; ++l) {
+            index[l] = base + off;
+            index_bytes[l] = pps_knn_index_bytes(n[l]);
+            off += align_up(index_bytes[l], 256);
+        }
+        int32_t* sel = reinterpret_cast<int32_t*>(base + off);
         const float* lv[5];
         lv[0] = pts + s * n0 * 3;
         for (int l = 1; l < 5; ++l) {
@@ -386,6 +403,11 @@ int pps_encoder_ids(const float* pts, int64_t b, int64_t n0, const float* rotati
             const int a = pair1[p][0], c = pair1[p][1];
             PPS_TRY(knn_query_impl(index[a], n[a], lv[c], n[c], 1, out->ids1[p] + s * n[c], nullptr, st));
         }
+    }
+    // join: the caller's stream continues when every side stream is done
+    for (int i = 0; i < nstreams; ++i) {
+        PPS_CUDA(cudaEventRecord(ev_join[i], side[i]));
+        PPS_CUDA(cudaStreamWaitEvent(user, ev_join[i], 0));
     }
     return PPS_OK;
 }
