@@ -59,12 +59,11 @@ class PPSurfModel(_Base):
         self.test_step_outputs = []
 
     # ---- a1: latent averaging loop (source/poco_model.py:200-237) ----------------------------------------------
-    def latent_schedule(self, n: int, generator: typing.Optional[torch.Generator] = None) -> typing.List[torch.Tensor]:
-        """index sets of the latent loop (source/poco_model.py:207-224).  They depend only on the visit counts, never on
-        network output, so the whole schedule is drawn on the host before any pass runs."""
+    def latent_schedule(self, n: int, generator: typing.Optional[torch.Generator] = None) -> typing.Iterator[torch.Tensor]:
+        """index sets of the latent loop (source/poco_model.py:207-224), lazily.  They depend only on the visit counts,
+        never on network output, so the host draws the next sets while the device still works on the previous batch."""
         sub = self.gen_subsample_manifold
         counts = np.zeros(n, dtype=np.int64)
-        passes = []
         for current in range(self.gen_subsample_manifold_iter):
             while counts.min() < current + 1:
                 valid = torch.from_numpy(np.nonzero(counts == current)[0])
@@ -75,8 +74,7 @@ class PPSurfModel(_Base):
                 else:
                     ids = torch.arange(n)
                 counts[np.unique(ids.numpy())] += 1  # `counts[ids] += 1` counts a repeated id once
-                passes.append(ids)
-        return passes
+                yield ids
 
     def encode_cloud(self, pts_bcn: torch.Tensor, generator: typing.Optional[torch.Generator] = None,
                      prog_bar=None, batch_passes: int = 16) -> torch.Tensor:
@@ -89,10 +87,12 @@ class PPSurfModel(_Base):
         dev = pts.device
         latent = torch.zeros((n, self.network_latent_size), dtype=torch.float32, device=dev)
         counts = torch.zeros((n,), dtype=torch.float32, device=dev)
-        passes = self.latent_schedule(n, generator)
+        schedule = self.latent_schedule(n, generator)
         iteration = 0
-        for b0 in range(0, len(passes), batch_passes):
-            group = passes[b0:b0 + batch_passes]
+        while True:
+            group = [ids for _, ids in zip(range(batch_passes), schedule)]
+            if not group:
+                break
             ids_dev = [ids.to(dev) for ids in group]
             batch = torch.stack([pts[i] for i in ids_dev], dim=0).transpose(1, 2).contiguous()  # [B,3,sub]
             part = self.network.get_latent({'pts': batch})['latents']  # [B,latent,sub]

@@ -43,7 +43,7 @@ for bp in (8, 16):
     net.sampling_seed = 42
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    sched = model.latent_schedule(100000, torch.Generator().manual_seed(42))
+    sched = list(model.latent_schedule(100000, torch.Generator().manual_seed(42)))
     t_sched = time.perf_counter() - t0
     t0 = time.perf_counter()
     model.encode_cloud(pts, generator=torch.Generator().manual_seed(42), batch_passes=bp)
