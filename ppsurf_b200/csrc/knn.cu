@@ -322,223 +322,6 @@ __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restri
     }
 }
 
-// ---- one warp, kGroup queries AT ONCE (k <= 64) ----------------------------------------------------------------------
-// Consecutive queries (grid order) visit almost the same nodes, so a warp carries kGroup of them through ONE traversal:
-// node and point loads, the stack and the child ranking are shared; every query keeps its own sorted list and bound.  A
-// node is skipped only if every query of the group prunes it, a point is offered to every query whose bound it beats.
-constexpr int kGroup = 8;
-
-template <int SLOTS>
-__global__ void __launch_bounds__(256) knn_group_kernel(const KnnHeader* __restrict__ hdr, const float4* __restrict__ sorted,
-                                                        const int* __restrict__ cell_start, const float* __restrict__ queries,
-                                                        long long nq, int k, int32_t* __restrict__ idx_out,
-                                                        float* __restrict__ d2_out) {
-    __shared__ unsigned int stack_s[8][8 * kMaxLevels + 8];
-    const unsigned int full = 0xffffffffu;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long q_first = ((long long)blockIdx.x * 8 + warp) * kGroup;
-    if (q_first >= nq) return;
-    unsigned int* stack = stack_s[warp];
-    const int L = hdr->levels;
-    const float ox = hdr->origin[0], oy = hdr->origin[1], oz = hdr->origin[2];
-    const float cell = hdr->cell;
-    const float pad = cell * 1e-3f;
-    const int wslot = (k - 1) >> 5, wlane = (k - 1) & 31;
-
-    float qx[kGroup], qy[kGroup], qz[kGroup], worst[kGroup];
-    int worst_i[kGroup];
-    float ld[kGroup][SLOTS];
-    int li[kGroup][SLOTS];
-#pragma unroll
-    for (int r = 0; r < kGroup; ++r) {
-        const long long qi = q_first + r < nq ? q_first + r : nq - 1;  // surplus slots repeat the last query (not written)
-        qx[r] = queries[3 * qi];
-        qy[r] = queries[3 * qi + 1];
-        qz[r] = queries[3 * qi + 2];
-        worst[r] = INFINITY;
-        worst_i[r] = 0x7fffffff;
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s) {
-            ld[r][s] = INFINITY;
-            li[r][s] = 0x7fffffff;
-        }
-    }
-    // lane l evaluates boxes for query (l & 7); its coordinates / bound are picked with a select chain (registers cannot be
-    // indexed dynamically)
-    const int myq = lane & 7;
-    float mqx = qx[0], mqy = qy[0], mqz = qz[0];
-#pragma unroll
-    for (int r = 1; r < kGroup; ++r)
-        if (myq == r) {
-            mqx = qx[r];
-            mqy = qy[r];
-            mqz = qz[r];
-        }
-    auto my_worst = [&]() {
-        float w = worst[0];
-#pragma unroll
-        for (int r = 1; r < kGroup; ++r)
-            if (myq == r) w = worst[r];
-        return w;
-    };
-    auto box_dist = [&](int level, int cx, int cy, int cz) -> float {  // for this lane's query
-        float size = cell * float(1 << (L - level));
-        float lx = ox + cx * size - pad, ly = oy + cy * size - pad, lz = oz + cz * size - pad;
-        float hx = lx + size + 2 * pad, hy = ly + size + 2 * pad, hz = lz + size + 2 * pad;
-        float dx = fmaxf(fmaxf(lx - mqx, mqx - hx), 0.f);
-        float dy = fmaxf(fmaxf(ly - mqy, mqy - hy), 0.f);
-        float dz = fmaxf(fmaxf(lz - mqz, mqz - hz), 0.f);
-        return (dx * dx + dy * dy + dz * dz) * 0.99999f;
-    };
-
-    int sp = 1;
-    if (lane == 0) stack[0] = 0u;
-    __syncwarp();
-    while (sp > 0) {
-        const unsigned int nd = stack[--sp];
-        const int level = nd >> 21, cx = nd & 127, cy = (nd >> 7) & 127, cz = (nd >> 14) & 127;
-        // skip the node only if EVERY query of the group prunes it (lanes 0..7 hold one query each)
-        if (__ballot_sync(full, lane < kGroup && box_dist(level, cx, cy, cz) <= my_worst()) == 0u) continue;
-        const unsigned int code = morton3(cx, cy, cz);
-        const int sh = 3 * (L - level);
-        const int lo = cell_start[code << sh], hi = cell_start[(code + 1u) << sh];
-        const int cnt = hi - lo;
-        if (cnt == 0) continue;
-        bool scan = cnt <= 32 || level == L;
-        if (!scan) {
-            // 8 children x 8 queries = 64 box tests: lane l takes child (l >> 3) and (l >> 3) + 4 for its query (l & 7)
-            const int sh2 = sh - 3;
-            const unsigned int cbase = code * 8u;
-            const float w = my_worst();
-            float dmin[2];
-            bool okq[2];
-#pragma unroll
-            for (int hhalf = 0; hhalf < 2; ++hhalf) {
-                const int ch = (lane >> 3) + 4 * hhalf;
-                const int ccx = cx * 2 + (ch & 1), ccy = cy * 2 + ((ch >> 1) & 1), ccz = cz * 2 + (ch >> 2);
-                const float d = box_dist(level + 1, ccx, ccy, ccz);
-                okq[hhalf] = d <= w;
-                // minimum over the 8 queries (lanes sharing l >> 3): the child's rank key
-                float m = d;
-#pragma unroll
-                for (int o = 4; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(full, m, o, 8));
-                dmin[hhalf] = m;
-            }
-            const unsigned int ok0 = __ballot_sync(full, okq[0]), ok1 = __ballot_sync(full, okq[1]);
-            // lanes 0..7 now act for child `lane`
-            bool nonempty = false, ok = false;
-            float d = INFINITY;
-            unsigned int child = 0;
-            {
-                const int ch = lane & 7;
-                // child ch was evaluated by lanes [8 (ch & 3), +8) in half (ch >> 2): fetch both halves, then select
-                const float d0 = __shfl_sync(full, dmin[0], (ch & 3) * 8), d1 = __shfl_sync(full, dmin[1], (ch & 3) * 8);
-                d = ch < 4 ? d0 : d1;
-                const unsigned int okmask = ch < 4 ? ok0 : ok1;
-                const bool any_ok = ((okmask >> ((ch & 3) * 8)) & 0xFFu) != 0u;
-                if (lane < 8) {
-                    const int clo = cell_start[(cbase + ch) << sh2], chi = cell_start[(cbase + ch + 1u) << sh2];
-                    nonempty = chi > clo;
-                    ok = nonempty && any_ok;
-                    const int ccx = cx * 2 + (ch & 1), ccy = cy * 2 + ((ch >> 1) & 1), ccz = cz * 2 + (ch >> 2);
-                    child = ((unsigned int)(level + 1) << 21) | ccx | (ccy << 7) | (ccz << 14);
-                } else {
-                    d = INFINITY;
-                }
-            }
-            const unsigned int m = __ballot_sync(full, ok);
-            if (cnt <= kScanMax && m == __ballot_sync(full, nonempty)) {
-                scan = true;  // nothing can be pruned: stream through the node's contiguous range
-            } else {
-                int rank = 0;
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    const float dt = __shfl_sync(full, d, t);
-                    if (((m >> t) & 1u) && (dt > d || (dt == d && t < lane))) ++rank;
-                }
-                if (ok) stack[sp + rank] = child;
-                sp += __popc(m);
-                __syncwarp();
-            }
-        }
-        if (scan) {
-            for (int base = lo; base < hi; base += 32) {
-                const int i = base + lane;
-                float px = 0.f, py = 0.f, pz = 0.f;
-                int pi = 0x7fffffff;
-                const bool inb = i < hi;
-                if (inb) {
-                    const float4 p = sorted[i];
-                    px = p.x;
-                    py = p.y;
-                    pz = p.z;
-                    pi = __float_as_int(p.w);
-                }
-#pragma unroll
-                for (int r = 0; r < kGroup; ++r) {
-                    const float dx = qx[r] - px, dy = qy[r] - py, dz = qz[r] - pz;
-                    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                    unsigned int mask = __ballot_sync(full, inb && cand_less(d2, pi, worst[r], worst_i[r]));
-                    while (mask) {
-                        const int src = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        const float vd = __shfl_sync(full, d2, src);
-                        const int vi = __shfl_sync(full, pi, src);
-                        if (!cand_less(vd, vi, worst[r], worst_i[r])) continue;
-                        int pos = 0;
-#pragma unroll
-                        for (int s = 0; s < SLOTS; ++s) pos += __popc(__ballot_sync(full, cand_less(ld[r][s], li[r][s], vd, vi)));
-#pragma unroll
-                        for (int s = SLOTS - 1; s >= 0; --s) {
-                            float pd = __shfl_up_sync(full, ld[r][s], 1);
-                            int pj = __shfl_up_sync(full, li[r][s], 1);
-                            if (s > 0) {
-                                const float cd = __shfl_sync(full, ld[r][s - 1], 31);
-                                const int cj = __shfl_sync(full, li[r][s - 1], 31);
-                                if (lane == 0) {
-                                    pd = cd;
-                                    pj = cj;
-                                }
-                            }
-                            const int g = s * 32 + lane;
-                            if (g == pos) {
-                                ld[r][s] = vd;
-                                li[r][s] = vi;
-                            } else if (g > pos) {
-                                ld[r][s] = pd;
-                                li[r][s] = pj;
-                            }
-                        }
-                        worst[r] = __shfl_sync(full, ld[r][wslot < SLOTS ? wslot : SLOTS - 1], wlane);
-                        worst_i[r] = __shfl_sync(full, li[r][wslot < SLOTS ? wslot : SLOTS - 1], wlane);
-                    }
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < kGroup; ++r) {
-        const long long qi = q_first + r;
-        if (qi >= nq) break;
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s) {
-            const int g = s * 32 + lane;
-            if (g < k) {
-                idx_out[qi * k + g] = li[r][s];
-                if (d2_out) d2_out[qi * k + g] = ld[r][s];
-            }
-        }
-    }
-}
-
-template <int SLOTS>
-static int launch_group(const KnnHeader* hdr, const float4* sorted, const int* cell_start, const float* queries, int64_t q, int k,
-                        int32_t* idx_out, float* d2_out, cudaStream_t st) {
-    knn_group_kernel<SLOTS><<<(unsigned)ceil_div(q, 8 * kGroup), 256, 0, st>>>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out);
-    PPS_LAUNCH_CHECK();
-    return PPS_OK;
-}
-
 template <int SLOTS>
 static int launch_query(const KnnHeader* hdr, const float4* sorted, const int* cell_start, const float* queries,
                         int64_t q, int k, int32_t* idx_out, float* d2_out, cudaStream_t st) {
@@ -558,8 +341,8 @@ int knn_query_impl(const void* index, int64_t n, const float* queries, int64_t q
     const KnnHeader* hdr = reinterpret_cast<const KnnHeader*>(base + l.header);
     const float4* sorted = reinterpret_cast<const float4*>(base + l.sorted);
     const int* cell_start = reinterpret_cast<const int*>(base + l.cell_start);
-    if (k <= 32) return launch_group<1>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out, st);
-    if (k <= 64) return launch_group<2>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out, st);
+    if (k <= 32) return launch_query<1>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out, st);
+    if (k <= 64) return launch_query<2>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out, st);
     if (k <= 128) return launch_query<4>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out, st);
     if (k <= 224) return launch_query<7>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out, st);
     return launch_query<16>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out, st);
