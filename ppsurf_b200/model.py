@@ -55,7 +55,7 @@ class PPSurfModel(_Base):
         self.pointnet_latent_size = pointnet_latent_size
         self.network = PPSurfNetwork(in_channels=in_channels, latent_size=network_latent_size, out_channels=out_channels,
                                      k=k, num_pts_local=num_pts_local, pointnet_latent_size=pointnet_latent_size,
-                                     decode_chunk=min(int(rec_batch_size), 16384))
+                                     decode_chunk=min(int(rec_batch_size), ops.DEFAULT_CHUNK))
         self.test_step_outputs = []
 
     # ---- a1: latent averaging loop (source/poco_model.py:200-237) ----------------------------------------------

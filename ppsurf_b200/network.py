@@ -141,7 +141,7 @@ def _ids32(t: torch.Tensor) -> torch.Tensor:
 class PPSurfNetwork(_Base):
 
     def __init__(self, in_channels, latent_size, out_channels, k, num_pts_local, pointnet_latent_size,
-                 decode_chunk=16384, decode_path=None):
+                 decode_chunk=ops.DEFAULT_CHUNK, decode_path=None):
         super().__init__()
         self.latent_size = latent_size
         self.k = k

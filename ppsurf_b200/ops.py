@@ -9,6 +9,10 @@ from . import _lib
 from ._lib import check, lib
 
 
+# queries per decode launch: 148 SMs x 128-row tiles, i.e. whole waves for every persistent tensor-core kernel
+DEFAULT_CHUNK = 148 * 128
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -89,7 +93,7 @@ def grid_queries(r, step, bmin_pad, first=0, count=None, device='cuda'):
 class Decoder:
     """Per-cloud decoder state: kNN index + hoisted fc1 table; decodes query batches through ``pps_decoder_decode``."""
 
-    def __init__(self, packed, pts: torch.Tensor, latents: torch.Tensor, chunk: int = 16384, path: int = 0):
+    def __init__(self, packed, pts: torch.Tensor, latents: torch.Tensor, chunk: int = 18944, path: int = 0):
         """``pts [N,3]``, ``latents [N,C]`` point-major fp32 on the device."""
         self.packed = packed
         self.pts = pts.contiguous()
