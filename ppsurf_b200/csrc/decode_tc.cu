@@ -44,7 +44,9 @@ constexpr int kOffRing = kOffAlo + kABytes;                  // 132096
 constexpr int kOffBias = kOffRing + kStages * kStageBytes;   // 214016: b2[256] b3[256] bq[64]
 constexpr int kOffAttp = kOffBias + (256 + 256 + 64) * 4;    // 216320: [head half][query][64] partial head sums
 constexpr int kOffPool = kOffAttp + 2 * 2 * 64 * 4;          // 217344: [lane group][256] partial pooled sums
-constexpr int kOffBar = kOffPool + 4 * 256 * 4;              // 221440: full[5] empty[5] accum chunk[4]
+constexpr int kOffW1 = kOffPool + 4 * 256 * 4;               // 221440: fc1 xyz weights [256][3]
+constexpr int kOffVq = kOffW1 + 768 * 4;                     // 224512: W1_xyz . q for the tile's 2 queries [2][256]
+constexpr int kOffBar = kOffVq + 2 * 256 * 4;                // 226560: full[5] empty[5] accum chunk[4]
 constexpr int kOffTmem = kOffBar + (2 * kStages + 1 + kChunks) * 8;
 constexpr int kSmemBytes = kOffTmem + 16 + 1024;             // + alignment slack
 
@@ -73,13 +75,18 @@ __global__ void __launch_bounds__(kThreads, 1)
     float* s_bias = reinterpret_cast<float*>(smem + kOffBias);
     float* s_attp = reinterpret_cast<float*>(smem + kOffAttp);
     float* s_pool = reinterpret_cast<float*>(smem + kOffPool);
+    float* s_w1 = reinterpret_cast<float*>(smem + kOffW1);
+    float* s_vq = reinterpret_cast<float*>(smem + kOffVq);
     volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + kOffTmem);
     const uint32_t bar_full = sbase + kOffBar, bar_empty = bar_full + 8 * kStages, bar_accum = bar_empty + 8 * kStages,
                    bar_chunk = bar_accum + 8;
 
-    for (int e = tid; e < 256; e += kThreads) {
-        s_bias[e] = b2[e];
-        s_bias[256 + e] = b3[e];
+    for (int e = tid; e < 768; e += kThreads) {
+        s_w1[e] = w1_xyz[e];
+        if (e < 256) {
+            s_bias[e] = b2[e];
+            s_bias[256 + e] = b3[e];
+        }
         if (e < 64) s_bias[512 + e] = bq[e];
     }
     if (tid == 0) {
@@ -196,40 +203,65 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int lane_grp = warp & 3;         // TMEM lanes this warp may touch: 32*lane_grp .. +31
         const int half = ew >> 2;              // which half of every 64-column chunk (E2/E3) / which query (scores)
         const int row = lane_grp * 32 + lane;  // accumulator row (= TMEM lane) of this thread
-        float w1[8][3];                        // fc1 xyz weights of the 8 channels this lane gathers
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-#pragma unroll
-            for (int d = 0; d < 3; ++d) w1[c][d] = w1_xyz[(8 * lane + c) * 3 + d];
         uint32_t accum_phase = 0;
         long long t_gather = 0, t_wait = 0, t_epi = 0, t_att = 0, t_mark = clock64();
+        long long t_w[3] = {0, 0, 0};
 
         for (long long it = 0; it < iters; ++it) {
             long long tile = blockIdx.x + it * gridDim.x;
             const bool live = tile < ntiles;  // surplus iteration: same work on the last tile, nothing is written
             tile = live ? tile : ntiles - 1;
-            // ---- gather: h1 = relu(U[idx] + W1_xyz.q) -> A_hi/A_lo; warp ew owns rows 16*ew .. +15, lane owns k8 block `lane`
-#pragma unroll 8
-            for (int i = 0; i < 16; ++i) {
-                const int r = ew * 16 + i;
-                long long q = 2 * tile + (r >> 6);
-                q = q < nq ? q : nq - 1;
-                const int src = idx[q * ks + (r & 63)];
-                const float qx = queries[3 * q], qy = queries[3 * q + 1], qz = queries[3 * q + 2];
-                const float4* urow = reinterpret_cast<const float4*>(table + (size_t)src * kC) + 2 * lane;
-                const float4 u0 = urow[0], u1 = urow[1];
-                float x[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+            // ---- W1_xyz . q for the two queries of the tile (the previous tile's readers are behind the end-of-tile barrier)
+            {
+                const int et = tid - 64;  // 0..255 = channel, both queries
 #pragma unroll
-                for (int c = 0; c < 8; ++c) x[c] = fmaxf(x[c] + (w1[c][0] * qx + w1[c][1] * qy + w1[c][2] * qz), 0.f);
-                uint4 hi, lo;
-                split8(x, hi, lo);
-                *reinterpret_cast<uint4*>(smem + kOffAhi + lane * kALbo + r * 16) = hi;
-                *reinterpret_cast<uint4*>(smem + kOffAlo + lane * kALbo + r * 16) = lo;
+                for (int ql = 0; ql < 2; ++ql) {
+                    long long q = 2 * tile + ql;
+                    q = q < nq ? q : nq - 1;
+                    s_vq[ql * 256 + et] = s_w1[3 * et] * queries[3 * q] + s_w1[3 * et + 1] * queries[3 * q + 1] +
+                                          s_w1[3 * et + 2] * queries[3 * q + 2];
+                }
             }
-            fence_async_smem();
-            tc_fence_before();
+            epi_barrier();
+            // ---- gather: h1 = relu(U[idx] + W1_xyz.q) -> A_hi/A_lo, one 64-column chunk after the other so that fc2's first
+            // k-steps start after a quarter of the gather.  Warp ew owns rows 16*ew .. +15 (all of one query); per chunk a lane
+            // owns k8 block (lane & 7) of row 4*i + (lane >> 3): 8 lanes read 256 contiguous bytes of a table row
+            {
+                const int kb = lane & 7, rs = lane >> 3;
+                const int ql = (ew * 16) >> 6;
+                long long q = 2 * tile + ql;
+                q = q < nq ? q : nq - 1;
+                int src[4];
 #pragma unroll
-            for (int c = 0; c < kChunks; ++c) mbar_arrive(bar_chunk + 8 * c);
+                for (int i = 0; i < 4; ++i) src[i] = idx[q * ks + ((ew * 16 + 4 * i + rs) & 63)];
+#pragma unroll 1
+                for (int c = 0; c < kChunks; ++c) {
+                    const float4 v0 = *reinterpret_cast<const float4*>(s_vq + ql * 256 + c * 64 + kb * 8);
+                    const float4 v1 = *reinterpret_cast<const float4*>(s_vq + ql * 256 + c * 64 + kb * 8 + 4);
+                    float4 u[4][2];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4* urow = reinterpret_cast<const float4*>(table + (size_t)src[i] * kC + c * 64) + 2 * kb;
+                        u[i][0] = urow[0];
+                        u[i][1] = urow[1];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = ew * 16 + 4 * i + rs;
+                        float x[8] = {u[i][0].x + v0.x, u[i][0].y + v0.y, u[i][0].z + v0.z, u[i][0].w + v0.w,
+                                      u[i][1].x + v1.x, u[i][1].y + v1.y, u[i][1].z + v1.z, u[i][1].w + v1.w};
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) x[t] = fmaxf(x[t], 0.f);
+                        uint4 hi, lo;
+                        split8(x, hi, lo);
+                        *reinterpret_cast<uint4*>(smem + kOffAhi + (c * 8 + kb) * kALbo + r * 16) = hi;
+                        *reinterpret_cast<uint4*>(smem + kOffAlo + (c * 8 + kb) * kALbo + r * 16) = lo;
+                    }
+                    fence_async_smem();
+                    tc_fence_before();
+                    mbar_arrive(bar_chunk + 8 * c);
+                }
+            }
             {
                 const long long now = clock64();
                 t_gather += now - t_mark;
