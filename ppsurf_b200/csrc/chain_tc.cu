@@ -103,11 +103,7 @@ __device__ __forceinline__ void load_rows(const Ctx& c, const float* __restrict_
     }
 }
 
-__device__ __forceinline__ void tile_ready(const Ctx& c) {
-    fence_async_smem();
-    tc_fence_before();
-    mbar_arrive(c.bar_ready);
-}
+__device__ __forceinline__ void tile_ready(const Ctx& c) { warp_arrive(c.bar_ready, threadIdx.x & 31); }
 
 // epilogue warps: accumulator (128 x n at column dcol) -> v + bias (ReLU optional) -> operand tile
 template <bool RELU>
@@ -139,7 +135,7 @@ __device__ __forceinline__ void epi_to_tile(const Ctx& c, uint32_t dcol, int n, 
 }
 
 __device__ __forceinline__ void setup(Ctx& c, uint8_t* smem_raw, int tid, int warp) {
-    c.smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    c.smem = smem_raw;  // used directly so that the compiler keeps the shared address space (LDS/STS)
     c.sbase = smem_u32(c.smem);
     c.bar_full = c.sbase + kOffBar;
     c.bar_empty = c.bar_full + 8 * kStages;
@@ -154,10 +150,10 @@ __device__ __forceinline__ void setup(Ctx& c, uint8_t* smem_raw, int tid, int wa
             mbar_init(c.bar_empty + 8 * i, 1);
         }
         mbar_init(c.bar_accum, 1);
-        mbar_init(c.bar_ready, kEpiThreads);
+        mbar_init(c.bar_ready, kEpiThreads / 32);  // one elected arrival per warp
         mbar_init(c.bar_afree, 1);
-        mbar_init(c.bar_tfree, kEpiThreads);
-        mbar_init(c.bar_tfree + 8, kEpiThreads);
+        mbar_init(c.bar_tfree, kEpiThreads / 32);
+        mbar_init(c.bar_tfree + 8, kEpiThreads / 32);
         mbar_init(c.bar_accum2, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -185,7 +181,7 @@ constexpr size_t kPackMlp = size_t(4) * (256 * 256 + 256 * 128 + 256 * 256 + 256
 __global__ void __launch_bounds__(kThreads, 1)
     stn_fc_tc_kernel(const float* __restrict__ g, long long nq, const uint8_t* __restrict__ wpack, const float* __restrict__ b1,
                      const float* __restrict__ b2, const float* __restrict__ b3, float* __restrict__ tmat) {
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     Ctx c;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     setup(c, smem_raw, tid, warp);
@@ -286,7 +282,8 @@ __global__ void __launch_bounds__(kThreads, 1)
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(c.bar_tfree + 8 * buf);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(c.bar_tfree + 8 * buf);
             }
         }
     }
@@ -299,7 +296,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                   const uint8_t* __restrict__ wpack, const float* __restrict__ bias_feat, const float* __restrict__ b0,
                   const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
                   float* __restrict__ logits_out, float* __restrict__ occ_out) {
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     Ctx c;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     setup(c, smem_raw, tid, warp);

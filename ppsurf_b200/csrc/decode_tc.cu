@@ -68,8 +68,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     projection_tc_kernel(const float* __restrict__ table, const float* __restrict__ queries, const int32_t* __restrict__ idx, int ks,
                          long long nq, const uint8_t* __restrict__ wpack, const float* __restrict__ b2, const float* __restrict__ b3,
                          const float* __restrict__ bq, const float* __restrict__ w1_xyz, float* __restrict__ pooled, long long* prof) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem[];  // used directly: the compiler keeps the shared address space (LDS/STS)
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float* s_bias = reinterpret_cast<float*>(smem + kOffBias);
@@ -95,7 +94,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             mbar_init(bar_empty + 8 * i, CS);  // every CTA of the cluster releases the slot in every member
         }
         mbar_init(bar_accum, 1);
-        for (int i = 0; i < kChunks; ++i) mbar_init(bar_chunk + 8 * i, kEpiThreads);
+        for (int i = 0; i < kChunks; ++i) mbar_init(bar_chunk + 8 * i, kEpiWarps);  // one elected arrival per warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -207,6 +206,14 @@ __global__ void __launch_bounds__(kThreads, 1)
         long long t_gather = 0, t_wait = 0, t_epi = 0, t_att = 0, t_mark = clock64();
         long long t_w[3] = {0, 0, 0};
 
+        int src_next[4];
+        {
+            long long t0 = blockIdx.x < ntiles ? blockIdx.x : ntiles - 1;
+            long long q = 2 * t0 + ((ew * 16) >> 6);
+            q = q < nq ? q : nq - 1;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) src_next[i] = idx[q * ks + ((ew * 16 + 4 * i + (lane >> 3)) & 63)];
+        }
         for (long long it = 0; it < iters; ++it) {
             long long tile = blockIdx.x + it * gridDim.x;
             const bool live = tile < ntiles;  // surplus iteration: same work on the last tile, nothing is written
@@ -229,27 +236,41 @@ __global__ void __launch_bounds__(kThreads, 1)
             {
                 const int kb = lane & 7, rs = lane >> 3;
                 const int ql = (ew * 16) >> 6;
-                long long q = 2 * tile + ql;
-                q = q < nq ? q : nq - 1;
                 int src[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) src[i] = idx[q * ks + ((ew * 16 + 4 * i + rs) & 63)];
-#pragma unroll 1
+                for (int i = 0; i < 4; ++i) src[i] = src_next[i];
+                {  // neighbour ids of the NEXT tile: their latency hides behind this tile
+                    long long tn = blockIdx.x + (it + 1) * gridDim.x;
+                    tn = tn < ntiles ? tn : ntiles - 1;
+                    long long q = 2 * tn + ql;
+                    q = q < nq ? q : nq - 1;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) src_next[i] = idx[q * ks + ((ew * 16 + 4 * i + rs) & 63)];
+                }
+                float4 u[2][4][2];  // double-buffered in registers: chunk c+1 is in flight while chunk c is converted
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4* urow = reinterpret_cast<const float4*>(table + (size_t)src[i] * kC) + 2 * kb;
+                    u[0][i][0] = urow[0];
+                    u[0][i][1] = urow[1];
+                }
+#pragma unroll
                 for (int c = 0; c < kChunks; ++c) {
+                    if (c + 1 < kChunks) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4* urow = reinterpret_cast<const float4*>(table + (size_t)src[i] * kC + (c + 1) * 64) + 2 * kb;
+                            u[(c + 1) & 1][i][0] = urow[0];
+                            u[(c + 1) & 1][i][1] = urow[1];
+                        }
+                    }
                     const float4 v0 = *reinterpret_cast<const float4*>(s_vq + ql * 256 + c * 64 + kb * 8);
                     const float4 v1 = *reinterpret_cast<const float4*>(s_vq + ql * 256 + c * 64 + kb * 8 + 4);
-                    float4 u[4][2];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4* urow = reinterpret_cast<const float4*>(table + (size_t)src[i] * kC + c * 64) + 2 * kb;
-                        u[i][0] = urow[0];
-                        u[i][1] = urow[1];
-                    }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int r = ew * 16 + 4 * i + rs;
-                        float x[8] = {u[i][0].x + v0.x, u[i][0].y + v0.y, u[i][0].z + v0.z, u[i][0].w + v0.w,
-                                      u[i][1].x + v1.x, u[i][1].y + v1.y, u[i][1].z + v1.z, u[i][1].w + v1.w};
+                        const float4 a = u[c & 1][i][0], b = u[c & 1][i][1];
+                        float x[8] = {a.x + v0.x, a.y + v0.y, a.z + v0.z, a.w + v0.w, b.x + v1.x, b.y + v1.y, b.z + v1.z, b.w + v1.w};
 #pragma unroll
                         for (int t = 0; t < 8; ++t) x[t] = fmaxf(x[t], 0.f);
                         uint4 hi, lo;
@@ -257,9 +278,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                         *reinterpret_cast<uint4*>(smem + kOffAhi + (c * 8 + kb) * kALbo + r * 16) = hi;
                         *reinterpret_cast<uint4*>(smem + kOffAlo + (c * 8 + kb) * kALbo + r * 16) = lo;
                     }
-                    fence_async_smem();
-                    tc_fence_before();
-                    mbar_arrive(bar_chunk + 8 * c);
+                    warp_arrive(bar_chunk + 8 * c, lane);
                 }
             }
             {
@@ -283,22 +302,29 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll 1
                 for (int cb = 0; cb < kChunks; ++cb) {
                     const int col0 = cb * 64 + half * 32;
-                    float v[32];
-                    tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + dcol + col0, v);
+                    uint32_t v[32];
+                    tmem_ld32_issue(tmem + ((uint32_t)(lane_grp * 32) << 16) + dcol + col0, v);
+                    float4 bv[8];  // the chunk's bias, fetched while the TMEM load is in flight
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) bv[c] = *reinterpret_cast<const float4*>(bias + col0 + 4 * c);
+                    tmem_ld_wait(v);
 #pragma unroll
                     for (int kb = 0; kb < 4; ++kb) {
                         float x[8];
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) x[c] = fmaxf(v[kb * 8 + c] + bias[col0 + kb * 8 + c], 0.f);
+                        for (int c = 0; c < 2; ++c) {
+                            x[4 * c + 0] = fmaxf(__uint_as_float(v[kb * 8 + 4 * c + 0]) + bv[2 * kb + c].x, 0.f);
+                            x[4 * c + 1] = fmaxf(__uint_as_float(v[kb * 8 + 4 * c + 1]) + bv[2 * kb + c].y, 0.f);
+                            x[4 * c + 2] = fmaxf(__uint_as_float(v[kb * 8 + 4 * c + 2]) + bv[2 * kb + c].z, 0.f);
+                            x[4 * c + 3] = fmaxf(__uint_as_float(v[kb * 8 + 4 * c + 3]) + bv[2 * kb + c].w, 0.f);
+                        }
                         uint4 hi, lo;
                         split8(x, hi, lo);
                         const int kblk = (col0 >> 3) + kb;
                         *reinterpret_cast<uint4*>(smem + kOffAhi + kblk * kALbo + row * 16) = hi;
                         *reinterpret_cast<uint4*>(smem + kOffAlo + kblk * kALbo + row * 16) = lo;
                     }
-                    fence_async_smem();
-                    tc_fence_before();
-                    mbar_arrive(bar_chunk + 8 * cb);
+                    warp_arrive(bar_chunk + 8 * cb, lane);
                 }
                 {
                     const long long now = clock64();
@@ -319,13 +345,16 @@ __global__ void __launch_bounds__(kThreads, 1)
             if (lane_grp < 2) {
                 float e[64];
                 {
-                    float v[32];
-                    tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + half * 64, v);
+                    uint32_t v0[32], v1[32];
+                    tmem_ld32_issue(tmem + ((uint32_t)(lane_grp * 32) << 16) + half * 64, v0);
+                    tmem_ld32_issue(tmem + ((uint32_t)(lane_grp * 32) << 16) + half * 64 + 32, v1);
+                    tmem_ld_wait(v0);
+                    tmem_ld_wait(v1);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) e[j] = v[j];
-                    tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + half * 64 + 32, v);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) e[32 + j] = v[j];
+                    for (int j = 0; j < 32; ++j) {
+                        e[j] = __uint_as_float(v0[j]);
+                        e[32 + j] = __uint_as_float(v1[j]);
+                    }
                 }
                 // softmax over the 64 neighbours (the head's bias shifts every score alike and cancels)
                 float m = e[0];
@@ -363,10 +392,20 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll 1
                 for (int cb = 0; cb < kChunks; ++cb) {
                     const int col0 = cb * 64 + half * 32;
-                    float v[32];
-                    tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + 256u + col0, v);
+                    uint32_t vr[32];
+                    tmem_ld32_issue(tmem + ((uint32_t)(lane_grp * 32) << 16) + 256u + col0, vr);
+                    float4 bv[8];
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) v[c] = a * fmaxf(v[c] + bias[col0 + c], 0.f);
+                    for (int c = 0; c < 8; ++c) bv[c] = *reinterpret_cast<const float4*>(bias + col0 + 4 * c);
+                    tmem_ld_wait(vr);
+                    float v[32];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        v[4 * c + 0] = a * fmaxf(__uint_as_float(vr[4 * c + 0]) + bv[c].x, 0.f);
+                        v[4 * c + 1] = a * fmaxf(__uint_as_float(vr[4 * c + 1]) + bv[c].y, 0.f);
+                        v[4 * c + 2] = a * fmaxf(__uint_as_float(vr[4 * c + 2]) + bv[c].z, 0.f);
+                        v[4 * c + 3] = a * fmaxf(__uint_as_float(vr[4 * c + 3]) + bv[c].w, 0.f);
+                    }
 #pragma unroll
                     for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
                         const bool upper = (lane & off) != 0;

@@ -50,8 +50,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                   const float* __restrict__ bs1, const float* __restrict__ bs2, const float* __restrict__ bs3,
                   float* __restrict__ a1_out, float* __restrict__ g_out) {
     using namespace stn;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem[];  // used directly: the compiler keeps the shared address space (LDS/STS)
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float* s_par = reinterpret_cast<float*>(smem + kOffPar);
@@ -81,7 +80,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
             mbar_init(bar_empty + 8 * i, 1);
         }
         mbar_init(bar_accum, 1);
-        mbar_init(bar_aready, kPnEpiThreads);
+        mbar_init(bar_aready, kPnEpiThreads / 32);  // one elected arrival per warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -204,9 +203,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                     *reinterpret_cast<uint4*>(smem + kOffAlo + (hf * 4 + kb) * kPnLbo + r * 16) = lo;
                 }
             }
-            fence_async_smem();
-            tc_fence_before();
-            mbar_arrive(bar_aready);
+            warp_arrive(bar_aready, lane);
 
             const long long q_row = 2 * tile + (row >> 6);
             const int p_row = row & 63;
@@ -241,9 +238,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                         *reinterpret_cast<uint4*>(smem + kOffAlo + kblk * kPnLbo + row * 16) = lo;
                     }
                 }
-                fence_async_smem();
-                tc_fence_before();
-                mbar_arrive(bar_aready);
+                warp_arrive(bar_aready, lane);
             }
             // ---- stn.conv3 transposed: TMEM lane = feature, columns = rows of the tile; max over the patch's points
             mbar_wait(bar_accum, accum_phase);
@@ -306,8 +301,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                    const uint8_t* __restrict__ wpack, const float* __restrict__ b1, const float* __restrict__ b2,
                    const float* __restrict__ wq, float* __restrict__ pooled) {
     using namespace feat;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem[];  // used directly: the compiler keeps the shared address space (LDS/STS)
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float* s_b1 = reinterpret_cast<float*>(smem + kOffPar);
@@ -330,7 +324,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
             mbar_init(bar_empty + 8 * i, 1);
         }
         mbar_init(bar_accum, 1);
-        mbar_init(bar_aready, kPnEpiThreads);
+        mbar_init(bar_aready, kPnEpiThreads / 32);  // one elected arrival per warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -455,9 +449,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                 *reinterpret_cast<uint4*>(smem + kOffT + (2 * ql) * kTBytes + kb * kTLbo + i * 16) = hi;
                 *reinterpret_cast<uint4*>(smem + kOffT + (2 * ql + 1) * kTBytes + kb * kTLbo + i * 16) = lo;
             }
-            fence_async_smem();
-            tc_fence_before();
-            mbar_arrive(bar_aready);
+            warp_arrive(bar_aready, lane);
 
             const long long q_row = 2 * tile + (row >> 6);
             const bool row_valid = q_row < nq && (row & 63) < P;
@@ -479,9 +471,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                     *reinterpret_cast<uint4*>(smem + kOffAlo + (half * 4 + kb) * kPnLbo + row * 16) = lo;
                 }
             }
-            fence_async_smem();
-            tc_fence_before();
-            mbar_arrive(bar_aready);
+            warp_arrive(bar_aready, lane);
             // ---- conv1: bias + ReLU -> operand tile
             mbar_wait(bar_accum, accum_phase);
             accum_phase ^= 1;
@@ -500,9 +490,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                     *reinterpret_cast<uint4*>(smem + kOffAlo + (half * 4 + kb) * kPnLbo + row * 16) = lo;
                 }
             }
-            fence_async_smem();
-            tc_fence_before();
-            mbar_arrive(bar_aready);
+            warp_arrive(bar_aready, lane);
             // ---- conv2: bias + ReLU -> c2 (hi/lo tile for the pooling) and this thread's share of the attention logit
             mbar_wait(bar_accum, accum_phase);
             accum_phase ^= 1;
