@@ -29,15 +29,17 @@ constexpr int kKB = kC / 8;                 // k8 blocks per row
 constexpr int kALbo = kRows * 16 + 16;      // bytes between k8 blocks of an activation tile (padded)
 constexpr int kABytes = kKB * kALbo;        // 66048
 constexpr int kStageBytes = 16384;          // one k16 step of a 256-wide layer: W_hi 8 KB + W_lo 8 KB
-constexpr int kStageBytesQ = 8192;          // fc_query as the M operand: 128 rows (64 heads + 64 zero rows) x k16, hi + lo
+constexpr int kStageBytesQ = 8192;          // fc_query as the M operand: 128 rows (64 zero rows + 64 heads) x k16, hi + lo
 constexpr int kStages = 5;
 constexpr int kKSteps = kC / 16;            // 16 k16 steps per layer
 constexpr int kChunks = 4;                  // a layer's K range is released to the MMA warp in 4 chunks of 64 columns
-constexpr int kEpiWarps = 8;
-constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kThreads = 64 + kEpiThreads;  // 320
+constexpr int kGWarps = 8;                  // gather + fc2/fc3 epilogues
+constexpr int kSWarps = 6;                  // softmax + attention pooling
+constexpr int kGThreads = kGWarps * 32;
+constexpr int kSThreads = kSWarps * 32;
+constexpr int kThreads = 64 + kGThreads + kSThreads;  // 512
 
-// shared memory map (bytes from the 1024-aligned base)
+// shared memory map (bytes from the base)
 constexpr int kOffAhi = 0;
 constexpr int kOffAlo = kOffAhi + kABytes;
 constexpr int kOffRing = kOffAlo + kABytes;                  // 132096
@@ -46,24 +48,30 @@ constexpr int kOffAttp = kOffBias + (256 + 256 + 64) * 4;    // 216320: [head ha
 constexpr int kOffPool = kOffAttp + 2 * 2 * 64 * 4;          // 217344: [lane group][256] partial pooled sums
 constexpr int kOffW1 = kOffPool + 4 * 256 * 4;               // 221440: fc1 xyz weights [256][3]
 constexpr int kOffVq = kOffW1 + 768 * 4;                     // 224512: W1_xyz . q for the tile's 2 queries [2][256]
-constexpr int kOffBar = kOffVq + 2 * 256 * 4;                // 226560: full[5] empty[5] accum chunk[4]
-constexpr int kOffTmem = kOffBar + (2 * kStages + 1 + kChunks) * 8;
-constexpr int kSmemBytes = kOffTmem + 16 + 1024;             // + alignment slack
+constexpr int kOffBar = kOffVq + 2 * 256 * 4;                // 226560: full[5] empty[5] acc[3] chunk[4] d0free d1free
+constexpr int kNumBars = 2 * kStages + 3 + kChunks + 2;
+constexpr int kOffTmem = kOffBar + kNumBars * 8;
+constexpr int kSmemBytes = kOffTmem + 16;
 
 // packed weights in global memory: [fc2: 16 stages][fc3: 16 stages][fc_query: 16 stages]
 constexpr size_t kPackBytes = size_t(2) * kKSteps * kStageBytes + size_t(kKSteps) * kStageBytesQ;
 
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+__device__ __forceinline__ void g_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kGThreads) : "memory"); }
+__device__ __forceinline__ void s_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(kSThreads) : "memory"); }
 
 // Pipeline of one tile (2 queries x 64 neighbours):
-//   gather -> fc2 (D0) -> E2 -> fc3 (D1) -> E3 -> fc_query^T (D0) -> softmax / head mean / pooling
-// The epilogue E_l rewrites the operand tile in place 64 columns at a time and releases each chunk through its own
-// mbarrier, so layer l+1's MMAs (other accumulator) start after the first quarter of E_l and overlap the rest.
-// fc_query is computed TRANSPOSED (heads on the TMEM lanes, the tile's rows on the columns): the softmax over a
-// query's 64 neighbours is then a reduction inside one thread; the mean over heads is a butterfly across lanes.
-// CS = CTAs per cluster: the CTAs of a cluster consume the same weight stages in lockstep, each fetches 1/CS of a stage and
-// multicasts it into every member's ring slot (the weight stream is L2-bandwidth bound: 16 KB per 384 tensor cycles and SM)
-template <int CS>
+//   gather -> fc2 (D0) -> E2 -> fc3 (D1) -> E3 -> fc_query^T (D0) -> softmax / head mean / pooling from D1
+// Warp roles (512 threads, one persistent CTA per SM):
+//   warp 0       weight producer: cp.async.bulk of pre-packed k16 weight stages into a 5-slot ring
+//   warp 1       MMA issuer (one thread)
+//   warps 2..9   G group: gather of the fc1 table rows (+ W1_xyz.q, ReLU, fp16 hi/lo split) and the fc2 / fc3 epilogues.  Every
+//                epilogue rewrites the operand tile in place 64 columns at a time and releases each chunk through its own
+//                mbarrier, so the next layer's MMAs (other accumulator) overlap it.
+//   warps 10..15 S group: softmax over the neighbours, head mean and the attention pooling of tile t run while the G group and
+//                the tensor pipe are already working on tile t+1 (D0 is handed back as soon as the scores are in registers,
+//                D1 when the pooling has read fc3's accumulator).
+// fc_query is computed TRANSPOSED (heads on TMEM lanes 64..127, the tile's rows on the columns): the softmax over a query's
+// 64 neighbours is then a reduction inside one thread; the mean over heads is a recursive halving across lanes.
 __global__ void __launch_bounds__(kThreads, 1)
     projection_tc_kernel(const float* __restrict__ table, const float* __restrict__ queries, const int32_t* __restrict__ idx, int ks,
                          long long nq, const uint8_t* __restrict__ wpack, const float* __restrict__ b2, const float* __restrict__ b3,
@@ -77,8 +85,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     float* s_w1 = reinterpret_cast<float*>(smem + kOffW1);
     float* s_vq = reinterpret_cast<float*>(smem + kOffVq);
     volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + kOffTmem);
-    const uint32_t bar_full = sbase + kOffBar, bar_empty = bar_full + 8 * kStages, bar_accum = bar_empty + 8 * kStages,
-                   bar_chunk = bar_accum + 8;
+    const uint32_t bar_full = sbase + kOffBar, bar_empty = bar_full + 8 * kStages, bar_acc = bar_empty + 8 * kStages,
+                   bar_chunk = bar_acc + 8 * 3, bar_d0free = bar_chunk + 8 * kChunks, bar_d1free = bar_d0free + 8;
 
     for (int e = tid; e < 768; e += kThreads) {
         s_w1[e] = w1_xyz[e];
@@ -91,10 +99,12 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (tid == 0) {
         for (int i = 0; i < kStages; ++i) {
             mbar_init(bar_full + 8 * i, 1);
-            mbar_init(bar_empty + 8 * i, CS);  // every CTA of the cluster releases the slot in every member
+            mbar_init(bar_empty + 8 * i, 1);
         }
-        mbar_init(bar_accum, 1);
-        for (int i = 0; i < kChunks; ++i) mbar_init(bar_chunk + 8 * i, kEpiWarps);  // one elected arrival per warp
+        for (int i = 0; i < 3; ++i) mbar_init(bar_acc + 8 * i, 1);  // accumulator of fc2 / fc3 / fc_query complete
+        for (int i = 0; i < kChunks; ++i) mbar_init(bar_chunk + 8 * i, kGWarps);  // one elected arrival per G warp
+        mbar_init(bar_d0free, 4);        // the four softmax warps hold the scores in registers
+        mbar_init(bar_d1free, kSWarps);  // the pooling has read fc3's accumulator
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -103,15 +113,11 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     tc_fence_before();
     __syncthreads();
-    if (CS > 1) cluster_sync_all();  // barriers of every member are initialised before any remote arrive / multicast
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
 
     const long long ntiles = (nq + 1) / 2;
-    // every CTA runs the same number of iterations (lockstep weight ring); surplus iterations redo the last tile silently
-    const long long iters = (ntiles + gridDim.x - 1) / gridDim.x;
-    constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1u);
-    const uint32_t crank = CS > 1 ? cluster_ctarank() : 0u;
+    const long long iters = ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     if (warp == 0) {
         // ---------------------------------------------------------------- weight producer
@@ -124,13 +130,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                     for (int s = 0; s < kKSteps; ++s) {
                         mbar_wait(bar_empty + 8 * slot, phase ^ 1);
                         mbar_expect_tx(bar_full + 8 * slot, bytes);
-                        if (CS == 1) {
-                            bulk_copy(sbase + kOffRing + slot * kStageBytes, src, bytes, bar_full + 8 * slot);
-                        } else {
-                            const uint32_t part = bytes / CS;
-                            bulk_copy_multicast(sbase + kOffRing + slot * kStageBytes + crank * part, src + crank * part, part,
-                                                bar_full + 8 * slot, kMask);
-                        }
+                        bulk_copy(sbase + kOffRing + slot * kStageBytes, src, bytes, bar_full + 8 * slot);
                         src += bytes;
                         if (++slot == kStages) {
                             slot = 0;
@@ -144,11 +144,17 @@ __global__ void __launch_bounds__(kThreads, 1)
         // ---------------------------------------------------------------- MMA issuer
         if (lane == 0) {
             uint32_t slot = 0, phase = 0, chunk_phase = 0;
-            long long t_chunk = 0, t_full = 0, t_total = clock64();
+            long long t_chunk = 0, t_full = 0, t_dfree = 0, t_total = clock64();
             for (long long it = 0; it < iters; ++it) {
                 for (int layer = 0; layer < 3; ++layer) {
                     const uint32_t idesc = umma_idesc(layer < 2 ? 256 : 128);
                     const uint32_t dcol = layer == 1 ? 256u : 0u;
+                    if (it > 0 && layer < 2) {  // the S group has taken what it needs of the previous tile out of this accumulator
+                        const long long t0 = clock64();
+                        mbar_wait(layer == 0 ? bar_d0free : bar_d1free, (uint32_t)((it - 1) & 1));
+                        tc_fence_after();
+                        t_dfree += clock64() - t0;
+                    }
                     for (int s = 0; s < kKSteps; ++s) {
                         long long t0 = clock64();
                         if ((s & 3) == 0) {  // operand columns [64c, 64c+64) written by the previous stage of the pipeline
@@ -170,79 +176,69 @@ __global__ void __launch_bounds__(kThreads, 1)
                             umma(tmem + dcol, x_hi, w_hi, idesc, s > 0 ? 1u : 0u);
                             umma(tmem + dcol, x_lo, w_hi, idesc, 1u);
                             umma(tmem + dcol, x_hi, w_lo, idesc, 1u);
-                        } else {  // scores^T[head, row] = Wq[head, :] . h3[row, :]
+                        } else {  // scores^T[64 + head, row] = Wq[head, :] . h3[row, :]
                             const uint64_t w_hi = umma_desc(wst, 128 * 16, 128);
                             const uint64_t w_lo = umma_desc(wst + 4096, 128 * 16, 128);
                             umma(tmem, w_hi, x_hi, idesc, s > 0 ? 1u : 0u);
                             umma(tmem, w_hi, x_lo, idesc, 1u);
                             umma(tmem, w_lo, x_hi, idesc, 1u);
                         }
-                        if (CS == 1)
-                            tc_commit(bar_empty + 8 * slot);  // frees the ring slot when these MMAs have read it
-                        else
-                            tc_commit_multicast(bar_empty + 8 * slot, kMask);  // ... in every member of the cluster
+                        tc_commit(bar_empty + 8 * slot);  // frees the ring slot when these MMAs have read it
                         if (++slot == kStages) {
                             slot = 0;
                             phase ^= 1;
                         }
                     }
-                    tc_commit(bar_accum);  // accumulator of this layer complete
+                    tc_commit(bar_acc + 8 * layer);  // accumulator of this layer complete
                     chunk_phase ^= 1;
                 }
             }
-            if (prof && blockIdx.x == 0) {  // cycles: [0] MMA warp total, [1] waiting for operand chunks, [2] waiting for weights
+            if (prof && blockIdx.x == 0) {  // cycles: MMA warp total, waiting for operand chunks / weights / the S group
                 prof[0] = clock64() - t_total;
                 prof[1] = t_chunk;
                 prof[2] = t_full;
+                prof[3] = t_dfree;
             }
         }
-    } else {
-        // ---------------------------------------------------------------- gather + epilogue warps
+    } else if (warp < 2 + kGWarps) {
+        // ---------------------------------------------------------------- G group: gather + fc2 / fc3 epilogues
         const int ew = warp - 2;               // 0..7
+        const int gt = tid - 64;               // 0..255
         const int lane_grp = warp & 3;         // TMEM lanes this warp may touch: 32*lane_grp .. +31
-        const int half = ew >> 2;              // which half of every 64-column chunk (E2/E3) / which query (scores)
+        const int half = ew >> 2;              // which half of every 64-column chunk
         const int row = lane_grp * 32 + lane;  // accumulator row (= TMEM lane) of this thread
-        uint32_t accum_phase = 0;
-        long long t_gather = 0, t_wait = 0, t_epi = 0, t_att = 0, t_mark = clock64();
-        long long t_w[3] = {0, 0, 0};
+        const int kb = lane & 7, rs = lane >> 3;
+        const int ql = (ew * 16) >> 6;         // the query whose rows this warp gathers
+        long long t_gather = 0, t_wait = 0, t_epi = 0, t_mark = clock64();
 
         int src_next[4];
         {
-            long long t0 = blockIdx.x < ntiles ? blockIdx.x : ntiles - 1;
-            long long q = 2 * t0 + ((ew * 16) >> 6);
+            long long q = 2 * (long long)blockIdx.x + ql;
             q = q < nq ? q : nq - 1;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) src_next[i] = idx[q * ks + ((ew * 16 + 4 * i + (lane >> 3)) & 63)];
+            for (int i = 0; i < 4; ++i) src_next[i] = idx[q * ks + ((ew * 16 + 4 * i + rs) & 63)];
         }
         for (long long it = 0; it < iters; ++it) {
-            long long tile = blockIdx.x + it * gridDim.x;
-            const bool live = tile < ntiles;  // surplus iteration: same work on the last tile, nothing is written
-            tile = live ? tile : ntiles - 1;
-            // ---- W1_xyz . q for the two queries of the tile (the previous tile's readers are behind the end-of-tile barrier)
-            {
-                const int et = tid - 64;  // 0..255 = channel, both queries
+            const long long tile = blockIdx.x + it * gridDim.x;
+            // ---- W1_xyz . q for the two queries of the tile.  Every G warp is past the previous tile's gather (this warp saw
+            // fc2's accumulator complete, which needs every warp's chunk arrivals), so s_vq may be overwritten
 #pragma unroll
-                for (int ql = 0; ql < 2; ++ql) {
-                    long long q = 2 * tile + ql;
-                    q = q < nq ? q : nq - 1;
-                    s_vq[ql * 256 + et] = s_w1[3 * et] * queries[3 * q] + s_w1[3 * et + 1] * queries[3 * q + 1] +
-                                          s_w1[3 * et + 2] * queries[3 * q + 2];
-                }
+            for (int t = 0; t < 2; ++t) {
+                long long q = 2 * tile + t;
+                q = q < nq ? q : nq - 1;
+                s_vq[t * 256 + gt] = s_w1[3 * gt] * queries[3 * q] + s_w1[3 * gt + 1] * queries[3 * q + 1] +
+                                     s_w1[3 * gt + 2] * queries[3 * q + 2];
             }
-            epi_barrier();
+            g_barrier();
             // ---- gather: h1 = relu(U[idx] + W1_xyz.q) -> A_hi/A_lo, one 64-column chunk after the other so that fc2's first
             // k-steps start after a quarter of the gather.  Warp ew owns rows 16*ew .. +15 (all of one query); per chunk a lane
             // owns k8 block (lane & 7) of row 4*i + (lane >> 3): 8 lanes read 256 contiguous bytes of a table row
             {
-                const int kb = lane & 7, rs = lane >> 3;
-                const int ql = (ew * 16) >> 6;
                 int src[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) src[i] = src_next[i];
-                {  // neighbour ids of the NEXT tile: their latency hides behind this tile
-                    long long tn = blockIdx.x + (it + 1) * gridDim.x;
-                    tn = tn < ntiles ? tn : ntiles - 1;
-                    long long q = 2 * tn + ql;
+                if (it + 1 < iters) {  // neighbour ids of the NEXT tile: their latency hides behind this tile
+                    long long q = 2 * (tile + gridDim.x) + ql;
                     q = q < nq ? q : nq - 1;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) src_next[i] = idx[q * ks + ((ew * 16 + 4 * i + rs) & 63)];
@@ -253,6 +249,14 @@ __global__ void __launch_bounds__(kThreads, 1)
                     const float4* urow = reinterpret_cast<const float4*>(table + (size_t)src[i] * kC) + 2 * kb;
                     u[0][i][0] = urow[0];
                     u[0][i][1] = urow[1];
+                }
+                if (it > 0) {  // the operand tile is free when fc_query of the previous tile has read it
+                    mbar_wait(bar_acc + 16, (uint32_t)((it - 1) & 1));
+                }
+                {
+                    const long long now = clock64();
+                    t_wait += now - t_mark;
+                    t_mark = now;
                 }
 #pragma unroll
                 for (int c = 0; c < kChunks; ++c) {
@@ -289,8 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 
             // ---- fc2 / fc3 epilogues: D -> +bias, ReLU, split -> A in place, released chunk by chunk
             for (int layer = 0; layer < 2; ++layer) {
-                mbar_wait(bar_accum, accum_phase);
-                accum_phase ^= 1;
+                mbar_wait(bar_acc + 8 * layer, (uint32_t)(it & 1));
                 tc_fence_after();
                 {
                     const long long now = clock64();
@@ -309,18 +312,18 @@ __global__ void __launch_bounds__(kThreads, 1)
                     for (int c = 0; c < 8; ++c) bv[c] = *reinterpret_cast<const float4*>(bias + col0 + 4 * c);
                     tmem_ld_wait(v);
 #pragma unroll
-                    for (int kb = 0; kb < 4; ++kb) {
+                    for (int k8 = 0; k8 < 4; ++k8) {
                         float x[8];
 #pragma unroll
                         for (int c = 0; c < 2; ++c) {
-                            x[4 * c + 0] = fmaxf(__uint_as_float(v[kb * 8 + 4 * c + 0]) + bv[2 * kb + c].x, 0.f);
-                            x[4 * c + 1] = fmaxf(__uint_as_float(v[kb * 8 + 4 * c + 1]) + bv[2 * kb + c].y, 0.f);
-                            x[4 * c + 2] = fmaxf(__uint_as_float(v[kb * 8 + 4 * c + 2]) + bv[2 * kb + c].z, 0.f);
-                            x[4 * c + 3] = fmaxf(__uint_as_float(v[kb * 8 + 4 * c + 3]) + bv[2 * kb + c].w, 0.f);
+                            x[4 * c + 0] = fmaxf(__uint_as_float(v[k8 * 8 + 4 * c + 0]) + bv[2 * k8 + c].x, 0.f);
+                            x[4 * c + 1] = fmaxf(__uint_as_float(v[k8 * 8 + 4 * c + 1]) + bv[2 * k8 + c].y, 0.f);
+                            x[4 * c + 2] = fmaxf(__uint_as_float(v[k8 * 8 + 4 * c + 2]) + bv[2 * k8 + c].z, 0.f);
+                            x[4 * c + 3] = fmaxf(__uint_as_float(v[k8 * 8 + 4 * c + 3]) + bv[2 * k8 + c].w, 0.f);
                         }
                         uint4 hi, lo;
                         split8(x, hi, lo);
-                        const int kblk = (col0 >> 3) + kb;
+                        const int kblk = (col0 >> 3) + k8;
                         *reinterpret_cast<uint4*>(smem + kOffAhi + kblk * kALbo + row * 16) = hi;
                         *reinterpret_cast<uint4*>(smem + kOffAlo + kblk * kALbo + row * 16) = lo;
                     }
@@ -332,22 +335,38 @@ __global__ void __launch_bounds__(kThreads, 1)
                     t_mark = now;
                 }
             }
-
-            // ---- scores^T: TMEM lane = head (lanes 0..63 are real), columns = rows of the tile; this warp's query = half
-            mbar_wait(bar_accum, accum_phase);
-            accum_phase ^= 1;
+        }
+        if (prof && blockIdx.x == 0 && tid == 64) {  // cycles of G warp 0: gather, waiting for MMAs, E2 + E3
+            prof[4] = t_gather;
+            prof[5] = t_wait;
+            prof[6] = t_epi;
+        }
+    } else {
+        // ---------------------------------------------------------------- S group: softmax, head mean, attention pooling
+        const int sw = warp - 2 - kGWarps;     // 0..5: warps 10..15 own TMEM lane groups 2,3,0,1,2,3
+        const int st = tid - 64 - kGThreads;   // 0..191
+        const int lane_grp = warp & 3;
+        const int row = lane_grp * 32 + lane;
+        const bool heads = lane_grp >= 2;      // scores^T lives on lanes 64..127: two warps per lane group, one per query
+        const int sq = sw >> 2;                // the query whose softmax this warp computes (heads only)
+        // pooling: rows 0..63 (lane groups 0,1) have one warp each -> all 8 column blocks; rows 64..127 have two warps each
+        const int cb0 = heads ? 4 * sq : 0, cb1 = heads ? 4 * sq + 4 : 8;
+        long long t_wait = 0, t_soft = 0, t_pool = 0, t_mark = clock64();
+        for (long long it = 0; it < iters; ++it) {
+            const long long tile = blockIdx.x + it * gridDim.x;
+            mbar_wait(bar_acc + 16, (uint32_t)(it & 1));
             tc_fence_after();
             {
                 const long long now = clock64();
                 t_wait += now - t_mark;
                 t_mark = now;
             }
-            if (lane_grp < 2) {
+            if (heads) {
                 float e[64];
                 {
                     uint32_t v0[32], v1[32];
-                    tmem_ld32_issue(tmem + ((uint32_t)(lane_grp * 32) << 16) + half * 64, v0);
-                    tmem_ld32_issue(tmem + ((uint32_t)(lane_grp * 32) << 16) + half * 64 + 32, v1);
+                    tmem_ld32_issue(tmem + ((uint32_t)(lane_grp * 32) << 16) + sq * 64, v0);
+                    tmem_ld32_issue(tmem + ((uint32_t)(lane_grp * 32) << 16) + sq * 64 + 32, v1);
                     tmem_ld_wait(v0);
                     tmem_ld_wait(v1);
 #pragma unroll
@@ -356,6 +375,9 @@ __global__ void __launch_bounds__(kThreads, 1)
                         e[32 + j] = __uint_as_float(v1[j]);
                     }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_d0free);  // fc2 of the next tile may overwrite the scores
                 // softmax over the 64 neighbours (the head's bias shifts every score alike and cancels)
                 float m = e[0];
 #pragma unroll
@@ -380,24 +402,33 @@ __global__ void __launch_bounds__(kThreads, 1)
                         e[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
                     }
                 }
-                *reinterpret_cast<float2*>(s_attp + (lane_grp * 2 + half) * 64 + 2 * lane) = make_float2(e[0], e[1]);
+                *reinterpret_cast<float2*>(s_attp + ((lane_grp - 2) * 2 + sq) * 64 + 2 * lane) = make_float2(e[0], e[1]);
             }
-            tc_fence_before();
-            epi_barrier();
+            s_barrier();
+            {
+                const long long now = clock64();
+                t_soft += now - t_mark;
+                t_mark = now;
+            }
             // pooled[q, :] = sum_j att_j * h3[j, :] straight from the fp32 accumulator of fc3 (still in TMEM): every thread
             // scales its row, the 32 rows of a warp are summed by recursive halving (lane l ends with column l of the block)
             {
                 const float a = (s_attp[(row >> 6) * 64 + (row & 63)] + s_attp[(2 + (row >> 6)) * 64 + (row & 63)]) * (1.f / kHeads);
                 const float* bias = s_bias + 256;
 #pragma unroll 1
-                for (int cb = 0; cb < kChunks; ++cb) {
-                    const int col0 = cb * 64 + half * 32;
+                for (int cb = cb0; cb < cb1; ++cb) {
+                    const int col0 = cb * 32;
                     uint32_t vr[32];
                     tmem_ld32_issue(tmem + ((uint32_t)(lane_grp * 32) << 16) + 256u + col0, vr);
                     float4 bv[8];
 #pragma unroll
                     for (int c = 0; c < 8; ++c) bv[c] = *reinterpret_cast<const float4*>(bias + col0 + 4 * c);
                     tmem_ld_wait(vr);
+                    if (cb == cb1 - 1) {  // last read of fc3's accumulator: fc3 of the next tile may overwrite it
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_d1free);
+                    }
                     float v[32];
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
@@ -419,35 +450,28 @@ __global__ void __launch_bounds__(kThreads, 1)
                     s_pool[lane_grp * 256 + col0 + lane] = v[0];
                 }
             }
-            tc_fence_before();
-            epi_barrier();
-            {
-                const int et = tid - 64;
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    const int ql = t, c = et;
-                    const long long q = 2 * tile + ql;
-                    if (q < nq && live) pooled[q * kC + c] = s_pool[(2 * ql) * 256 + c] + s_pool[(2 * ql + 1) * 256 + c];
-                }
+            s_barrier();
+            for (int e = st; e < 2 * kC; e += kSThreads) {
+                const int t = e >> 8, c = e & 255;
+                const long long q = 2 * tile + t;
+                if (q < nq) pooled[q * kC + c] = s_pool[(2 * t) * 256 + c] + s_pool[(2 * t + 1) * 256 + c];
             }
-            epi_barrier();  // every warp is done with A and the head sums before the next tile's gather overwrites them
+            s_barrier();  // the head sums and partial pooled sums are consumed before the next tile overwrites them
             {
                 const long long now = clock64();
-                t_att += now - t_mark;
+                t_pool += now - t_mark;
                 t_mark = now;
             }
         }
-        if (prof && blockIdx.x == 0 && tid == 64) {  // cycles of epilogue warp 0: gather, waiting for MMAs, E2+E3, softmax+pooling
-            prof[3] = t_gather;
-            prof[4] = t_wait;
-            prof[5] = t_epi;
-            prof[6] = t_att;
+        if (prof && blockIdx.x == 0 && st == 0) {  // cycles of S warp 0: waiting for fc_query, softmax, pooling
+            prof[7] = t_wait;
+            prof[8] = t_soft;
+            prof[9] = t_pool;
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (CS > 1) cluster_sync_all();  // no member exits while a peer may still multicast into it or arrive on its barriers
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
@@ -457,9 +481,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 
 }  // namespace tc
 
-static int g_tc_cluster = 1;             // CTAs per cluster (1, 2 or 4) sharing multicast weight stages.  Measured on B200:
-                                         // 2 = no gain (the ring refill is latency-, not L2-bandwidth-bound), 4 strands 16 SMs
-static long long* g_tc_prof = nullptr;  // device buffer of 8 counters, set by pps_debug_tc_profile
+static long long* g_tc_prof = nullptr;  // device buffer of 16 counters, set by pps_debug_tc_profile
 
 size_t projection_tc_workspace(const pps_decoder_weights*, int64_t) { return 256; }
 
@@ -471,40 +493,16 @@ int projection_tc_impl(const pps_decoder_weights* w, const float* table, const f
     if (q == 0) return PPS_OK;
     static bool configured = false;
     if (!configured) {
-        PPS_CUDA(cudaFuncSetAttribute(tc::projection_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
-        PPS_CUDA(cudaFuncSetAttribute(tc::projection_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
-        PPS_CUDA(cudaFuncSetAttribute(tc::projection_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+        PPS_CUDA(cudaFuncSetAttribute(tc::projection_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
         configured = true;
     }
-    long long ntiles = (q + 1) / 2;
-    int cs = g_tc_cluster;
-    if (ntiles < 2 * cs) cs = 1;
-    int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
-    grid -= grid % cs;  // whole clusters only; 148 = 4 * 37
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(tc::kThreads);
-    cfg.dynamicSmemBytes = tc::kSmemBytes;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cs;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    const long long ntiles = (q + 1) / 2;
+    const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
     const uint8_t* wp = static_cast<const uint8_t*>(w->tc_wpack);
-    long long nq = q;
+    const long long nq = q;
     profile_begin(st);
-    if (cs == 4)
-        PPS_CUDA(cudaLaunchKernelEx(&cfg, tc::projection_tc_kernel<4>, table, queries, idx, k_stride, nq, wp, w->b2, w->b3, w->bq,
-                                    w->w1_xyz, pooled, g_tc_prof));
-    else if (cs == 2)
-        PPS_CUDA(cudaLaunchKernelEx(&cfg, tc::projection_tc_kernel<2>, table, queries, idx, k_stride, nq, wp, w->b2, w->b3, w->bq,
-                                    w->w1_xyz, pooled, g_tc_prof));
-    else
-        PPS_CUDA(cudaLaunchKernelEx(&cfg, tc::projection_tc_kernel<1>, table, queries, idx, k_stride, nq, wp, w->b2, w->b3, w->bq,
-                                    w->w1_xyz, pooled, g_tc_prof));
+    tc::projection_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, st>>>(table, queries, idx, k_stride, nq, wp, w->b2, w->b3, w->bq,
+                                                                       w->w1_xyz, pooled, g_tc_prof);
     PPS_LAUNCH_CHECK();
     profile_end(st);
     return PPS_OK;
@@ -513,8 +511,8 @@ int projection_tc_impl(const pps_decoder_weights* w, const float* table, const f
 }  // namespace pps
 
 extern "C" size_t pps_decoder_tc_pack_bytes(void) { return pps::tc::kPackBytes; }
-// debug: CTA 0 of projection_tc_kernel writes its per-phase cycle counters into `counters` (8 x int64, device memory);
+// debug: CTA 0 of projection_tc_kernel writes its per-phase cycle counters into `counters` (16 x int64, device memory);
 // pass NULL to switch the instrumentation output off
 extern "C" void pps_debug_tc_profile(long long* counters) { pps::g_tc_prof = counters; }
-// tuning knob: CTAs per cluster (1, 2, 4) sharing multicast weight stages in the tensor-core projection kernel
-extern "C" void pps_debug_tc_cluster(int cs) { pps::g_tc_cluster = (cs == 4 || cs == 2) ? cs : 1; }
+// retired tuning knob (cluster multicast of the weight stages measured no gain on B200); kept so that the ABI is stable
+extern "C" void pps_debug_tc_cluster(int) {}

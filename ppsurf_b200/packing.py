@@ -98,7 +98,8 @@ def pack_decoder(sd, device, k, num_pts_local, prefix='') -> Packed:
     p.put('m2_w', _mat(sd, m + '2.0.weight'), device)
     p.put('m2_b', _f64(sd, m + '2.0.bias'), device)
     if latent == 256 and st.heads == 64:
-        wq_pad = torch.cat([_mat(sd, g + 'fc_query.weight'), torch.zeros(64, latent, dtype=torch.float64)])  # M operand: 128 rows
+        # M operand of the transposed fc_query: 64 zero rows, then the 64 heads (TMEM lanes 64..127)
+        wq_pad = torch.cat([torch.zeros(64, latent, dtype=torch.float64), _mat(sd, g + 'fc_query.weight')])
         pack = torch.cat([tc_pack_matrix(_mat(sd, g + 'fc2.weight')), tc_pack_matrix(_mat(sd, g + 'fc3.weight')),
                           tc_pack_matrix(wq_pad)])
         assert pack.numel() == _lib.lib.pps_decoder_tc_pack_bytes()

@@ -20,11 +20,11 @@ dec = ops.Decoder(net.packed()['decoder'], pts, lat, chunk=16384, path=1)
 step, bmin_pad, _ = ppsurf_b200.PPSurfModel.grid_definition(pts.cpu().numpy(), 129, 1)
 qry = ops.grid_queries(131, step, bmin_pad, first=131 * 131 * 60, count=16384, device=dev)
 idx = dec.index.query(qry, 64)
-counters = torch.zeros(8, dtype=torch.int64, device=dev)
+counters = torch.zeros(16, dtype=torch.int64, device=dev)
 tiles = (16384 // 2 + 147) // 148
-names = ['mma_total', 'mma_wait_chunk', 'mma_wait_weights', 'epi_gather', 'epi_wait_mma', 'epi_E2E3', 'epi_softmax_pool']
+names = ['mma_total', 'mma_wait_chunk', 'mma_wait_weights', 'mma_wait_sgroup', 'g_gather', 'g_wait', 'g_E2E3', 's_wait', 's_softmax', 's_pool']
 ref = None
-for cs in (1, 2, 4):
+for cs in (1,):
     _lib.lib.pps_debug_tc_cluster(cs)
     for it in range(3):
         _lib.lib.pps_debug_tc_profile(counters.data_ptr())
