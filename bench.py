@@ -46,7 +46,9 @@ def parse_args():
     ap.add_argument('--chunk', type=int, default=18944,
                     help='queries per decode launch; 18944 = 148 SMs x 128 rows: whole waves for every tensor-core kernel')
     ap.add_argument('--latents', default='encoder', choices=['encoder', 'random'])
-    ap.add_argument('--cpu-sample', type=int, default=4096, help='queries of the CPU baseline sample')
+    ap.add_argument('--cpu-sample', type=int, default=65536,
+                    help='queries of the CPU baseline sample (about 10-15 s of host work on 16 cores)')
+    ap.add_argument('--ref-sample', type=int, default=16384, help='queries per step of the --impl reference arm')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-run', action='store_true', help='for ncu captures only: no minimum warm-up, no e2e leg')
     return ap.parse_args()
@@ -118,17 +120,29 @@ def workload_name(args):
 # CPU legs (oracle = checker / baseline only)
 # ---------------------------------------------------------------------------------------------------------------------
 
+REFERENCE_BATCH = 50000  # rec_batch_size of configs/poco.yaml:52: the reference rebuilds its kd-tree once per such batch
+CPU_SUB_BATCH = 8192     # the network part runs in sub-batches so that the [Q,64,259] intermediates stay below ~1 GB
+
+
 def cpu_decode(oracle, weights, pts, latents_cn, queries, num_pts_local):
     """the reference's per-batch work on the host cores: kd-tree build + k=64 / k=P queries, patch normalisation, both
     branches, MLP, softmax difference (reference formulation, torch CPU ops on all threads)"""
     import torch
     from oracle import ppsurf_oracle_torch as oracle_torch
     kmax = max(64, num_pts_local)
-    idx, _ = oracle.knn_kdtree(pts, queries, kmax)
-    loc = oracle.normalize_patches(pts[idx[:, :num_pts_local]], queries)
-    occ, _ = oracle_torch.from_latent(weights, torch.from_numpy(pts), torch.from_numpy(np.ascontiguousarray(latents_cn.T)),
-                                      torch.from_numpy(queries), torch.from_numpy(idx[:, :64].copy()), torch.from_numpy(loc))
-    return occ.numpy()
+    pts_t = torch.from_numpy(pts)
+    lat_t = torch.from_numpy(np.ascontiguousarray(latents_cn.T))
+    out = np.empty((queries.shape[0],), dtype=np.float32)
+    for b0 in range(0, queries.shape[0], REFERENCE_BATCH):
+        qb = queries[b0:b0 + REFERENCE_BATCH]
+        idx, _ = oracle.knn_kdtree(pts, qb, kmax)  # builds the tree, like source/base/proximity.py:84-89 per batch
+        loc = oracle.normalize_patches(pts[idx[:, :num_pts_local]], qb)
+        for s0 in range(0, qb.shape[0], CPU_SUB_BATCH):
+            sl = slice(s0, s0 + CPU_SUB_BATCH)
+            occ, _ = oracle_torch.from_latent(weights, pts_t, lat_t, torch.from_numpy(qb[sl]),
+                                              torch.from_numpy(idx[sl, :64].copy()), torch.from_numpy(loc[sl]))
+            out[b0 + s0:b0 + s0 + occ.shape[0]] = occ.numpy()
+    return out
 
 
 def run_reference(args):
@@ -141,7 +155,7 @@ def run_reference(args):
     rng = np.random.default_rng(7)
     latents = rng.standard_normal((256, args.points)).astype(np.float32)
     grid = oracle.dense_grid_queries(pts, args.resolution, 1)
-    sample = args.cpu_sample
+    sample = args.ref_sample
     times = []
     for s in range(args.warmup + args.steps):
         q = grid[rng.choice(grid.shape[0], sample, replace=False)]
@@ -167,6 +181,40 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------------------------------------------------
+
+def fkaconv_roofline(net, dev, peaks, batch=64):
+    """secondary roofline: the FKAConv layer resnetb01.cv1 (32->32 @ 10000 points, k=16) at a batch whose
+    unique bytes exceed the L2, as achieved GB/s of its UNIQUE HBM bytes
+    B*[N_in*(C_in+3)*4 + N_s*16*4 + N_s*12 + N_s*C_out*4] + C_in*C_out*64 against the measured HBM peak"""
+    import torch
+    from ppsurf_b200 import ops, synthetic
+    w = net.packed()['encoder']['resnetb01']['cv1']
+    cin, cout, n = w.struct.cin, w.struct.cout, 10000
+    clouds = [torch.from_numpy(synthetic.synthetic_cloud(n, 10 + i)).to(dev) for i in range(4)]
+    p = torch.stack(clouds).repeat(batch // 4, 1, 1).contiguous()
+    ids = torch.stack([ops.knn(c, c, 16) for c in clouds]).repeat(batch // 4, 1, 1).contiguous()
+    x = torch.randn((batch, n, cin), device=dev)
+    for _ in range(3):
+        ops.fkaconv(w, x, p, p, ids)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    reps = 5
+    for _ in range(reps):
+        ops.fkaconv(w, x, p, p, ids)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    unique = batch * (n * (cin + 3) * 4 + n * 16 * 4 + n * 12 + n * cout * 4) + cin * cout * 64
+    flops = 2.0 * batch * n * (16 * 16 * cin + 16 * cin * cout)
+    achieved = unique / (ms * 1e-3) / 1e9
+    return {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'],
+            'traffic': None, 'kernel': 'pps_fkaconv_forward (fka_weight x3 + fka_feat + contraction), resnetb01.cv1 32->32 @ 10000 pts, '
+            'k=16, batch {}'.format(batch), 'ms_per_call': ms, 'unique_bytes': unique,
+            'fp32_tflops': flops / (ms * 1e-3) / 1e12,
+            'note': 'arithmetic intensity {:.0f} FLOP per unique byte: above the fp32 SIMT machine balance, so the layer is '
+                    'compute-bound before it is HBM-bound'.format(flops / unique)}
+
 
 def run_b200(args):
     import torch
@@ -327,6 +375,8 @@ def run_b200(args):
             'clocks': clocks.summary(),
             'encoder_s': encoder_s, 'broadcast_ms': broadcast_ms,
         }
+        if not args.profile_run:
+            out['roofline_fkaconv'] = fkaconv_roofline(net, dev, peaks)
         if not args.no_cpu_baseline and world == 1:
             from oracle import ppsurf_oracle as oracle  # CPU baseline + checker leg only
             weights = {k: v.numpy() for k, v in sd.items()}
@@ -338,7 +388,7 @@ def run_b200(args):
             t0 = time.perf_counter()
             ref = cpu_decode(oracle, weights, pts_np, lat_cn, q_np, args.num_pts_local)
             dt = time.perf_counter() - t0
-            out['cpu_baseline'] = {'value': args.cpu_sample / dt / 1e6, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
+            out['cpu_baseline'] = {'value': args.cpu_sample / dt / 1e6, 'unit': UNIT, 'cores': __import__('torch').get_num_threads(), 'kind': 'port',
                                    'sample': '{} random vertices of the same grid, torch-CPU oracle + scipy cKDTree (kd-tree rebuilt '
                                              'per batch like the reference), {:.1f} s'.format(args.cpu_sample, dt)}
             out['max_abs_err_vs_oracle'] = float(np.abs(occ[torch.from_numpy(sel).to(dev)].cpu().numpy() - ref).max())

@@ -209,6 +209,32 @@ int pps_decoder_pointnet(const pps_decoder_weights* w, const float* patches /* [
 int pps_grid_queries(int r, float step, float bmin_pad, int64_t first, int64_t count, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * a11 / f1  region-growing bookkeeping of the occupancy volume, on the device
+ *     replaces  _create_volume's masks   source/poco_utils.py:178-254
+ *               (_dilate_binary 181-196, np.argwhere 210-213, volume[mask] = z 229, sign-change frontier 232-244)
+ * Voxels are C-order linear indices into the r^3 volume (r = resolution + 2*padding); every list comes out in ascending
+ * index order (= np.argwhere order).  volume f32 [r^3] (NaN = not decoded), to_see u8 [r^3].
+ *   pps_region_init      volume = NaN, to_see = 1
+ *   pps_region_pending   voxels within `dilation` of a seed (clipped box) that are not decoded yet -> out_ids, *out_count
+ *                        (device scalars; a voxel decoded in an earlier sweep keeps its value: the decode is deterministic)
+ *   pps_region_queries   ids -> coordinates idx * step + bmin_pad (separate fp32 multiply and add)
+ *   pps_region_scatter   volume[ids] = values
+ *   pps_region_frontier  to_see[seeds] = 0; the new seeds are the to_see voxels with value >= 0 within `dilation` of a seed
+ *                        with value <= 0, or with value <= 0 within `dilation` of a seed with value >= 0
+ *   pps_region_finish    the `padding` outer layers = out_value   (poco_utils.py:246-251)
+ * out_ids must hold r^3 entries; workspace: pps_region_workspace_bytes(r).
+ * ------------------------------------------------------------------------------------------------------------- */
+size_t pps_region_workspace_bytes(int r);
+int pps_region_init(int r, float* volume, uint8_t* to_see, void* stream);
+int pps_region_pending(const int32_t* seeds, int64_t n_seeds, int r, int dilation, const float* volume, void* workspace,
+                       size_t workspace_bytes, int32_t* out_ids, long long* out_count, void* stream);
+int pps_region_queries(const int32_t* ids, int64_t n, int r, float step, float bmin_pad, float* out, void* stream);
+int pps_region_scatter(const int32_t* ids, const float* values, int64_t n, float* volume, void* stream);
+int pps_region_frontier(const int32_t* seeds, int64_t n_seeds, int r, int dilation, const float* volume, uint8_t* to_see,
+                        void* workspace, size_t workspace_bytes, int32_t* out_ids, long long* out_count, void* stream);
+int pps_region_finish(float* volume, int r, int padding, float out_value, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * a2  quantised support sampling and the encoder's index tensors
  *     replaces  sampling_quantized   source/poco_data_loader.py:59-134   (torch_geometric voxel_grid + host loop)
  *               get_fkaconv_ids      source/poco_data_loader.py:137-209  (4 samplings at ratio 1/4, 13 kNN tensors)

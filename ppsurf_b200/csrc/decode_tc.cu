@@ -75,7 +75,7 @@ __device__ __forceinline__ void s_barrier() { asm volatile("bar.sync 2, %0;" ::"
 __global__ void __launch_bounds__(kThreads, 1)
     projection_tc_kernel(const float* __restrict__ table, const float* __restrict__ queries, const int32_t* __restrict__ idx, int ks,
                          long long nq, const uint8_t* __restrict__ wpack, const float* __restrict__ b2, const float* __restrict__ b3,
-                         const float* __restrict__ bq, const float* __restrict__ w1_xyz, float* __restrict__ pooled, long long* prof) {
+                         const float* __restrict__ bq, const float* __restrict__ w1_xyz, float* __restrict__ pooled, long long* prof, int variant) {
     extern __shared__ __align__(1024) uint8_t smem[];  // used directly: the compiler keeps the shared address space (LDS/STS)
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -129,8 +129,18 @@ __global__ void __launch_bounds__(kThreads, 1)
                     const uint32_t bytes = layer < 2 ? kStageBytes : kStageBytesQ;
                     for (int s = 0; s < kKSteps; ++s) {
                         mbar_wait(bar_empty + 8 * slot, phase ^ 1);
-                        mbar_expect_tx(bar_full + 8 * slot, bytes);
-                        bulk_copy(sbase + kOffRing + slot * kStageBytes, src, bytes, bar_full + 8 * slot);
+                        if (variant == 2) {  // experiment: half the bytes (wrong results, timing only)
+                            mbar_expect_tx(bar_full + 8 * slot, bytes / 2);
+                            bulk_copy(sbase + kOffRing + slot * kStageBytes, src, bytes / 2, bar_full + 8 * slot);
+                        } else if (variant == 1) {  // experiment: four parallel copies per stage
+                            mbar_expect_tx(bar_full + 8 * slot, bytes);
+                            for (int p = 0; p < 4; ++p)
+                                bulk_copy(sbase + kOffRing + slot * kStageBytes + p * (bytes / 4), src + p * (bytes / 4), bytes / 4,
+                                          bar_full + 8 * slot);
+                        } else {
+                            mbar_expect_tx(bar_full + 8 * slot, bytes);
+                            bulk_copy(sbase + kOffRing + slot * kStageBytes, src, bytes, bar_full + 8 * slot);
+                        }
                         src += bytes;
                         if (++slot == kStages) {
                             slot = 0;
@@ -481,6 +491,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 
 }  // namespace tc
 
+static int g_tc_variant = 0;             // debug experiments on the weight stream (pps_debug_tc_cluster)
 static long long* g_tc_prof = nullptr;  // device buffer of 16 counters, set by pps_debug_tc_profile
 
 size_t projection_tc_workspace(const pps_decoder_weights*, int64_t) { return 256; }
@@ -502,7 +513,7 @@ int projection_tc_impl(const pps_decoder_weights* w, const float* table, const f
     const long long nq = q;
     profile_begin(st);
     tc::projection_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, st>>>(table, queries, idx, k_stride, nq, wp, w->b2, w->b3, w->bq,
-                                                                       w->w1_xyz, pooled, g_tc_prof);
+                                                                       w->w1_xyz, pooled, g_tc_prof, g_tc_variant);
     PPS_LAUNCH_CHECK();
     profile_end(st);
     return PPS_OK;
@@ -514,5 +525,5 @@ extern "C" size_t pps_decoder_tc_pack_bytes(void) { return pps::tc::kPackBytes; 
 // debug: CTA 0 of projection_tc_kernel writes its per-phase cycle counters into `counters` (16 x int64, device memory);
 // pass NULL to switch the instrumentation output off
 extern "C" void pps_debug_tc_profile(long long* counters) { pps::g_tc_prof = counters; }
-// retired tuning knob (cluster multicast of the weight stages measured no gain on B200); kept so that the ABI is stable
-extern "C" void pps_debug_tc_cluster(int) {}
+// debug knob for experiments on the weight stream of the projection kernel (0 = product path)
+extern "C" void pps_debug_tc_cluster(int v) { pps::g_tc_variant = v; }

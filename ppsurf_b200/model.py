@@ -3,8 +3,8 @@
 (source/poco_utils.py:26-254) with every per-query step on the device.  Selected from the reference CLI with
 ``--model.class_path ppsurf_b200.PPSurfModel``; ``pps.py`` itself is not edited.
 
-What stays on the host, as in the reference: file I/O, the region-growing bookkeeping masks (numpy), marching cubes
-(scikit-image) and mesh cleaning (trimesh)  --  the rows SURVEY.md §8f ranks as "next".
+What stays on the host, as in the reference: file I/O, marching cubes (scikit-image) and mesh cleaning (trimesh)  --  rows
+SURVEY.md §8f ranks as "next"; the region-growing masks and frontier lists are on the device (``ops.RegionVolume``).
 """
 import os
 import typing
@@ -131,56 +131,32 @@ class PPSurfModel(_Base):
     def create_volume(self, decoder: ops.Decoder, input_points: np.ndarray, resolution: int, padding: int = 1,
                       dilation_size: int = 2, out_value: float = 1.0, prog_bar=None, pc_file_in: str = 'unknown') -> np.ndarray:
         """region-growing evaluation: only voxels within ``dilation_size`` of an input point, then of a sign change, are
-        decoded (source/poco_utils.py:178-254).  Masks live on the host like the reference's, the dilation is one
-        separable max-filter instead of the reference's per-point Python loop."""
+        decoded (source/poco_utils.py:178-254).  Masks, frontier lists, query coordinates and the volume live on the
+        device (``ops.RegionVolume``); the host reads one list length per step and the finished volume."""
+        volume = self.create_volume_device(decoder, input_points, resolution, padding, dilation_size, out_value, prog_bar,
+                                           pc_file_in)
+        return volume.cpu().numpy().astype(np.float64)
+
+    def create_volume_device(self, decoder: ops.Decoder, input_points: np.ndarray, resolution: int, padding: int = 1,
+                             dilation_size: int = 2, out_value: float = 1.0, prog_bar=None,
+                             pc_file_in: str = 'unknown') -> torch.Tensor:
         step, bmin_pad, pts_ids = self.grid_definition(input_points, resolution, padding)
         r = resolution + 2 * padding
-        shape = (r, r, r)
         dev = decoder.pts.device
-
-        def dilate(ids: np.ndarray) -> np.ndarray:
-            m = np.zeros(shape, dtype=bool)
-            if ids.shape[0] == 0:
-                return m
-            m[ids[:, 0], ids[:, 1], ids[:, 2]] = True
-            for ax in range(3):  # box dilation [-d, +d] along each axis
-                acc = m.copy()
-                for s in range(1, dilation_size + 1):
-                    lo = [slice(None)] * 3
-                    hi = [slice(None)] * 3
-                    lo[ax], hi[ax] = slice(0, r - s), slice(s, r)
-                    acc[tuple(hi)] |= m[tuple(lo)]
-                    acc[tuple(lo)] |= m[tuple(hi)]
-                m = acc
-            return m
-
-        volume = np.full(shape, np.nan, dtype=np.float64)
-        to_see = np.ones(shape, dtype=bool)
-        pts_ids = pts_ids.astype(np.int64)
+        region = ops.RegionVolume(r, dilation_size, dev)
+        lin = np.unique((pts_ids[:, 0].astype(np.int64) * r + pts_ids[:, 1]) * r + pts_ids[:, 2]).astype(np.int32)
+        seeds = torch.from_numpy(lin).to(dev)
         sweep = 0
-        while pts_ids.shape[0] > 0:
-            mask = dilate(pts_ids)
-            coord = torch.from_numpy(np.argwhere(mask).astype(np.float32)).to(dev)
-            queries = coord * float(step) + float(bmin_pad)  # same two fp32 roundings as poco_utils.py:213
-            z = self.occupancy(decoder, queries).cpu().numpy().astype(np.float64)
-            volume[mask] = z
-            to_see[pts_ids[:, 0], pts_ids[:, 1], pts_ids[:, 2]] = False
-            v = volume[pts_ids[:, 0], pts_ids[:, 1], pts_ids[:, 2]]
-            mask_neg, mask_pos = dilate(pts_ids[v <= 0]), dilate(pts_ids[v >= 0])
-            with np.errstate(invalid='ignore'):
-                new_mask = (mask_neg & (volume >= 0) & to_see) | (mask_pos & (volume <= 0) & to_see)
-            pts_ids = np.argwhere(new_mask).astype(np.int64)
+        while seeds.shape[0] > 0:
+            ids = region.pending(seeds)
+            if ids.shape[0] > 0:
+                region.scatter(ids, self.occupancy(decoder, region.queries(ids, step, bmin_pad)))
+            seeds = region.frontier(seeds, sweep & 1)
             sweep += 1
             if prog_bar is not None:
                 prog_bar.predict_progress_bar.set_postfix_str(
                     '{}, occ sweep {}'.format(os.path.basename(pc_file_in), sweep), refresh=True)
-        for ax in range(3):
-            sl = [slice(None)] * 3
-            sl[ax] = slice(0, padding)
-            volume[tuple(sl)] = out_value
-            sl[ax] = slice(-padding, None)
-            volume[tuple(sl)] = out_value
-        return volume
+        return region.finish(padding, out_value)
 
     # ---- mesh extraction (host libraries, "next" rows of SURVEY.md §8f) --------------------------------------------
     def extract_mesh(self, decoder: ops.Decoder, volume: np.ndarray, step, bmin_pad, refine_iter: int, prog_bar=None,
@@ -236,6 +212,67 @@ class PPSurfModel(_Base):
 
     def forward(self, batch):
         return self.network.forward(batch)
+
+    # ---- loss / metrics of the test and validation steps (source/poco_model.py:75-118,134-162) ----------------------
+    def compute_loss(self, pred: torch.Tensor, batch_data: dict):
+        """cross entropy of the 2-class logits ``pred [B,2,Q]`` against ``occ [B,Q]`` (source/poco_model.py:75-88)"""
+        occ_loss = torch.nn.functional.cross_entropy(input=pred, target=batch_data['occ'], reduction='none')
+        loss_components = torch.stack([occ_loss])
+        loss_components_mean = torch.stack([torch.mean(occ_loss)])
+        return loss_components_mean.mean(), loss_components_mean, loss_components
+
+    @staticmethod
+    def calc_metrics(pred: torch.Tensor, gt_data: dict) -> dict:
+        """accuracy / precision / recall / F1 of ``argmax(pred)`` against ``occ`` with the reference's key names and NaN
+        conventions (source/poco_model.py:90-102, source/base/metrics.py:10-84)"""
+        predicted = (torch.argmax(pred, dim=1).squeeze() > 0)
+        gt = (gt_data['occ'].squeeze() > 0)
+        if gt.shape != predicted.shape:
+            raise ValueError('The ground truth matrix and the predicted matrix have different sizes!')
+        n = float(gt.numel())
+        tp = float((predicted & gt).sum())
+        fp = float((predicted & ~gt).sum())
+        fn = float((~predicted & gt).sum())
+        tn = n - tp - fp - fn
+        nan = float('NaN')
+        res = {'predictions': n, 'pred_gt': n, 'positives': tp + fp, 'pos_gt': tp + fn, 'true_neg': tn,
+               'negatives': n - tp - fp, 'neg_gt': n - tp - fn, 'true_pos': tp, 'true': tp + tn, 'false_pos': fp,
+               'false_neg': fn, 'false': fp + fn}
+        res['accuracy'] = nan if n == 0 else (tp + tn) / n
+        res['precision'] = nan if tp + fp == 0 else tp / (tp + fp)
+        res['recall'] = nan if tp + fn == 0 else tp / (tp + fn)
+        pr = res['precision'] + res['recall']
+        res['f1_score'] = nan if pr == 0 else 2.0 * res['precision'] * res['recall'] / pr  # NaN operands propagate
+        res['abs_dist_rms'] = np.nan
+        return res
+
+    def get_loss_and_metrics(self, pred, batch):
+        loss, loss_components_mean, loss_components = self.compute_loss(pred=pred, batch_data=batch)
+        return loss, loss_components_mean, loss_components, self.calc_metrics(pred=pred, gt_data=batch)
+
+    def validation_step(self, batch, batch_idx):
+        pred = self.network.forward(batch)
+        loss, _, _, _ = self.get_loss_and_metrics(pred, batch)
+        return loss
+
+    def training_step(self, batch, batch_idx):
+        raise NotImplementedError('ppsurf_b200 implements the inference hot path (predict / test); the backward pass of '
+                                  'BASELINE config 5 (fit) is not built yet -- train with the reference module')
+
+    def test_step(self, batch, batch_idx):
+        """source/poco_model.py:134-162: forward on the stored query points, loss and classification metrics"""
+        pred = self.network.forward(batch)
+        if batch['shape_id'].shape[0] != 1:
+            raise NotImplementedError('batch size > 1 not supported')
+        loss, loss_components_mean, loss_components = self.compute_loss(pred=pred, batch_data=batch)
+        metrics_dict = self.calc_metrics(pred=pred, gt_data=batch)
+        pc_file_in = batch['pc_file_in'][0]
+        results = {'shape_id': batch['shape_id'].squeeze(0), 'pc_file_in': pc_file_in, 'loss': loss,
+                   'loss_components_mean': loss_components_mean.squeeze(0), 'loss_components': loss_components.squeeze(0),
+                   'metrics_dict': metrics_dict}
+        self.test_step_outputs.append(results)
+        self.get_prog_bar().test_progress_bar.set_postfix_str('pc_file: {}'.format(os.path.basename(pc_file_in)), refresh=True)
+        return results
 
     def reconstruct(self, pts_ms: torch.Tensor, resolution: typing.Optional[int] = None, dense: bool = False,
                     prog_bar=None, pc_file_in: str = 'unknown') -> dict:

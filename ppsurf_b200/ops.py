@@ -90,6 +90,52 @@ def grid_queries(r, step, bmin_pad, first=0, count=None, device='cuda'):
     return out
 
 
+class RegionVolume:
+    """Occupancy volume with the region-growing bookkeeping of ``_create_volume`` (source/poco_utils.py:178-254) on the
+    device: ``volume [r,r,r]`` fp32 (NaN = not decoded), ``to_see`` mask, frontier lists as C-order linear indices."""
+
+    def __init__(self, r: int, dilation: int, device):
+        self.r, self.dilation = int(r), int(dilation)
+        total = self.r ** 3
+        self.volume = torch.empty((total,), dtype=torch.float32, device=device)
+        self.to_see = torch.empty((total,), dtype=torch.uint8, device=device)
+        self.ws = torch.empty(lib.pps_region_workspace_bytes(self.r), dtype=torch.uint8, device=device)
+        self.lists = [torch.empty((total,), dtype=torch.int32, device=device) for _ in range(3)]
+        self.count = torch.zeros((1,), dtype=torch.int64, device=device)
+        check(lib.pps_region_init(self.r, _ptr(self.volume), _ptr(self.to_see), _stream()))
+
+    def _count(self) -> int:
+        return int(self.count.item())  # the one host synchronisation per list
+
+    def pending(self, seeds: torch.Tensor) -> torch.Tensor:
+        """voxels within ``dilation`` of a seed that have no value yet (ascending index order)"""
+        out = self.lists[0]
+        check(lib.pps_region_pending(_ptr(seeds, torch.int32), seeds.shape[0], self.r, self.dilation, _ptr(self.volume),
+                                     _ptr(self.ws), self.ws.numel(), _ptr(out), _ptr(self.count), _stream()))
+        return out[:self._count()]
+
+    def queries(self, ids: torch.Tensor, step, bmin_pad) -> torch.Tensor:
+        out = torch.empty((ids.shape[0], 3), dtype=torch.float32, device=ids.device)
+        check(lib.pps_region_queries(_ptr(ids, torch.int32), ids.shape[0], self.r, float(step), float(bmin_pad), _ptr(out),
+                                     _stream()))
+        return out
+
+    def scatter(self, ids: torch.Tensor, values: torch.Tensor):
+        check(lib.pps_region_scatter(_ptr(ids, torch.int32), _ptr(values, torch.float32), ids.shape[0], _ptr(self.volume),
+                                     _stream()))
+
+    def frontier(self, seeds: torch.Tensor, slot: int) -> torch.Tensor:
+        """takes ``seeds`` off ``to_see`` and returns the sign-change frontier around them (written to list ``slot``)"""
+        out = self.lists[1 + slot]
+        check(lib.pps_region_frontier(_ptr(seeds, torch.int32), seeds.shape[0], self.r, self.dilation, _ptr(self.volume),
+                                      _ptr(self.to_see), _ptr(self.ws), self.ws.numel(), _ptr(out), _ptr(self.count), _stream()))
+        return out[:self._count()]
+
+    def finish(self, padding: int, out_value: float) -> torch.Tensor:
+        check(lib.pps_region_finish(_ptr(self.volume), self.r, int(padding), float(out_value), _stream()))
+        return self.volume.view(self.r, self.r, self.r)
+
+
 class Decoder:
     """Per-cloud decoder state: kNN index + hoisted fc1 table; decodes query batches through ``pps_decoder_decode``."""
 

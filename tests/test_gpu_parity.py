@@ -349,6 +349,33 @@ def test_region_growing_golden(dev, net):
     assert np.nanmax(np.abs(vol - g['volume'])) < 1e-5
 
 
+def test_region_growing_device_vs_oracle(dev, oracle):
+    """device bookkeeping (ops.RegionVolume) against the oracle's create_volume on a field with several sign changes, zeros
+    exactly on grid vertices and seeds on the volume border (clipped dilation boxes)"""
+    import ppsurf_b200
+    model = ppsurf_b200.PPSurfModel(256, ['imp_surf_sign'], 3, 2, 64, 0.0, False, 'x.txt', 'results', 0.05, 't', 256, 1, 10000, 33, 50,
+                                    50000, 0, 1)
+
+    class FakeDecoder:
+        pts = torch.zeros((1, 3), device=dev)
+
+    rng = np.random.default_rng(3)
+    pts = np.concatenate([oracle.synthetic_cloud(700, seed=5), rng.uniform(-0.5, 0.5, (40, 3)).astype(np.float32),
+                          np.array([[-0.5, -0.5, -0.5], [0.5, 0.5, 0.5]], dtype=np.float32)])
+
+    def field_np(q):
+        q = q.astype(np.float64)
+        v = np.sin(9.0 * q[:, 0]) * np.cos(7.0 * q[:, 1]) + 0.5 * (np.linalg.norm(q, axis=1) - 0.4)
+        return np.where(np.abs(q[:, 2]) < 1e-6, 0.0, v).astype(np.float32)  # a plane of exact zeros
+
+    model.occupancy = lambda dec, q: torch.from_numpy(field_np(q.cpu().numpy())).to(dev)
+    for res in (17, 33):
+        vol = model.create_volume(FakeDecoder(), pts, res)
+        ref = oracle.create_volume(field_np, pts, res)
+        np.testing.assert_array_equal(np.isnan(vol), np.isnan(ref))
+        np.testing.assert_array_equal(vol[~np.isnan(vol)], ref[~np.isnan(ref)])
+
+
 def test_predict_pipeline_small(dev, net, oracle, weights):
     """encode_cloud (latent loop) + region-grown volume on a small cloud; the decode inside the volume is checked
     against the float64 oracle on the same latents"""
@@ -446,3 +473,36 @@ def test_tensor_core_path_matches_fp32_path(dev, net, oracle):
 
 def weights_for(net):
     return {k: v.detach().cpu().numpy() for k, v in net.state_dict().items()}
+
+
+def test_test_step_matches_oracle_forward(dev, oracle, weights):
+    """`pps.py test` path (source/poco_model.py:134-162): network.forward on a batch that carries its own ids, cross-entropy
+    loss and classification metrics against the oracle's forward on the same batch"""
+    import ppsurf_b200
+    model = ppsurf_b200.PPSurfModel(256, ['imp_surf_sign'], 3, 2, 64, 0.0, False, 'x.txt', 'results', 0.05, 'test', 256, 10, 10000,
+                                    129, 50, 50000, 10, 0)
+    model.network.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in weights.items()}, strict=True)
+    model = model.to(dev)
+    rng = np.random.default_rng(17)
+    pts = oracle.synthetic_cloud(4200, seed=23)
+    model.network.sampling_seed = 3
+    batch = model.network.spatial_ids(cu(pts.T[None], dev))
+    batch['pts'] = cu(pts.T[None], dev)
+    qry = (pts[rng.integers(0, 4200, 300)] + 0.02 * rng.standard_normal((300, 3))).astype(np.float32)
+    occ = (np.linalg.norm(qry, axis=1) < 0.4).astype(np.int64)
+    batch['pts_query'] = cu(qry[None], dev)
+    batch['pts_local_ps'] = cu(oracle.get_pts_local_ps(pts, qry, 50)[None], dev)
+    batch['occ'] = cu(occ[None], dev)
+    batch['shape_id'] = torch.tensor([0])
+    batch['pc_file_in'] = ['synthetic.xyz']
+    ref_in = {k: v.cpu().numpy() for k, v in batch.items() if isinstance(v, torch.Tensor) and k not in ('occ', 'shape_id')}
+    res = model.test_step(batch, 0)
+    ref_logits = oracle.network_forward(weights, ref_in)
+    ref_loss = torch.nn.functional.cross_entropy(torch.from_numpy(ref_logits), torch.from_numpy(occ[None]))
+    assert abs(float(res['loss']) - float(ref_loss)) < 1e-4
+    margin = np.abs(ref_logits[0, 0] - ref_logits[0, 1]) > 1e-3  # labels are only defined away from exact ties
+    ref_lab = np.argmax(ref_logits[0], axis=0)
+    assert res['metrics_dict']['predictions'] == 300.0
+    if margin.all():
+        assert res['metrics_dict']['true_pos'] == float(((ref_lab == 1) & (occ == 1)).sum())
+    assert len(model.test_step_outputs) == 1 and res['pc_file_in'] == 'synthetic.xyz'

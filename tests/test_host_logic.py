@@ -135,3 +135,30 @@ def test_synthetic_generators_match_oracle(oracle, weights):
     for k in sd:
         np.testing.assert_array_equal(sd[k].numpy(), np.asarray(weights[k]), err_msg=k)
     np.testing.assert_array_equal(synthetic.synthetic_cloud(1000, 3), oracle.synthetic_cloud(1000, 3))
+
+
+def test_loss_and_metrics_follow_the_reference_formulas():
+    """compute_loss / calc_metrics of the module mirror against a direct restatement of source/poco_model.py:75-102 and
+    source/base/metrics.py:41-84 (int32 sums of predicted / ground-truth indicator vectors)"""
+    import ppsurf_b200
+    g = torch.Generator().manual_seed(5)
+    pred = torch.randn((1, 2, 500), generator=g)
+    occ = (torch.rand((1, 500), generator=g) > 0.4).to(torch.int64)
+    model = ppsurf_b200.PPSurfModel.__new__(ppsurf_b200.PPSurfModel)
+    loss, mean, comps = ppsurf_b200.PPSurfModel.compute_loss(model, pred, {'occ': occ})
+    ref = torch.nn.functional.cross_entropy(pred, occ, reduction='none')
+    assert comps.shape == (1, 1, 500) and torch.equal(comps[0], ref)
+    assert float(loss) == pytest.approx(float(ref.mean())) and mean.shape == (1,)
+    m = ppsurf_b200.PPSurfModel.calc_metrics(pred, {'occ': occ})
+    p_int = (torch.argmax(pred, dim=1).to(torch.float32).squeeze() > 0).to(torch.int32)
+    g_int = (occ.squeeze() > 0).to(torch.int32)
+    tp = float(((p_int + g_int) == 2).sum())
+    fp = float(((p_int * 2 + g_int) == 2).sum())
+    fn = float(((p_int + 2 * g_int) == 2).sum())
+    tn = 500.0 - float(torch.nonzero(p_int + g_int).shape[0])
+    assert (m['true_pos'], m['false_pos'], m['false_neg'], m['true_neg']) == (tp, fp, fn, tn)
+    assert m['accuracy'] == (tp + tn) / 500.0 and m['precision'] == tp / (tp + fp) and m['recall'] == tp / (tp + fn)
+    assert m['f1_score'] == pytest.approx(2.0 * m['precision'] * m['recall'] / (m['precision'] + m['recall']))
+    # degenerate case: nothing predicted positive -> precision NaN, F1 NaN (reference conventions)
+    m0 = ppsurf_b200.PPSurfModel.calc_metrics(torch.tensor([[[1.0, 1.0], [0.0, 0.0]]]), {'occ': torch.tensor([[1, 0]])})
+    assert np.isnan(m0['precision']) and m0['recall'] == 0.0 and np.isnan(m0['f1_score'])

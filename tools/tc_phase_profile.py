@@ -24,7 +24,7 @@ counters = torch.zeros(16, dtype=torch.int64, device=dev)
 tiles = (16384 // 2 + 147) // 148
 names = ['mma_total', 'mma_wait_chunk', 'mma_wait_weights', 'mma_wait_sgroup', 'g_gather', 'g_wait', 'g_E2E3', 's_wait', 's_softmax', 's_pool']
 ref = None
-for cs in (1,):
+for cs in (0, 1, 2):
     _lib.lib.pps_debug_tc_cluster(cs)
     for it in range(3):
         _lib.lib.pps_debug_tc_profile(counters.data_ptr())
@@ -42,4 +42,4 @@ for cs in (1,):
         cs, e0.elapsed_time(e1) * 200, float((out - ref).abs().max())))
     print('   ' + '  '.join('{}={:.0f}'.format(k, v / tiles) for k, v in zip(names, c)))
 _lib.lib.pps_debug_tc_profile(None)
-_lib.lib.pps_debug_tc_cluster(1)
+_lib.lib.pps_debug_tc_cluster(0)
