@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                     float v[32];
                     tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + col0, v);
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) v[c] = row_valid ? fmaxf(v[c] + bias[col0 + c], 0.f) : 0.f;
+                    for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c] + bias[col0 + c], 0.f);  // padding rows carry finite values nobody reads
                     if (layer == 0 && row_valid) {  // a1 feeds the feature transform of pn_feat_kernel
                         float4* dst = reinterpret_cast<float4*>(a1_out + (q_row * P + p_row) * 64 + col0);
 #pragma unroll
@@ -452,7 +452,6 @@ __global__ void __launch_bounds__(kPnThreads, 2)
             warp_arrive(bar_aready, lane);
 
             const long long q_row = 2 * tile + (row >> 6);
-            const bool row_valid = q_row < nq && (row & 63) < P;
             // ---- x' = T . a1 (no bias, no activation; may be negative) -> operand tile
             mbar_wait(bar_accum, accum_phase);
             accum_phase ^= 1;
@@ -464,7 +463,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                 for (int kb = 0; kb < 4; ++kb) {
                     float x8[8];
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) x8[c] = row_valid ? v[kb * 8 + c] : 0.f;
+                    for (int c = 0; c < 8; ++c) x8[c] = v[kb * 8 + c];
                     uint4 hi, lo;
                     split8_signed(x8, hi, lo);
                     *reinterpret_cast<uint4*>(smem + kOffAhi + (half * 4 + kb) * kPnLbo + row * 16) = hi;
@@ -483,7 +482,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                 for (int kb = 0; kb < 4; ++kb) {
                     float x8[8];
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) x8[c] = row_valid ? fmaxf(v[kb * 8 + c] + s_b1[half * 32 + kb * 8 + c], 0.f) : 0.f;
+                    for (int c = 0; c < 8; ++c) x8[c] = fmaxf(v[kb * 8 + c] + s_b1[half * 32 + kb * 8 + c], 0.f);
                     uint4 hi, lo;
                     split8(x8, hi, lo);
                     *reinterpret_cast<uint4*>(smem + kOffAhi + (half * 4 + kb) * kPnLbo + row * 16) = hi;
@@ -503,7 +502,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                     tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + col0, v);
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
-                        v[c] = row_valid ? fmaxf(v[c] + s_b2[col0 + c], 0.f) : 0.f;
+                        v[c] = fmaxf(v[c] + s_b2[col0 + c], 0.f);
                         logit = fmaf(v[c], s_wq[col0 + c], logit);
                     }
 #pragma unroll

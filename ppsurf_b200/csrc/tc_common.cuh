@@ -21,19 +21,25 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// try_wait suspends the warp in hardware until the phase completes or the time hint (ns) runs out, so a waiting warp issues a
+// handful of instructions instead of spinning; the clock is only consulted every 64 wake-ups
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
-    long long t0 = clock64();
-    while (true) {
+    long long t0 = 0;
+    for (uint32_t spins = 0;; ++spins) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(bar), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(20000u)
             : "memory");
         if (done) break;
-        if (clock64() - t0 > kSpinLimit) __trap();
+        if ((spins & 63u) == 63u) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > kSpinLimit) __trap();
+        }
     }
 }
 __device__ __forceinline__ void bulk_copy(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
