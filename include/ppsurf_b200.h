@@ -161,6 +161,8 @@ size_t pps_decoder_tc_pack_bytes(void);
 void pps_debug_tc_profile(long long* counters);
 /* tuning knob: CTAs per cluster (1, 2 or 4) that share multicast weight stages in the projection kernel (default 1) */
 void pps_debug_tc_cluster(int cs);
+/* debug: number of CTA pairs (2-CTA clusters) of the projection kernel the device holds at once */
+int pps_debug_tc_max_clusters(void);
 size_t pps_decoder_tc_pn_stn_bytes(void);
 size_t pps_decoder_tc_pn_feat_bytes(void);
 size_t pps_decoder_tc_stn_fc_bytes(void);

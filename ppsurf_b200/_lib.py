@@ -69,6 +69,7 @@ SIGNATURES = {
     'pps_decoder_tc_pack_bytes': (size_t, []),
     'pps_debug_tc_profile': (None, [c_voidp]),
     'pps_debug_tc_cluster': (None, [i32]),
+    'pps_debug_tc_max_clusters': (i32, []),
     'pps_decoder_tc_pn_stn_bytes': (size_t, []),
     'pps_decoder_tc_pn_feat_bytes': (size_t, []),
     'pps_decoder_tc_stn_fc_bytes': (size_t, []),

@@ -28,9 +28,10 @@ constexpr int kNbrs = 64;                   // neighbours per query
 constexpr int kKB = kC / 8;                 // k8 blocks per row
 constexpr int kALbo = kRows * 16 + 16;      // bytes between k8 blocks of an activation tile (padded)
 constexpr int kABytes = kKB * kALbo;        // 66048
-constexpr int kStageBytes = 16384;          // one k16 step of a 256-wide layer: W_hi 8 KB + W_lo 8 KB
-constexpr int kStageBytesQ = 8192;          // fc_query as the M operand: 128 rows (64 zero rows + 64 heads) x k16, hi + lo
-constexpr int kStages = 5;
+constexpr int kStageBytes = 8192;           // ring slot = what ONE CTA of the pair holds of a k16 step: 128 weight rows, hi 4 KB + lo 4 KB
+                                            // (fc2 / fc3: this CTA's half of the 256 output features; fc_query as the M operand:
+                                            // 64 zero rows + 64 heads, the same in both CTAs)
+constexpr int kStages = 10;
 constexpr int kKSteps = kC / 16;            // 16 k16 steps per layer
 constexpr int kChunks = 4;                  // a layer's K range is released to the MMA warp in 4 chunks of 64 columns
 constexpr int kGWarps = 8;                  // gather + fc2/fc3 epilogues
@@ -48,22 +49,27 @@ constexpr int kOffAttp = kOffBias + (256 + 256 + 64) * 4;    // 216320: [head ha
 constexpr int kOffPool = kOffAttp + 2 * 2 * 64 * 4;          // 217344: [lane group][256] partial pooled sums
 constexpr int kOffW1 = kOffPool + 4 * 256 * 4;               // 221440: fc1 xyz weights [256][3]
 constexpr int kOffVq = kOffW1 + 768 * 4;                     // 224512: W1_xyz . q for the tile's 2 queries [2][256]
-constexpr int kOffBar = kOffVq + 2 * 256 * 4;                // 226560: full[5] empty[5] acc[3] chunk[4] d0free d1free
+constexpr int kOffBar = kOffVq + 2 * 256 * 4;                // 226560: full[10] empty[10] acc[3] chunk[4] d0free d1free
 constexpr int kNumBars = 2 * kStages + 3 + kChunks + 2;
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmem + 16;
 
-// packed weights in global memory: [fc2: 16 stages][fc3: 16 stages][fc_query: 16 stages]
-constexpr size_t kPackBytes = size_t(2) * kKSteps * kStageBytes + size_t(kKSteps) * kStageBytesQ;
+// packed weights in global memory: [fc2: 16 stages x (CTA 0 half, CTA 1 half)][fc3: likewise][fc_query: 16 stages]
+constexpr size_t kPackBytes = size_t(2) * kKSteps * 2 * kStageBytes + size_t(kKSteps) * kStageBytes;
 
 __device__ __forceinline__ void g_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kGThreads) : "memory"); }
 __device__ __forceinline__ void s_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(kSThreads) : "memory"); }
 
 // Pipeline of one tile (2 queries x 64 neighbours):
 //   gather -> fc2 (D0) -> E2 -> fc3 (D1) -> E3 -> fc_query^T (D0) -> softmax / head mean / pooling from D1
+// The kernel runs as CTA PAIRS (cluster of 2, tcgen05 cta_group::2): every MMA is M=256 = the two CTAs' 128-row tiles, each CTA
+// holds only its half of the weight stage (B operand) and the pair shares it, which halves the shared-memory traffic and the
+// L2 weight stream per row -- with one CTA per MMA the kernel is shared-memory-bandwidth bound (36 KB of operand reads + 16 KB
+// of weight refill per 384 tensor cycles).  Rank 0 issues the MMAs of the pair; barriers that gate them live in rank 0 and
+// collect arrivals from both CTAs; completions are multicast to both.
 // Warp roles (512 threads, one persistent CTA per SM):
-//   warp 0       weight producer: cp.async.bulk of pre-packed k16 weight stages into a 5-slot ring
-//   warp 1       MMA issuer (one thread)
+//   warp 0       weight producer: cp.async.bulk of this CTA's half of the pre-packed k16 weight stages into a 10-slot ring
+//   warp 1       rank 0: MMA issuer (one thread); rank 1: relays "my half of the stage has landed" to rank 0
 //   warps 2..9   G group: gather of the fc1 table rows (+ W1_xyz.q, ReLU, fp16 hi/lo split) and the fc2 / fc3 epilogues.  Every
 //                epilogue rewrites the operand tile in place 64 columns at a time and releases each chunk through its own
 //                mbarrier, so the next layer's MMAs (other accumulator) overlap it.
@@ -87,6 +93,10 @@ __global__ void __launch_bounds__(kThreads, 1)
     volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + kOffTmem);
     const uint32_t bar_full = sbase + kOffBar, bar_empty = bar_full + 8 * kStages, bar_acc = bar_empty + 8 * kStages,
                    bar_chunk = bar_acc + 8 * 3, bar_d0free = bar_chunk + 8 * kChunks, bar_d1free = bar_d0free + 8;
+    const uint32_t crank = cluster_ctarank();  // 0 = leader of the pair
+    // the barriers that gate the pair's MMAs, in the leader's shared memory (valid from either CTA)
+    const uint32_t lead_full = map_to_cta(bar_full, 0), lead_chunk = map_to_cta(bar_chunk, 0),
+                   lead_d0free = map_to_cta(bar_d0free, 0), lead_d1free = map_to_cta(bar_d1free, 0);
 
     for (int e = tid; e < 768; e += kThreads) {
         s_w1[e] = w1_xyz[e];
@@ -98,50 +108,47 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     if (tid == 0) {
         for (int i = 0; i < kStages; ++i) {
-            mbar_init(bar_full + 8 * i, 1);
+            mbar_init(bar_full + 8 * i, crank == 0 ? 2 : 1);  // leader: own producer + the peer's relay
             mbar_init(bar_empty + 8 * i, 1);
         }
         for (int i = 0; i < 3; ++i) mbar_init(bar_acc + 8 * i, 1);  // accumulator of fc2 / fc3 / fc_query complete
-        for (int i = 0; i < kChunks; ++i) mbar_init(bar_chunk + 8 * i, kGWarps);  // one elected arrival per G warp
-        mbar_init(bar_d0free, 4);        // the four softmax warps hold the scores in registers
-        mbar_init(bar_d1free, kSWarps);  // the pooling has read fc3's accumulator
+        for (int i = 0; i < kChunks; ++i) mbar_init(bar_chunk + 8 * i, 2 * kGWarps);  // one elected arrival per G warp of the pair
+        mbar_init(bar_d0free, 2 * 4);        // the softmax warps of both CTAs hold the scores in registers
+        mbar_init(bar_d1free, 2 * kSWarps);  // the pooling of both CTAs has read fc3's accumulator
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kOffTmem), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kOffTmem), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();  // the barriers of both CTAs are initialised before any remote arrival or multicast commit
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
 
-    const long long ntiles = (nq + 1) / 2;
-    const long long iters = ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // tile = 2 queries x 64 neighbours; pair-tile = the two tiles of a CTA pair; both CTAs of a pair run the same number of
+    // iterations (a tile past the end works on clamped queries and writes nothing)
+    const long long npt = (nq + 3) / 4;
+    const long long pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const long long iters = npt > pair ? (npt - pair + npairs - 1) / npairs : 0;
+    const long long tile0 = 2 * pair + crank, tile_step = 2 * npairs;
 
     if (warp == 0) {
         // ---------------------------------------------------------------- weight producer
         if (lane == 0) {
             uint32_t slot = 0, phase = 0;
             for (long long it = 0; it < iters; ++it) {
-                const uint8_t* src = wpack;
                 for (int layer = 0; layer < 3; ++layer) {
-                    const uint32_t bytes = layer < 2 ? kStageBytes : kStageBytesQ;
+                    // fc2 / fc3: this CTA's half of every stage; fc_query: the whole (128-row) stage
+                    const uint8_t* src = layer < 2 ? wpack + (size_t)layer * kKSteps * 2 * kStageBytes + crank * kStageBytes
+                                                   : wpack + (size_t)2 * kKSteps * 2 * kStageBytes;
+                    const uint32_t stride = layer < 2 ? 2 * kStageBytes : kStageBytes;
                     for (int s = 0; s < kKSteps; ++s) {
                         mbar_wait(bar_empty + 8 * slot, phase ^ 1);
-                        if (variant == 2) {  // experiment: half the bytes (wrong results, timing only)
-                            mbar_expect_tx(bar_full + 8 * slot, bytes / 2);
-                            bulk_copy(sbase + kOffRing + slot * kStageBytes, src, bytes / 2, bar_full + 8 * slot);
-                        } else if (variant == 1) {  // experiment: four parallel copies per stage
-                            mbar_expect_tx(bar_full + 8 * slot, bytes);
-                            for (int p = 0; p < 4; ++p)
-                                bulk_copy(sbase + kOffRing + slot * kStageBytes + p * (bytes / 4), src + p * (bytes / 4), bytes / 4,
-                                          bar_full + 8 * slot);
-                        } else {
-                            mbar_expect_tx(bar_full + 8 * slot, bytes);
-                            bulk_copy(sbase + kOffRing + slot * kStageBytes, src, bytes, bar_full + 8 * slot);
-                        }
-                        src += bytes;
+                        mbar_expect_tx(bar_full + 8 * slot, kStageBytes);
+                        bulk_copy(sbase + kOffRing + slot * kStageBytes, src, kStageBytes, bar_full + 8 * slot);
+                        src += stride;
                         if (++slot == kStages) {
                             slot = 0;
                             phase ^= 1;
@@ -151,28 +158,28 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
         }
     } else if (warp == 1) {
-        // ---------------------------------------------------------------- MMA issuer
-        if (lane == 0) {
+        if (lane == 0 && crank == 0) {
+            // ---------------------------------------------------------------- MMA issuer of the pair
             uint32_t slot = 0, phase = 0, chunk_phase = 0;
             long long t_chunk = 0, t_full = 0, t_dfree = 0, t_total = clock64();
             for (long long it = 0; it < iters; ++it) {
                 for (int layer = 0; layer < 3; ++layer) {
-                    const uint32_t idesc = umma_idesc(layer < 2 ? 256 : 128);
+                    const uint32_t idesc = umma_idesc2(256);
                     const uint32_t dcol = layer == 1 ? 256u : 0u;
-                    if (it > 0 && layer < 2) {  // the S group has taken what it needs of the previous tile out of this accumulator
+                    if (it > 0 && layer < 2) {  // the S groups have taken what they need of the previous tiles out of this accumulator
                         const long long t0 = clock64();
-                        mbar_wait(layer == 0 ? bar_d0free : bar_d1free, (uint32_t)((it - 1) & 1));
+                        mbar_wait_cluster(layer == 0 ? bar_d0free : bar_d1free, (uint32_t)((it - 1) & 1));
                         tc_fence_after();
                         t_dfree += clock64() - t0;
                     }
                     for (int s = 0; s < kKSteps; ++s) {
                         long long t0 = clock64();
-                        if ((s & 3) == 0) {  // operand columns [64c, 64c+64) written by the previous stage of the pipeline
-                            mbar_wait(bar_chunk + 8 * (s >> 2), chunk_phase);
+                        if ((s & 3) == 0) {  // operand columns [64c, 64c+64) of BOTH tiles written by the previous stage of the pipeline
+                            mbar_wait_cluster(bar_chunk + 8 * (s >> 2), chunk_phase);
                             tc_fence_after();
                         }
                         long long t1 = clock64();
-                        mbar_wait(bar_full + 8 * slot, phase);
+                        mbar_wait_cluster(bar_full + 8 * slot, phase);  // both halves of the weight stage have landed
                         tc_fence_after();
                         t_chunk += t1 - t0;
                         t_full += clock64() - t1;
@@ -180,34 +187,43 @@ __global__ void __launch_bounds__(kThreads, 1)
                         const uint64_t x_hi = umma_desc(sbase + kOffAhi + a_off, kALbo, 128);
                         const uint64_t x_lo = umma_desc(sbase + kOffAlo + a_off, kALbo, 128);
                         const uint32_t wst = sbase + kOffRing + slot * kStageBytes;
-                        if (layer < 2) {
-                            const uint64_t w_hi = umma_desc(wst, 256 * 16, 128);
-                            const uint64_t w_lo = umma_desc(wst + 8192, 256 * 16, 128);
-                            umma(tmem + dcol, x_hi, w_hi, idesc, s > 0 ? 1u : 0u);
-                            umma(tmem + dcol, x_lo, w_hi, idesc, 1u);
-                            umma(tmem + dcol, x_hi, w_lo, idesc, 1u);
-                        } else {  // scores^T[64 + head, row] = Wq[head, :] . h3[row, :]
-                            const uint64_t w_hi = umma_desc(wst, 128 * 16, 128);
-                            const uint64_t w_lo = umma_desc(wst + 4096, 128 * 16, 128);
-                            umma(tmem, w_hi, x_hi, idesc, s > 0 ? 1u : 0u);
-                            umma(tmem, w_hi, x_lo, idesc, 1u);
-                            umma(tmem, w_lo, x_hi, idesc, 1u);
+                        const uint64_t w_hi = umma_desc(wst, 128 * 16, 128);
+                        const uint64_t w_lo = umma_desc(wst + 4096, 128 * 16, 128);
+                        if (layer < 2) {  // D[256 rows, 256 features]: B = the two CTAs' 128-feature halves
+                            umma2(tmem + dcol, x_hi, w_hi, idesc, s > 0 ? 1u : 0u);
+                            umma2(tmem + dcol, x_lo, w_hi, idesc, 1u);
+                            umma2(tmem + dcol, x_hi, w_lo, idesc, 1u);
+                        } else {  // scores^T[64 + head, row of either tile] = Wq[head, :] . h3[row, :]  (both CTAs compute all 256 columns)
+                            umma2(tmem, w_hi, x_hi, idesc, s > 0 ? 1u : 0u);
+                            umma2(tmem, w_hi, x_lo, idesc, 1u);
+                            umma2(tmem, w_lo, x_hi, idesc, 1u);
                         }
-                        tc_commit(bar_empty + 8 * slot);  // frees the ring slot when these MMAs have read it
+                        tc_commit2(bar_empty + 8 * slot);  // frees the ring slot of both CTAs when these MMAs have read it
                         if (++slot == kStages) {
                             slot = 0;
                             phase ^= 1;
                         }
                     }
-                    tc_commit(bar_acc + 8 * layer);  // accumulator of this layer complete
+                    tc_commit2(bar_acc + 8 * layer);  // accumulator of this layer complete, in both CTAs
                     chunk_phase ^= 1;
                 }
             }
-            if (prof && blockIdx.x == 0) {  // cycles: MMA warp total, waiting for operand chunks / weights / the S group
+            if (prof && blockIdx.x == 0) {  // cycles: MMA warp total, waiting for operand chunks / weights / the S groups
                 prof[0] = clock64() - t_total;
                 prof[1] = t_chunk;
                 prof[2] = t_full;
                 prof[3] = t_dfree;
+            }
+        } else if (lane == 0) {
+            // ---------------------------------------------------------------- peer: tell the leader when my half of a stage is here
+            uint32_t slot = 0, phase = 0;
+            for (long long n = 0; n < iters * 3 * kKSteps; ++n) {
+                mbar_wait(bar_full + 8 * slot, phase);
+                mbar_arrive_cluster(lead_full + 8 * slot);
+                if (++slot == kStages) {
+                    slot = 0;
+                    phase ^= 1;
+                }
             }
         }
     } else if (warp < 2 + kGWarps) {
@@ -223,13 +239,13 @@ __global__ void __launch_bounds__(kThreads, 1)
 
         int src_next[4];
         {
-            long long q = 2 * (long long)blockIdx.x + ql;
+            long long q = 2 * tile0 + ql;
             q = q < nq ? q : nq - 1;
 #pragma unroll
             for (int i = 0; i < 4; ++i) src_next[i] = idx[q * ks + ((ew * 16 + 4 * i + rs) & 63)];
         }
         for (long long it = 0; it < iters; ++it) {
-            const long long tile = blockIdx.x + it * gridDim.x;
+            const long long tile = tile0 + it * tile_step;
             // ---- W1_xyz . q for the two queries of the tile.  Every G warp is past the previous tile's gather (this warp saw
             // fc2's accumulator complete, which needs every warp's chunk arrivals), so s_vq may be overwritten
 #pragma unroll
@@ -248,7 +264,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) src[i] = src_next[i];
                 if (it + 1 < iters) {  // neighbour ids of the NEXT tile: their latency hides behind this tile
-                    long long q = 2 * (tile + gridDim.x) + ql;
+                    long long q = 2 * (tile + tile_step) + ql;
                     q = q < nq ? q : nq - 1;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) src_next[i] = idx[q * ks + ((ew * 16 + 4 * i + rs) & 63)];
@@ -292,7 +308,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                         *reinterpret_cast<uint4*>(smem + kOffAhi + (c * 8 + kb) * kALbo + r * 16) = hi;
                         *reinterpret_cast<uint4*>(smem + kOffAlo + (c * 8 + kb) * kALbo + r * 16) = lo;
                     }
-                    warp_arrive(bar_chunk + 8 * c, lane);
+                    warp_arrive_cluster(lead_chunk + 8 * c, lane);
                 }
             }
             {
@@ -337,7 +353,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                         *reinterpret_cast<uint4*>(smem + kOffAhi + kblk * kALbo + row * 16) = hi;
                         *reinterpret_cast<uint4*>(smem + kOffAlo + kblk * kALbo + row * 16) = lo;
                     }
-                    warp_arrive(bar_chunk + 8 * cb, lane);
+                    warp_arrive_cluster(lead_chunk + 8 * cb, lane);
                 }
                 {
                     const long long now = clock64();
@@ -362,8 +378,9 @@ __global__ void __launch_bounds__(kThreads, 1)
         // pooling: rows 0..63 (lane groups 0,1) have one warp each -> all 8 column blocks; rows 64..127 have two warps each
         const int cb0 = heads ? 4 * sq : 0, cb1 = heads ? 4 * sq + 4 : 8;
         long long t_wait = 0, t_soft = 0, t_pool = 0, t_mark = clock64();
+        const uint32_t score_col = 128u * crank;  // scores^T columns = rows of the pair's two tiles; mine start here
         for (long long it = 0; it < iters; ++it) {
-            const long long tile = blockIdx.x + it * gridDim.x;
+            const long long tile = tile0 + it * tile_step;
             mbar_wait(bar_acc + 16, (uint32_t)(it & 1));
             tc_fence_after();
             {
@@ -375,8 +392,8 @@ __global__ void __launch_bounds__(kThreads, 1)
                 float e[64];
                 {
                     uint32_t v0[32], v1[32];
-                    tmem_ld32_issue(tmem + ((uint32_t)(lane_grp * 32) << 16) + sq * 64, v0);
-                    tmem_ld32_issue(tmem + ((uint32_t)(lane_grp * 32) << 16) + sq * 64 + 32, v1);
+                    tmem_ld32_issue(tmem + ((uint32_t)(lane_grp * 32) << 16) + score_col + sq * 64, v0);
+                    tmem_ld32_issue(tmem + ((uint32_t)(lane_grp * 32) << 16) + score_col + sq * 64 + 32, v1);
                     tmem_ld_wait(v0);
                     tmem_ld_wait(v1);
 #pragma unroll
@@ -387,7 +404,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_d0free);  // fc2 of the next tile may overwrite the scores
+                if (lane == 0) mbar_arrive_cluster(lead_d0free);  // fc2 of the next tile may overwrite the scores
                 // softmax over the 64 neighbours (the head's bias shifts every score alike and cancels)
                 float m = e[0];
 #pragma unroll
@@ -437,7 +454,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                     if (cb == cb1 - 1) {  // last read of fc3's accumulator: fc3 of the next tile may overwrite it
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_d1free);
+                        if (lane == 0) mbar_arrive_cluster(lead_d1free);
                     }
                     float v[32];
 #pragma unroll
@@ -482,10 +499,12 @@ __global__ void __launch_bounds__(kThreads, 1)
 
     tc_fence_before();
     __syncthreads();
+    __syncwarp();
+    cluster_sync_all();  // neither CTA exits (or frees its TMEM) while the peer may still arrive on its barriers or read its tile
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
     }
 }
 
@@ -507,13 +526,25 @@ int projection_tc_impl(const pps_decoder_weights* w, const float* table, const f
         PPS_CUDA(cudaFuncSetAttribute(tc::projection_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
         configured = true;
     }
-    const long long ntiles = (q + 1) / 2;
-    const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
+    const long long npt = (q + 3) / 4;  // pair-tiles of 4 queries
+    const int pairs = (int)(npt < kNumSMs / 2 ? npt : kNumSMs / 2);
     const uint8_t* wp = static_cast<const uint8_t*>(w->tc_wpack);
     const long long nq = q;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(tc::kThreads);
+    cfg.dynamicSmemBytes = tc::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;  // CTA pairs: the two CTAs of a cluster sit on the two SMs of one TPC
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     profile_begin(st);
-    tc::projection_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, st>>>(table, queries, idx, k_stride, nq, wp, w->b2, w->b3, w->bq,
-                                                                       w->w1_xyz, pooled, g_tc_prof, g_tc_variant);
+    PPS_CUDA(cudaLaunchKernelEx(&cfg, tc::projection_tc_kernel, table, queries, idx, k_stride, nq, wp, w->b2, w->b3, w->bq, w->w1_xyz,
+                                pooled, g_tc_prof, g_tc_variant));
     PPS_LAUNCH_CHECK();
     profile_end(st);
     return PPS_OK;
@@ -525,5 +556,23 @@ extern "C" size_t pps_decoder_tc_pack_bytes(void) { return pps::tc::kPackBytes; 
 // debug: CTA 0 of projection_tc_kernel writes its per-phase cycle counters into `counters` (16 x int64, device memory);
 // pass NULL to switch the instrumentation output off
 extern "C" void pps_debug_tc_profile(long long* counters) { pps::g_tc_prof = counters; }
+// debug: how many CTA pairs of projection_tc_kernel the device can hold at once (-1 on error)
+extern "C" int pps_debug_tc_max_clusters(void) {
+    cudaFuncSetAttribute(pps::tc::projection_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pps::tc::kSmemBytes);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(pps::kNumSMs);
+    cfg.blockDim = dim3(pps::tc::kThreads);
+    cfg.dynamicSmemBytes = pps::tc::kSmemBytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = -1;
+    if (cudaOccupancyMaxActiveClusters(&n, pps::tc::projection_tc_kernel, &cfg) != cudaSuccess) return -1;
+    return n;
+}
 // debug knob for experiments on the weight stream of the projection kernel (0 = product path)
 extern "C" void pps_debug_tc_cluster(int v) { pps::g_tc_variant = v; }

@@ -75,6 +75,66 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// ---- CTA pair (cta_group::2) helpers ---------------------------------------------------------------------------------
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+// arrival on a barrier that may live in the peer CTA.  Default semantics (release at CTA scope) on purpose: a cluster-scope
+// release / acquire compiles to MEMBAR.ALL.GPU + CCTL.IVALL (L1 invalidation) and made the kernel 70 % slower.  What the pair
+// needs is weaker: this CTA's shared-memory writes have been performed and made visible to the async proxy
+// (fence.proxy.async.shared::cta) before the arrival leaves the SM; the consumer is the tensor core reading this SM's memory.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait on a LOCAL barrier whose arrivals may come from the peer CTA (CTA-scope acquire, see mbar_arrive_cluster)
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    long long t0 = 0;
+    for (uint32_t spins = 0;; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity), "r"(20000u)
+            : "memory");
+        if (done) break;
+        if ((spins & 63u) == 63u) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > kSpinLimit) __trap();
+        }
+    }
+}
+// every lane has made its shared-memory writes visible to the async proxy (of either CTA of the pair), lane 0 arrives on the
+// barrier at `cluster_addr`
+__device__ __forceinline__ void warp_arrive_cluster(uint32_t cluster_addr, int lane) {
+    fence_async_smem();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cluster(cluster_addr);
+}
+__device__ __forceinline__ void umma2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// completion of all prior MMAs of the pair -> the barrier at the same offset in both CTAs
+__device__ __forceinline__ void tc_commit2(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+// instruction descriptor kind::f16 for the CTA pair: D fp32, A/B fp16, both K-major, M=256 (128 rows per CTA)
+__host__ __device__ constexpr uint32_t umma_idesc2(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((256u >> 4) << 24); }
+
 // UMMA shared-memory descriptor, K-major, no swizzle: core matrix = 8 rows x 16 B (128 contiguous bytes);
 // LBO = byte distance between the two k8 halves of a k16 step, SBO = byte distance between 8-row groups; version 1 (sm_100)
 __device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {

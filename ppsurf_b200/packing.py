@@ -100,8 +100,10 @@ def pack_decoder(sd, device, k, num_pts_local, prefix='') -> Packed:
     if latent == 256 and st.heads == 64:
         # M operand of the transposed fc_query: 64 zero rows, then the 64 heads (TMEM lanes 64..127)
         wq_pad = torch.cat([torch.zeros(64, latent, dtype=torch.float64), _mat(sd, g + 'fc_query.weight')])
-        pack = torch.cat([tc_pack_matrix(_mat(sd, g + 'fc2.weight')), tc_pack_matrix(_mat(sd, g + 'fc3.weight')),
-                          tc_pack_matrix(wq_pad)])
+        def pair_pack(w):  # per k16 stage: [CTA 0: features 0..127 | CTA 1: features 128..255], each hi 4 KB + lo 4 KB
+            a, b = tc_pack_matrix(w[:128]).view(16, -1), tc_pack_matrix(w[128:]).view(16, -1)
+            return torch.stack([a, b], dim=1).reshape(-1)
+        pack = torch.cat([pair_pack(_mat(sd, g + 'fc2.weight')), pair_pack(_mat(sd, g + 'fc3.weight')), tc_pack_matrix(wq_pad)])
         assert pack.numel() == _lib.lib.pps_decoder_tc_pack_bytes()
         p.tensors['tc_wpack'] = pack.to(device)
         st.tc_wpack = p.tensors['tc_wpack'].data_ptr()

@@ -16,15 +16,16 @@ net = net.to(dev)
 n = 100000
 pts = torch.from_numpy(synthetic.synthetic_cloud(n, 42)).to(dev)
 lat = torch.from_numpy(np.random.default_rng(7).standard_normal((n, 256)).astype(np.float32)).to(dev)
-dec = ops.Decoder(net.packed()['decoder'], pts, lat, chunk=16384, path=1)
+dec = ops.Decoder(net.packed()['decoder'], pts, lat, chunk=18944, path=1)
 step, bmin_pad, _ = ppsurf_b200.PPSurfModel.grid_definition(pts.cpu().numpy(), 129, 1)
-qry = ops.grid_queries(131, step, bmin_pad, first=131 * 131 * 60, count=16384, device=dev)
+qry = ops.grid_queries(131, step, bmin_pad, first=131 * 131 * 60, count=18944, device=dev)
 idx = dec.index.query(qry, 64)
 counters = torch.zeros(16, dtype=torch.int64, device=dev)
-tiles = (16384 // 2 + 147) // 148
+tiles = 18944 // 4 // 74
 names = ['mma_total', 'mma_wait_chunk', 'mma_wait_weights', 'mma_wait_sgroup', 'g_gather', 'g_wait', 'g_E2E3', 's_wait', 's_softmax', 's_pool']
 ref = None
-for cs in (0, 1, 2):
+print('CTA pairs resident at once:', _lib.lib.pps_debug_tc_max_clusters())
+for cs in (0,):
     _lib.lib.pps_debug_tc_cluster(cs)
     for it in range(3):
         _lib.lib.pps_debug_tc_profile(counters.data_ptr())
