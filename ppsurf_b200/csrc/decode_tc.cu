@@ -300,9 +300,9 @@ __global__ void __launch_bounds__(kThreads, 1)
                     for (int i = 0; i < 4; ++i) {
                         const int r = ew * 16 + 4 * i + rs;
                         const float4 a = u[c & 1][i][0], b = u[c & 1][i][1];
-                        float x[8] = {a.x + v0.x, a.y + v0.y, a.z + v0.z, a.w + v0.w, b.x + v1.x, b.y + v1.y, b.z + v1.z, b.w + v1.w};
-#pragma unroll
-                        for (int t = 0; t < 8; ++t) x[t] = fmaxf(x[t], 0.f);
+                        const float raw[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                        float x[8];
+                        bias_relu8(x, raw, v0, v1);
                         uint4 hi, lo;
                         split8(x, hi, lo);
                         *reinterpret_cast<uint4*>(smem + kOffAhi + (c * 8 + kb) * kALbo + r * 16) = hi;
@@ -339,14 +339,10 @@ __global__ void __launch_bounds__(kThreads, 1)
                     tmem_ld_wait(v);
 #pragma unroll
                     for (int k8 = 0; k8 < 4; ++k8) {
-                        float x[8];
+                        float x[8], raw[8];
 #pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            x[4 * c + 0] = fmaxf(__uint_as_float(v[k8 * 8 + 4 * c + 0]) + bv[2 * k8 + c].x, 0.f);
-                            x[4 * c + 1] = fmaxf(__uint_as_float(v[k8 * 8 + 4 * c + 1]) + bv[2 * k8 + c].y, 0.f);
-                            x[4 * c + 2] = fmaxf(__uint_as_float(v[k8 * 8 + 4 * c + 2]) + bv[2 * k8 + c].z, 0.f);
-                            x[4 * c + 3] = fmaxf(__uint_as_float(v[k8 * 8 + 4 * c + 3]) + bv[2 * k8 + c].w, 0.f);
-                        }
+                        for (int c = 0; c < 8; ++c) raw[c] = __uint_as_float(v[k8 * 8 + c]);
+                        bias_relu8(x, raw, bv[2 * k8], bv[2 * k8 + 1]);
                         uint4 hi, lo;
                         split8(x, hi, lo);
                         const int kblk = (col0 >> 3) + k8;

@@ -219,8 +219,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                     const int col0 = (layer < 2 ? half * 32 : half * 64) + cb * 32;
                     float v[32];
                     tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + col0, v);
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c] + bias[col0 + c], 0.f);  // padding rows carry finite values nobody reads
+                    bias_relu32(v, bias + col0);  // padding rows carry finite values nobody reads
                     if (layer == 0 && row_valid) {  // a1 feeds the feature transform of pn_feat_kernel
                         float4* dst = reinterpret_cast<float4*>(a1_out + (q_row * P + p_row) * 64 + col0);
 #pragma unroll
@@ -478,11 +477,12 @@ __global__ void __launch_bounds__(kPnThreads, 2)
             {
                 float v[32];
                 tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + half * 32, v);
+                bias_relu32(v, s_b1 + half * 32);
 #pragma unroll
                 for (int kb = 0; kb < 4; ++kb) {
                     float x8[8];
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) x8[c] = fmaxf(v[kb * 8 + c] + s_b1[half * 32 + kb * 8 + c], 0.f);
+                    for (int c = 0; c < 8; ++c) x8[c] = v[kb * 8 + c];
                     uint4 hi, lo;
                     split8(x8, hi, lo);
                     *reinterpret_cast<uint4*>(smem + kOffAhi + (half * 4 + kb) * kPnLbo + row * 16) = hi;
@@ -500,11 +500,9 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                     const int col0 = half * 64 + cb * 32;
                     float v[32];
                     tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + col0, v);
+                    bias_relu32(v, s_b2 + col0);
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        v[c] = fmaxf(v[c] + s_b2[col0 + c], 0.f);
-                        logit = fmaf(v[c], s_wq[col0 + c], logit);
-                    }
+                    for (int c = 0; c < 32; ++c) logit = fmaf(v[c], s_wq[col0 + c], logit);
 #pragma unroll
                     for (int kb = 0; kb < 4; ++kb) {
                         float x8[8];

@@ -203,33 +203,72 @@ __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
     if (lane == 0) mbar_arrive(bar);
 }
 
+// ---- packed fp32 pairs (Blackwell FADD2 / FFMA2): one issue slot for two lanes of work; the epilogues are issue-bound
+__device__ __forceinline__ void add2(float& r0, float& r1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 a, b, c;\n\t"
+        "mov.b64 a, {%2, %3};\n\t"
+        "mov.b64 b, {%4, %5};\n\t"
+        "add.rn.f32x2 c, a, b;\n\t"
+        "mov.b64 {%0, %1}, c;\n\t}"
+        : "=f"(r0), "=f"(r1)
+        : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void sub2(float& r0, float& r1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 a, b, c;\n\t"
+        "mov.b64 a, {%2, %3};\n\t"
+        "mov.b64 b, {%4, %5};\n\t"
+        "sub.rn.f32x2 c, a, b;\n\t"
+        "mov.b64 {%0, %1}, c;\n\t}"
+        : "=f"(r0), "=f"(r1)
+        : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+// two fp32 -> packed fp16x2 (first argument in the low half), round to nearest, SATURATING to +-65504: the conversion itself
+// clamps to the fp16 range, no separate min / max
+__device__ __forceinline__ uint32_t cvt_pack_sat(float lo_half, float hi_half) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_half), "f"(lo_half));
+    return r;
+}
+
 // fp32 -> fp16 hi + fp16 lo, 8 values -> two 16-byte vectors.  hi is the value TRUNCATED to fp16's 10 explicit mantissa
-// bits (a mask, so hi converts exactly and x - hi is exact), lo = fp16(x - hi): hi + lo carries 21 mantissa bits.  Both
-// conversions are the packed 2-in-1 cvt.rn.f16x2.f32, i.e. one conversion instruction per element instead of three
-// (the conversion pipe, not the FMA pipe, bounds the epilogues).  Inputs are clamped to the fp16 range.
+// bits (a mask, so hi converts exactly and x - hi is exact), lo = fp16(x - hi): hi + lo carries 21 mantissa bits.  Per pair of
+// values: 2 LOP, 1 FADD2, 2 packed conversions  --  4 issue slots per element with the bias add and the ReLU.
 __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
     const float ah = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u), bh = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
-    const __half2 h = __floats2half2_rn(ah, bh);
-    const __half2 l = __floats2half2_rn(a - ah, b - bh);
-    hi = *reinterpret_cast<const uint32_t*>(&h);
-    lo = *reinterpret_cast<const uint32_t*>(&l);
+    float la, lb;
+    sub2(la, lb, a, b, ah, bh);
+    hi = cvt_pack_sat(ah, bh);
+    lo = cvt_pack_sat(la, lb);
 }
-// non-negative inputs (after ReLU)
+// inputs of either sign; out-of-range values saturate to +-65504 in the conversion
 __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
     uint32_t h[4], l[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) split_pair(fminf(x[2 * i], 65000.f), fminf(x[2 * i + 1], 65000.f), h[i], l[i]);
+    for (int i = 0; i < 4; ++i) split_pair(x[2 * i], x[2 * i + 1], h[i], l[i]);
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
-// inputs of either sign (pre-activation quantities, transform matrices)
-__device__ __forceinline__ void split8_signed(const float (&x)[8], uint4& hi, uint4& lo) {
-    uint32_t h[4], l[4];
+__device__ __forceinline__ void split8_signed(const float (&x)[8], uint4& hi, uint4& lo) { split8(x, hi, lo); }
+// x[i] = relu(v[i] + b[i]) for 8 values with packed adds
+__device__ __forceinline__ void bias_relu8(float (&x)[8], const float (&v)[8], const float4& b0, const float4& b1) {
+    add2(x[0], x[1], v[0], v[1], b0.x, b0.y);
+    add2(x[2], x[3], v[2], v[3], b0.z, b0.w);
+    add2(x[4], x[5], v[4], v[5], b1.x, b1.y);
+    add2(x[6], x[7], v[6], v[7], b1.z, b1.w);
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-        split_pair(fminf(fmaxf(x[2 * i], -65000.f), 65000.f), fminf(fmaxf(x[2 * i + 1], -65000.f), 65000.f), h[i], l[i]);
-    hi = make_uint4(h[0], h[1], h[2], h[3]);
-    lo = make_uint4(l[0], l[1], l[2], l[3]);
+    for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.f);
+}
+
+// v[c] = relu(v[c] + bias[c]) for 32 accumulator columns, bias 16-byte aligned in shared memory
+__device__ __forceinline__ void bias_relu32(float (&v)[32], const float* bias) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float4 b = *reinterpret_cast<const float4*>(bias + 4 * c);
+        add2(v[4 * c], v[4 * c + 1], v[4 * c], v[4 * c + 1], b.x, b.y);
+        add2(v[4 * c + 2], v[4 * c + 3], v[4 * c + 2], v[4 * c + 3], b.z, b.w);
+    }
+#pragma unroll
+    for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c], 0.f);
 }
 
 }  // namespace tc
