@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 }  // namespace tc
 
 static int g_tc_variant = 0;             // debug experiments on the weight stream (pps_debug_tc_cluster)
-long long* g_tc_prof = nullptr;  // device buffer of 16 counters, set by pps_debug_tc_profile
+static long long* g_tc_prof = nullptr;  // device buffer of 16 counters, set by pps_debug_tc_profile
 
 size_t projection_tc_workspace(const pps_decoder_weights*, int64_t) { return 256; }
 

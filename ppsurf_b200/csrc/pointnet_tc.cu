@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
     pn_stn_kernel(const float* __restrict__ patches, long long nq, int P, const uint8_t* __restrict__ wpack,
                   const float* __restrict__ w0a, const float* __restrict__ b0a, const float* __restrict__ b0b,
                   const float* __restrict__ bs1, const float* __restrict__ bs2, const float* __restrict__ bs3,
-                  float* __restrict__ a1_out, float* __restrict__ g_out, long long* prof) {
+                  float* __restrict__ a1_out, float* __restrict__ g_out) {
     using namespace stn;
     extern __shared__ __align__(1024) uint8_t smem[];  // used directly: the compiler keeps the shared address space (LDS/STS)
     const uint32_t sbase = smem_u32(smem);
@@ -117,12 +117,9 @@ __global__ void __launch_bounds__(kPnThreads, 2)
     } else if (warp == 1) {
         if (lane == 0) {
             uint32_t slot = 0, phase = 0, ready_phase = 0;
-            long long t_ready = 0, t_total = clock64();
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 for (int layer = 0; layer < 4; ++layer) {
-                    const long long tw = clock64();
                     mbar_wait(bar_aready, ready_phase);
-                    t_ready += clock64() - tw;
                     ready_phase ^= 1;
                     tc_fence_after();
                     if (layer < 3) {
@@ -172,22 +169,12 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                     tc_commit(bar_accum);
                 }
             }
-            if (prof && blockIdx.x == 0) {
-                prof[16] = clock64() - t_total;
-                prof[17] = t_ready;
-            }
         }
     } else {
         const int ew = warp - 2, et = tid - 64;
         const int lane_grp = warp & 3, half = ew >> 2;
         const int row = lane_grp * 32 + lane;  // TMEM lane of this thread
         uint32_t accum_phase = 0;
-        long long t_ph[6] = {0, 0, 0, 0, 0, 0}, t_mark = clock64();  // gather, wait acc (layers 0-2), epilogues 0-2, wait stn3, max
-        auto lap = [&](int i) {
-            const long long now = clock64();
-            t_ph[i] += now - t_mark;
-            t_mark = now;
-        };
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             // ---- gather + conv0a (SIMT, K=3): thread = (row, half of the 64 channels)
             {
@@ -217,7 +204,6 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                 }
             }
             warp_arrive(bar_aready, lane);
-            lap(0);
 
             const long long q_row = 2 * tile + (row >> 6);
             const int p_row = row & 63;
@@ -227,8 +213,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                 mbar_wait(bar_accum, accum_phase);
                 accum_phase ^= 1;
                 tc_fence_after();
-                lap(1);
-                const float* bias = layer == 0 ? s_b0b : (layer == 1 ? s_bs1 : s_bs2);
+                    const float* bias = layer == 0 ? s_b0b : (layer == 1 ? s_bs1 : s_bs2);
                 const int nload = layer < 2 ? 1 : 2;  // 32 or 64 columns per thread
                 for (int cb = 0; cb < nload; ++cb) {
                     const int col0 = (layer < 2 ? half * 32 : half * 64) + cb * 32;
@@ -253,13 +238,11 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                     }
                 }
                 warp_arrive(bar_aready, lane);
-                lap(2);
-            }
+                }
             // ---- stn.conv3 transposed: TMEM lane = feature, columns = rows of the tile; max over the patch's points
             mbar_wait(bar_accum, accum_phase);
             accum_phase ^= 1;
             tc_fence_after();
-            lap(3);
             {
                 const long long q = 2 * tile + half;  // this warp's column half = one query
                 for (int fb = 0; fb < 2; ++fb) {
@@ -276,12 +259,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                 }
             }
             tc_fence_before();
-            lap(4);
             // the next tile's gather overwrites the operand tile: the MMAs that read it are complete (accum barrier)
-        }
-        if (prof && blockIdx.x == 0 && tid == 64) {
-#pragma unroll
-            for (int i = 0; i < 5; ++i) prof[18 + i] = t_ph[i];
         }
     }
     tc_fence_before();
@@ -605,8 +583,6 @@ int linear_impl(const float* x, const float* w, const float* bias, const float* 
 bool chain_tc_supported(const pps_decoder_weights* w);
 int stn_fc_tc_impl(const pps_decoder_weights* w, const float* g, int64_t q, float* tmat, cudaStream_t st);
 
-extern long long* g_tc_prof;  // debug counters (decode_tc.cu)
-
 bool pointnet_tc_supported(const pps_decoder_weights* w) {
     return w->tc_pn_stn != nullptr && w->tc_pn_feat != nullptr && w->num_pts_local <= 64 && w->stn_size == 256 && w->latent == 256;
 }
@@ -628,7 +604,7 @@ int pointnet_tc_impl(const pps_decoder_weights* w, const float* patches, int64_t
     const int grid_c = (int)(ntiles < 2 * kNumSMs ? ntiles : 2 * kNumSMs);
     tc::pn_stn_kernel<<<grid_a, tc::kPnThreads, tc::stn::kSmemBytes, st>>>(patches, q, P, static_cast<const uint8_t*>(w->tc_pn_stn),
                                                                           w->pn0a_w, w->pn0a_b, w->pn0b_b, w->stn1_b, w->stn2_b,
-                                                                          w->stn3_b, a1, g, g_tc_prof);
+                                                                          w->stn3_b, a1, g);
     PPS_LAUNCH_CHECK();
     if (chain_tc_supported(w)) {
         PPS_TRY(stn_fc_tc_impl(w, g, q, tmat, st));
