@@ -310,6 +310,10 @@ int pps_global_max(const float* x, int64_t b, int64_t n, int c, float* out, void
  * ------------------------------------------------------------------------------------------------------------- */
 int pps_latent_accumulate(const float* partial, const int32_t* ids, int64_t n, int c, float* latent, float* counts,
                           void* stream);
+/* row-selecting variant: latent[ids[i]] += partial[rows[i]] (partial [*,c] point-major, c % 4 == 0); the caller passes each
+ * destination once per call (de-duplicated pass), calls of different passes are ordered on the stream */
+int pps_latent_accumulate_rows(const float* partial, const int32_t* rows, const int32_t* ids, int64_t n, int c, float* latent,
+                               float* counts, void* stream);
 int pps_latent_finalize(float* latent, const float* counts, int64_t n, int c, void* stream);
 
 #ifdef __cplusplus

@@ -100,6 +100,7 @@ SIGNATURES = {
     'pps_gather_max': (i32, [c_f32p, c_i32p, i64, i64, i64, i32, i32, c_f32p, c_voidp]),
     'pps_global_max': (i32, [c_f32p, i64, i64, i32, c_f32p, c_voidp]),
     'pps_latent_accumulate': (i32, [c_f32p, c_i32p, i64, i32, c_f32p, c_f32p, c_voidp]),
+    'pps_latent_accumulate_rows': (i32, [c_f32p, c_i32p, c_i32p, i64, i32, c_f32p, c_f32p, c_voidp]),
     'pps_latent_finalize': (i32, [c_f32p, c_f32p, i64, i32, c_voidp]),
 }
 

@@ -282,6 +282,25 @@ __global__ void latent_accumulate_kernel(const float* __restrict__ partial, cons
     if (ch == 0) counts[dst] += 1.f;
 }
 
+// same with a row selection: partial row rows[i] goes to point ids[i] (the caller removed duplicate ids of the pass)
+__global__ void latent_accumulate_rows_kernel(const float* __restrict__ partial, const int32_t* __restrict__ rows,
+                                              const int32_t* __restrict__ ids, long long n, int c, float* latent, float* counts) {
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n * (c / 4)) return;
+    const long long i = e / (c / 4);
+    const int c4 = int(e % (c / 4));
+    const int dst = ids[i];
+    const float4 v = reinterpret_cast<const float4*>(partial + (size_t)rows[i] * c)[c4];
+    float4* d = reinterpret_cast<float4*>(latent + (size_t)dst * c) + c4;
+    float4 o = *d;
+    o.x += v.x;
+    o.y += v.y;
+    o.z += v.z;
+    o.w += v.w;
+    *d = o;
+    if (c4 == 0) counts[dst] += 1.f;
+}
+
 __global__ void latent_finalize_kernel(float* latent, const float* __restrict__ counts, long long n, int c) {
     long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n * c) return;
@@ -380,6 +399,17 @@ int pps_latent_accumulate(const float* partial, const int32_t* ids, int64_t n, i
     if (n == 0) return PPS_OK;
     latent_accumulate_kernel<<<(unsigned)ceil_div(n * c, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(partial, ids, n, c,
                                                                                                            latent, counts);
+    PPS_LAUNCH_CHECK();
+    return PPS_OK;
+}
+
+int pps_latent_accumulate_rows(const float* partial, const int32_t* rows, const int32_t* ids, int64_t n, int c, float* latent,
+                               float* counts, void* stream) {
+    PPS_CHECK_ARG(partial && rows && ids && latent && counts && n >= 0 && c >= 4 && c % 4 == 0,
+                  "pps_latent_accumulate_rows: bad arguments (c must be a multiple of 4)");
+    if (n == 0) return PPS_OK;
+    latent_accumulate_rows_kernel<<<(unsigned)ceil_div(n * (c / 4), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        partial, rows, ids, n, c, latent, counts);
     PPS_LAUNCH_CHECK();
     return PPS_OK;
 }

@@ -7,6 +7,8 @@ What stays on the host, as in the reference: file I/O, marching cubes (scikit-im
 SURVEY.md §8f ranks as "next"; the region-growing masks and frontier lists are on the device (``ops.RegionVolume``).
 """
 import os
+import queue
+import threading
 import typing
 
 import numpy as np
@@ -89,22 +91,56 @@ class PPSurfModel(_Base):
         counts = torch.zeros((n,), dtype=torch.float32, device=dev)
         schedule = self.latent_schedule(n, generator)
         iteration = 0
+        sub = min(self.gen_subsample_manifold, n)
+
+        def prepare(group):
+            # one host->device copy per batch: the point ids of every pass, the first occurrence of every distinct id
+            # (torch semantics of `latent[ids] += x` with repeated ids: one writer wins, counted once) as rows of the
+            # batch's point-major output and as destination points
+            ids_np = [ids.numpy() for ids in group]
+            firsts = [np.unique(a, return_index=True)[1] for a in ids_np]
+            rows = np.concatenate([f + k * sub for k, f in enumerate(firsts)]).astype(np.int32)
+            dsts = np.concatenate([a[f] for a, f in zip(ids_np, firsts)]).astype(np.int32)
+            packed = torch.from_numpy(np.concatenate([np.concatenate(ids_np).astype(np.int32), rows, dsts])).pin_memory()
+            return len(group), [f.shape[0] for f in firsts], packed
+
+        # the schedule depends only on the host-side visit counts, never on network output: a producer thread draws and
+        # prepares the next batches while the device works on the current one (numpy / torch release the GIL)
+        batches: queue.Queue = queue.Queue(maxsize=3)
+
+        def producer():
+            try:
+                while True:
+                    group = [ids for _, ids in zip(range(batch_passes), schedule)]
+                    batches.put(prepare(group) if group else None)
+                    if not group:
+                        return
+            except BaseException as err:  # surfaces in the consumer
+                batches.put(err)
+
+        thread = threading.Thread(target=producer, daemon=True)
+        thread.start()
         while True:
-            group = [ids for _, ids in zip(range(batch_passes), schedule)]
-            if not group:
+            item = batches.get()
+            if item is None:
                 break
-            ids_dev = [ids.to(dev) for ids in group]
-            batch = torch.stack([pts[i] for i in ids_dev], dim=0).transpose(1, 2).contiguous()  # [B,3,sub]
-            part = self.network.get_latent({'pts': batch})['latents']  # [B,latent,sub]
-            for k, ids in enumerate(group):
-                # torch semantics of `latent[ids] += x` with repeated ids: one writer wins, counted once
-                _, first = np.unique(ids.numpy(), return_index=True)
-                sel = torch.from_numpy(first).to(dev)
-                ops.latent_accumulate(part[k].transpose(0, 1)[sel].contiguous(), ids_dev[k][sel].to(torch.int32).contiguous(),
-                                      latent, counts)
+            if isinstance(item, BaseException):
+                raise item
+            b, n_first, packed = item
+            packed = packed.to(dev, non_blocking=True)
+            total_first = sum(n_first)
+            all_ids, rows_dev, dsts_dev = packed[:b * sub], packed[b * sub:b * sub + total_first], packed[b * sub + total_first:]
+            batch = pts[all_ids.long()].view(b, sub, 3).transpose(1, 2).contiguous()  # [B,3,sub]
+            part = self.network.get_latent({'pts': batch})['latents']  # [B,latent,sub], a view of the point-major result
+            part_pm = part.transpose(1, 2).contiguous().view(b * sub, -1)  # no copy when the view is already point-major
+            off = 0
+            for nf in n_first:  # pass order is kept: a point revisited inside the batch accumulates in the reference's order
+                ops.latent_accumulate_rows(part_pm, rows_dev[off:off + nf], dsts_dev[off:off + nf], latent, counts)
+                off += nf
                 iteration += 1
             if prog_bar is not None:
                 prog_bar.predict_progress_bar.set_postfix_str('get_latent iter: {}'.format(iteration), refresh=True)
+        thread.join()
         ops.latent_finalize(latent, counts)
         return latent.transpose(0, 1).unsqueeze(0)
 

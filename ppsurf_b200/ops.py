@@ -290,6 +290,13 @@ def latent_accumulate(partial, ids, latent, counts):
                                     _ptr(latent, torch.float32), _ptr(counts, torch.float32), _stream()))
 
 
+def latent_accumulate_rows(partial, rows, ids, latent, counts):
+    """``latent[ids[i]] += partial[rows[i]]``, ``counts[ids[i]] += 1``; ``partial [R,C]`` point-major, ``rows`` / ``ids`` int32"""
+    check(lib.pps_latent_accumulate_rows(_ptr(partial, torch.float32), _ptr(rows, torch.int32), _ptr(ids, torch.int32),
+                                         ids.shape[0], latent.shape[1], _ptr(latent, torch.float32), _ptr(counts, torch.float32),
+                                         _stream()))
+
+
 def latent_finalize(latent, counts):
     check(lib.pps_latent_finalize(_ptr(latent, torch.float32), _ptr(counts, torch.float32), latent.shape[0],
                                   latent.shape[1], _stream()))

@@ -37,7 +37,7 @@ def wrap(name, fn):
 
 net.spatial_ids = wrap('spatial_ids', orig_ids)
 net.encode = wrap('encode', orig_enc)
-for bp in (8, 16):
+for bp in (16, 16):
     for k in acc:
         acc[k] = 0.0
     net.sampling_seed = 42
