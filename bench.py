@@ -43,8 +43,8 @@ def parse_args():
     ap.add_argument('--points', type=int, default=100000)
     ap.add_argument('--resolution', type=int, default=129)
     ap.add_argument('--num-pts-local', type=int, default=50)
-    ap.add_argument('--chunk', type=int, default=18944,
-                    help='queries per decode launch; 18944 = 148 SMs x 128 rows: whole waves for every tensor-core kernel')
+    ap.add_argument('--chunk', type=int, default=37888,
+                    help='queries per decode launch; 37888 = 2 x 148 SMs x 128 rows: whole waves for every tensor-core kernel')
     ap.add_argument('--latents', default='encoder', choices=['encoder', 'random'])
     ap.add_argument('--cpu-sample', type=int, default=65536,
                     help='queries of the CPU baseline sample (about 10-15 s of host work on 16 cores)')

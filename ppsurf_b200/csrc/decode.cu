@@ -277,6 +277,7 @@ struct DecodeBuffers {
     float* a1;
     float* patches;
     float* pooled;
+    float* pooled_super;  // global-branch output of a whole super-chunk (tensor-core path)
     float* feat_proj;
     float* g;
     float* f1;
@@ -304,6 +305,7 @@ static bool carve(const pps_decoder_weights* w, int64_t chunk, void* ws, size_t 
     b.a1 = a.take<float>((size_t)chunk * P * 64);
     b.patches = a.take<float>((size_t)chunk * P * 3);
     b.pooled = a.take<float>((size_t)chunk * C);
+    b.pooled_super = a.take<float>((size_t)chunk * kKnnSuper * C);
     b.feat_proj = a.take<float>((size_t)chunk * C);
     b.g = a.take<float>((size_t)chunk * S);
     b.f1 = a.take<float>((size_t)chunk * (S / 2));
@@ -383,17 +385,17 @@ static int pointnet_run(const pps_decoder_weights* w, const float* patches, int6
 
 // one decode chunk; `idx`/`d2` [q,kmax] are this chunk's rows of the neighbour search
 static int decode_chunk(const pps_decoder_weights* w, const float* pts, const float* table, const float* queries, int64_t q,
-                        const int32_t* idx, const float* d2, DecodeBuffers& b, float* logits_out, float* occ_out, int path,
-                        cudaStream_t st) {
+                        const int32_t* idx, const float* d2, DecodeBuffers& b, const float* pooled_proj, float* logits_out,
+                        float* occ_out, int path, cudaStream_t st) {
     const int C = w->latent, P = w->num_pts_local;
     const int kmax = kmax_of(w);
     patch_normalize_kernel<<<(unsigned)ceil_div(q * P, 256), 256, 0, st>>>(pts, queries, idx, d2, q, P, kmax, b.patches);
     PPS_LAUNCH_CHECK();
     if (path == 1 && pointnet_tc_supported(w) && chain_tc_supported(w)) {
-        // all-tensor-core tail: both pooled vectors go straight into the chain kernel (merged value matrices + MLP + head)
-        PPS_TRY(projection_tc_impl(w, table, queries, idx, kmax, q, b.tc_ws, b.tc_ws_bytes, b.pooled, st));
+        // all-tensor-core tail: both pooled vectors go straight into the chain kernel (merged value matrices + MLP + head);
+        // the global branch of the whole super-chunk has already run (decode_super), `pooled_proj` are this chunk's rows
         PPS_TRY(pointnet_tc_impl(w, b.patches, q, b.a1, b.g, b.f1, b.f2, b.tmat, b.pooled128, st));
-        return mlp_tc_impl(w, b.pooled, b.pooled128, q, logits_out, occ_out, st);
+        return mlp_tc_impl(w, pooled_proj, b.pooled128, q, logits_out, occ_out, st);
     }
     PPS_TRY(projection_run(w, table, queries, idx, kmax, q, b, b.feat_proj, path, st));
     PPS_TRY(pointnet_run(w, b.patches, q, b, b.feat_proj, b.feat, path, st));
@@ -411,10 +413,16 @@ static int decode_super(const pps_decoder_weights* w, const void* knn_index, con
     const int kmax = kmax_of(w);
     PPS_TRY(knn_query_impl(knn_index, n, queries, q, kmax, b.idx, b.d2, st));
     if (idx_out) PPS_CUDA(cudaMemcpyAsync(idx_out, b.idx, (size_t)q * kmax * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    // tensor-core path: the global branch runs over the whole super-chunk in ONE launch.  Its working set (the 97 MB fc1 table
+    // + the weight pack) then stays in the L2 instead of being evicted between chunks by the local branch, which streams
+    // ~0.6 GB of a1 / T per chunk through the cache
+    const bool all_tc = path == 1 && pointnet_tc_supported(w) && chain_tc_supported(w);
+    if (all_tc) PPS_TRY(projection_tc_impl(w, table, queries, b.idx, kmax, q, b.tc_ws, b.tc_ws_bytes, b.pooled_super, st));
     for (int64_t s = 0; s < q; s += chunk) {
         int64_t c = q - s < chunk ? q - s : chunk;
         PPS_TRY(decode_chunk(w, pts, table, queries + 3 * s, c, b.idx + s * kmax, b.d2 + s * kmax, b,
-                             logits_out ? logits_out + 2 * s : nullptr, occ_out ? occ_out + s : nullptr, path, st));
+                             all_tc ? b.pooled_super + (size_t)s * w->latent : nullptr, logits_out ? logits_out + 2 * s : nullptr,
+                             occ_out ? occ_out + s : nullptr, path, st));
     }
     return PPS_OK;
 }

@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                     chunk_phase ^= 1;
                 }
             }
+            if (prof) prof[32 + pair] = clock64() - t_total;  // every pair's total, to see the spread over the chip
             if (prof && blockIdx.x == 0) {  // cycles: MMA warp total, waiting for operand chunks / weights / the S groups
                 prof[0] = clock64() - t_total;
                 prof[1] = t_chunk;
@@ -328,20 +329,23 @@ __global__ void __launch_bounds__(kThreads, 1)
                 }
                 const float* bias = s_bias + layer * 256;
                 const uint32_t dcol = layer == 1 ? 256u : 0u;
-#pragma unroll 1
+                // the TMEM load of chunk cb+1 is in flight while chunk cb is converted (register double buffer)
+                uint32_t v[2][32];
+                tmem_ld32_issue(tmem + ((uint32_t)(lane_grp * 32) << 16) + dcol + half * 32, v[0]);
+#pragma unroll
                 for (int cb = 0; cb < kChunks; ++cb) {
                     const int col0 = cb * 64 + half * 32;
-                    uint32_t v[32];
-                    tmem_ld32_issue(tmem + ((uint32_t)(lane_grp * 32) << 16) + dcol + col0, v);
                     float4 bv[8];  // the chunk's bias, fetched while the TMEM load is in flight
 #pragma unroll
                     for (int c = 0; c < 8; ++c) bv[c] = *reinterpret_cast<const float4*>(bias + col0 + 4 * c);
-                    tmem_ld_wait(v);
+                    tmem_ld_wait(v[cb & 1]);
+                    if (cb + 1 < kChunks)
+                        tmem_ld32_issue(tmem + ((uint32_t)(lane_grp * 32) << 16) + dcol + col0 + 64, v[(cb + 1) & 1]);
 #pragma unroll
                     for (int k8 = 0; k8 < 4; ++k8) {
                         float x[8], raw[8];
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) raw[c] = __uint_as_float(v[k8 * 8 + c]);
+                        for (int c = 0; c < 8; ++c) raw[c] = __uint_as_float(v[cb & 1][k8 * 8 + c]);
                         bias_relu8(x, raw, bv[2 * k8], bv[2 * k8 + 1]);
                         uint4 hi, lo;
                         split8(x, hi, lo);

@@ -10,7 +10,7 @@ from ._lib import check, lib
 
 
 # queries per decode launch: 148 SMs x 128-row tiles, i.e. whole waves for every persistent tensor-core kernel
-DEFAULT_CHUNK = 148 * 128
+DEFAULT_CHUNK = 2 * 148 * 128  # whole waves for every tensor-core kernel (tiles of 2 or 128 queries, 148 or 296 CTAs)
 
 
 def _stream():

@@ -20,7 +20,7 @@ dec = ops.Decoder(net.packed()['decoder'], pts, lat, chunk=18944, path=1)
 step, bmin_pad, _ = ppsurf_b200.PPSurfModel.grid_definition(pts.cpu().numpy(), 129, 1)
 qry = ops.grid_queries(131, step, bmin_pad, first=131 * 131 * 60, count=18944, device=dev)
 idx = dec.index.query(qry, 64)
-counters = torch.zeros(16, dtype=torch.int64, device=dev)
+counters = torch.zeros(128, dtype=torch.int64, device=dev)
 tiles = 18944 // 4 // 74
 names = ['mma_total', 'mma_wait_chunk', 'mma_wait_weights', 'mma_wait_sgroup', 'g_gather', 'g_wait', 'g_E2E3', 's_wait', 's_softmax', 's_pool']
 ref = None
@@ -42,5 +42,7 @@ for cs in (0,):
     print('cluster size {}: {:.1f} us per chunk (incl. value matrix), max |diff| vs cs=1 {:.2e}'.format(
         cs, e0.elapsed_time(e1) * 200, float((out - ref).abs().max())))
     print('   ' + '  '.join('{}={:.0f}'.format(k, v / tiles) for k, v in zip(names, c)))
+    per_pair = c[32:32 + 74] / tiles
+    print('   per-pair cycles per tile: min {:.0f} median {:.0f} max {:.0f}; slowest pairs {}'.format(per_pair.min(), np.median(per_pair), per_pair.max(), np.argsort(per_pair)[-5:]))
 _lib.lib.pps_debug_tc_profile(None)
 _lib.lib.pps_debug_tc_cluster(0)
