@@ -10,12 +10,7 @@
 //   x.W ~= x_hi.W_hi + x_lo.W_hi + x_hi.W_lo   (fp32 accumulation in TMEM),
 // i.e. three tcgen05.mma per k-step; the dropped x_lo.W_lo term is O(2^-22) relative.
 //
-// Roles (320 threads, one CTA per SM, persistent over tiles):
-//   warp 0      weight producer: cp.async.bulk (TMA bulk copy, UBLKCP) of pre-packed k16 weight stages into a 3-slot ring
-//   warp 1      MMA issuer: tcgen05.mma (SS, M=128, N=256/64, K=16) + tcgen05.commit onto mbarriers; owns the TMEM allocation
-//   warps 2..9  gather + epilogues: table rows -> fp16 hi/lo operand tiles in shared memory (UMMA canonical K-major layout,
-//               no swizzle, k8-blocks padded by 16 B so that row-wise AND k-wise accesses are bank-conflict free),
-//               tcgen05.ld of the accumulators, bias + ReLU + re-split, softmax / pooling
+// Roles, the CTA-pair scheme and the per-tile pipeline are described above projection_tc_kernel.
 #include "tc_common.cuh"
 
 namespace pps {
