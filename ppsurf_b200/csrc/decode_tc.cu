@@ -73,10 +73,18 @@ __device__ __forceinline__ void s_barrier() { asm volatile("bar.sync 2, %0;" ::"
 //                D1 when the pooling has read fc3's accumulator).
 // fc_query is computed TRANSPOSED (heads on TMEM lanes 64..127, the tile's rows on the columns): the softmax over a query's
 // 64 neighbours is then a reduction inside one thread; the mean over heads is a recursive halving across lanes.
+// cycle counter of the instrumented build only: the product kernel (PROF = false) carries no clock reads -- the MMA issuer's loop
+// is on the critical path (a stray branch in it cost 8 % of the kernel)
+template <bool PROF>
+__device__ __forceinline__ long long tick() {
+    return PROF ? clock64() : 0ll;
+}
+
+template <bool PROF>
 __global__ void __launch_bounds__(kThreads, 1)
     projection_tc_kernel(const float* __restrict__ table, const float* __restrict__ queries, const int32_t* __restrict__ idx, int ks,
                          long long nq, const uint8_t* __restrict__ wpack, const float* __restrict__ b2, const float* __restrict__ b3,
-                         const float* __restrict__ bq, const float* __restrict__ w1_xyz, float* __restrict__ pooled, long long* prof, int variant) {
+                         const float* __restrict__ bq, const float* __restrict__ w1_xyz, float* __restrict__ pooled, long long* prof) {
     extern __shared__ __align__(1024) uint8_t smem[];  // used directly: the compiler keeps the shared address space (LDS/STS)
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -156,28 +164,28 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (lane == 0 && crank == 0) {
             // ---------------------------------------------------------------- MMA issuer of the pair
             uint32_t slot = 0, phase = 0, chunk_phase = 0;
-            long long t_chunk = 0, t_full = 0, t_dfree = 0, t_total = clock64();
+            long long t_chunk = 0, t_full = 0, t_dfree = 0, t_total = tick<PROF>();
             for (long long it = 0; it < iters; ++it) {
                 for (int layer = 0; layer < 3; ++layer) {
                     const uint32_t idesc = umma_idesc2(256);
                     const uint32_t dcol = layer == 1 ? 256u : 0u;
                     if (it > 0 && layer < 2) {  // the S groups have taken what they need of the previous tiles out of this accumulator
-                        const long long t0 = clock64();
+                        const long long t0 = tick<PROF>();
                         mbar_wait_cluster(layer == 0 ? bar_d0free : bar_d1free, (uint32_t)((it - 1) & 1));
                         tc_fence_after();
-                        t_dfree += clock64() - t0;
+                        t_dfree += tick<PROF>() - t0;
                     }
                     for (int s = 0; s < kKSteps; ++s) {
-                        long long t0 = clock64();
+                        long long t0 = tick<PROF>();
                         if ((s & 3) == 0) {  // operand columns [64c, 64c+64) of BOTH tiles written by the previous stage of the pipeline
                             mbar_wait_cluster(bar_chunk + 8 * (s >> 2), chunk_phase);
                             tc_fence_after();
                         }
-                        long long t1 = clock64();
+                        long long t1 = tick<PROF>();
                         mbar_wait_cluster(bar_full + 8 * slot, phase);  // both halves of the weight stage have landed
                         tc_fence_after();
                         t_chunk += t1 - t0;
-                        t_full += clock64() - t1;
+                        t_full += tick<PROF>() - t1;
                         const uint32_t a_off = 2 * s * kALbo;
                         const uint64_t x_hi = umma_desc(sbase + kOffAhi + a_off, kALbo, 128);
                         const uint64_t x_lo = umma_desc(sbase + kOffAlo + a_off, kALbo, 128);
@@ -203,9 +211,9 @@ __global__ void __launch_bounds__(kThreads, 1)
                     chunk_phase ^= 1;
                 }
             }
-            if (prof) prof[32 + pair] = clock64() - t_total;  // every pair's total, to see the spread over the chip
-            if (prof && blockIdx.x == 0) {  // cycles: MMA warp total, waiting for operand chunks / weights / the S groups
-                prof[0] = clock64() - t_total;
+            if (PROF && prof) prof[32 + pair] = tick<PROF>() - t_total;  // every pair's total, to see the spread over the chip
+            if (PROF && prof && blockIdx.x == 0) {  // cycles: MMA warp total, waiting for operand chunks / weights / the S groups
+                prof[0] = tick<PROF>() - t_total;
                 prof[1] = t_chunk;
                 prof[2] = t_full;
                 prof[3] = t_dfree;
@@ -231,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int row = lane_grp * 32 + lane;  // accumulator row (= TMEM lane) of this thread
         const int kb = lane & 7, rs = lane >> 3;
         const int ql = (ew * 16) >> 6;         // the query whose rows this warp gathers
-        long long t_gather = 0, t_wait = 0, t_epi = 0, t_mark = clock64();
+        long long t_gather = 0, t_wait = 0, t_epi = 0, t_mark = tick<PROF>();
 
         int src_next[4];
         {
@@ -276,7 +284,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                     mbar_wait(bar_acc + 16, (uint32_t)((it - 1) & 1));
                 }
                 {
-                    const long long now = clock64();
+                    const long long now = tick<PROF>();
                     t_wait += now - t_mark;
                     t_mark = now;
                 }
@@ -308,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                 }
             }
             {
-                const long long now = clock64();
+                const long long now = tick<PROF>();
                 t_gather += now - t_mark;
                 t_mark = now;
             }
@@ -318,7 +326,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                 mbar_wait(bar_acc + 8 * layer, (uint32_t)(it & 1));
                 tc_fence_after();
                 {
-                    const long long now = clock64();
+                    const long long now = tick<PROF>();
                     t_wait += now - t_mark;
                     t_mark = now;
                 }
@@ -351,7 +359,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                     warp_arrive_cluster(lead_chunk + 8 * cb, lane);
                 }
                 {
-                    const long long now = clock64();
+                    const long long now = tick<PROF>();
                     t_epi += now - t_mark;
                     t_mark = now;
                 }
@@ -372,14 +380,14 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int sq = sw >> 2;                // the query whose softmax this warp computes (heads only)
         // pooling: rows 0..63 (lane groups 0,1) have one warp each -> all 8 column blocks; rows 64..127 have two warps each
         const int cb0 = heads ? 4 * sq : 0, cb1 = heads ? 4 * sq + 4 : 8;
-        long long t_wait = 0, t_soft = 0, t_pool = 0, t_mark = clock64();
+        long long t_wait = 0, t_soft = 0, t_pool = 0, t_mark = tick<PROF>();
         const uint32_t score_col = 128u * crank;  // scores^T columns = rows of the pair's two tiles; mine start here
         for (long long it = 0; it < iters; ++it) {
             const long long tile = tile0 + it * tile_step;
             mbar_wait(bar_acc + 16, (uint32_t)(it & 1));
             tc_fence_after();
             {
-                const long long now = clock64();
+                const long long now = tick<PROF>();
                 t_wait += now - t_mark;
                 t_mark = now;
             }
@@ -428,7 +436,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
             s_barrier();
             {
-                const long long now = clock64();
+                const long long now = tick<PROF>();
                 t_soft += now - t_mark;
                 t_mark = now;
             }
@@ -480,7 +488,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
             s_barrier();  // the head sums and partial pooled sums are consumed before the next tile overwrites them
             {
-                const long long now = clock64();
+                const long long now = tick<PROF>();
                 t_pool += now - t_mark;
                 t_mark = now;
             }
@@ -505,7 +513,6 @@ __global__ void __launch_bounds__(kThreads, 1)
 
 }  // namespace tc
 
-static int g_tc_variant = 0;             // debug experiments on the weight stream (pps_debug_tc_cluster)
 static long long* g_tc_prof = nullptr;  // device buffer of 16 counters, set by pps_debug_tc_profile
 
 size_t projection_tc_workspace(const pps_decoder_weights*, int64_t) { return 256; }
@@ -518,7 +525,8 @@ int projection_tc_impl(const pps_decoder_weights* w, const float* table, const f
     if (q == 0) return PPS_OK;
     static bool configured = false;
     if (!configured) {
-        PPS_CUDA(cudaFuncSetAttribute(tc::projection_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+        PPS_CUDA(cudaFuncSetAttribute(tc::projection_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+        PPS_CUDA(cudaFuncSetAttribute(tc::projection_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
         configured = true;
     }
     const long long npt = (q + 3) / 4;  // pair-tiles of 4 queries
@@ -538,8 +546,12 @@ int projection_tc_impl(const pps_decoder_weights* w, const float* table, const f
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     profile_begin(st);
-    PPS_CUDA(cudaLaunchKernelEx(&cfg, tc::projection_tc_kernel, table, queries, idx, k_stride, nq, wp, w->b2, w->b3, w->bq, w->w1_xyz,
-                                pooled, g_tc_prof, g_tc_variant));
+    if (g_tc_prof)  // instrumented build, tools/tc_phase_profile.py only
+        PPS_CUDA(cudaLaunchKernelEx(&cfg, tc::projection_tc_kernel<true>, table, queries, idx, k_stride, nq, wp, w->b2, w->b3, w->bq,
+                                    w->w1_xyz, pooled, g_tc_prof));
+    else
+        PPS_CUDA(cudaLaunchKernelEx(&cfg, tc::projection_tc_kernel<false>, table, queries, idx, k_stride, nq, wp, w->b2, w->b3, w->bq,
+                                    w->w1_xyz, pooled, g_tc_prof));
     PPS_LAUNCH_CHECK();
     profile_end(st);
     return PPS_OK;
@@ -553,7 +565,7 @@ extern "C" size_t pps_decoder_tc_pack_bytes(void) { return pps::tc::kPackBytes; 
 extern "C" void pps_debug_tc_profile(long long* counters) { pps::g_tc_prof = counters; }
 // debug: how many CTA pairs of projection_tc_kernel the device can hold at once (-1 on error)
 extern "C" int pps_debug_tc_max_clusters(void) {
-    cudaFuncSetAttribute(pps::tc::projection_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pps::tc::kSmemBytes);
+    cudaFuncSetAttribute(pps::tc::projection_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pps::tc::kSmemBytes);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(pps::kNumSMs);
     cfg.blockDim = dim3(pps::tc::kThreads);
@@ -566,8 +578,8 @@ extern "C" int pps_debug_tc_max_clusters(void) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int n = -1;
-    if (cudaOccupancyMaxActiveClusters(&n, pps::tc::projection_tc_kernel, &cfg) != cudaSuccess) return -1;
+    if (cudaOccupancyMaxActiveClusters(&n, pps::tc::projection_tc_kernel<false>, &cfg) != cudaSuccess) return -1;
     return n;
 }
-// debug knob for experiments on the weight stream of the projection kernel (0 = product path)
-extern "C" void pps_debug_tc_cluster(int v) { pps::g_tc_variant = v; }
+// retired debug knob (cluster multicast / weight-stream experiments); kept so that the ABI is stable
+extern "C" void pps_debug_tc_cluster(int) {}
