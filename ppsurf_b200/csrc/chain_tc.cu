@@ -78,6 +78,30 @@ __device__ __forceinline__ void mma_layer(const Ctx& c, Ring& r, uint32_t dcol, 
     }
 }
 
+// transposed variant for a 256-row weight block: D^T[128 rows of W (half mh), 128 tile rows] at columns dcol + 128*mh, i.e. the
+// weights are the M operand and the activation tile the N operand -- the accumulator then holds FEATURES on the TMEM lanes, and
+// an epilogue thread's 32 registers are 32 consecutive tile rows of one feature
+__device__ __forceinline__ void mma_layer_t(const Ctx& c, Ring& r, uint32_t dcol, int ksteps) {
+    const uint32_t idesc = umma_idesc(128);
+    for (int s = 0; s < ksteps; ++s) {
+        mbar_wait(c.bar_full + 8 * r.slot, r.phase);
+        tc_fence_after();
+        const uint64_t x_hi = umma_desc(c.sbase + kOffAhi + 2 * s * kLbo, kLbo, 128);
+        const uint64_t x_lo = umma_desc(c.sbase + kOffAlo + 2 * s * kLbo, kLbo, 128);
+        const uint32_t wst = c.sbase + kOffRing + r.slot * kSlot;  // [hi: 2 k8 blocks x 256 rows x 16 B][lo: likewise]
+#pragma unroll
+        for (int mh = 0; mh < 2; ++mh) {
+            const uint64_t w_hi = umma_desc(wst + mh * 128 * 16, 256 * 16, 128);
+            const uint64_t w_lo = umma_desc(wst + 256 * 32 + mh * 128 * 16, 256 * 16, 128);
+            umma(c.tmem + dcol + 128 * mh, w_hi, x_hi, idesc, s > 0 ? 1u : 0u);
+            umma(c.tmem + dcol + 128 * mh, w_hi, x_lo, idesc, 1u);
+            umma(c.tmem + dcol + 128 * mh, w_lo, x_hi, idesc, 1u);
+        }
+        tc_commit(c.bar_empty + 8 * r.slot);
+        r.advance();
+    }
+}
+
 // epilogue warps: fp32 rows of `src` (row pitch ld, K columns, K in {64,128,256}) -> operand tile; rows >= nrows are zero
 __device__ __forceinline__ void load_rows(const Ctx& c, const float* __restrict__ src, long long row0, long long nrows, int K, int ld,
                                           int ew, int lane) {
@@ -231,7 +255,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                     mbar_wait(c.bar_tfree + 8 * buf, tfree_phase[buf] ^ 1);
                     tfree_phase[buf] ^= 1;
                     tc_fence_after();
-                    mma_layer(c, r, buf * 256, 256, 4, false);
+                    mma_layer_t(c, r, buf * 256, 4);  // fc3 block nb, transposed: coalesced T stores
                     // one completion barrier PER accumulator: the issuer can run a block ahead of the epilogue, and a single
                     // barrier advancing two phases would alias in the parity wait
                     tc_commit(buf ? c.bar_accum2 : c.bar_accum);
@@ -256,7 +280,6 @@ __global__ void __launch_bounds__(kThreads, 1)
             tc_fence_after();
             epi_to_tile<true>(c, 0, 64, par + 128, lane_grp, half, lane);
             tile_ready(c);
-            const long long q = row0 + row;
             for (int nb = 0; nb < 16; ++nb) {
                 const int buf = nb & 1;
                 if (buf) {
@@ -267,19 +290,21 @@ __global__ void __launch_bounds__(kThreads, 1)
                     accum_phase ^= 1;
                 }
                 tc_fence_after();
+                // accumulator columns [128*mh, +128) = the tile's queries for features nb*256 + mh*128 + (TMEM lane).  This warp:
+                // lanes of its lane group, query chunks 2*half and 2*half+1.  For a fixed register the 32 lanes write 32
+                // consecutive features of one query: one 128-byte line per store instruction (the row-per-thread layout wrote
+                // 32 different lines per instruction and was bound by LSU wavefronts)
 #pragma unroll 1
                 for (int cb = 0; cb < 4; ++cb) {
-                    const int col0 = half * 128 + cb * 32;
+                    const int mh = cb >> 1, qc = 2 * half + (cb & 1);
                     float v[32];
-                    tmem_ld32(c.tmem + ((uint32_t)(lane_grp * 32) << 16) + buf * 256 + col0, v);
-                    if (q < nq) {
-                        const float* bias = par + 192 + nb * 256 + col0;
-                        float4* dst = reinterpret_cast<float4*>(tmat + q * 4096 + nb * 256 + col0);
+                    tmem_ld32(c.tmem + ((uint32_t)(lane_grp * 32) << 16) + buf * 256 + mh * 128 + qc * 32, v);
+                    const int f = nb * 256 + mh * 128 + row;
+                    const float bias = par[192 + f];
+                    float* dst = tmat + (row0 + qc * 32) * 4096 + f;
 #pragma unroll
-                        for (int t = 0; t < 8; ++t)
-                            dst[t] = make_float4(v[4 * t] + bias[4 * t], v[4 * t + 1] + bias[4 * t + 1], v[4 * t + 2] + bias[4 * t + 2],
-                                                 v[4 * t + 3] + bias[4 * t + 3]);
-                    }
+                    for (int j = 0; j < 32; ++j)
+                        if (row0 + qc * 32 + j < nq) dst[(size_t)j * 4096] = v[j] + bias;
                 }
                 tc_fence_before();
                 __syncwarp();

@@ -182,8 +182,8 @@ __global__ void __launch_bounds__(kThreads, 1)
                             tc_fence_after();
                         }
                         long long t1 = tick<PROF>();
-                        mbar_wait_cluster(bar_full + 8 * slot, phase);  // both halves of the weight stage have landed
-                        tc_fence_after();
+                        mbar_wait_cluster(bar_full + 8 * slot, phase);  // both halves of the weight stage have landed (TMA writes:
+                                                                        // async proxy -> async proxy, no tcgen05 fence needed)
                         t_chunk += t1 - t0;
                         t_full += tick<PROF>() - t1;
                         const uint32_t a_off = 2 * s * kALbo;
