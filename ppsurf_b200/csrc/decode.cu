@@ -302,7 +302,7 @@ static bool carve(const pps_decoder_weights* w, int64_t chunk, void* ws, size_t 
     b.bufA = a.take<float>(rows * wide);
     b.bufB = a.take<float>(rows * wide);
     b.score = a.take<float>((size_t)chunk * K * w->heads);
-    b.a1 = a.take<float>((size_t)chunk * P * 64);
+    b.a1 = a.take<float>((size_t)chunk * (P > 64 ? P : 64) * 64);  // tensor-core path: tile-major with 64 point slots per query
     b.patches = a.take<float>((size_t)chunk * P * 3);
     b.pooled = a.take<float>((size_t)chunk * C);
     b.pooled_super = a.take<float>((size_t)chunk * kKnnSuper * C);

@@ -220,10 +220,16 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                     float v[32];
                     tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + col0, v);
                     bias_relu32(v, bias + col0);  // padding rows carry finite values nobody reads
-                    if (layer == 0 && row_valid) {  // a1 feeds the feature transform of pn_feat_kernel
-                        float4* dst = reinterpret_cast<float4*>(a1_out + (q_row * P + p_row) * 64 + col0);
+                    if (layer == 0 && row_valid) {
+                        // a1 feeds the feature transform of pn_feat_kernel.  Global layout = the operand tile's: [tile][k8 block]
+                        // [row][8 floats], so the 32 lanes (= 32 consecutive rows) of a store instruction cover 1 KB instead of
+                        // 32 different 256-byte rows (the row-major layout made this epilogue LSU-wavefront bound)
 #pragma unroll
-                        for (int c4 = 0; c4 < 8; ++c4) dst[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+                        for (int kb = 0; kb < 4; ++kb) {
+                            float4* dst = reinterpret_cast<float4*>(a1_out + ((tile * 8 + (col0 >> 3) + kb) * 128 + row) * 8);
+                            dst[0] = make_float4(v[8 * kb], v[8 * kb + 1], v[8 * kb + 2], v[8 * kb + 3]);
+                            dst[1] = make_float4(v[8 * kb + 4], v[8 * kb + 5], v[8 * kb + 6], v[8 * kb + 7]);
+                        }
                     }
 #pragma unroll
                     for (int kb = 0; kb < 4; ++kb) {
@@ -412,15 +418,16 @@ __global__ void __launch_bounds__(kPnThreads, 2)
         const int row = lane_grp * 32 + lane;
         uint32_t accum_phase = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            // ---- load a1 rows (coalesced: 8 lanes x 32 B per row, 4 rows per warp instruction) and split
+            // ---- load a1 (tile-major [tile][k8 block][row][8 floats], written by pn_stn_kernel): warp ew takes k8 block ew,
+            // lanes are rows -> 1 KB per load instruction, conflict-free 512-byte shared-memory stores
 #pragma unroll 2
             for (int i = 0; i < 4; ++i) {
-                const int r = ew * 16 + i * 4 + (lane >> 3), kb = lane & 7;
+                const int r = i * 32 + lane, kb = ew;
                 const long long q = 2 * tile + (r >> 6);
                 const int p = r & 63;
                 float v[8];
                 if (q < nq && p < P) {
-                    const float4* src = reinterpret_cast<const float4*>(a1 + (q * P + p) * 64) + 2 * kb;
+                    const float4* src = reinterpret_cast<const float4*>(a1 + ((tile * 8 + kb) * 128 + r) * 8);
                     const float4 u0 = src[0], u1 = src[1];
                     v[0] = u0.x; v[1] = u0.y; v[2] = u0.z; v[3] = u0.w;
                     v[4] = u1.x; v[5] = u1.y; v[6] = u1.z; v[7] = u1.w;
@@ -587,7 +594,7 @@ bool pointnet_tc_supported(const pps_decoder_weights* w) {
     return w->tc_pn_stn != nullptr && w->tc_pn_feat != nullptr && w->num_pts_local <= 64 && w->stn_size == 256 && w->latent == 256;
 }
 
-// local branch on the tensor cores: patches [q,P,3] -> pooled128 [q,128]; scratch: a1 [q*P,64], g [q,256], f1 [q,128],
+// local branch on the tensor cores: patches [q,P,3] -> pooled128 [q,128]; scratch: a1 [tiles,8,128,8] (tile-major, 64 point slots per query), g [q,256], f1 [q,128],
 // f2 [q,64], tmat [q,4096]
 int pointnet_tc_impl(const pps_decoder_weights* w, const float* patches, int64_t q, float* a1, float* g, float* f1, float* f2,
                      float* tmat, float* pooled128, cudaStream_t st) {
