@@ -6,7 +6,7 @@ grid of a 100k-point synthetic cloud, ppsurf_50nn, latents and points resident o
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 One step = one pass of the hot path (kNN k=64 -> patches -> both branches -> MLP -> softmax difference) over this rank's
-contiguous slab of the grid.  N>1: the grid is split into N slabs (strong scaling of the fixed 131^3 volume), rank 0
+share of the grid.  N>1: the vertex list is dealt to the N ranks in blocks (strong scaling of the fixed 131^3 volume), rank 0
 encodes the cloud and the latents travel in ONE NCCL broadcast before the timed region; the decode itself needs no
 collective.  Prints one JSON line (rank 0).  `--impl reference` times the CPU restatement of the reference (oracle/,
 torch-CPU ops + scipy kd-tree, all host threads) on a bounded sample of the same workload.
@@ -108,6 +108,22 @@ def grid_shard(total, world, rank):
     """contiguous slab [first, first+count) of the flattened C-order vertex list"""
     first = total * rank // world
     return first, total * (rank + 1) // world - first
+
+
+GRID_BLOCK = 4736  # vertices per dealt block (= 37 x 128): small enough to balance 8 ranks within 2 %, a multiple of the kNN run
+
+
+def grid_blocks(total, world, rank, block=GRID_BLOCK):
+    """blocks of `block` consecutive vertices of the flattened C-order list, dealt round-robin: rank r decodes blocks r, r+G,
+    ...  Contiguous slabs are not balanced -- the neighbour search costs up to 10x more per vertex in the middle of the volume
+    than near the surface -- a dealt split gives every rank the same mix.  Returns [(first, count), ...]; one span for G = 1"""
+    if world == 1:
+        return [(0, total)]
+    spans = []
+    for b in range(rank, (total + block - 1) // block, world):
+        first = b * block
+        spans.append((first, min(block, total - first)))
+    return spans
 
 
 def workload_name(args):
@@ -279,9 +295,11 @@ def run_b200(args):
     dec = net.decoder_for(pts_bcn, latents)
     r = args.resolution + 2
     total = r ** 3
-    first, count = grid_shard(total, world, rank)
+    spans = grid_blocks(total, world, rank)
+    count = sum(c for _, c in spans)
     step, bmin_pad, _ = model.grid_definition(pts_np, args.resolution, 1)
-    queries = ops.grid_queries(r, step, bmin_pad, first=first, count=count, device=dev)
+    queries = torch.cat([ops.grid_queries(r, step, bmin_pad, first=f, count=c, device=dev) for f, c in spans]) if len(spans) > 1 \
+        else ops.grid_queries(r, step, bmin_pad, first=spans[0][0], count=count, device=dev)
     occ = torch.empty((count,), dtype=torch.float32, device=dev)
     ws = dec.workspace(min(args.chunk, count))
     stream = torch.cuda.current_stream()
@@ -358,7 +376,7 @@ def run_b200(args):
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': warmup,
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
             'dtype': 'f32' if args.path == 0 else 'f32 via split-fp16 tensor cores (fp32 accumulate)', 'data': 'synthetic',
-            'config': {'workload': workload_name(args), 'parallelism': 'grid slabs x{}'.format(world), 'chunk': args.chunk,
+            'config': {'workload': workload_name(args), 'parallelism': 'grid blocks of {} vertices dealt round-robin x{}'.format(GRID_BLOCK, world), 'chunk': args.chunk,
                        'decode_path': args.path, 'latents': args.latents,
                        'l2': 'working set per step (fc1 table {} MB + >2 GB of chunk activations) exceeds the 126 MB L2'.format(
                            args.points * 1024 // 2 ** 20),

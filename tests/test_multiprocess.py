@@ -60,3 +60,21 @@ def test_grid_shard_covers_every_vertex_once():
             assert spans[0][0] == 0 and sum(c for _, c in spans) == total
             assert all(a[0] + a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+
+
+def test_grid_blocks_partition_and_balance():
+    """the dealt block split used by bench.py: every vertex exactly once, rank loads within one block of each other"""
+    sys.path.insert(0, ROOT)
+    import bench
+    for total in (19 ** 3, 131 ** 3, 259 ** 3, 7):
+        for world in (1, 2, 3, 4, 8):
+            seen = np.zeros(total, dtype=np.int32)
+            loads = []
+            for r in range(world):
+                spans = bench.grid_blocks(total, world, r)
+                loads.append(sum(c for _, c in spans))
+                for f, c in spans:
+                    assert c > 0 and f + c <= total
+                    seen[f:f + c] += 1
+            assert np.all(seen == 1)
+            assert max(loads) - min(loads) <= bench.GRID_BLOCK
