@@ -181,27 +181,80 @@ __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restri
     const int wslot = (k - 1) >> 5, wlane = (k - 1) & 31;  // where the k-th best lives
     float bound = INFINITY;  // upper bound of this query's k-th distance, seeded from the previous query of the run
     float pqx = 0.f, pqy = 0.f, pqz = 0.f;
+    float ld[SLOTS];  // the k best so far, sorted ascending by (dist2, index): element g = slot*32 + lane
+    int li[SLOTS];    // original point index
+    int lp[SLOTS];    // position in the Morton-sorted array (to re-evaluate the list for the next query of the run)
 
     for (int rq = 0; rq < kRun; ++rq) {
         const long long qi = q_first + rq;
         if (qi >= nq) break;
-        float ld[SLOTS];
-        int li[SLOTS];
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s) {
-            ld[s] = INFINITY;
-            li[s] = 0x7fffffff;
-        }
         const float qx = queries[3 * qi], qy = queries[3 * qi + 1], qz = queries[3 * qi + 2];
-        if (rq > 0) {
+        float worst = INFINITY;
+        int worst_i = 0x7fffffff;
+        constexpr bool kReseed = SLOTS == 2;  // 32 < k <= 64 (the decoder's grid-ordered queries): the previous list seeds this one
+        if (kReseed && rq > 0) {
+            // Consecutive grid queries share most of their neighbours.  Re-evaluate the previous query's list for this query
+            // (its entries are real points, so the k-th of them bounds the k-th distance from the first node on) and sort it
+            // by (dist2, index) with a bitonic network over the SLOTS*32 entries.  The traversal then only has to find the few
+            // NEW neighbours; points already in the list are recognised by their index when they are scanned again.  (One-by-one
+            // insertion of ~350 candidates per query was 58 % of the kernel's instructions.)
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) {
+                const float4 p = sorted[lp[s]];
+                const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+                ld[s] = li[s] == 0x7fffffff ? INFINITY  // an empty entry (fewer points than list entries) stays empty
+                                            : __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            }
+#pragma unroll
+            for (int kk = 2; kk <= SLOTS * 32; kk <<= 1) {
+#pragma unroll
+                for (int j = kk >> 1; j >= 1; j >>= 1) {
+                    if (j >= 32) {  // partner = the other slot of this lane (SLOTS == 2, j == 32): ascending over the whole list
+                        if (SLOTS == 2 && cand_less(ld[SLOTS - 1], li[SLOTS - 1], ld[0], li[0])) {
+                            const float td = ld[0];
+                            const int ti = li[0], tp = lp[0];
+                            ld[0] = ld[SLOTS - 1];
+                            li[0] = li[SLOTS - 1];
+                            lp[0] = lp[SLOTS - 1];
+                            ld[SLOTS - 1] = td;
+                            li[SLOTS - 1] = ti;
+                            lp[SLOTS - 1] = tp;
+                        }
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < SLOTS; ++s) {
+                            const int g = s * 32 + lane;
+                            const float od = __shfl_xor_sync(full, ld[s], j);
+                            const int oi = __shfl_xor_sync(full, li[s], j);
+                            const int op = __shfl_xor_sync(full, lp[s], j);
+                            const bool take_min = ((g & j) == 0) == ((g & kk) == 0);
+                            const bool other_less = cand_less(od, oi, ld[s], li[s]);
+                            if (take_min == other_less) {
+                                ld[s] = od;
+                                li[s] = oi;
+                                lp[s] = op;
+                            }
+                        }
+                    }
+                }
+            }
+            worst = __shfl_sync(full, ld[wslot < SLOTS ? wslot : SLOTS - 1], wlane);
+            worst_i = __shfl_sync(full, li[wslot < SLOTS ? wslot : SLOTS - 1], wlane);
+            bound = INFINITY;
+        } else {
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) {
+                ld[s] = INFINITY;
+                li[s] = 0x7fffffff;
+                lp[s] = 0;
+            }
+        }
+        if (!kReseed && rq > 0) {
             // triangle inequality: the k neighbours of the previous query lie within sqrt(kth_prev) + |q - q_prev| of q
             const float dx = qx - pqx, dy = qy - pqy, dz = qz - pqz;
             const float r = sqrtf(bound) + sqrtf(dx * dx + dy * dy + dz * dz);
             bound = r * r * 1.0001f + 1e-30f;
         }
-        float worst = INFINITY;
-        int worst_i = 0x7fffffff;
-
         auto box_dist = [&](int level, int cx, int cy, int cz) -> float {
             float size = cell * float(1 << (L - level));
             float lx = ox + cx * size - pad, ly = oy + cy * size - pad, lz = oz + cz * size - pad;
@@ -275,7 +328,14 @@ __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restri
                         mask &= mask - 1;
                         const float vd = __shfl_sync(full, d2, src);
                         const int vi = __shfl_sync(full, pi, src);
+                        const int vp = base + src;
                         if (!cand_less(vd, vi, worst, worst_i)) continue;  // the bound may have tightened meanwhile
+                        if (kReseed && rq > 0) {  // already in the list (carried over from the previous query)?
+                            bool dup = false;
+#pragma unroll
+                            for (int s = 0; s < SLOTS; ++s) dup |= li[s] == vi;
+                            if (__any_sync(full, dup)) continue;
+                        }
                         int pos = 0;  // number of list elements smaller than the candidate
 #pragma unroll
                         for (int s = 0; s < SLOTS; ++s) pos += __popc(__ballot_sync(full, cand_less(ld[s], li[s], vd, vi)));
@@ -283,21 +343,26 @@ __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restri
                         for (int s = SLOTS - 1; s >= 0; --s) {
                             float pd = __shfl_up_sync(full, ld[s], 1);
                             int pj = __shfl_up_sync(full, li[s], 1);
+                            int pp = __shfl_up_sync(full, lp[s], 1);
                             if (s > 0) {
                                 const float cd = __shfl_sync(full, ld[s - 1], 31);
                                 const int cj = __shfl_sync(full, li[s - 1], 31);
+                                const int cp = __shfl_sync(full, lp[s - 1], 31);
                                 if (lane == 0) {
                                     pd = cd;
                                     pj = cj;
+                                    pp = cp;
                                 }
                             }
                             const int g = s * 32 + lane;
                             if (g == pos) {
                                 ld[s] = vd;
                                 li[s] = vi;
+                                lp[s] = vp;
                             } else if (g > pos) {
                                 ld[s] = pd;
                                 li[s] = pj;
+                                lp[s] = pp;
                             }
                         }
                         worst = __shfl_sync(full, ld[wslot < SLOTS ? wslot : SLOTS - 1], wlane);

@@ -15,7 +15,7 @@ pts = torch.from_numpy(pts_np).to(dev)
 step, bmin_pad, _ = ppsurf_b200.PPSurfModel.grid_definition(pts_np, 129, 1)
 qry = ops.grid_queries(131, step, bmin_pad, device=dev)
 index = ops.KnnIndex(pts)
-for k in (64, 16):
+for k in (64, 64, 16):
     index.query(qry[:100000], k)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
