@@ -15,6 +15,7 @@
 namespace pps {
 
 constexpr int kMaxLevels = 7;  // 128^3 finest cells, 21-bit codes
+constexpr int kDirectMaxShift = 2;  // seeded queries whose search ball spans at most 3 cells of 4 finest cells go straight to those cells
 constexpr int kScanMax = 1024;  // an unprunable node with at most this many points is scanned as one contiguous range
 constexpr int kRun = 8;        // consecutive queries handled by one warp (each seeds the next one's pruning bound)
 
@@ -265,7 +266,114 @@ __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restri
             return (dx * dx + dy * dy + dz * dz) * 0.99999f;  // conservative lower bound
         };
 
-        int sp = 1;
+        // scan the contiguous range [lo, hi) of the Morton-sorted points, 32 at a time
+        auto scan_range = [&](int lo, int hi) {
+            for (int base = lo; base < hi; base += 32) {
+                const int i = base + lane;
+                float d2 = INFINITY;
+                int pi = 0x7fffffff;
+                if (i < hi) {
+                    const float4 p = sorted[i];
+                    const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+                    d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                    pi = __float_as_int(p.w);
+                }
+                unsigned int mask = __ballot_sync(full, i < hi && d2 <= bound && cand_less(d2, pi, worst, worst_i));
+                while (mask) {
+                    const int src = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const float vd = __shfl_sync(full, d2, src);
+                    const int vi = __shfl_sync(full, pi, src);
+                    const int vp = base + src;
+                    if (!cand_less(vd, vi, worst, worst_i)) continue;  // the bound may have tightened meanwhile
+                    if (kReseed && rq > 0) {  // already in the list (carried over from the previous query)?
+                        bool dup = false;
+#pragma unroll
+                        for (int s = 0; s < SLOTS; ++s) dup |= li[s] == vi;
+                        if (__any_sync(full, dup)) continue;
+                    }
+                    int pos = 0;  // number of list elements smaller than the candidate
+#pragma unroll
+                    for (int s = 0; s < SLOTS; ++s) pos += __popc(__ballot_sync(full, cand_less(ld[s], li[s], vd, vi)));
+#pragma unroll
+                    for (int s = SLOTS - 1; s >= 0; --s) {
+                        float pd = __shfl_up_sync(full, ld[s], 1);
+                        int pj = __shfl_up_sync(full, li[s], 1);
+                        int pp = __shfl_up_sync(full, lp[s], 1);
+                        if (s > 0) {
+                            const float cd = __shfl_sync(full, ld[s - 1], 31);
+                            const int cj = __shfl_sync(full, li[s - 1], 31);
+                            const int cp = __shfl_sync(full, lp[s - 1], 31);
+                            if (lane == 0) {
+                                pd = cd;
+                                pj = cj;
+                                pp = cp;
+                            }
+                        }
+                        const int g = s * 32 + lane;
+                        if (g == pos) {
+                            ld[s] = vd;
+                            li[s] = vi;
+                            lp[s] = vp;
+                        } else if (g > pos) {
+                            ld[s] = pd;
+                            li[s] = pj;
+                            lp[s] = pp;
+                        }
+                    }
+                    worst = __shfl_sync(full, ld[wslot < SLOTS ? wslot : SLOTS - 1], wlane);
+                    worst_i = __shfl_sync(full, li[wslot < SLOTS ? wslot : SLOTS - 1], wlane);
+                }
+            }
+        };
+
+        // ---- seeded query: no tree walk.  Every point within sqrt(worst) of q lies in the cells that the ball's bounding box
+        // touches; at the finest level where that box spans at most 3 cells per axis those are <= 27 cells = 27 contiguous
+        // ranges of the sorted array, tested by 27 lanes at once and scanned one after the other
+        bool walked = false;
+        if (kReseed && rq > 0 && worst < INFINITY) {
+            const float r = sqrtf(worst) * 1.0001f + pad;
+            const int top = (1 << L) - 1;
+            int lo_c[3], hi_c[3];
+            {
+                const float qq[3] = {qx, qy, qz}, oo[3] = {ox, oy, oz};
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {  // the same cell expression as knn_codes (monotone in the coordinate)
+                    lo_c[a] = min(max(int(floorf((qq[a] - r - oo[a]) / cell)), 0), top);
+                    hi_c[a] = min(max(int(floorf((qq[a] + r - oo[a]) / cell)), 0), top);
+                }
+            }
+            int shc = 0;
+            while (shc < L && (((hi_c[0] >> shc) - (lo_c[0] >> shc)) > 2 || ((hi_c[1] >> shc) - (lo_c[1] >> shc)) > 2 ||
+                               ((hi_c[2] >> shc) - (lo_c[2] >> shc)) > 2))
+                ++shc;
+            const int level = L - shc;
+            if (shc <= kDirectMaxShift) {  // larger balls: the tree prunes better than a 27-cell box
+
+            int clo = 0, chi = 0;
+            float d = INFINITY;
+            if (lane < 27) {
+                const int cx = (lo_c[0] >> shc) + lane % 3, cy = (lo_c[1] >> shc) + (lane / 3) % 3, cz = (lo_c[2] >> shc) + lane / 9;
+                if (cx <= (hi_c[0] >> shc) && cy <= (hi_c[1] >> shc) && cz <= (hi_c[2] >> shc)) {
+                    const unsigned int code = morton3(cx, cy, cz);
+                    clo = cell_start[code << (3 * shc)];
+                    chi = cell_start[(code + 1u) << (3 * shc)];
+                    d = box_dist(level, cx, cy, cz);
+                }
+            }
+            unsigned int m = __ballot_sync(full, chi > clo && d <= worst);
+            while (m) {
+                const int t = __ffs(m) - 1;
+                m &= m - 1;
+                const int lo = __shfl_sync(full, clo, t), hi = __shfl_sync(full, chi, t);
+                if (__shfl_sync(full, d, t) > worst) continue;  // the k-th distance may have shrunk meanwhile
+                scan_range(lo, hi);
+            }
+            walked = true;
+            }
+        }
+
+        int sp = walked ? 0 : 1;
         if (lane == 0) stack[0] = 0u;  // root: level 0, cell (0,0,0)
         __syncwarp();
         while (sp > 0) {
@@ -311,65 +419,7 @@ __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restri
                     __syncwarp();
                 }
             }
-            if (scan) {
-                for (int base = lo; base < hi; base += 32) {
-                    const int i = base + lane;
-                    float d2 = INFINITY;
-                    int pi = 0x7fffffff;
-                    if (i < hi) {
-                        const float4 p = sorted[i];
-                        const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
-                        d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                        pi = __float_as_int(p.w);
-                    }
-                    unsigned int mask = __ballot_sync(full, i < hi && d2 <= bound && cand_less(d2, pi, worst, worst_i));
-                    while (mask) {
-                        const int src = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        const float vd = __shfl_sync(full, d2, src);
-                        const int vi = __shfl_sync(full, pi, src);
-                        const int vp = base + src;
-                        if (!cand_less(vd, vi, worst, worst_i)) continue;  // the bound may have tightened meanwhile
-                        if (kReseed && rq > 0) {  // already in the list (carried over from the previous query)?
-                            bool dup = false;
-#pragma unroll
-                            for (int s = 0; s < SLOTS; ++s) dup |= li[s] == vi;
-                            if (__any_sync(full, dup)) continue;
-                        }
-                        int pos = 0;  // number of list elements smaller than the candidate
-#pragma unroll
-                        for (int s = 0; s < SLOTS; ++s) pos += __popc(__ballot_sync(full, cand_less(ld[s], li[s], vd, vi)));
-#pragma unroll
-                        for (int s = SLOTS - 1; s >= 0; --s) {
-                            float pd = __shfl_up_sync(full, ld[s], 1);
-                            int pj = __shfl_up_sync(full, li[s], 1);
-                            int pp = __shfl_up_sync(full, lp[s], 1);
-                            if (s > 0) {
-                                const float cd = __shfl_sync(full, ld[s - 1], 31);
-                                const int cj = __shfl_sync(full, li[s - 1], 31);
-                                const int cp = __shfl_sync(full, lp[s - 1], 31);
-                                if (lane == 0) {
-                                    pd = cd;
-                                    pj = cj;
-                                    pp = cp;
-                                }
-                            }
-                            const int g = s * 32 + lane;
-                            if (g == pos) {
-                                ld[s] = vd;
-                                li[s] = vi;
-                                lp[s] = vp;
-                            } else if (g > pos) {
-                                ld[s] = pd;
-                                li[s] = pj;
-                                lp[s] = pp;
-                            }
-                        }
-                        worst = __shfl_sync(full, ld[wslot < SLOTS ? wslot : SLOTS - 1], wlane);
-                        worst_i = __shfl_sync(full, li[wslot < SLOTS ? wslot : SLOTS - 1], wlane);
-                    }
-                }
-            }
+            if (scan) scan_range(lo, hi);
         }
         // the list is sorted ascending by (dist2, index): element g = slot*32 + lane
 #pragma unroll
