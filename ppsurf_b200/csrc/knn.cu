@@ -169,12 +169,16 @@ __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restri
                                                        const int* __restrict__ cell_start, const float* __restrict__ queries,
                                                        long long nq, int k, int32_t* __restrict__ idx_out,
                                                        float* __restrict__ d2_out) {
+    // per warp: node code, and the node's range in the sorted array (loaded by the parent: no second round trip on the pop)
     __shared__ unsigned int stack_s[8][8 * kMaxLevels + 8];
+    __shared__ int stack_lo_s[8][8 * kMaxLevels + 8], stack_hi_s[8][8 * kMaxLevels + 8];
     const unsigned int full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long q_first = ((long long)blockIdx.x * 8 + warp) * kRun;
     if (q_first >= nq) return;
     unsigned int* stack = stack_s[warp];
+    int* stack_lo = stack_lo_s[warp];
+    int* stack_hi = stack_hi_s[warp];
     const int L = hdr->levels;
     const float ox = hdr->origin[0], oy = hdr->origin[1], oz = hdr->origin[2];
     const float cell = hdr->cell;
@@ -268,12 +272,15 @@ __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restri
 
         // scan the contiguous range [lo, hi) of the Morton-sorted points, 32 at a time
         auto scan_range = [&](int lo, int hi) {
+            float4 pn = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lo + lane < hi) pn = sorted[lo + lane];
             for (int base = lo; base < hi; base += 32) {
                 const int i = base + lane;
+                const float4 p = pn;
+                if (i + 32 < hi) pn = sorted[i + 32];  // the next 32 points are in flight while these are inserted
                 float d2 = INFINITY;
                 int pi = 0x7fffffff;
                 if (i < hi) {
-                    const float4 p = sorted[i];
                     const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
                     d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
                     pi = __float_as_int(p.w);
@@ -374,7 +381,11 @@ __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restri
         }
 
         int sp = walked ? 0 : 1;
-        if (lane == 0) stack[0] = 0u;  // root: level 0, cell (0,0,0)
+        if (lane == 0) {  // root: level 0, cell (0,0,0), all points
+            stack[0] = 0u;
+            stack_lo[0] = 0;
+            stack_hi[0] = hdr->n;
+        }
         __syncwarp();
         while (sp > 0) {
             const unsigned int nd = stack[--sp];
@@ -382,7 +393,7 @@ __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restri
             if (box_dist(level, cx, cy, cz) > fminf(worst, bound)) continue;
             const unsigned int code = morton3(cx, cy, cz);
             const int sh = 3 * (L - level);
-            const int lo = cell_start[code << sh], hi = cell_start[(code + 1u) << sh];
+            const int lo = stack_lo[sp], hi = stack_hi[sp];
             const int cnt = hi - lo;
             if (cnt == 0) continue;
             bool scan = cnt <= 32 || level == L;
@@ -393,8 +404,10 @@ __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restri
                 bool ok = false, nonempty = false;
                 float d = INFINITY;
                 unsigned int child = 0;
+                int clo = 0, chi = 0;
                 if (lane < 8) {
-                    const int clo = cell_start[(cbase + lane) << sh2], chi = cell_start[(cbase + lane + 1u) << sh2];
+                    clo = cell_start[(cbase + lane) << sh2];
+                    chi = cell_start[(cbase + lane + 1u) << sh2];
                     const int ccx = cx * 2 + (lane & 1), ccy = cy * 2 + ((lane >> 1) & 1), ccz = cz * 2 + (lane >> 2);
                     d = box_dist(level + 1, ccx, ccy, ccz);
                     nonempty = chi > clo;
@@ -414,7 +427,11 @@ __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restri
                         const float dt = __shfl_sync(full, d, t);
                         if (((m >> t) & 1u) && (dt > d || (dt == d && t < lane))) ++rank;
                     }
-                    if (ok) stack[sp + rank] = child;
+                    if (ok) {
+                        stack[sp + rank] = child;
+                        stack_lo[sp + rank] = clo;
+                        stack_hi[sp + rank] = chi;
+                    }
                     sp += __popc(m);
                     __syncwarp();
                 }
