@@ -26,7 +26,8 @@ bool chain_tc_supported(const pps_decoder_weights* w);
 int mlp_tc_impl(const pps_decoder_weights* w, const float* pooled_proj, const float* pooled_pn, int64_t q, float* logits_out,
                 float* occ_out, cudaStream_t st);
 int pointnet_tc_impl(const pps_decoder_weights* w, const float* patches, int64_t q, float* a1, float* g, float* f1, float* f2,
-                     float* tmat, float* pooled128, cudaStream_t st);
+                     float* tmat, float* pooled128, float* partial, cudaStream_t st);
+size_t pointnet_tc_partial_floats(const pps_decoder_weights* w, int64_t q);
 
 // ---------------------------------------------------------------------------------------------------------------
 // patches (a7)
@@ -284,6 +285,7 @@ struct DecodeBuffers {
     float* f2;
     float* tmat;
     float* pooled128;
+    float* pn_partial;  // attention-pooling partials of patches that span several half-tiles (tensor-core path, P > 64)
     float* feat;
     float* m0;
     float* m1;
@@ -302,7 +304,7 @@ static bool carve(const pps_decoder_weights* w, int64_t chunk, void* ws, size_t 
     b.bufA = a.take<float>(rows * wide);
     b.bufB = a.take<float>(rows * wide);
     b.score = a.take<float>((size_t)chunk * K * w->heads);
-    b.a1 = a.take<float>((size_t)chunk * (P > 64 ? P : 64) * 64);  // tensor-core path: tile-major with 64 point slots per query
+    b.a1 = a.take<float>((size_t)chunk * ((P + 63) / 64) * 64 * 64 + 8192);  // tensor-core path: tile-major, 64 point slots per half-tile
     b.patches = a.take<float>((size_t)chunk * P * 3);
     b.pooled = a.take<float>((size_t)chunk * C);
     b.pooled_super = a.take<float>((size_t)chunk * kKnnSuper * C);
@@ -312,6 +314,7 @@ static bool carve(const pps_decoder_weights* w, int64_t chunk, void* ws, size_t 
     b.f2 = a.take<float>((size_t)chunk * (S / 4));
     b.tmat = a.take<float>((size_t)chunk * 4096);
     b.pooled128 = a.take<float>((size_t)chunk * 128);
+    b.pn_partial = a.take<float>(pointnet_tc_partial_floats(w, chunk) + 4);
     b.feat = a.take<float>((size_t)chunk * C);
     b.m0 = a.take<float>((size_t)chunk * C);
     b.m1 = a.take<float>((size_t)chunk * C);
@@ -358,7 +361,7 @@ static int pointnet_run(const pps_decoder_weights* w, const float* patches, int6
                         const float* residual, float* feat_out, int path, cudaStream_t st) {
     const int C = w->latent, P = w->num_pts_local, S = w->stn_size;
     if (path == 1 && pointnet_tc_supported(w)) {
-        PPS_TRY(pointnet_tc_impl(w, patches, q, b.a1, b.g, b.f1, b.f2, b.tmat, b.pooled128, st));
+        PPS_TRY(pointnet_tc_impl(w, patches, q, b.a1, b.g, b.f1, b.f2, b.tmat, b.pooled128, b.pn_partial, st));
         return linear_impl(b.pooled128, w->pnv_w, w->pnv_b, residual, nullptr, feat_out, q, C, 128, 128, C, 0, st);
     }
     int64_t m = q * P;
@@ -394,7 +397,7 @@ static int decode_chunk(const pps_decoder_weights* w, const float* pts, const fl
     if (path == 1 && pointnet_tc_supported(w) && chain_tc_supported(w)) {
         // all-tensor-core tail: both pooled vectors go straight into the chain kernel (merged value matrices + MLP + head);
         // the global branch of the whole super-chunk has already run (decode_super), `pooled_proj` are this chunk's rows
-        PPS_TRY(pointnet_tc_impl(w, b.patches, q, b.a1, b.g, b.f1, b.f2, b.tmat, b.pooled128, st));
+        PPS_TRY(pointnet_tc_impl(w, b.patches, q, b.a1, b.g, b.f1, b.f2, b.tmat, b.pooled128, b.pn_partial, st));
         return mlp_tc_impl(w, pooled_proj, b.pooled128, q, logits_out, occ_out, st);
     }
     PPS_TRY(projection_run(w, table, queries, idx, kmax, q, b, b.feat_proj, path, st));

@@ -1,7 +1,7 @@
 // Tensor-core path of the decoder's local branch (PointNetfeat with feature-STN and attention pooling,
-// source/base/nn.py:305-373,162-190,84-96) for patches of P <= 64 points: two persistent warp-specialised tcgen05 kernels
-// on tiles of 128 rows = 2 queries x 64 point slots (rows >= P are zero padding), same split-fp16 scheme and roles as
-// decode_tc.cu.
+// source/base/nn.py:305-373,162-190,84-96) for patches of P <= 256 points: two persistent warp-specialised tcgen05 kernels
+// on tiles of 128 rows = two half-tiles of 64 point slots (rows >= P are padding; patches of up to 256 points span up to
+// four half-tiles, merged by an atomic max / an online-softmax combine), same split-fp16 scheme and roles as decode_tc.cu.
 //
 //   pn_stn_kernel   patches -> conv0a (SIMT, K=3) -> conv0b -> [a1 to global] -> stn.conv1 -> stn.conv2 -> stn.conv3
 //                   computed TRANSPOSED (weights as the M=128 operand, the activation tile as the N=128 operand) so that
@@ -25,6 +25,22 @@ constexpr int kPnEpiThreads = 256;
 __device__ __forceinline__ void pn_epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kPnEpiThreads) : "memory"); }
 
 // bytes of the packed weights
+// Patches of P <= 64 points fill one 64-row half-tile per query; larger patches (ppsurf_200nn: P = 200) span G = ceil(P/64)
+// consecutive half-tiles.  Half-tile ht = 2*tile + (row >> 6) belongs to query ht / G and holds its points [64*(ht % G), +64).
+struct PnRow {
+    long long q;
+    int p;
+};
+__device__ __forceinline__ PnRow pn_row(long long tile, int row, int G) {
+    const long long ht = 2 * tile + (row >> 6);
+    PnRow r;
+    r.q = ht / G;
+    r.p = int(ht % G) * 64 + (row & 63);
+    return r;
+}
+
+constexpr int kPartialStride = 132;  // floats per (query, half-tile) partial of the attention pooling: pooled[128], max, sum, pad
+
 constexpr size_t kPackStnBytes = size_t(4) * 4096 * 2 + size_t(4) * 8192 + size_t(16) * 8192;  // conv0b, stn1, stn2, stn3
 constexpr size_t kPackFeatBytes = size_t(4) * 4096 + size_t(4) * 8192;                         // conv1, conv2
 
@@ -45,7 +61,7 @@ constexpr int kTmemCols = 256;
 }  // namespace stn
 
 __global__ void __launch_bounds__(kPnThreads, 2)
-    pn_stn_kernel(const float* __restrict__ patches, long long nq, int P, const uint8_t* __restrict__ wpack,
+    pn_stn_kernel(const float* __restrict__ patches, long long nq, int P, int G, const uint8_t* __restrict__ wpack,
                   const float* __restrict__ w0a, const float* __restrict__ b0a, const float* __restrict__ b0b,
                   const float* __restrict__ bs1, const float* __restrict__ bs2, const float* __restrict__ bs3,
                   float* __restrict__ a1_out, float* __restrict__ g_out) {
@@ -92,7 +108,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
-    const long long ntiles = (nq + 1) / 2;
+    const long long ntiles = (nq * G + 1) / 2;
 
     // weight stages of one tile, in issue order: (bytes per stage, number of stages)
     // conv0b 4x4096, stn1 4x4096, stn2 4x8192, stn3 16x8192
@@ -179,8 +195,9 @@ __global__ void __launch_bounds__(kPnThreads, 2)
             // ---- gather + conv0a (SIMT, K=3): thread = (row, half of the 64 channels)
             {
                 const int r = et & 127, hf = et >> 7;
-                const long long q = 2 * tile + (r >> 6);
-                const int p = r & 63;
+                const PnRow pr = pn_row(tile, r, G);
+                const long long q = pr.q;
+                const int p = pr.p;
                 const bool valid = q < nq && p < P;
                 float x = 0.f, y = 0.f, z = 0.f;
                 if (valid) {
@@ -205,9 +222,8 @@ __global__ void __launch_bounds__(kPnThreads, 2)
             }
             warp_arrive(bar_aready, lane);
 
-            const long long q_row = 2 * tile + (row >> 6);
-            const int p_row = row & 63;
-            const bool row_valid = q_row < nq && p_row < P;
+            const PnRow prow = pn_row(tile, row, G);
+            const bool row_valid = prow.q < nq && prow.p < P;
             // ---- conv0b / stn.conv1 (64 wide) and stn.conv2 (128 wide): bias + ReLU -> operand tile (in place)
             for (int layer = 0; layer < 3; ++layer) {
                 mbar_wait(bar_accum, accum_phase);
@@ -250,7 +266,8 @@ __global__ void __launch_bounds__(kPnThreads, 2)
             accum_phase ^= 1;
             tc_fence_after();
             {
-                const long long q = 2 * tile + half;  // this warp's column half = one query
+                const PnRow ph = pn_row(tile, half * 64, G);  // this warp's column half = one half-tile of one query
+                const long long q = ph.q;
                 for (int fb = 0; fb < 2; ++fb) {
                     float m = -INFINITY;
                     for (int cb = 0; cb < 2; ++cb) {
@@ -258,10 +275,16 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                         tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + fb * 128 + half * 64 + cb * 32, v);
 #pragma unroll
                         for (int c = 0; c < 32; ++c)
-                            if (cb * 32 + c < P) m = fmaxf(m, v[c]);
+                            if (ph.p + cb * 32 + c < P) m = fmaxf(m, v[c]);
                     }
                     const int f = fb * 128 + row;
-                    if (q < nq) g_out[q * 256 + f] = fmaxf(m + s_bs3[f], 0.f);  // ReLU and max commute
+                    if (q < nq) {
+                        const float val = fmaxf(m + s_bs3[f], 0.f);  // ReLU and max commute
+                        if (G == 1)
+                            g_out[q * 256 + f] = val;
+                        else  // the patch spans several half-tiles: max over them (val >= 0, g zeroed by the host: int order = float order)
+                            atomicMax(reinterpret_cast<int*>(g_out + q * 256 + f), __float_as_int(val));
+                    }
                 }
             }
             tc_fence_before();
@@ -302,9 +325,9 @@ __device__ __forceinline__ int c2_lo(int kblk) { return kblk < 8 ? kOffAlo + kbl
 }  // namespace feat
 
 __global__ void __launch_bounds__(kPnThreads, 2)
-    pn_feat_kernel(const float* __restrict__ a1, const float* __restrict__ tmat, long long nq, int P,
+    pn_feat_kernel(const float* __restrict__ a1, const float* __restrict__ tmat, long long nq, int P, int G,
                    const uint8_t* __restrict__ wpack, const float* __restrict__ b1, const float* __restrict__ b2,
-                   const float* __restrict__ wq, float* __restrict__ pooled) {
+                   const float* __restrict__ wq, float* __restrict__ pooled, float* __restrict__ partial) {
     using namespace feat;
     extern __shared__ __align__(1024) uint8_t smem[];  // used directly: the compiler keeps the shared address space (LDS/STS)
     const uint32_t sbase = smem_u32(smem);
@@ -341,7 +364,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
-    const long long ntiles = (nq + 1) / 2;
+    const long long ntiles = (nq * G + 1) / 2;
 
     if (warp == 0) {
         if (lane == 0) {  // conv1 4x4096, conv2 4x8192 per tile
@@ -423,8 +446,9 @@ __global__ void __launch_bounds__(kPnThreads, 2)
 #pragma unroll 2
             for (int i = 0; i < 4; ++i) {
                 const int r = i * 32 + lane, kb = ew;
-                const long long q = 2 * tile + (r >> 6);
-                const int p = r & 63;
+                const PnRow pr = pn_row(tile, r, G);
+                const long long q = pr.q;
+                const int p = pr.p;
                 float v[8];
                 if (q < nq && p < P) {
                     const float4* src = reinterpret_cast<const float4*>(a1 + ((tile * 8 + kb) * 128 + r) * 8);
@@ -445,7 +469,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
             for (int t = 0; t < 4; ++t) {
                 const int e = et + 256 * t;
                 const int ql = e >> 9, i = (e >> 3) & 63, kb = e & 7;
-                long long q = 2 * tile + ql;
+                long long q = (2 * tile + ql) / G;  // the query of half-tile ql
                 q = q < nq ? q : nq - 1;
                 const float4* src = reinterpret_cast<const float4*>(tmat + q * 4096 + i * 64) + 2 * kb;
                 const float4 u0 = src[0], u1 = src[1];
@@ -528,12 +552,22 @@ __global__ void __launch_bounds__(kPnThreads, 2)
             pn_epi_barrier();
             // ---- softmax over the patch's points: thread per row
             if (et < 128) {
-                const int r0 = (et >> 6) * 64, p = et & 63;
+                const int r0 = (et >> 6) * 64, pj = et & 63;
+                const PnRow ph = pn_row(tile, r0, G);       // first row of this half-tile: its query and first point
+                const int nv = min(64, max(P - ph.p, 0));  // valid points of the half-tile
                 float m = -INFINITY;
-                for (int j = 0; j < P; ++j) m = fmaxf(m, s_part[r0 + j] + s_part[128 + r0 + j]);
+                for (int j = 0; j < nv; ++j) m = fmaxf(m, s_part[r0 + j] + s_part[128 + r0 + j]);
                 float sum = 0.f;
-                for (int j = 0; j < P; ++j) sum += expf(s_part[r0 + j] + s_part[128 + r0 + j] - m);
-                s_att[et] = p < P ? expf(s_part[et] + s_part[128 + et] - m) / sum : 0.f;  // the query bias cancels in the softmax
+                for (int j = 0; j < nv; ++j) sum += expf(s_part[r0 + j] + s_part[128 + r0 + j] - m);
+                const float e = pj < nv ? expf(s_part[et] + s_part[128 + et] - m) : 0.f;  // the query bias cancels in the softmax
+                // one half-tile per query: normalise here.  Several: keep exp(l - m_h), the combine kernel merges the half-tiles'
+                // (m_h, sum_h, pooled_h) like an online softmax
+                s_att[et] = G == 1 ? e / sum : e;
+                if (G > 1 && pj == 0 && ph.q < nq) {
+                    float* dst = partial + (ph.q * G + ph.p / 64) * kPartialStride;
+                    dst[128] = m;
+                    dst[129] = sum;
+                }
             }
             pn_epi_barrier();
             // ---- pooled[q, 8kb..] = sum_p att_p c2[p, .]: warp ew owns k8 blocks ew and ew + 8
@@ -563,9 +597,10 @@ __global__ void __launch_bounds__(kPnThreads, 2)
 #pragma unroll
                     for (int c = 0; c < 8; ++c)
                         for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
-                    const long long q = 2 * tile + ql;
-                    if (lane == 0 && q < nq) {
-                        float4* dst = reinterpret_cast<float4*>(pooled + q * 128 + kb * 8);
+                    const PnRow ph = pn_row(tile, ql * 64, G);
+                    if (lane == 0 && ph.q < nq) {
+                        float4* dst = G == 1 ? reinterpret_cast<float4*>(pooled + ph.q * 128 + kb * 8)
+                                             : reinterpret_cast<float4*>(partial + (ph.q * G + ph.p / 64) * kPartialStride + kb * 8);
                         dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
                         dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
                     }
@@ -583,6 +618,25 @@ __global__ void __launch_bounds__(kPnThreads, 2)
     }
 }
 
+// merges the G half-tile partials of a query: pooled = sum_h e^(m_h - M) pooled_h / sum_h e^(m_h - M) sum_h,  M = max_h m_h
+__global__ void pn_combine_kernel(const float* __restrict__ partial, long long nq, int G, float* __restrict__ pooled) {
+    const long long q = blockIdx.x;
+    const int c = threadIdx.x;  // 128 channels
+    if (q >= nq) return;
+    const float* base = partial + q * G * kPartialStride;
+    float M = -INFINITY;
+    for (int h = 0; h < G; ++h) M = fmaxf(M, base[h * kPartialStride + 128]);
+    float num = 0.f, den = 0.f;
+    for (int h = 0; h < G; ++h) {
+        const float m = base[h * kPartialStride + 128];
+        if (m == -INFINITY) continue;  // a half-tile without valid points
+        const float w = expf(m - M);
+        num = fmaf(w, base[h * kPartialStride + c], num);
+        den = fmaf(w, base[h * kPartialStride + 129], den);
+    }
+    pooled[q * 128 + c] = num / den;
+}
+
 }  // namespace tc
 
 int linear_impl(const float* x, const float* w, const float* bias, const float* residual, const int32_t* gather,
@@ -591,13 +645,13 @@ bool chain_tc_supported(const pps_decoder_weights* w);
 int stn_fc_tc_impl(const pps_decoder_weights* w, const float* g, int64_t q, float* tmat, cudaStream_t st);
 
 bool pointnet_tc_supported(const pps_decoder_weights* w) {
-    return w->tc_pn_stn != nullptr && w->tc_pn_feat != nullptr && w->num_pts_local <= 64 && w->stn_size == 256 && w->latent == 256;
+    return w->tc_pn_stn != nullptr && w->tc_pn_feat != nullptr && w->num_pts_local <= 256 && w->stn_size == 256 && w->latent == 256;
 }
 
 // local branch on the tensor cores: patches [q,P,3] -> pooled128 [q,128]; scratch: a1 [tiles,8,128,8] (tile-major, 64 point slots per query), g [q,256], f1 [q,128],
 // f2 [q,64], tmat [q,4096]
 int pointnet_tc_impl(const pps_decoder_weights* w, const float* patches, int64_t q, float* a1, float* g, float* f1, float* f2,
-                     float* tmat, float* pooled128, cudaStream_t st) {
+                     float* tmat, float* pooled128, float* partial, cudaStream_t st) {
     if (q == 0) return PPS_OK;
     static bool configured = false;
     if (!configured) {
@@ -606,12 +660,13 @@ int pointnet_tc_impl(const pps_decoder_weights* w, const float* patches, int64_t
         configured = true;
     }
     const int P = w->num_pts_local, S = w->stn_size;
-    const long long ntiles = (q + 1) / 2;
-    const int grid_a = (int)(ntiles < 2 * kNumSMs ? ntiles : 2 * kNumSMs);
-    const int grid_c = (int)(ntiles < 2 * kNumSMs ? ntiles : 2 * kNumSMs);
-    tc::pn_stn_kernel<<<grid_a, tc::kPnThreads, tc::stn::kSmemBytes, st>>>(patches, q, P, static_cast<const uint8_t*>(w->tc_pn_stn),
-                                                                          w->pn0a_w, w->pn0a_b, w->pn0b_b, w->stn1_b, w->stn2_b,
-                                                                          w->stn3_b, a1, g);
+    const int G = (P + 63) / 64;  // 64-row half-tiles per query
+    const long long ntiles = (q * G + 1) / 2;
+    const int grid = (int)(ntiles < 2 * kNumSMs ? ntiles : 2 * kNumSMs);
+    if (G > 1) PPS_CUDA(cudaMemsetAsync(g, 0, (size_t)q * 256 * sizeof(float), st));  // the half-tiles' maxima meet in an atomicMax
+    tc::pn_stn_kernel<<<grid, tc::kPnThreads, tc::stn::kSmemBytes, st>>>(patches, q, P, G, static_cast<const uint8_t*>(w->tc_pn_stn),
+                                                                        w->pn0a_w, w->pn0a_b, w->pn0b_b, w->stn1_b, w->stn2_b,
+                                                                        w->stn3_b, a1, g);
     PPS_LAUNCH_CHECK();
     if (chain_tc_supported(w)) {
         PPS_TRY(stn_fc_tc_impl(w, g, q, tmat, st));
@@ -620,10 +675,20 @@ int pointnet_tc_impl(const pps_decoder_weights* w, const float* patches, int64_t
         PPS_TRY(linear_impl(f1, w->stnf2_w, w->stnf2_b, nullptr, nullptr, f2, q, S / 4, S / 2, S / 2, S / 4, 1, st));
         PPS_TRY(linear_impl(f2, w->stnf3_w, w->stnf3_b, nullptr, nullptr, tmat, q, 4096, S / 4, S / 4, 4096, 0, st));
     }
-    tc::pn_feat_kernel<<<grid_c, tc::kPnThreads, tc::feat::kSmemBytes, st>>>(a1, tmat, q, P, static_cast<const uint8_t*>(w->tc_pn_feat),
-                                                                            w->pn1_b, w->pn2_b, w->pnq_w, pooled128);
+    tc::pn_feat_kernel<<<grid, tc::kPnThreads, tc::feat::kSmemBytes, st>>>(a1, tmat, q, P, G, static_cast<const uint8_t*>(w->tc_pn_feat),
+                                                                          w->pn1_b, w->pn2_b, w->pnq_w, pooled128, partial);
     PPS_LAUNCH_CHECK();
+    if (G > 1) {
+        tc::pn_combine_kernel<<<(unsigned)q, 128, 0, st>>>(partial, q, G, pooled128);
+        PPS_LAUNCH_CHECK();
+    }
     return PPS_OK;
+}
+
+// floats of the per-(query, half-tile) attention-pooling partials (0 when every patch fits one half-tile)
+size_t pointnet_tc_partial_floats(const pps_decoder_weights* w, int64_t q) {
+    const int G = (w->num_pts_local + 63) / 64;
+    return G > 1 ? (size_t)q * G * tc::kPartialStride : 0;
 }
 
 }  // namespace pps

@@ -299,23 +299,27 @@ def test_from_latent_reference_interface(dev, net):
     assert np.abs(out3.cpu().numpy() - g['logits']).max() < LOGIT_TOL
 
 
-def test_decode_200nn(dev, oracle):
-    """P=200 (ppsurf_200nn): the kNN runs with k=200, the global branch uses the first 64"""
+@pytest.mark.parametrize('npl', [200, 100, 64, 130])
+def test_decode_large_patches(dev, oracle, npl):
+    """P > 64 (ppsurf_200nn: P = 200): the kNN runs with k = max(64, P), the global branch uses the first 64; on the tensor-core
+    path a patch spans ceil(P/64) half-tiles whose maxima / attention partials are merged (atomic max, online softmax)"""
     import ppsurf_b200
-    from ppsurf_b200 import ops
     w = oracle.make_state_dict(43)
-    net = ppsurf_b200.PPSurfNetwork(3, 256, 2, 64, 200, 256)
+    net = ppsurf_b200.PPSurfNetwork(3, 256, 2, 64, npl, 256)
     net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in w.items()}, strict=True)
     net = net.to(dev)
     rng = np.random.default_rng(9)
     pts = oracle.synthetic_cloud(3000, seed=31)
     latents = rng.standard_normal((1, 256, 3000)).astype(np.float32)
-    qry = (pts[rng.integers(0, 3000, 40)] + 0.03 * rng.standard_normal((40, 3))).astype(np.float32)
-    out = net.from_latent({'pts': cu(pts.T[None], dev), 'latents': cu(latents, dev), 'pts_query': torch.from_numpy(qry[None])})
+    qry = (pts[rng.integers(0, 3000, 45)] + 0.03 * rng.standard_normal((45, 3))).astype(np.float32)
     data = {'pts': pts.T[None], 'latents': latents, 'pts_query': qry[None],
-            'pts_local_ps': oracle.get_pts_local_ps(pts, qry, 200)[None]}
+            'pts_local_ps': oracle.get_pts_local_ps(pts, qry, npl)[None]}
     ref = oracle.from_latent(w, data, dtype=np.float64)
-    assert np.abs(out.cpu().numpy() - ref).max() < LOGIT_TOL
+    for path in (1, 0):
+        net.decode_path = path
+        net._decoder_cache = None
+        out = net.from_latent({'pts': cu(pts.T[None], dev), 'latents': cu(latents, dev), 'pts_query': torch.from_numpy(qry[None])})
+        assert np.abs(out.cpu().numpy() - ref).max() < LOGIT_TOL, 'path {}'.format(path)
 
 
 def test_grid_queries_bit_exact(dev, oracle):
