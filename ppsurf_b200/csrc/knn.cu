@@ -196,7 +196,8 @@ __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restri
         const float qx = queries[3 * qi], qy = queries[3 * qi + 1], qz = queries[3 * qi + 2];
         float worst = INFINITY;
         int worst_i = 0x7fffffff;
-        constexpr bool kReseed = SLOTS == 2;  // 32 < k <= 64 (the decoder's grid-ordered queries): the previous list seeds this one
+        // 32 < k <= 256 (the decoder's grid-ordered queries; list sizes 64 / 128 / 256): the previous list seeds this one
+        constexpr bool kReseed = SLOTS == 2 || SLOTS == 4 || SLOTS == 8;
         if (kReseed && rq > 0) {
             // Consecutive grid queries share most of their neighbours.  Re-evaluate the previous query's list for this query
             // (its entries are real points, so the k-th of them bounds the k-th distance from the first node on) and sort it
@@ -214,16 +215,25 @@ __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restri
             for (int kk = 2; kk <= SLOTS * 32; kk <<= 1) {
 #pragma unroll
                 for (int j = kk >> 1; j >= 1; j >>= 1) {
-                    if (j >= 32) {  // partner = the other slot of this lane (SLOTS == 2, j == 32): ascending over the whole list
-                        if (SLOTS == 2 && cand_less(ld[SLOTS - 1], li[SLOTS - 1], ld[0], li[0])) {
-                            const float td = ld[0];
-                            const int ti = li[0], tp = lp[0];
-                            ld[0] = ld[SLOTS - 1];
-                            li[0] = li[SLOTS - 1];
-                            lp[0] = lp[SLOTS - 1];
-                            ld[SLOTS - 1] = td;
-                            li[SLOTS - 1] = ti;
-                            lp[SLOTS - 1] = tp;
+                    if (j >= 32) {  // partner = slot s ^ (j / 32) of the same lane: compare-exchange inside the thread
+                        const int ms = j >> 5;
+#pragma unroll
+                        for (int s = 0; s < SLOTS; ++s) {
+                            if ((s & ms) != 0) continue;
+                            const int t = s | ms;
+                            if (t >= SLOTS) continue;
+                            const bool asc = ((s * 32) & kk) == 0;  // bit kk of g is the same for both partners (kk > j)
+                            const bool swap = asc ? cand_less(ld[t], li[t], ld[s], li[s]) : cand_less(ld[s], li[s], ld[t], li[t]);
+                            if (swap) {
+                                const float td = ld[s];
+                                const int ti = li[s], tp = lp[s];
+                                ld[s] = ld[t];
+                                li[s] = li[t];
+                                lp[s] = lp[t];
+                                ld[t] = td;
+                                li[t] = ti;
+                                lp[t] = tp;
+                            }
                         }
                     } else {
 #pragma unroll
@@ -476,7 +486,7 @@ int knn_query_impl(const void* index, int64_t n, const float* queries, int64_t q
     if (k <= 32) return launch_query<1>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out, st);
     if (k <= 64) return launch_query<2>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out, st);
     if (k <= 128) return launch_query<4>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out, st);
-    if (k <= 224) return launch_query<7>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out, st);
+    if (k <= 256) return launch_query<8>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out, st);
     return launch_query<16>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out, st);
 }
 

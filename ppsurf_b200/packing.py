@@ -109,7 +109,7 @@ def pack_decoder(sd, device, k, num_pts_local, prefix='') -> Packed:
         st.tc_wpack = p.tensors['tc_wpack'].data_ptr()
     else:
         st.tc_wpack = None
-    if latent == 256 and st.stn_size == 256 and num_pts_local <= 64:
+    if latent == 256 and st.stn_size == 256 and num_pts_local <= 256:
         t = p.tensors
         w3 = t['stn3_w'].to('cpu', torch.float64)
         stn = torch.cat([tc_pack_matrix(t['pn0b_w'].cpu()), tc_pack_matrix(t['stn1_w'].cpu()), tc_pack_matrix(t['stn2_w'].cpu()),

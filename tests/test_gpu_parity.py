@@ -64,13 +64,28 @@ def test_knn_golden(dev, oracle):
     np.testing.assert_array_equal(small.cpu().numpy(), g['idx_small'])
 
 
-@pytest.mark.parametrize('n,q,k', [(20000, 3000, 64), (3000, 500, 200), (2500, 2500, 16), (39, 39, 16), (700, 100, 300)])
+@pytest.mark.parametrize('n,q,k', [(20000, 3000, 64), (3000, 500, 200), (2500, 2500, 16), (39, 39, 16), (700, 100, 300), (5000, 800, 100),
+                                   (150, 64, 100)])
 def test_knn_vs_oracle(dev, oracle, n, q, k):
     from ppsurf_b200 import ops
     rng = np.random.default_rng(n + k)
     pts = oracle.synthetic_cloud(n, seed=n)
     qry = np.concatenate([pts[rng.integers(0, n, q // 2)] + 0.01 * rng.standard_normal((q // 2, 3)),
                           rng.uniform(-0.6, 0.6, (q - q // 2, 3))]).astype(np.float32)
+    idx, d2 = ops.knn(cu(pts, dev), cu(qry, dev), k, return_dist=True)
+    ref_idx, _ = oracle.knn(pts, qry, k)
+    assert_knn_equal(oracle, pts, qry, idx.cpu().numpy(), d2.cpu().numpy(), ref_idx)
+
+
+@pytest.mark.parametrize('k', [64, 100, 200])
+def test_knn_grid_ordered_queries(dev, oracle, k):
+    """consecutive grid vertices (the decoder's query order): every query is seeded with its predecessor's neighbour list and,
+    near the surface, goes straight to the cells around its search ball -- the result must still be the exact kNN"""
+    from ppsurf_b200 import ops
+    n = 30000
+    pts = oracle.synthetic_cloud(n, seed=77)
+    ax = np.linspace(-0.5, 0.5, 24, dtype=np.float32)
+    qry = np.stack(np.meshgrid(ax, ax, ax, indexing='ij'), axis=-1).reshape(-1, 3)  # C order: z fastest, like the volume
     idx, d2 = ops.knn(cu(pts, dev), cu(qry, dev), k, return_dist=True)
     ref_idx, _ = oracle.knn(pts, qry, k)
     assert_knn_equal(oracle, pts, qry, idx.cpu().numpy(), d2.cpu().numpy(), ref_idx)
