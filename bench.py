@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument('--ref-sample', type=int, default=16384, help='queries per step of the --impl reference arm')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-run', action='store_true', help='for ncu captures only: no minimum warm-up, no e2e leg')
+    ap.add_argument('--shard-of', type=int, default=0,
+                    help='debug: decode only the share rank 0 would get in a job of this many ranks (single process)')
     return ap.parse_args()
 
 
@@ -65,19 +67,22 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """samples nvidia-smi while the timed region runs"""
+    """samples nvidia-smi (every 100 ms) from before the warm-up to the end of the timed region; `mark()` is called when the timed
+    region starts.  The summary uses the samples taken after the mark; a timed region shorter than the sampling period (many
+    GPUs, few steps) falls back to the samples of the warm-up steps, which run the identical workload"""
 
     def __init__(self, index):
         self.index = index
         self.rows = []
         self.proc = None
+        self.t_mark = None
 
     def __enter__(self):
         q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
-                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -87,21 +92,26 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(',')]))
+
+    def mark(self):
+        self.t_mark = time.perf_counter()
 
     def __exit__(self, *exc):
         if self.proc is not None:
-            time.sleep(0.25)
+            time.sleep(0.15)
             self.proc.terminate()
             self.thread.join(timeout=2)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        timed = [r for t, r in self.rows if self.t_mark is not None and t >= self.t_mark]
+        rows = timed if timed else [r for _, r in self.rows[1:]] or [r for _, r in self.rows]  # [0] may predate the load
+        sm = [float(r[0]) for r in rows if r and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == 'active'})
+        reasons = sorted({names[i] for r in rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == 'active'})
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': reasons, 'samples': len(sm)}
+                'reasons': reasons, 'samples': len(sm), 'window': 'timed region' if timed else 'warm-up + timed region'}
 
 
 def grid_shard(total, world, rank):
@@ -250,6 +260,8 @@ def run_b200(args):
     dev = torch.device('cuda', local_rank)
     ops.require_device()
     if world > 1:
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'  # the version banner goes to stdout: the bench prints ONE line there
         dist.init_process_group('nccl', device_id=dev)
     lib = _lib.lib
 
@@ -295,7 +307,7 @@ def run_b200(args):
     dec = net.decoder_for(pts_bcn, latents)
     r = args.resolution + 2
     total = r ** 3
-    spans = grid_blocks(total, world, rank)
+    spans = grid_blocks(total, args.shard_of, 0) if (args.shard_of > 1 and world == 1) else grid_blocks(total, world, rank)
     count = sum(c for _, c in spans)
     step, bmin_pad, _ = model.grid_definition(pts_np, args.resolution, 1)
     queries = torch.cat([ops.grid_queries(r, step, bmin_pad, first=f, count=c, device=dev) for f, c in spans]) if len(spans) > 1 \
@@ -315,14 +327,15 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     warmup = args.warmup if args.profile_run else max(args.warmup, 3)
-    for _ in range(warmup):
-        one_step()
-    barrier()
-    launches0 = lib.pps_launch_count()
-    lib.pps_profile_enable(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
+        for _ in range(warmup):
+            one_step()
         barrier()
+        launches0 = lib.pps_launch_count()
+        lib.pps_profile_enable(1)
+        barrier()
+        clocks.mark()
         e0.record()
         for _ in range(args.steps):
             one_step()
