@@ -145,7 +145,7 @@ typedef struct pps_decoder_weights {
     /* tensor-core pack of fc2 / fc3 / fc_query for path 1 (pps_decoder_tc_pack_bytes() bytes, nullable): per layer 16
      * k16 stages, each [W_hi k8-block 0 | W_hi k8-block 1 | W_lo block 0 | W_lo block 1], a block = N rows x 8 fp16 */
     const void* tc_wpack;
-    /* same stage format for the local branch (P <= 64): [conv0b | stn.conv1 | stn.conv2 | stn.conv3 rows 0-127 | rows
+    /* same stage format for the local branch (P <= 256): [conv0b | stn.conv1 | stn.conv2 | stn.conv3 rows 0-127 | rows
      * 128-255] and [conv1 | conv2]; pps_decoder_tc_pn_stn_bytes() / pps_decoder_tc_pn_feat_bytes() bytes, nullable */
     const void* tc_pn_stn;
     const void* tc_pn_feat;
@@ -180,7 +180,7 @@ size_t pps_decoder_workspace_bytes(const pps_decoder_weights* w, int64_t chunk);
  *   logits_out [q,2] f32 or NULL;  occ_out [q] f32 (softmax(l)[0] - softmax(l)[1]) or NULL.
  *   idx_out [q,kmax] int32 or NULL (the neighbour ids, = reference proj_ids for the first w->k columns).
  *   path: 0 = fp32 SIMT kernels, 1 = tcgen05 split-fp16 tensor-core kernels (both branches; the local branch needs
- *   P <= 64 and otherwise stays on the fp32 kernels). */
+ *   P <= 256 -- a patch then spans ceil(P/64) half-tiles -- and otherwise stays on the fp32 kernels). */
 int pps_decoder_decode(const pps_decoder_weights* w, const void* knn_index, const float* pts, const float* table,
                        int64_t n, const float* queries, int64_t q, int64_t chunk, void* workspace,
                        size_t workspace_bytes, float* logits_out, float* occ_out, int32_t* idx_out, int path,
