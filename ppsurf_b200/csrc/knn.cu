@@ -282,75 +282,64 @@ __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restri
 
         // scan the contiguous range [lo, hi) of the Morton-sorted points, 32 at a time
         auto scan_range = [&](int lo, int hi) {
-            // four steps (128 points) are in flight per lane: a long range scanned by a lone warp (queries near the centre of a
-            // closed surface, the tail of a launch) is bound by the load latency, not by the insertions
-            float4 pf[4];
+            float4 pn = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lo + lane < hi) pn = sorted[lo + lane];
+            for (int base = lo; base < hi; base += 32) {
+                const int i = base + lane;
+                const float4 p = pn;
+                if (i + 32 < hi) pn = sorted[i + 32];  // the next 32 points are in flight while these are inserted
+                float d2 = INFINITY;
+                int pi = 0x7fffffff;
+                if (i < hi) {
+                    const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+                    d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                    pi = __float_as_int(p.w);
+                }
+                unsigned int mask = __ballot_sync(full, i < hi && d2 <= bound && cand_less(d2, pi, worst, worst_i));
+                while (mask) {
+                    const int src = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const float vd = __shfl_sync(full, d2, src);
+                    const int vi = __shfl_sync(full, pi, src);
+                    const int vp = base + src;
+                    if (!cand_less(vd, vi, worst, worst_i)) continue;  // the bound may have tightened meanwhile
+                    if (kReseed && rq > 0) {  // already in the list (carried over from the previous query)?
+                        bool dup = false;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                pf[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (lo + 32 * u + lane < hi) pf[u] = sorted[lo + 32 * u + lane];
-            }
-            for (int base4 = lo; base4 < hi; base4 += 128) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int base = base4 + 32 * u;
-                    if (base >= hi) break;
-                    const int i = base + lane;
-                    const float4 p = pf[u];
-                    if (i + 128 < hi) pf[u] = sorted[i + 128];  // refill this slot four steps ahead
-                    float d2 = INFINITY;
-                    int pi = 0x7fffffff;
-                    if (i < hi) {
-                        const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
-                        d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                        pi = __float_as_int(p.w);
+                        for (int s = 0; s < SLOTS; ++s) dup |= li[s] == vi;
+                        if (__any_sync(full, dup)) continue;
                     }
-                    unsigned int mask = __ballot_sync(full, i < hi && d2 <= bound && cand_less(d2, pi, worst, worst_i));
-                    while (mask) {
-                        const int src = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        const float vd = __shfl_sync(full, d2, src);
-                        const int vi = __shfl_sync(full, pi, src);
-                        const int vp = base + src;
-                        if (!cand_less(vd, vi, worst, worst_i)) continue;  // the bound may have tightened meanwhile
-                        if (kReseed && rq > 0) {  // already in the list (carried over from the previous query)?
-                            bool dup = false;
-    #pragma unroll
-                            for (int s = 0; s < SLOTS; ++s) dup |= li[s] == vi;
-                            if (__any_sync(full, dup)) continue;
-                        }
-                        int pos = 0;  // number of list elements smaller than the candidate
-    #pragma unroll
-                        for (int s = 0; s < SLOTS; ++s) pos += __popc(__ballot_sync(full, cand_less(ld[s], li[s], vd, vi)));
-    #pragma unroll
-                        for (int s = SLOTS - 1; s >= 0; --s) {
-                            float pd = __shfl_up_sync(full, ld[s], 1);
-                            int pj = __shfl_up_sync(full, li[s], 1);
-                            int pp = __shfl_up_sync(full, lp[s], 1);
-                            if (s > 0) {
-                                const float cd = __shfl_sync(full, ld[s - 1], 31);
-                                const int cj = __shfl_sync(full, li[s - 1], 31);
-                                const int cp = __shfl_sync(full, lp[s - 1], 31);
-                                if (lane == 0) {
-                                    pd = cd;
-                                    pj = cj;
-                                    pp = cp;
-                                }
-                            }
-                            const int g = s * 32 + lane;
-                            if (g == pos) {
-                                ld[s] = vd;
-                                li[s] = vi;
-                                lp[s] = vp;
-                            } else if (g > pos) {
-                                ld[s] = pd;
-                                li[s] = pj;
-                                lp[s] = pp;
+                    int pos = 0;  // number of list elements smaller than the candidate
+#pragma unroll
+                    for (int s = 0; s < SLOTS; ++s) pos += __popc(__ballot_sync(full, cand_less(ld[s], li[s], vd, vi)));
+#pragma unroll
+                    for (int s = SLOTS - 1; s >= 0; --s) {
+                        float pd = __shfl_up_sync(full, ld[s], 1);
+                        int pj = __shfl_up_sync(full, li[s], 1);
+                        int pp = __shfl_up_sync(full, lp[s], 1);
+                        if (s > 0) {
+                            const float cd = __shfl_sync(full, ld[s - 1], 31);
+                            const int cj = __shfl_sync(full, li[s - 1], 31);
+                            const int cp = __shfl_sync(full, lp[s - 1], 31);
+                            if (lane == 0) {
+                                pd = cd;
+                                pj = cj;
+                                pp = cp;
                             }
                         }
-                        worst = __shfl_sync(full, ld[wslot < SLOTS ? wslot : SLOTS - 1], wlane);
-                        worst_i = __shfl_sync(full, li[wslot < SLOTS ? wslot : SLOTS - 1], wlane);
+                        const int g = s * 32 + lane;
+                        if (g == pos) {
+                            ld[s] = vd;
+                            li[s] = vi;
+                            lp[s] = vp;
+                        } else if (g > pos) {
+                            ld[s] = pd;
+                            li[s] = pj;
+                            lp[s] = pp;
+                        }
                     }
+                    worst = __shfl_sync(full, ld[wslot < SLOTS ? wslot : SLOTS - 1], wlane);
+                    worst_i = __shfl_sync(full, li[wslot < SLOTS ? wslot : SLOTS - 1], wlane);
                 }
             }
         };
