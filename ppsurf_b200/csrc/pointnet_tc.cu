@@ -34,8 +34,13 @@ struct PnRow {
 __device__ __forceinline__ PnRow pn_row(long long tile, int row, int G) {
     const long long ht = 2 * tile + (row >> 6);
     PnRow r;
-    r.q = ht / G;
-    r.p = int(ht % G) * 64 + (row & 63);
+    if (G == 1) {  // the common case (P <= 64) must not pay for 64-bit divisions: they cost 6 % of the whole decode
+        r.q = ht;
+        r.p = row & 63;
+    } else {
+        r.q = ht / G;
+        r.p = int(ht - r.q * G) * 64 + (row & 63);
+    }
     return r;
 }
 
@@ -60,12 +65,15 @@ constexpr int kSmemBytes = kOffTmem + 16 + 1024;     // ~103 KB -> two CTAs per 
 constexpr int kTmemCols = 256;
 }  // namespace stn
 
+// MULTI = false: every patch fits one half-tile (P <= 64, G == 1): the instantiation carries no divisions and no partials
+template <bool MULTI>
 __global__ void __launch_bounds__(kPnThreads, 2)
-    pn_stn_kernel(const float* __restrict__ patches, long long nq, int P, int G, const uint8_t* __restrict__ wpack,
+    pn_stn_kernel(const float* __restrict__ patches, long long nq, int P, int G_arg, const uint8_t* __restrict__ wpack,
                   const float* __restrict__ w0a, const float* __restrict__ b0a, const float* __restrict__ b0b,
                   const float* __restrict__ bs1, const float* __restrict__ bs2, const float* __restrict__ bs3,
                   float* __restrict__ a1_out, float* __restrict__ g_out) {
     using namespace stn;
+    const int G = MULTI ? G_arg : 1;
     extern __shared__ __align__(1024) uint8_t smem[];  // used directly: the compiler keeps the shared address space (LDS/STS)
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -324,11 +332,13 @@ __device__ __forceinline__ int c2_hi(int kblk) { return kblk < 8 ? kOffAhi + kbl
 __device__ __forceinline__ int c2_lo(int kblk) { return kblk < 8 ? kOffAlo + kblk * kPnLbo : kOffT + kABytes + (kblk - 8) * kPnLbo; }
 }  // namespace feat
 
+template <bool MULTI>
 __global__ void __launch_bounds__(kPnThreads, 2)
-    pn_feat_kernel(const float* __restrict__ a1, const float* __restrict__ tmat, long long nq, int P, int G,
+    pn_feat_kernel(const float* __restrict__ a1, const float* __restrict__ tmat, long long nq, int P, int G_arg,
                    const uint8_t* __restrict__ wpack, const float* __restrict__ b1, const float* __restrict__ b2,
                    const float* __restrict__ wq, float* __restrict__ pooled, float* __restrict__ partial) {
     using namespace feat;
+    const int G = MULTI ? G_arg : 1;
     extern __shared__ __align__(1024) uint8_t smem[];  // used directly: the compiler keeps the shared address space (LDS/STS)
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -469,7 +479,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
             for (int t = 0; t < 4; ++t) {
                 const int e = et + 256 * t;
                 const int ql = e >> 9, i = (e >> 3) & 63, kb = e & 7;
-                long long q = (2 * tile + ql) / G;  // the query of half-tile ql
+                long long q = G == 1 ? 2 * tile + ql : (2 * tile + ql) / G;  // the query of half-tile ql
                 q = q < nq ? q : nq - 1;
                 const float4* src = reinterpret_cast<const float4*>(tmat + q * 4096 + i * 64) + 2 * kb;
                 const float4 u0 = src[0], u1 = src[1];
@@ -655,8 +665,10 @@ int pointnet_tc_impl(const pps_decoder_weights* w, const float* patches, int64_t
     if (q == 0) return PPS_OK;
     static bool configured = false;
     if (!configured) {
-        PPS_CUDA(cudaFuncSetAttribute(tc::pn_stn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::stn::kSmemBytes));
-        PPS_CUDA(cudaFuncSetAttribute(tc::pn_feat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::feat::kSmemBytes));
+        PPS_CUDA(cudaFuncSetAttribute(tc::pn_stn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::stn::kSmemBytes));
+        PPS_CUDA(cudaFuncSetAttribute(tc::pn_stn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::stn::kSmemBytes));
+        PPS_CUDA(cudaFuncSetAttribute(tc::pn_feat_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::feat::kSmemBytes));
+        PPS_CUDA(cudaFuncSetAttribute(tc::pn_feat_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::feat::kSmemBytes));
         configured = true;
     }
     const int P = w->num_pts_local, S = w->stn_size;
@@ -664,9 +676,13 @@ int pointnet_tc_impl(const pps_decoder_weights* w, const float* patches, int64_t
     const long long ntiles = (q * G + 1) / 2;
     const int grid = (int)(ntiles < 2 * kNumSMs ? ntiles : 2 * kNumSMs);
     if (G > 1) PPS_CUDA(cudaMemsetAsync(g, 0, (size_t)q * 256 * sizeof(float), st));  // the half-tiles' maxima meet in an atomicMax
-    tc::pn_stn_kernel<<<grid, tc::kPnThreads, tc::stn::kSmemBytes, st>>>(patches, q, P, G, static_cast<const uint8_t*>(w->tc_pn_stn),
-                                                                        w->pn0a_w, w->pn0a_b, w->pn0b_b, w->stn1_b, w->stn2_b,
-                                                                        w->stn3_b, a1, g);
+    const uint8_t* pack_stn = static_cast<const uint8_t*>(w->tc_pn_stn);
+    if (G > 1)
+        tc::pn_stn_kernel<true><<<grid, tc::kPnThreads, tc::stn::kSmemBytes, st>>>(patches, q, P, G, pack_stn, w->pn0a_w, w->pn0a_b,
+                                                                                  w->pn0b_b, w->stn1_b, w->stn2_b, w->stn3_b, a1, g);
+    else
+        tc::pn_stn_kernel<false><<<grid, tc::kPnThreads, tc::stn::kSmemBytes, st>>>(patches, q, P, 1, pack_stn, w->pn0a_w, w->pn0a_b,
+                                                                                   w->pn0b_b, w->stn1_b, w->stn2_b, w->stn3_b, a1, g);
     PPS_LAUNCH_CHECK();
     if (chain_tc_supported(w)) {
         PPS_TRY(stn_fc_tc_impl(w, g, q, tmat, st));
@@ -675,8 +691,13 @@ int pointnet_tc_impl(const pps_decoder_weights* w, const float* patches, int64_t
         PPS_TRY(linear_impl(f1, w->stnf2_w, w->stnf2_b, nullptr, nullptr, f2, q, S / 4, S / 2, S / 2, S / 4, 1, st));
         PPS_TRY(linear_impl(f2, w->stnf3_w, w->stnf3_b, nullptr, nullptr, tmat, q, 4096, S / 4, S / 4, 4096, 0, st));
     }
-    tc::pn_feat_kernel<<<grid, tc::kPnThreads, tc::feat::kSmemBytes, st>>>(a1, tmat, q, P, G, static_cast<const uint8_t*>(w->tc_pn_feat),
-                                                                          w->pn1_b, w->pn2_b, w->pnq_w, pooled128, partial);
+    const uint8_t* pack_feat = static_cast<const uint8_t*>(w->tc_pn_feat);
+    if (G > 1)
+        tc::pn_feat_kernel<true><<<grid, tc::kPnThreads, tc::feat::kSmemBytes, st>>>(a1, tmat, q, P, G, pack_feat, w->pn1_b, w->pn2_b,
+                                                                                    w->pnq_w, pooled128, partial);
+    else
+        tc::pn_feat_kernel<false><<<grid, tc::kPnThreads, tc::feat::kSmemBytes, st>>>(a1, tmat, q, P, 1, pack_feat, w->pn1_b, w->pn2_b,
+                                                                                     w->pnq_w, pooled128, partial);
     PPS_LAUNCH_CHECK();
     if (G > 1) {
         tc::pn_combine_kernel<<<(unsigned)q, 128, 0, st>>>(partial, q, G, pooled128);
