@@ -56,6 +56,22 @@ def parse_args():
     return ap.parse_args()
 
 
+class QuietStdout:
+    """Everything any library writes to file descriptor 1 while the bench runs (NCCL prints its version banner there) goes to
+    stderr; `emit` writes the ONE JSON line of the contract to the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(line, flush=True)
+        os.dup2(2, 1)
+
+
 def measured_peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -253,6 +269,7 @@ def run_b200(args):
     import ppsurf_b200
     from ppsurf_b200 import _lib, ops, synthetic
 
+    quiet = QuietStdout()
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -260,8 +277,6 @@ def run_b200(args):
     dev = torch.device('cuda', local_rank)
     ops.require_device()
     if world > 1:
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-            os.environ['NCCL_DEBUG'] = 'WARN'  # the version banner goes to stdout: the bench prints ONE line there
         dist.init_process_group('nccl', device_id=dev)
     lib = _lib.lib
 
@@ -440,7 +455,7 @@ def run_b200(args):
             diff = np.abs(got - ref)
             out['vs_float64_kdtree'] = {'max_abs_diff': float(diff.max()), 'queries_above_1e-4': int((diff > 1e-4).sum()),
                                         'sample': int(args.cpu_sample)}
-        print(json.dumps(out))
+        quiet.emit(json.dumps(out))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -162,3 +162,14 @@ def test_loss_and_metrics_follow_the_reference_formulas():
     # degenerate case: nothing predicted positive -> precision NaN, F1 NaN (reference conventions)
     m0 = ppsurf_b200.PPSurfModel.calc_metrics(torch.tensor([[[1.0, 1.0], [0.0, 0.0]]]), {'occ': torch.tensor([[1, 0]])})
     assert np.isnan(m0['precision']) and m0['recall'] == 0.0 and np.isnan(m0['f1_score'])
+
+
+def test_bench_emits_one_clean_stdout_line():
+    """bench.py's contract: ONE JSON line on stdout.  Library chatter on fd 1 (NCCL prints its version banner there) must land
+    on stderr"""
+    import subprocess
+    import sys
+    code = ('import os, sys; sys.path.insert(0, {!r}); import bench; q = bench.QuietStdout(); os.write(1, b"banner\\n"); '
+            'print("chatter"); q.emit("{{\\"ok\\": 1}}"); print("more")').format(ROOT)
+    p = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, check=True)
+    assert p.stdout == '{"ok": 1}\n' and 'banner' in p.stderr and 'more' in p.stderr
