@@ -173,3 +173,36 @@ def test_bench_emits_one_clean_stdout_line():
             'print("chatter"); q.emit("{{\\"ok\\": 1}}"); print("more")').format(ROOT)
     p = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, check=True)
     assert p.stdout == '{"ok": 1}\n' and 'banner' in p.stderr and 'more' in p.stderr
+
+
+def test_tensor_core_pack_layout(weights):
+    """The projection kernel's weight pack, decoded on the CPU exactly the way the kernel addresses it: stage s of layer l holds,
+    for each CTA r of the pair, rows [128r, 128r+128) of W as [hi k8-block 0 | hi k8-block 1 | lo block 0 | lo block 1] with
+    blocks of [128 rows][8 fp16]; fc_query is ONE 128-row block per stage (64 zero rows, then the 64 heads).  hi + lo must
+    reproduce the fp32 weights to 2^-21 relative."""
+    from ppsurf_b200 import packing
+    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in weights.items()}
+    p = packing.pack_decoder(sd, 'cpu', 64, 50)
+    pack = p.tensors['tc_wpack'].numpy().view(np.float16)  # 2 bytes per element
+    stage_elems = 8192 // 2  # one CTA's ring slot
+
+    def block(stage_base, r0, rows=128):  # -> [rows, 16] float32 (hi + lo) of one 8 KB slot
+        slot = pack[stage_base:stage_base + stage_elems].astype(np.float32)
+        hi = slot[:2048].reshape(2, rows, 8)   # [k8 block][row][8]
+        lo = slot[2048:].reshape(2, rows, 8)
+        return (hi + lo).transpose(1, 0, 2).reshape(rows, 16)
+
+    for layer, name in enumerate(('projection.fc2.weight', 'projection.fc3.weight')):
+        w = np.asarray(weights[name]).reshape(256, 256).astype(np.float32)
+        for s in (0, 7, 15):
+            for r in (0, 1):
+                got = block((layer * 16 + s) * 2 * stage_elems + r * stage_elems, 0)
+                ref = w[128 * r:128 * r + 128, 16 * s:16 * s + 16]
+                assert np.abs(got - ref).max() <= 2.0 ** -20 * np.abs(ref).max()
+    wq = np.asarray(weights['projection.fc_query.weight']).reshape(64, 256).astype(np.float32)
+    base = 2 * 16 * 2 * stage_elems
+    for s in (0, 9):
+        got = block(base + s * stage_elems, 0)
+        assert np.all(got[:64] == 0.0)
+        assert np.abs(got[64:] - wq[:, 16 * s:16 * s + 16]).max() <= 2.0 ** -20 * np.abs(wq).max()
+    assert pack.size * 2 == 2 * 16 * 16384 + 16 * 8192
