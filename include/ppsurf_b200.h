@@ -157,9 +157,10 @@ typedef struct pps_decoder_weights {
 } pps_decoder_weights;
 
 size_t pps_decoder_tc_pack_bytes(void);
-/* debug aid: CTA 0 of the tensor-core projection kernel writes per-phase cycle counters (8 x int64, device memory) */
+/* debug aid: while `counters` (128 x int64, device memory) is set, the projection runs as its instrumented instance: CTA 0 writes
+ * per-phase cycle counters [0..9], every CTA pair its total [32 + pair] (tools/tc_phase_profile.py); NULL switches it off */
 void pps_debug_tc_profile(long long* counters);
-/* tuning knob: CTAs per cluster (1, 2 or 4) that share multicast weight stages in the projection kernel (default 1) */
+/* retired tuning knob (no-op, kept for ABI stability) */
 void pps_debug_tc_cluster(int cs);
 /* debug: number of CTA pairs (2-CTA clusters) of the projection kernel the device holds at once */
 int pps_debug_tc_max_clusters(void);

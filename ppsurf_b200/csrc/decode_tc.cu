@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 
 }  // namespace tc
 
-static long long* g_tc_prof = nullptr;  // device buffer of 16 counters, set by pps_debug_tc_profile
+static long long* g_tc_prof = nullptr;  // device buffer of 128 counters, set by pps_debug_tc_profile
 
 size_t projection_tc_workspace(const pps_decoder_weights*, int64_t) { return 256; }
 
@@ -560,7 +560,7 @@ int projection_tc_impl(const pps_decoder_weights* w, const float* table, const f
 }  // namespace pps
 
 extern "C" size_t pps_decoder_tc_pack_bytes(void) { return pps::tc::kPackBytes; }
-// debug: CTA 0 of projection_tc_kernel writes its per-phase cycle counters into `counters` (16 x int64, device memory);
+// debug: CTA 0 of projection_tc_kernel writes its per-phase cycle counters into `counters` (128 x int64, device memory);
 // pass NULL to switch the instrumentation output off
 extern "C" void pps_debug_tc_profile(long long* counters) { pps::g_tc_prof = counters; }
 // debug: how many CTA pairs of projection_tc_kernel the device can hold at once (-1 on error)
