@@ -129,3 +129,25 @@ def test_torch_timing_twin_matches(oracle, weights):
                                  torch.from_numpy(g['pts_local_ps']))
     assert np.abs(logits.numpy().T[None] - g['logits']).max() < 1e-4
     assert np.abs(occ.numpy() - g['occ'][0]).max() < 1e-4
+
+
+def test_real_cloud_region_grown_volume(oracle, weights, weights_digest):
+    """BASELINE configs[0] plumbing on REAL data: 3000 vertices of an abc_minimal cloud, normalised, decoded and region-grown at
+    gen_resolution_global = 17 by the unmodified reference (its _create_volume, from_latent, normalize_patches and the kd-tree
+    stand-in); the oracle's restatement of the same chain must produce the same volume"""
+    g = load_golden('real_volume')
+    assert str(g['digest']) == weights_digest
+    pts = g['pts']
+    latents = np.random.default_rng(int(g['latents_seed'])).standard_normal((1, 256, pts.shape[0])).astype(np.float32)
+    assert abs(float(latents.astype(np.float64).sum()) - float(g['latents_sum'])) < 1e-6
+
+    def predict(q):
+        data = {'pts': pts.T[None], 'latents': latents, 'pts_query': q[None],
+                'pts_local_ps': oracle.get_pts_local_ps(pts, q, 50)[None]}
+        return oracle.occupancy_from_logits(oracle.from_latent(weights, data))[0]
+
+    vol = oracle.create_volume(predict, pts, 17)
+    np.testing.assert_array_equal(np.isnan(vol), np.isnan(g['volume']))
+    finite = vol[~np.isnan(vol)]
+    assert np.isnan(vol).any() and finite.min() < -0.5 and finite.max() > 0.5  # region-grown, with an inside and an outside
+    assert np.nanmax(np.abs(vol - g['volume'])) < 2e-5
