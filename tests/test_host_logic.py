@@ -206,3 +206,22 @@ def test_tensor_core_pack_layout(weights):
         assert np.all(got[:64] == 0.0)
         assert np.abs(got[64:] - wq[:, 16 * s:16 * s + 16]).max() <= 2.0 ** -20 * np.abs(wq).max()
     assert pack.size * 2 == 2 * 16 * 16384 + 16 * 8192
+
+
+def test_latent_schedule_of_the_module():
+    """PPSurfModel.latent_schedule (source/poco_model.py:207-224): subsets of gen_subsample_manifold points until every point has
+    been visited gen_subsample_manifold_iter times; a cloud smaller than the subset is encoded whole, once per iteration"""
+    import ppsurf_b200
+    model = ppsurf_b200.PPSurfModel(256, ['imp_surf_sign'], 3, 2, 64, 0.0, False, 'x.txt', 'results', 0.05, 't', 256, 3, 10000, 17, 50,
+                                    50000, 0, 0)
+    n = 25000
+    counts = np.zeros(n, dtype=np.int64)
+    sched = list(model.latent_schedule(n, torch.Generator().manual_seed(3)))
+    for ids in sched:
+        assert ids.shape[0] == 10000 and int(ids.min()) >= 0 and int(ids.max()) < n
+        counts[np.unique(ids.numpy())] += 1
+    assert counts.min() >= 3 and len(sched) >= 8
+    again = list(model.latent_schedule(n, torch.Generator().manual_seed(3)))
+    assert len(again) == len(sched) and all(torch.equal(a, b) for a, b in zip(again, sched))  # a seed reproduces the schedule
+    small = list(model.latent_schedule(500, torch.Generator().manual_seed(1)))
+    assert len(small) == 3 and all(torch.equal(s, torch.arange(500)) for s in small)
