@@ -37,7 +37,7 @@ def parse_args():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference', 'reference-gpu'])
     ap.add_argument('--path', type=int, default=int(os.environ.get('PPS_DECODE_PATH', '1')),
                     help='1 = tcgen05 split-fp16 kernels (default), 0 = fp32 SIMT kernels')
     ap.add_argument('--points', type=int, default=100000)
@@ -50,6 +50,9 @@ def parse_args():
                     help='queries of the CPU baseline sample (about 10-15 s of host work on 16 cores)')
     ap.add_argument('--ref-sample', type=int, default=16384, help='queries per step of the --impl reference arm')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-reference-gpu', action='store_true', help='skip the reference-modules-on-this-B200 leg of the b200 arm')
+    ap.add_argument('--no-predict', action='store_true', help='skip the e2e_predict block (encoder + region-grown shell)')
+    ap.add_argument('--refgpu-batches', type=int, default=2, help='50 000-query batches the reference-on-GPU leg times')
     ap.add_argument('--profile-run', action='store_true', help='for ncu captures only: no minimum warm-up, no e2e leg')
     ap.add_argument('--shard-of', type=int, default=0,
                     help='debug: decode only the share rank 0 would get in a job of this many ranks (single process)')
@@ -195,6 +198,10 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    import torch
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU baseline must use every host core regardless of the launcher
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
     from oracle import ppsurf_oracle as oracle
     weights = oracle.make_state_dict(42)
     pts = oracle.synthetic_cloud(args.points, 42)
@@ -212,16 +219,97 @@ def run_reference(args):
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
     value = sample / (ms * 1e-3) / 1e6
-    cores = os.cpu_count()
+    cores = torch.get_num_threads()
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': workload_name(args), 'step': 'bounded sample of {} grid vertices per step'.format(sample)},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                         'sample': '{} random vertices of the same grid per step, torch-CPU oracle + scipy cKDTree'.format(sample)},
+                         'sample': '{} random vertices of the same grid per step, torch-CPU oracle + scipy cKDTree, torch threads {} '
+                                   '(set explicitly; host cores {})'.format(sample, cores, os.cpu_count())},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0}))
+
+
+def reference_gpu_decode(oracle, weights_dev, pts, pts_dev, lat_dev, queries, num_pts_local, tree=None):
+    """one `rec_batch_size` batch the way the reference's GPU predict path runs it: CPU kd-tree
+    k=P query on the tree built once per cloud + numpy patch normalisation + H2D (source/poco_utils.py:63-72), CPU kd-tree
+    REBUILD + k=64 query + H2D (source/poco_model.py:385, source/base/proximity.py:84-89), the network's torch-eager ops on the
+    GPU under TF32 'high' (source/cli.py:88) and fp16 autocast (configs/poco.yaml:10 precision 16-mixed), softmax difference,
+    blocking D2H (poco_utils.py:79-81).  The torch ops are the oracle's torch twin of the reference modules moved to the
+    device; /root/reference itself does not exist on the GPU box."""
+    import torch
+    from scipy.spatial import cKDTree
+    from oracle import ppsurf_oracle_torch as oracle_torch
+    dev = pts_dev.device
+    if tree is None:
+        tree = cKDTree(pts, leafsize=10)
+    _, idx_p = tree.query(queries, k=num_pts_local, workers=-1)
+    loc = oracle.normalize_patches(pts[idx_p], queries)
+    loc_dev = torch.from_numpy(loc).to(dev)
+    _, idx64 = cKDTree(pts, leafsize=10).query(queries, k=64, workers=-1)  # rebuilt per batch like kdtree_query_oneshot
+    idx_dev = torch.from_numpy(idx64.astype(np.int64)).to(dev)
+    q_dev = torch.from_numpy(queries).to(dev)
+    with torch.autocast('cuda', dtype=torch.float16):
+        occ, _ = oracle_torch.from_latent(weights_dev, pts_dev, lat_dev, q_dev, idx_dev, loc_dev)
+    return occ.float().cpu().numpy()
+
+
+def time_reference_gpu(args, dev, pts_np, latents_cn, grid_queries_np, batches):
+    """Mquery/s of the reference's GPU predict path on this box; `batches` batches of 50 000 (25 000 for 200nn) consecutive grid
+    vertices from the middle of the volume, after one warm-up batch"""
+    import torch
+    from scipy.spatial import cKDTree
+    from oracle import ppsurf_oracle as oracle
+    from oracle import ppsurf_oracle_torch as oracle_torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    old = torch.get_float32_matmul_precision()
+    torch.set_float32_matmul_precision('high')
+    try:
+        weights_dev = oracle_torch.to_device(oracle.make_state_dict(42), dev)
+        pts_dev = torch.from_numpy(pts_np).to(dev)
+        lat_dev = torch.from_numpy(np.ascontiguousarray(latents_cn.T)).to(dev)
+        batch = 25000 if args.num_pts_local >= 200 else REFERENCE_BATCH
+        mid = grid_queries_np.shape[0] // 2
+        tree = cKDTree(pts_np, leafsize=10)
+        out, times = None, []
+        for b in range(-1, batches):
+            q = grid_queries_np[mid + max(b, 0) * batch: mid + (max(b, 0) + 1) * batch]
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = reference_gpu_decode(oracle, weights_dev, pts_np, pts_dev, lat_dev, q, args.num_pts_local, tree)
+            torch.cuda.synchronize()
+            if b >= 0:
+                times.append(time.perf_counter() - t0)
+        per_batch = float(np.mean(times))
+        return {'value': batch / per_batch / 1e6, 'unit': UNIT, 'ms_per_batch': per_batch * 1e3, 'batch': batch, 'batches': batches,
+                'host_threads': torch.get_num_threads(),
+                'what': 'reference GPU predict path on this B200: torch-eager modules (oracle torch twin) on the device, TF32 high + fp16 '
+                        'autocast, CPU cKDTree (k=P on the per-cloud tree, tree REBUILT + k=64 per batch), numpy patch normalisation, '
+                        'H2D / D2H per batch'}, out
+    finally:
+        torch.set_float32_matmul_precision(old)
+
+
+def run_reference_gpu(args):
+    """`--impl reference-gpu`: the arm the north star's >= 10x target is defined against"""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import torch
+    from oracle import ppsurf_oracle as oracle
+    dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0')))
+    pts = oracle.synthetic_cloud(args.points, 42)
+    latents = np.random.default_rng(7).standard_normal((256, args.points)).astype(np.float32)
+    grid = oracle.dense_grid_queries(pts, args.resolution, 1)
+    res, _ = time_reference_gpu(args, dev, pts, latents, grid, max(args.steps, 1))
+    print(json.dumps({
+        'impl': 'reference-gpu', 'metric': METRIC, 'value': res['value'], 'unit': UNIT, 'n_gpus': 1, 'steps': args.steps,
+        'warmup': 1, 'ms_per_step': res['ms_per_batch'], 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'dtype': 'tf32 + fp16 autocast', 'data': 'synthetic',
+        'config': {'workload': workload_name(args), 'step': 'one rec_batch_size batch of {} grid vertices'.format(res['batch'])},
+        'reference_gpu': res, 'gpu_launches': 0}))
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -260,6 +348,31 @@ def fkaconv_roofline(net, dev, peaks, batch=64):
             'fp32_tflops': flops / (ms * 1e-3) / 1e12,
             'note': 'arithmetic intensity {:.0f} FLOP per unique byte: above the fp32 SIMT machine balance, so the layer is '
                     'compute-bound before it is HBM-bound'.format(flops / unique)}
+
+
+def predict_block(model, pts_np, dev, args):
+    """secondary metric: the real predict path of one cloud through PPSurfModel.reconstruct -- encoder (latent loop),
+    per-cloud decoder setup, region-grown shell decode -- wall clock, host in / host out"""
+    import torch
+    pts_ms = torch.from_numpy(pts_np[None].copy()).to(dev)
+    model.network.sampling_seed = 42
+    best = None
+    for _ in range(2):
+        torch.manual_seed(42)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rec = model.reconstruct(pts_ms, resolution=args.resolution)
+        torch.cuda.synchronize()
+        total = time.perf_counter() - t0
+        if best is None or total < best['total_s']:
+            st = dict(model.last_reconstruct_stats)
+            best = {'total_s': total, 'encoder_s': st['encoder_s'], 'setup_ms': st['setup_s'] * 1e3, 'shell_decode_s': st['volume_s'],
+                    'shell_queries': st['shell_queries'], 'sweeps': st['sweeps'],
+                    'shell_mquery_per_s': st['shell_queries'] / st['volume_s'] / 1e6,
+                    'decoded_fraction_of_grid': st['shell_queries'] / float((args.resolution + 2) ** 3)}
+    best['what'] = 'PPSurfModel.reconstruct(pts [1,N,3]): encode_cloud (>=10 encodings per point) + decoder_for + create_volume (region ' \
+                   'growing, source/poco_utils.py:178-254), volume returned to the host; best of 2'
+    return best
 
 
 def run_b200(args):
@@ -309,17 +422,35 @@ def run_b200(args):
             encoder_s = time.perf_counter() - t0  # 10 encodings per point on random 10k-point subsets = ~100 passes
         else:
             latents = torch.from_numpy(np.random.default_rng(7).standard_normal((1, 256, args.points)).astype(np.float32)).to(dev)
-    broadcast_ms = None
+    broadcast_ms = broadcast_first_ms = None
     if world > 1:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         dist.barrier()
+        t0 = time.perf_counter()
+        dist.broadcast(latents, src=0)  # the first collective also builds the NCCL channels: reported separately
+        torch.cuda.synchronize()
+        broadcast_first_ms = (time.perf_counter() - t0) * 1e3
+        scratch = torch.empty_like(latents)
+        if rank == 0:
+            scratch.copy_(latents)
+        dist.broadcast(scratch, src=0)
+        dist.barrier()
         e0.record()
-        dist.broadcast(latents, src=0)
+        for _ in range(5):
+            dist.broadcast(scratch, src=0)
         e1.record()
         torch.cuda.synchronize()
-        broadcast_ms = e0.elapsed_time(e1)
+        broadcast_ms = e0.elapsed_time(e1) / 5  # steady state of the same 102 MB table
+        assert torch.equal(scratch, latents)
+        del scratch
 
-    dec = net.decoder_for(pts_bcn, latents)
+    net.decoder_for(pts_bcn, latents)  # warm (cub temp storage, first launches)
+    net._decoder_cache = None
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    dec = net.decoder_for(pts_bcn, latents)  # per-cloud setup: kNN index build + hoisted fc1 table
+    torch.cuda.synchronize()
+    setup_ms = (time.perf_counter() - t0) * 1e3
     r = args.resolution + 2
     total = r ** 3
     spans = grid_blocks(total, args.shard_of, 0) if (args.shard_of > 1 and world == 1) else grid_blocks(total, world, rank)
@@ -425,8 +556,10 @@ def run_b200(args):
                          'flop_per_row_executed': GEMM_FLOP_PER_ROW, 'peak_source': peaks['source'],
                          'whole_decode_tflops_reference_formulation': value * 1e6 * FLOP_PER_QUERY_REFERENCE / 1e12},
             'clocks': clocks.summary(),
-            'encoder_s': encoder_s, 'broadcast_ms': broadcast_ms,
+            'encoder_s': encoder_s, 'setup_ms': setup_ms, 'broadcast_ms': broadcast_ms, 'broadcast_first_ms': broadcast_first_ms,
         }
+        if not args.profile_run and not args.no_predict and world == 1:
+            out['e2e_predict'] = predict_block(model, pts_np, dev, args)
         if not args.profile_run:
             out['roofline_fkaconv'] = fkaconv_roofline(net, dev, peaks)
         if not args.no_cpu_baseline and world == 1:
@@ -455,6 +588,11 @@ def run_b200(args):
             diff = np.abs(got - ref)
             out['vs_float64_kdtree'] = {'max_abs_diff': float(diff.max()), 'queries_above_1e-4': int((diff > 1e-4).sum()),
                                         'sample': int(args.cpu_sample)}
+            if not args.no_reference_gpu:
+                grid_np = oracle.dense_grid_queries(pts_np, args.resolution, 1)
+                ref_gpu, _ = time_reference_gpu(args, dev, pts_np, lat_cn, grid_np, args.refgpu_batches)
+                ref_gpu['speedup_of_this_repo'] = {'device_resident': value / ref_gpu['value'], 'e2e_host_buffers': e2e_value / ref_gpu['value']}
+                out['reference_gpu'] = ref_gpu
         quiet.emit(json.dumps(out))
     if world > 1:
         dist.barrier()
@@ -465,6 +603,8 @@ def main():
     args = parse_args()
     if args.impl == 'reference':
         run_reference(args)
+    elif args.impl == 'reference-gpu':
+        run_reference_gpu(args)
     else:
         run_b200(args)
 

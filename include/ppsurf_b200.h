@@ -36,6 +36,10 @@ const char* pps_last_error(void);
 /* library version and the SM architecture the kernels were compiled for (100 for sm_100a) */
 int pps_version(void);
 int pps_compiled_arch(void);
+/* 64-bit digest of the CUDA sources and this header the library was built from (ppsurf_b200/build.py computes it, the
+ * Python binding recomputes it from the sources next to the library): a stale prebuilt binary cannot pass for the
+ * current sources */
+unsigned long long pps_source_hash(void);
 /* 0 if the current device can run the kernels, PPS_ERR_NO_DEVICE otherwise */
 int pps_check_device(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */

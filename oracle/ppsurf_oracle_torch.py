@@ -18,6 +18,11 @@ def _t(p, name):
     return v if isinstance(v, torch.Tensor) else torch.from_numpy(np.asarray(v))
 
 
+def to_device(p, device):
+    """the state dict as tensors on ``device`` (bench.py's reference-on-GPU arm: the reference modules moved with .cuda())"""
+    return {k: _t(p, k).to(device) for k in p}
+
+
 def _lin(p, name, x):
     """channel-last pointwise layer: x [..., Cin] -> [..., Cout]"""
     w = _t(p, name + '.weight')
@@ -50,7 +55,7 @@ def from_latent(p, pts, latents, queries, proj_ids, patches):
         t = torch.relu(_bn(p, n + 'stn2.bn3', _lin(p, n + 'stn2.conv3', t))).max(dim=1).values
         t = torch.relu(_bn(p, n + 'stn2.bn4', _lin(p, n + 'stn2.fc1', t)))
         t = torch.relu(_bn(p, n + 'stn2.bn5', _lin(p, n + 'stn2.fc2', t)))
-        t = (_lin(p, n + 'stn2.fc3', t) + torch.eye(64).reshape(1, -1)).view(-1, 64, 64)
+        t = (_lin(p, n + 'stn2.fc3', t) + torch.eye(64, device=t.device, dtype=t.dtype).reshape(1, -1)).view(-1, 64, 64)
         h = torch.einsum('qij,qpj->qpi', t, h)
         h = torch.relu(_bn(p, n + 'bn1', _lin(p, n + 'conv1', h)))
         h = torch.relu(_bn(p, n + 'bn2', _lin(p, n + 'conv2', h)))

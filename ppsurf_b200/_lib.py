@@ -55,6 +55,7 @@ class EncoderIdsOut(ctypes.Structure):
 SIGNATURES = {
     'pps_last_error': (ctypes.c_char_p, []),
     'pps_version': (i32, []),
+    'pps_source_hash': (ctypes.c_ulonglong, []),
     'pps_compiled_arch': (i32, []),
     'pps_check_device': (i32, []),
     'pps_launch_count': (ctypes.c_ulonglong, []),
@@ -108,7 +109,7 @@ SIGNATURES = {
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
-            '{} is missing. Build it with `python -m ppsurf_b200.build` (needs nvcc). '
+            '{} is missing. Build it with `python ppsurf_b200/build.py` (needs nvcc). '
             'ppsurf_b200 has no CPU or PyTorch fallback.'.format(LIB_PATH))
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
@@ -119,6 +120,23 @@ def _load():
 
 
 lib = _load()
+
+
+def source_hash_of_tree() -> int:
+    """digest of the CUDA sources next to this file, computed like ``ppsurf_b200/build.py`` does at build time"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('ppsurf_b200_build', os.path.join(HERE, 'build.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.source_hash()
+
+
+def assert_binary_matches_sources():
+    """raises when the loaded library was built from other sources than the ones in the tree (stale prebuilt .so)"""
+    built, tree = int(lib.pps_source_hash()), source_hash_of_tree()
+    if built != tree:
+        raise PpsError('libppsurf_b200.so is stale: built from sources with digest {:#x}, the tree has {:#x}; '
+                       'run `python ppsurf_b200/build.py`'.format(built, tree))
 
 
 def check(status: int):

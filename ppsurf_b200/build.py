@@ -19,6 +19,18 @@ def _nvcc():
     return nvcc
 
 
+def source_hash():
+    """first 8 bytes (as an int) of the sha256 over the CUDA sources and the public header, in a fixed order"""
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(f for f in os.listdir(CSRC) if f.endswith(('.cu', '.cuh', '.h')))
+    for path in [os.path.join(CSRC, f) for f in files] + [os.path.join(os.path.dirname(HERE), 'include', 'ppsurf_b200.h')]:
+        h.update(os.path.basename(path).encode())
+        with open(path, 'rb') as f:
+            h.update(f.read())
+    return int.from_bytes(h.digest()[:8], 'little')
+
+
 def _stale(target, deps):
     if not os.path.exists(target):
         return True
@@ -33,12 +45,17 @@ def build(force=False, verbose=False):
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h'))]
     headers.append(os.path.join(os.path.dirname(HERE), 'include', 'ppsurf_b200.h'))
     objs, procs = [], []
+    digest = source_hash()
+    stamp = os.path.join(obj_dir, 'source_hash.txt')
+    old_digest = open(stamp).read().strip() if os.path.exists(stamp) else ''
     for src in SOURCES:
         src_path = os.path.join(CSRC, src)
         obj = os.path.join(obj_dir, src.replace('.cu', '.o'))
         objs.append(obj)
-        if force or _stale(obj, [src_path] + headers):
-            cmd = [nvcc] + ARCH + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', src_path, '-o', obj]
+        # common.cu carries the digest of ALL sources (pps_source_hash): it is recompiled whenever any source changed
+        extra = ['-DPPS_SOURCE_HASH={}ull'.format(digest)] if src == 'common.cu' else []
+        if force or _stale(obj, [src_path] + headers) or (extra and old_digest != str(digest)):
+            cmd = [nvcc] + ARCH + FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + ['-c', src_path, '-o', obj]
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:
@@ -48,6 +65,8 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError('nvcc failed')
+    with open(stamp, 'w') as f:
+        f.write(str(digest))
     if force or procs or _stale(LIB_PATH, objs):
         cmd = [nvcc] + ARCH + ['-shared', '-Wno-deprecated-gpu-targets', '-o', LIB_PATH] + objs
         subprocess.check_call(cmd)

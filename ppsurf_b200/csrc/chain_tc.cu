@@ -121,7 +121,7 @@ __device__ __forceinline__ void load_rows(const Ctx& c, const float* __restrict_
             for (int t = 0; t < 8; ++t) v[t] = 0.f;
         }
         uint4 hi, lo;
-        split8_signed(v, hi, lo);
+        split8(v, hi, lo);
         *reinterpret_cast<uint4*>(c.smem + kOffAhi + kb * kLbo + r * 16) = hi;
         *reinterpret_cast<uint4*>(c.smem + kOffAlo + kb * kLbo + r * 16) = lo;
     }
@@ -147,10 +147,7 @@ __device__ __forceinline__ void epi_to_tile(const Ctx& c, uint32_t dcol, int n, 
                 x[t] = RELU ? fmaxf(y, 0.f) : y;
             }
             uint4 hi, lo;
-            if (RELU)
-                split8(x, hi, lo);
-            else
-                split8_signed(x, hi, lo);
+            split8(x, hi, lo);
             const int kblk = (col0 >> 3) + kb;
             *reinterpret_cast<uint4*>(c.smem + kOffAhi + kblk * kLbo + row * 16) = hi;
             *reinterpret_cast<uint4*>(c.smem + kOffAlo + kblk * kLbo + row * 16) = lo;

@@ -1,5 +1,6 @@
 #include <stdarg.h>
 
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -32,9 +33,37 @@ void profile_begin(cudaStream_t st) {
 void profile_end(cudaStream_t st) {
     if (g_profile) cudaEventRecord(next_event(), st);
 }
+
+// per-device pool of timing-disabled events for the host-buffer entry points (created once: the C ABI promises no
+// allocation per call)
+static std::mutex g_event_mutex;
+static cudaEvent_t g_dev_events[64][8];
+static int g_dev_event_count[64] = {0};
+cudaEvent_t* device_events(int count) {
+    int dev = 0;
+    if (count > 8 || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+        set_error("device_events: bad device or count");
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> lock(g_event_mutex);
+    while (g_dev_event_count[dev] < count) {
+        cudaError_t e = cudaEventCreateWithFlags(&g_dev_events[dev][g_dev_event_count[dev]], cudaEventDisableTiming);
+        if (e != cudaSuccess) {
+            set_error("device_events: %s", cudaGetErrorString(e));
+            return nullptr;
+        }
+        ++g_dev_event_count[dev];
+    }
+    return g_dev_events[dev];
+}
 }  // namespace pps
 
+#ifndef PPS_SOURCE_HASH
+#define PPS_SOURCE_HASH 0ull
+#endif
+
 extern "C" {
+unsigned long long pps_source_hash(void) { return PPS_SOURCE_HASH; }
 unsigned long long pps_launch_count(void) { return pps::g_launches; }
 void pps_profile_enable(int on) {
     pps::g_profile = on != 0;
@@ -54,7 +83,7 @@ int pps_profile_read(double* total_ms, long long* brackets) {
     return PPS_OK;
 }
 const char* pps_last_error(void) { return pps::g_err; }
-int pps_version(void) { return 100; }
+int pps_version(void) { return 200; }
 int pps_compiled_arch(void) { return 100; }
 int pps_check_device(void) {
     int dev = 0;

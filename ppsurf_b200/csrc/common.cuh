@@ -14,6 +14,8 @@ void count_launch();
 // optional CUDA-event bracket around the dominant kernel (bench.py's roofline); no-ops unless pps_profile_enable(1)
 void profile_begin(cudaStream_t st);
 void profile_end(cudaStream_t st);
+// `count` (<= 8) timing-disabled events of the current device, created on first use and kept for the process
+cudaEvent_t* device_events(int count);
 
 #define PPS_CHECK_ARG(cond, ...)                \
     do {                                        \

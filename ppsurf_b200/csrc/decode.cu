@@ -525,34 +525,39 @@ int pps_decoder_decode_host(const pps_decoder_weights* w, const void* knn_index,
     float* docc = dq + 3 * q;
     const int64_t super = chunk * kKnnSuper;
     int64_t nchunks = ceil_div(q, super);
-    // one event pair per super-chunk: upload on the copy stream, compute on `stream`, download on the copy stream
-    cudaEvent_t* up = new cudaEvent_t[nchunks];
-    cudaEvent_t* done = new cudaEvent_t[nchunks];
+    // upload on the copy stream, compute on `stream`, download on the copy stream; the upload of super-chunk i+1 is queued
+    // before the download of super-chunk i so that it overlaps the decode.  Four events per device, created once
+    // (pps::device_events) and used alternately: a cudaStreamWaitEvent captures the record that precedes it on the host.
+    cudaEvent_t* ev = device_events(4);
+    if (ev == nullptr) return PPS_ERR_CUDA;
+    cudaEvent_t* up = ev;
+    cudaEvent_t* done = ev + 2;
     int rc = PPS_OK;
-    for (int64_t i = 0; i < nchunks; ++i) {
-        cudaEventCreateWithFlags(&up[i], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming);
-    }
-    for (int64_t i = 0; i < nchunks && rc == PPS_OK; ++i) {
-        int64_t s = i * super, c = q - s < super ? q - s : super;
-        cudaMemcpyAsync(dq + 3 * s, queries_host + 3 * s, (size_t)c * 12, cudaMemcpyHostToDevice, cs);
-        cudaEventRecord(up[i], cs);
-    }
-    for (int64_t i = 0; i < nchunks && rc == PPS_OK; ++i) {
-        int64_t s = i * super, c = q - s < super ? q - s : super;
-        cudaStreamWaitEvent(st, up[i], 0);
+    cudaError_t ce = cudaSuccess;
+    auto upload = [&](int64_t i) {
+        const int64_t s = i * super, c = q - s < super ? q - s : super;
+        ce = cudaMemcpyAsync(dq + 3 * s, queries_host + 3 * s, (size_t)c * 12, cudaMemcpyHostToDevice, cs);
+        if (ce == cudaSuccess) ce = cudaEventRecord(up[i & 1], cs);
+    };
+    if (nchunks > 0) upload(0);
+    for (int64_t i = 0; i < nchunks && rc == PPS_OK && ce == cudaSuccess; ++i) {
+        const int64_t s = i * super, c = q - s < super ? q - s : super;
+        ce = cudaStreamWaitEvent(st, up[i & 1], 0);
+        if (ce != cudaSuccess) break;
+        if (i + 1 < nchunks) upload(i + 1);
+        if (ce != cudaSuccess) break;
         rc = decode_super(w, knn_index, pts, table, n, dq + 3 * s, c, chunk, b, nullptr, docc + s, nullptr, path, st);
-        cudaEventRecord(done[i], st);
-        cudaStreamWaitEvent(cs, done[i], 0);
-        cudaMemcpyAsync(occ_host + s, docc + s, (size_t)c * 4, cudaMemcpyDeviceToHost, cs);
+        if (rc != PPS_OK) break;
+        ce = cudaEventRecord(done[i & 1], st);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(cs, done[i & 1], 0);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(occ_host + s, docc + s, (size_t)c * 4, cudaMemcpyDeviceToHost, cs);
     }
+    // always drain both streams before returning: the caller owns the buffers again after this call
     cudaError_t e1 = cudaStreamSynchronize(st), e2 = cudaStreamSynchronize(cs);
-    for (int64_t i = 0; i < nchunks; ++i) {
-        cudaEventDestroy(up[i]);
-        cudaEventDestroy(done[i]);
+    if (rc == PPS_OK && ce != cudaSuccess) {
+        set_error("pps_decoder_decode_host: %s", cudaGetErrorString(ce));
+        return PPS_ERR_CUDA;
     }
-    delete[] up;
-    delete[] done;
     if (rc != PPS_OK) return rc;
     if (e1 != cudaSuccess || e2 != cudaSuccess) {
         set_error("pps_decoder_decode_host: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));

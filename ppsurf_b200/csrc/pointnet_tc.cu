@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                 const float4 u0 = src[0], u1 = src[1];
                 const float v[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
                 uint4 hi, lo;
-                split8_signed(v, hi, lo);
+                split8(v, hi, lo);
                 *reinterpret_cast<uint4*>(smem + kOffT + (2 * ql) * kTBytes + kb * kTLbo + i * 16) = hi;
                 *reinterpret_cast<uint4*>(smem + kOffT + (2 * ql + 1) * kTBytes + kb * kTLbo + i * 16) = lo;
             }
@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
 #pragma unroll
                     for (int c = 0; c < 8; ++c) x8[c] = v[kb * 8 + c];
                     uint4 hi, lo;
-                    split8_signed(x8, hi, lo);
+                    split8(x8, hi, lo);
                     *reinterpret_cast<uint4*>(smem + kOffAhi + (half * 4 + kb) * kPnLbo + row * 16) = hi;
                     *reinterpret_cast<uint4*>(smem + kOffAlo + (half * 4 + kb) * kPnLbo + row * 16) = lo;
                 }

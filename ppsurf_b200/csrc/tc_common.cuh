@@ -248,7 +248,6 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
-__device__ __forceinline__ void split8_signed(const float (&x)[8], uint4& hi, uint4& lo) { split8(x, hi, lo); }
 // x[i] = relu(v[i] + b[i]) for 8 values with packed adds
 __device__ __forceinline__ void bias_relu8(float (&x)[8], const float (&v)[8], const float4& b0, const float4& b1) {
     add2(x[0], x[1], v[0], v[1], b0.x, b0.y);

@@ -9,6 +9,7 @@ SURVEY.md §8f ranks as "next"; the region-growing masks and frontier lists are 
 import os
 import queue
 import threading
+import time
 import typing
 
 import numpy as np
@@ -183,8 +184,10 @@ class PPSurfModel(_Base):
         lin = np.unique((pts_ids[:, 0].astype(np.int64) * r + pts_ids[:, 1]) * r + pts_ids[:, 2]).astype(np.int32)
         seeds = torch.from_numpy(lin).to(dev)
         sweep = 0
+        decoded = 0
         while seeds.shape[0] > 0:
             ids = region.pending(seeds)
+            decoded += int(ids.shape[0])
             if ids.shape[0] > 0:
                 region.scatter(ids, self.occupancy(decoder, region.queries(ids, step, bmin_pad)))
             seeds = region.frontier(seeds, sweep & 1)
@@ -192,6 +195,7 @@ class PPSurfModel(_Base):
             if prog_bar is not None:
                 prog_bar.predict_progress_bar.set_postfix_str(
                     '{}, occ sweep {}'.format(os.path.basename(pc_file_in), sweep), refresh=True)
+        self.last_volume_stats = {'shell_queries': decoded, 'sweeps': sweep}
         return region.finish(padding, out_value)
 
     # ---- mesh extraction (host libraries, "next" rows of SURVEY.md §8f) --------------------------------------------
@@ -316,14 +320,25 @@ class PPSurfModel(_Base):
         definition and the decoder state (``predict_step`` adds meshing and export on top)."""
         resolution = resolution or self.gen_resolution_global
         pts_bcn = pts_ms.to(torch.float32).transpose(1, 2).contiguous()
+        self.network._decoder_cache = None  # a new cloud: nothing of the previous one may survive
+        dev = pts_bcn.device
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
         latents = self.encode_cloud(pts_bcn, prog_bar=prog_bar)
+        torch.cuda.synchronize(dev)
+        t1 = time.perf_counter()
         decoder = self.network.decoder_for(pts_bcn, latents)
+        torch.cuda.synchronize(dev)
+        t2 = time.perf_counter()
         input_points = pts_ms[0].cpu().numpy()
         step, bmin_pad, _ = self.grid_definition(input_points, resolution, 1)
+        self.last_volume_stats = {'shell_queries': (resolution + 2) ** 3, 'sweeps': 1}
         if dense:
             volume = self.dense_volume(decoder, input_points, resolution).cpu().numpy().astype(np.float64)
         else:
             volume = self.create_volume(decoder, input_points, resolution, prog_bar=prog_bar, pc_file_in=pc_file_in)
+        t3 = time.perf_counter()
+        self.last_reconstruct_stats = dict(self.last_volume_stats, encoder_s=t1 - t0, setup_s=t2 - t1, volume_s=t3 - t2)
         return {'volume': volume, 'step': step, 'bmin_pad': bmin_pad, 'decoder': decoder, 'latents': latents}
 
     def predict_step(self, batch: dict, batch_idx, dataloader_idx=0):

@@ -248,6 +248,7 @@ class PPSurfNetwork(_Base):
     # ---- reference surface -------------------------------------------------------------------------------------
     def forward(self, data):
         """train/test path (source/ppsurf_model.py:70-74): ids and ``proj_ids`` come with the batch"""
+        self._decoder_cache = None
         data['latents'] = self.encode(data).transpose(1, 2)
         return self.from_latent(data, has_proj_ids='proj_ids' in data)
 
@@ -260,15 +261,21 @@ class PPSurfNetwork(_Base):
         return data
 
     def decoder_for(self, pts_bcn: torch.Tensor, latents_bcn: torch.Tensor, sample: int = 0) -> ops.Decoder:
-        """per-cloud decoder state (kNN index + fc1 table), cached while the same tensors are passed again"""
-        key = (pts_bcn.data_ptr(), latents_bcn.data_ptr(), pts_bcn.shape, getattr(latents_bcn, '_version', 0), sample,
-               self.decode_chunk, self.decode_path)
-        if self._decoder_cache is None or self._decoder_cache[0] != key:
+        """per-cloud decoder state (kNN index + fc1 table), cached while THE SAME tensor objects are passed again (the
+        reference driver reuses one dict for every batch of a cloud, source/poco_utils.py:220-223).  The entry keeps strong
+        references to its source tensors and compares by identity and version counter: a recycled device address of a freed
+        tensor can therefore never alias another cloud.  ``forward`` and ``PPSurfModel.reconstruct`` drop the cache."""
+        entry = self._decoder_cache
+        if (entry is None or entry['pts'] is not pts_bcn or entry['latents'] is not latents_bcn
+                or entry['versions'] != (pts_bcn._version, latents_bcn._version)
+                or entry['key'] != (sample, self.decode_chunk, self.decode_path)):
             pts = pts_bcn[sample].to(torch.float32).transpose(0, 1).contiguous()
             lat = latents_bcn[sample].to(torch.float32).transpose(0, 1).contiguous()
             dec = ops.Decoder(self.packed()['decoder'], pts, lat, chunk=self.decode_chunk, path=self.decode_path)
-            self._decoder_cache = (key, dec)
-        return self._decoder_cache[1]
+            entry = {'pts': pts_bcn, 'latents': latents_bcn, 'versions': (pts_bcn._version, latents_bcn._version),
+                     'key': (sample, self.decode_chunk, self.decode_path), 'decoder': dec}
+            self._decoder_cache = entry
+        return entry['decoder']
 
     def from_latent(self, data: typing.Dict[str, torch.Tensor], has_proj_ids: bool = False) -> torch.Tensor:
         """source/ppsurf_model.py:82-117.  ``data``: ``pts [B,3,N]``, ``latents [B,C,N]``, ``pts_query [B,Q,3]`` (CPU or
@@ -279,7 +286,12 @@ class PPSurfNetwork(_Base):
         pts, latents = data['pts'], data['latents']
         dev = pts.device
         if pts.shape[1] != 3:
-            pts = pts.transpose(1, 2)
+            raise ValueError("from_latent: 'pts' must be [B,3,N] like the reference's, got {}".format(tuple(pts.shape)))
+        if 'pts_local_ps' in data:
+            loc = data['pts_local_ps']
+            if loc.dim() != 4 or loc.shape[2] != self.num_pts_local or loc.shape[3] != 3:
+                raise ValueError("from_latent: 'pts_local_ps' must be [B,Q,{},3] (num_pts_local of this network), got {}".format(
+                    self.num_pts_local, tuple(loc.shape)))
         pts_query = data['pts_query'].to(dev, torch.float32)
         if pts_query.dim() == 2:
             pts_query = pts_query.unsqueeze(0)

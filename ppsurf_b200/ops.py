@@ -77,7 +77,7 @@ def linear(x, w, bias=None, residual=None, gather=None, relu=False, out=None, ro
         raise ValueError('linear: x has {} columns, w expects {}'.format(x.shape[-1], k))
     if out is None:
         out = torch.empty((m, n), dtype=torch.float32, device=x.device)
-    check(lib.pps_linear(_ptr(x, torch.float32), _ptr(w, torch.float32), _ptr(bias), _ptr(residual),
+    check(lib.pps_linear(_ptr(x, torch.float32), _ptr(w, torch.float32), _ptr(bias, torch.float32), _ptr(residual, torch.float32),
                          _ptr(gather, torch.int32) if gather is not None else None, _ptr(out), m, n, k, x.stride(-2)
                          if x.dim() > 1 else k, n, 1 if relu else 0, _stream()))
     return out
@@ -210,7 +210,10 @@ class Decoder:
 
 
 def pointnet(packed, patches: torch.Tensor, path: int = 0):
-    """``patches [Q,P,3]`` -> ``[Q,C]`` local-branch features"""
+    """``patches [Q,P,3]`` -> ``[Q,C]`` local-branch features; ``P`` must be the ``num_pts_local`` the weights were packed for
+    (``pps_decoder_pointnet`` takes the patch size from the weight struct)"""
+    if patches.dim() != 3 or patches.shape[1] != packed.struct.num_pts_local or patches.shape[2] != 3:
+        raise ValueError('pointnet: patches must be [Q,{},3], got {}'.format(packed.struct.num_pts_local, tuple(patches.shape)))
     q = patches.shape[0]
     nbytes = lib.pps_decoder_workspace_bytes(packed.ref, max(q, 1))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=patches.device)

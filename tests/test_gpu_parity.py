@@ -525,3 +525,127 @@ def test_test_step_matches_oracle_forward(dev, oracle, weights):
     if margin.all():
         assert res['metrics_dict']['true_pos'] == float(((ref_lab == 1) & (occ == 1)).sum())
     assert len(model.test_step_outputs) == 1 and res['pc_file_in'] == 'synthetic.xyz'
+
+
+# ---- round 2: binary freshness, real data on the CUDA path, config 3 at size, rank stitching, decoder cache ---------------
+
+def test_binary_matches_sources(dev):
+    """the prebuilt libppsurf_b200.so that travels to the GPU box was built from exactly the sources in the tree"""
+    from ppsurf_b200 import _lib
+    _lib.assert_binary_matches_sources()
+    assert _lib.lib.pps_version() >= 200
+
+
+def _bare_model(resolution=17, npl=50):
+    import ppsurf_b200
+    return ppsurf_b200.PPSurfModel(256, ['imp_surf_sign'], 3, 2, 64, 0.0, False, 'x.txt', 'results', 0.05, 't', 256, 1, 10000,
+                                   resolution, npl, 50000, 0, 1)
+
+
+@pytest.mark.parametrize('path', [0, 1])
+def test_real_cloud_region_grown_volume_cuda(dev, net, weights_digest, path):
+    """BASELINE configs[0] plumbing on REAL data through the CUDA path: 3000 vertices of an abc_minimal cloud decoded and
+    region-grown at gen_resolution_global = 17; the golden volume was made by the UNMODIFIED reference (_create_volume,
+    from_latent, normalize_patches; tests/golden/make_golden.py).  Same NaN mask, values within the north-star tolerance."""
+    from ppsurf_b200 import ops
+    g = load_golden('real_volume')
+    assert str(g['digest']) == weights_digest
+    pts = g['pts']
+    latents = np.random.default_rng(int(g['latents_seed'])).standard_normal((1, 256, pts.shape[0])).astype(np.float32)
+    dec = ops.Decoder(net.packed()['decoder'], cu(pts, dev), cu(latents[0].T, dev), chunk=1000, path=path)
+    vol = _bare_model().create_volume(dec, pts, 17)
+    np.testing.assert_array_equal(np.isnan(vol), np.isnan(g['volume']))
+    assert np.isnan(vol).any() and np.nanmin(vol) < -0.5 and np.nanmax(vol) > 0.5
+    assert np.nanmax(np.abs(vol - g['volume'])) < LOGIT_TOL
+
+
+def test_config3_at_size(dev, oracle):
+    """BASELINE config 3 at its real sizes: ppsurf_200nn (P = 200), 250k-point cloud, a slab of the dense 131^3 grid.
+    Properties that do not need the oracle at size (ascending exact neighbours, chunk-size invariance, agreement of the
+    tensor-core and the fp32 path) plus a 256-query sample against the float64 oracle."""
+    import ppsurf_b200
+    from ppsurf_b200 import ops
+    w = oracle.make_state_dict(43)
+    net200 = ppsurf_b200.PPSurfNetwork(3, 256, 2, 64, 200, 256)
+    net200.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in w.items()}, strict=True)
+    net200 = net200.to(dev)
+    n = 250000
+    pts = oracle.synthetic_cloud(n, seed=42)
+    rng = np.random.default_rng(2)
+    latents = torch.from_numpy(rng.standard_normal((n, 256)).astype(np.float32)).to(dev)
+    step, bmin_pad, _ = ppsurf_b200.PPSurfModel.grid_definition(pts, 129, 1)
+    first, count = 131 * 131 * 24, 131 * 131 * 2  # two z-slabs that cut the sphere's surface: 34 322 queries
+    qry = ops.grid_queries(131, step, bmin_pad, first=first, count=count, device=dev)
+    packed = net200.packed()['decoder']
+    dec = ops.Decoder(packed, cu(pts, dev), latents, chunk=12500, path=1)
+    res = dec.decode(qry, want_logits=True, want_occ=True, want_idx=True)
+    idx, occ, logits = res['idx'].cpu().numpy(), res['occ'].cpu().numpy(), res['logits'].cpu().numpy()
+    assert idx.shape == (count, 200) and np.isfinite(logits).all() and np.all(np.abs(occ) <= 1.0)
+    q = qry.cpu().numpy()
+    d2 = oracle.sq_dist_f32(q[:, None, :], pts[idx.astype(np.int64)])
+    assert np.all(np.diff(d2, axis=1) >= 0)
+    srt = np.sort(idx, axis=1)
+    assert np.all(srt[:, 1:] != srt[:, :-1])
+    # chunk-size invariance (the reference batches 25 000 queries for 200nn, configs/ppsurf_200nn.yaml:8): bit identical
+    occ2 = ops.Decoder(packed, cu(pts, dev), latents, chunk=4097, path=1).decode(qry, want_logits=False, want_occ=True)['occ']
+    np.testing.assert_array_equal(occ, occ2.cpu().numpy())
+    # fp32 SIMT path on a part of the slab
+    part = slice(5000, 9000)
+    l0 = ops.Decoder(packed, cu(pts, dev), latents, chunk=2000, path=0).decode(qry[part].contiguous(), want_logits=True)['logits']
+    assert np.abs(l0.cpu().numpy() - logits[part]).max() < LOGIT_TOL
+    # a 256-query sample against the float64 oracle (exact neighbours from the brute-force oracle kNN)
+    sample = np.sort(rng.choice(count, 256, replace=False))
+    ref_idx, _ = oracle.knn(pts, q[sample], 200)
+    assert_knn_equal(oracle, pts, q[sample], idx[sample], None, ref_idx)
+    data = {'pts': pts.T[None], 'latents': latents.cpu().numpy().T[None], 'pts_query': q[sample][None],
+            'pts_local_ps': oracle.get_pts_local_ps(pts, q[sample], 200)[None], 'proj_ids': ref_idx[:, :64][None]}
+    ref = oracle.from_latent(w, data, dtype=np.float64)
+    assert np.abs(logits[sample].T[None] - ref).max() < LOGIT_TOL
+
+
+def test_dealt_blocks_stitch_to_the_one_rank_volume(dev, net, oracle):
+    """multi-GPU decode (bench.grid_blocks): the vertex list dealt to G ranks in blocks, each share decoded on its own, stitched
+    back == the volume one rank decodes, bit for bit (the occupancy of a vertex does not depend on its launch neighbours)"""
+    import bench
+    import ppsurf_b200
+    from ppsurf_b200 import ops
+    pts = oracle.synthetic_cloud(20000, seed=8)
+    latents = torch.from_numpy(np.random.default_rng(3).standard_normal((20000, 256)).astype(np.float32)).to(dev)
+    dec = ops.Decoder(net.packed()['decoder'], cu(pts, dev), latents, chunk=37888, path=1)
+    step, bmin_pad, _ = ppsurf_b200.PPSurfModel.grid_definition(pts, 33, 1)
+    r, total = 35, 35 ** 3
+    whole = dec.decode(ops.grid_queries(r, step, bmin_pad, device=dev), want_logits=False, want_occ=True)['occ'].cpu().numpy()
+    for world in (2, 8):
+        stitched = np.full((total,), np.nan, dtype=np.float32)
+        for rank in range(world):
+            spans = bench.grid_blocks(total, world, rank)
+            q = torch.cat([ops.grid_queries(r, step, bmin_pad, first=f, count=c, device=dev) for f, c in spans])
+            occ = dec.decode(q, want_logits=False, want_occ=True)['occ'].cpu().numpy()
+            off = 0
+            for f, c in spans:
+                stitched[f:f + c] = occ[off:off + c]
+                off += c
+        np.testing.assert_array_equal(stitched, whole)
+
+
+def test_two_same_shaped_clouds_back_to_back(dev, net, oracle):
+    """the per-cloud decoder cache must not serve the previous cloud's kNN index / fc1 table to a second
+    cloud of the same shape whose tensors landed on the recycled device addresses"""
+    rng = np.random.default_rng(11)
+    qry = torch.from_numpy(rng.uniform(-0.45, 0.45, (1, 300, 3)).astype(np.float32))
+    outs = []
+    for seed in (1, 2, 1):
+        pts = oracle.synthetic_cloud(5000, seed=seed) * (1.0 if seed == 1 else 0.8)
+        lat = np.random.default_rng(seed).standard_normal((1, 256, 5000)).astype(np.float32)
+        data = {'pts': cu(pts.T[None], dev), 'latents': cu(lat, dev), 'pts_query': qry}
+        a = net.from_latent(data).cpu().numpy()
+        b = net.from_latent(data).cpu().numpy()  # same dict again: served from the cache
+        np.testing.assert_array_equal(a, b)
+        outs.append(a)
+        del data
+        torch.cuda.empty_cache()
+    np.testing.assert_array_equal(outs[0], outs[2])
+    assert np.abs(outs[0] - outs[1]).max() > 1e-3  # a different cloud gives a different field
+    with pytest.raises(ValueError):
+        net.from_latent({'pts': cu(pts.T[None], dev), 'latents': cu(lat, dev), 'pts_query': qry,
+                         'pts_local_ps': torch.zeros((1, 300, 20, 3), device=dev)})
