@@ -166,6 +166,10 @@ size_t pps_decoder_tc_pack_bytes(void);
 void pps_debug_tc_profile(long long* counters);
 /* retired tuning knob (no-op, kept for ABI stability) */
 void pps_debug_tc_cluster(int cs);
+/* Split-fp16 terms of the tensor-core global branch (pass ablation, profiles/r02_pass_ablation.md): bit 3*layer + t with layer
+ * 0 = fc2, 1 = fc3, 2 = fc_query and t = 0: x_hi*w_hi (always on), 1: x_lo*w_hi, 2: x_hi*w_lo.  Default 0x1FF.  mask < 0 only
+ * reads.  Returns the previous mask. */
+int pps_decoder_tc_terms(int mask);
 /* debug: number of CTA pairs (2-CTA clusters) of the projection kernel the device holds at once */
 int pps_debug_tc_max_clusters(void);
 size_t pps_decoder_tc_pn_stn_bytes(void);
@@ -276,8 +280,10 @@ int pps_encoder_ids(const float* pts, int64_t b, int64_t n0, const float* rotati
  * cv_w is [cout, 16*cin] with column = m*cin + c  (repacked from the reference [cout,cin,1,16]); the eval
  * BatchNorm that always follows the layer (nn.py:441,519) is folded into cv_w / out_bias, out_relu applies its ReLU.
  * act: 0 ReLU (POCO), 1 SiLU (PPSurf).
- * Three launches of the kernel-weight MLP (InstanceNorm statistics 1, statistics 2, weights) and one fused
- * gather * weights kernel produce the [b*n_s, 16*cin] operand of the final contraction.
+ * Two statistics launches (InstanceNorm 1 and 2 are global per sample), then ONE fused kernel: index gather ->
+ * kernel-weight MLP -> neighbourhood weighted sum -> tcgen05 contraction -> bias / ReLU (csrc/fka_tc.cu; needs kn == 16,
+ * cin % 4 == 0, n_s >= 16, tc_pack).  Other shapes run the unfused fp32 kernels (third MLP launch, gather * weights kernel,
+ * fp32 contraction) through the same entry point.
  * ------------------------------------------------------------------------------------------------------------- */
 typedef struct pps_fkaconv_weights {
     int32_t cin, cout, act;
@@ -292,9 +298,17 @@ typedef struct pps_fkaconv_weights {
     const float* cv_w;     /* [cout,16*cin] */
     const float* out_bias; /* [cout], nullable */
     int32_t out_relu;
+    /* operand pack of the fused tensor-core kernel (csrc/fka_tc.cu), nullable: cv_w as fp16 hi/lo k16 stages in the
+     * shared-memory operand layout, K order k = ((c/2)*4 + m/4)*8 + (m%4)*2 + c%2, per slice of min(cout,256) rows;
+     * 4*16*cin*cout bytes.  NULL selects the unfused fp32 kernels. */
+    const void* tc_pack;
 } pps_fkaconv_weights;
 
-size_t pps_fkaconv_workspace_bytes(int64_t b, int64_t n_s, int cin);
+size_t pps_fkaconv_workspace_bytes(int64_t b, int64_t n_s, int cin); /* upper bound for any layer of that input width */
+/* exact requirement of one layer call (the fused kernel only needs the statistics: 512 B per sample) */
+size_t pps_fkaconv_workspace_bytes_for(const pps_fkaconv_weights* w, int kn, int64_t b, int64_t n_s);
+/* debug / parity: 0 forces the unfused fp32 kernels even when the fused kernel supports the shape (default 1) */
+void pps_debug_fka_fused(int on);
 int pps_fkaconv_forward(const pps_fkaconv_weights* w, const float* x, const float* pts, const float* support,
                         const int32_t* ids, int kn, int64_t b, int64_t n_in, int64_t n_s, void* workspace,
                         size_t workspace_bytes, float* out, void* stream);

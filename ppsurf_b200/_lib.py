@@ -42,7 +42,7 @@ class FKAConvWeights(ctypes.Structure):
         ('cin', ctypes.c_int32), ('cout', ctypes.c_int32), ('act', ctypes.c_int32),
         ('alpha', ctypes.c_float), ('beta', ctypes.c_float), ('norm_radius', ctypes.c_float),
         ('fc1', c_f32p), ('fc2', c_f32p), ('fc3', c_f32p), ('in1_w', c_f32p), ('in1_b', c_f32p), ('in2_w', c_f32p),
-        ('in2_b', c_f32p), ('cv_w', c_f32p), ('out_bias', c_f32p), ('out_relu', ctypes.c_int32),
+        ('in2_b', c_f32p), ('cv_w', c_f32p), ('out_bias', c_f32p), ('out_relu', ctypes.c_int32), ('tc_pack', c_voidp),
     ]
 
 
@@ -70,6 +70,7 @@ SIGNATURES = {
     'pps_decoder_tc_pack_bytes': (size_t, []),
     'pps_debug_tc_profile': (None, [c_voidp]),
     'pps_debug_tc_cluster': (None, [i32]),
+    'pps_decoder_tc_terms': (i32, [i32]),
     'pps_debug_tc_max_clusters': (i32, []),
     'pps_decoder_tc_pn_stn_bytes': (size_t, []),
     'pps_decoder_tc_pn_feat_bytes': (size_t, []),
@@ -96,6 +97,8 @@ SIGNATURES = {
     'pps_encoder_ids_workspace_bytes': (size_t, [i64]),
     'pps_encoder_ids': (i32, [c_f32p, i64, i64, c_f32p, i32, ctypes.c_uint32, c_voidp, size_t, ctypes.POINTER(EncoderIdsOut), c_voidp]),
     'pps_fkaconv_workspace_bytes': (size_t, [i64, i64, i32]),
+    'pps_fkaconv_workspace_bytes_for': (size_t, [ctypes.POINTER(FKAConvWeights), i32, i64, i64]),
+    'pps_debug_fka_fused': (None, [i32]),
     'pps_fkaconv_forward': (i32, [ctypes.POINTER(FKAConvWeights), c_f32p, c_f32p, c_f32p, c_i32p, i32, i64, i64, i64, c_voidp,
                                   size_t, c_f32p, c_voidp]),
     'pps_gather_max': (i32, [c_f32p, c_i32p, i64, i64, i64, i32, i32, c_f32p, c_voidp]),

@@ -80,11 +80,14 @@ __device__ __forceinline__ long long tick() {
     return PROF ? clock64() : 0ll;
 }
 
-template <bool PROF>
+// ABL = true (pass-ablation build, pps_decoder_tc_terms): bit 3*layer + t of term_mask enables split-fp16 term t of the layer
+// (0 = x_hi w_hi, 1 = x_lo w_hi, 2 = x_hi w_lo); the product instantiation issues all three unconditionally
+template <bool PROF, bool ABL>
 __global__ void __launch_bounds__(kThreads, 1)
     projection_tc_kernel(const float* __restrict__ table, const float* __restrict__ queries, const int32_t* __restrict__ idx, int ks,
                          long long nq, const uint8_t* __restrict__ wpack, const float* __restrict__ b2, const float* __restrict__ b3,
-                         const float* __restrict__ bq, const float* __restrict__ w1_xyz, float* __restrict__ pooled, long long* prof) {
+                         const float* __restrict__ bq, const float* __restrict__ w1_xyz, float* __restrict__ pooled, long long* prof,
+                         uint32_t term_mask) {
     extern __shared__ __align__(1024) uint8_t smem[];  // used directly: the compiler keeps the shared address space (LDS/STS)
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -192,14 +195,15 @@ __global__ void __launch_bounds__(kThreads, 1)
                         const uint32_t wst = sbase + kOffRing + slot * kStageBytes;
                         const uint64_t w_hi = umma_desc(wst, 128 * 16, 128);
                         const uint64_t w_lo = umma_desc(wst + 4096, 128 * 16, 128);
+                        const uint32_t lm = ABL ? (term_mask >> (3 * layer)) & 7u : 7u;
                         if (layer < 2) {  // D[256 rows, 256 features]: B = the two CTAs' 128-feature halves
                             umma2(tmem + dcol, x_hi, w_hi, idesc, s > 0 ? 1u : 0u);
-                            umma2(tmem + dcol, x_lo, w_hi, idesc, 1u);
-                            umma2(tmem + dcol, x_hi, w_lo, idesc, 1u);
+                            if (!ABL || (lm & 2u)) umma2(tmem + dcol, x_lo, w_hi, idesc, 1u);
+                            if (!ABL || (lm & 4u)) umma2(tmem + dcol, x_hi, w_lo, idesc, 1u);
                         } else {  // scores^T[64 + head, row of either tile] = Wq[head, :] . h3[row, :]  (both CTAs compute all 256 columns)
                             umma2(tmem, w_hi, x_hi, idesc, s > 0 ? 1u : 0u);
-                            umma2(tmem, w_hi, x_lo, idesc, 1u);
-                            umma2(tmem, w_lo, x_hi, idesc, 1u);
+                            if (!ABL || (lm & 2u)) umma2(tmem, w_hi, x_lo, idesc, 1u);
+                            if (!ABL || (lm & 4u)) umma2(tmem, w_lo, x_hi, idesc, 1u);
                         }
                         tc_commit2(bar_empty + 8 * slot);  // frees the ring slot of both CTAs when these MMAs have read it
                         if (++slot == kStages) {
@@ -513,7 +517,10 @@ __global__ void __launch_bounds__(kThreads, 1)
 
 }  // namespace tc
 
-static long long* g_tc_prof = nullptr;  // device buffer of 128 counters, set by pps_debug_tc_profile
+static long long* g_tc_prof = nullptr;
+static uint32_t g_tc_terms = 0x1FFu;  // split-fp16 terms per layer of projection_tc_kernel (pps_decoder_tc_terms)
+void set_tc_terms(uint32_t m) { g_tc_terms = m & 0x1FFu; }
+uint32_t get_tc_terms() { return g_tc_terms; }  // device buffer of 128 counters, set by pps_debug_tc_profile
 
 size_t projection_tc_workspace(const pps_decoder_weights*, int64_t) { return 256; }
 
@@ -525,8 +532,9 @@ int projection_tc_impl(const pps_decoder_weights* w, const float* table, const f
     if (q == 0) return PPS_OK;
     static bool configured = false;
     if (!configured) {
-        PPS_CUDA(cudaFuncSetAttribute(tc::projection_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
-        PPS_CUDA(cudaFuncSetAttribute(tc::projection_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+        PPS_CUDA(cudaFuncSetAttribute(tc::projection_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+        PPS_CUDA(cudaFuncSetAttribute(tc::projection_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+        PPS_CUDA(cudaFuncSetAttribute(tc::projection_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
         configured = true;
     }
     const long long npt = (q + 3) / 4;  // pair-tiles of 4 queries
@@ -546,12 +554,16 @@ int projection_tc_impl(const pps_decoder_weights* w, const float* table, const f
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     profile_begin(st);
+    const uint32_t mask = g_tc_terms;
     if (g_tc_prof)  // instrumented build, tools/tc_phase_profile.py only
-        PPS_CUDA(cudaLaunchKernelEx(&cfg, tc::projection_tc_kernel<true>, table, queries, idx, k_stride, nq, wp, w->b2, w->b3, w->bq,
-                                    w->w1_xyz, pooled, g_tc_prof));
+        PPS_CUDA(cudaLaunchKernelEx(&cfg, tc::projection_tc_kernel<true, false>, table, queries, idx, k_stride, nq, wp, w->b2, w->b3, w->bq,
+                                    w->w1_xyz, pooled, g_tc_prof, mask));
+    else if (mask != 0x1FFu)  // pass-ablation build (tools/pass_ablation.py)
+        PPS_CUDA(cudaLaunchKernelEx(&cfg, tc::projection_tc_kernel<false, true>, table, queries, idx, k_stride, nq, wp, w->b2, w->b3, w->bq,
+                                    w->w1_xyz, pooled, g_tc_prof, mask));
     else
-        PPS_CUDA(cudaLaunchKernelEx(&cfg, tc::projection_tc_kernel<false>, table, queries, idx, k_stride, nq, wp, w->b2, w->b3, w->bq,
-                                    w->w1_xyz, pooled, g_tc_prof));
+        PPS_CUDA(cudaLaunchKernelEx(&cfg, tc::projection_tc_kernel<false, false>, table, queries, idx, k_stride, nq, wp, w->b2, w->b3, w->bq,
+                                    w->w1_xyz, pooled, g_tc_prof, mask));
     PPS_LAUNCH_CHECK();
     profile_end(st);
     return PPS_OK;
@@ -565,7 +577,7 @@ extern "C" size_t pps_decoder_tc_pack_bytes(void) { return pps::tc::kPackBytes; 
 extern "C" void pps_debug_tc_profile(long long* counters) { pps::g_tc_prof = counters; }
 // debug: how many CTA pairs of projection_tc_kernel the device can hold at once (-1 on error)
 extern "C" int pps_debug_tc_max_clusters(void) {
-    cudaFuncSetAttribute(pps::tc::projection_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pps::tc::kSmemBytes);
+    cudaFuncSetAttribute(pps::tc::projection_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pps::tc::kSmemBytes);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(pps::kNumSMs);
     cfg.blockDim = dim3(pps::tc::kThreads);
@@ -578,8 +590,15 @@ extern "C" int pps_debug_tc_max_clusters(void) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int n = -1;
-    if (cudaOccupancyMaxActiveClusters(&n, pps::tc::projection_tc_kernel<false>, &cfg) != cudaSuccess) return -1;
+    if (cudaOccupancyMaxActiveClusters(&n, pps::tc::projection_tc_kernel<false, false>, &cfg) != cudaSuccess) return -1;
     return n;
 }
 // retired debug knob (cluster multicast / weight-stream experiments); kept so that the ABI is stable
 extern "C" void pps_debug_tc_cluster(int) {}
+// split-fp16 terms of the global branch's three GEMM layers: bit 3*layer + t, layer 0 = fc2, 1 = fc3, 2 = fc_query; t = 0: x_hi w_hi
+// (always issued), 1: x_lo w_hi, 2: x_hi w_lo.  0x1FF (default) = three terms everywhere.  Returns the previous mask.
+extern "C" int pps_decoder_tc_terms(int mask) {
+    const int old = (int)pps::get_tc_terms();
+    if (mask >= 0) pps::set_tc_terms((uint32_t)mask | 0x49u);
+    return old;
+}

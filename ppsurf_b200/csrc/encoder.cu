@@ -14,6 +14,9 @@ namespace pps {
 
 int linear_impl(const float* x, const float* w, const float* bias, const float* residual, const int32_t* gather,
                 float* y, int64_t m, int n, int k, int ldx, int ldy, int act, cudaStream_t st);
+bool fka_fused_supported(const pps_fkaconv_weights* w, int kn, int64_t n_s);
+int fka_fused_impl(const pps_fkaconv_weights* w, const float* x, const float* pts, const float* support, const int32_t* ids,
+                   int64_t b, int64_t n_in, int64_t n_s, const double* stats, float* out, cudaStream_t st);
 
 constexpr int kNbr = 16;   // max neighbours per support point (the reference always asks for 16, clamped to n_in)
 constexpr float kInEps = 1e-5f;
@@ -307,6 +310,8 @@ __global__ void latent_finalize_kernel(float* latent, const float* __restrict__ 
     latent[e] = latent[e] / counts[e / c];
 }
 
+static bool g_fka_fused = true;  // pps_debug_fka_fused(0) forces the unfused fp32 kernels (parity tests compare the two)
+
 struct FkaLayout {
     size_t stats, mat, feat, total;
 };
@@ -329,9 +334,17 @@ using namespace pps;
 
 extern "C" {
 
+void pps_debug_fka_fused(int on) { g_fka_fused = on != 0; }
+
 size_t pps_fkaconv_workspace_bytes(int64_t b, int64_t n_s, int cin) {
     if (b <= 0 || n_s <= 0 || cin <= 0) return 0;
     return fka_layout(b, n_s, cin).total;
+}
+
+size_t pps_fkaconv_workspace_bytes_for(const pps_fkaconv_weights* w, int kn, int64_t b, int64_t n_s) {
+    if (!w || b <= 0 || n_s <= 0) return 0;
+    if (g_fka_fused && fka_fused_supported(w, kn, n_s)) return align_up((size_t)b * 64 * sizeof(double), 256);  // statistics only
+    return fka_layout(b, n_s, w->cin).total;
 }
 
 int pps_fkaconv_forward(const pps_fkaconv_weights* w, const float* x, const float* pts, const float* support,
@@ -343,8 +356,10 @@ int pps_fkaconv_forward(const pps_fkaconv_weights* w, const float* x, const floa
                   "pps_fkaconv_forward: bad sizes b=%lld n_in=%lld n_s=%lld", (long long)b, (long long)n_in, (long long)n_s);
     PPS_CHECK_ARG(w->cin >= 1 && w->cout >= 1 && (w->act == 0 || w->act == 1), "pps_fkaconv_forward: bad weights");
     FkaLayout l = fka_layout(b, n_s, w->cin);
-    if (workspace_bytes < l.total) {
-        set_error("pps_fkaconv_forward: workspace %zu < required %zu", workspace_bytes, l.total);
+    const bool fused = g_fka_fused && fka_fused_supported(w, kn, n_s);
+    const size_t need = fused ? align_up((size_t)b * 64 * sizeof(double), 256) : l.total;
+    if (workspace_bytes < need) {
+        set_error("pps_fkaconv_forward: workspace %zu < required %zu", workspace_bytes, need);
         return PPS_ERR_WORKSPACE;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -361,6 +376,8 @@ int pps_fkaconv_forward(const pps_fkaconv_weights* w, const float* x, const floa
     fka_weight_kernel<2><<<grid, 256, 0, st>>>(pts, support, ids, (int)n_in, (int)n_s, kn, prm, w->fc1, w->fc2, w->fc3, w->in1_w,
                                                w->in1_b, w->in2_w, w->in2_b, stats, mat);
     PPS_LAUNCH_CHECK();
+    if (fused)
+        return fka_fused_impl(w, x, pts, support, ids, b, n_in, n_s, stats, out, st);
     fka_weight_kernel<3><<<grid, 256, 0, st>>>(pts, support, ids, (int)n_in, (int)n_s, kn, prm, w->fc1, w->fc2, w->fc3, w->in1_w,
                                                w->in1_b, w->in2_w, w->in2_b, stats, mat);
     PPS_LAUNCH_CHECK();

@@ -204,6 +204,9 @@ class PPSurfNetwork(_Base):
         ids = {key: _ids32(val) for key, val in data.items() if key.startswith('ids')}
         b, n0, _ = pts[0].shape
         x = torch.ones_like(pts[0])  # nn.py:517
+        cin0 = enc['cv0'].struct.cin  # the packed layer pads its 3 input channels to 4 (zero weights)
+        if cin0 != x.shape[-1]:
+            x = torch.nn.functional.pad(x, (0, cin0 - x.shape[-1]))
         x0 = ops.fkaconv(enc['cv0'], x, pts[0], pts[0], ids['ids00'])  # bn0 + ReLU folded (nn.py:519)
         x0 = self._resblock(enc['resnetb01'], x0, pts[0], pts[0], ids['ids00'])
         x1 = self._resblock(enc['resnetb10'], x0, pts[0], pts[1], ids['ids01'])

@@ -263,9 +263,11 @@ def encoder_ids(pts: torch.Tensor, rotations: torch.Tensor, seed: int) -> dict:
 def fkaconv(packed, x, pts, support, ids):
     """``x [B,Nin,Cin]``, ``pts [B,Nin,3]``, ``support [B,Ns,3]``, ``ids [B,Ns,kn<=16] int32`` -> ``[B,Ns,Cout]``"""
     b, n_in, cin = x.shape
+    if cin != packed.struct.cin:
+        raise ValueError('fkaconv: x has {} channels, the packed layer expects {}'.format(cin, packed.struct.cin))
     n_s = support.shape[1]
     kn = ids.shape[-1]
-    nbytes = lib.pps_fkaconv_workspace_bytes(b, n_s, cin)
+    nbytes = lib.pps_fkaconv_workspace_bytes_for(packed.ref, kn, b, n_s)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
     out = torch.empty((b, n_s, packed.struct.cout), dtype=torch.float32, device=x.device)
     check(lib.pps_fkaconv_forward(packed.ref, _ptr(x, torch.float32), _ptr(pts, torch.float32), _ptr(support, torch.float32),

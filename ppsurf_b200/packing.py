@@ -153,10 +153,25 @@ def tc_pack_matrix(w: torch.Tensor) -> torch.Tensor:
     return both.permute(2, 0, 3, 1, 4).contiguous().view(torch.uint8).reshape(-1)
 
 
+def fka_tc_pack(w_cm: torch.Tensor) -> torch.Tensor:
+    """``w_cm [cout, cin, 16]`` (c, m) -> operand pack of the fused kernel (csrc/fka_tc.cu): K order
+    k = ((c / 2) * 4 + m / 4) * 8 + (m % 4) * 2 + c % 2, k16 stages of [hi kb0 | hi kb1 | lo kb0 | lo kb1] per slice of
+    min(cout, 256) output rows (slices back to back)"""
+    cout, cin, _ = w_cm.shape
+    assert cin % 4 == 0
+    # [cout, cpair, cc, s, mm] -> [cout, cpair, s, mm, cc]
+    wk = w_cm.reshape(cout, cin // 2, 2, 4, 4).permute(0, 1, 3, 4, 2).reshape(cout, 16 * cin)
+    nsl = min(cout, 256)
+    return torch.cat([tc_pack_matrix(wk[i:i + nsl]) for i in range(0, cout, nsl)])
+
+
 def pack_fkaconv(sd, name, device, act, bn=None) -> Packed:
-    """``name`` = FKAConvLayer prefix; ``bn`` = the BatchNorm that follows it (folded, with its ReLU)."""
+    """``name`` = FKAConvLayer prefix; ``bn`` = the BatchNorm that follows it (folded, with its ReLU).  An input width that is
+    not a multiple of 4 (cv0: 3 channels) is zero-padded to the next multiple: the caller pads ``x`` the same way."""
     p = Packed(_lib.FKAConvWeights())
     cv = _f64(sd, name + '.cv.weight')  # [cout,cin,1,16]
+    if cv.shape[1] % 4:
+        cv = torch.cat([cv, torch.zeros(cv.shape[0], 4 - cv.shape[1] % 4, 1, 16, dtype=cv.dtype)], dim=1)
     cout, cin = cv.shape[0], cv.shape[1]
     w = cv[:, :, 0, :].permute(0, 2, 1).reshape(cout, 16 * cin)
     st = p.struct
@@ -173,6 +188,12 @@ def pack_fkaconv(sd, name, device, act, bn=None) -> Packed:
         st.out_bias = None
         st.out_relu = 0
     p.put('cv_w', w, device)
+    nsl = min(cout, 256)
+    if nsl in (32, 64, 128, 256) and cout % nsl == 0:
+        p.tensors['tc_pack'] = fka_tc_pack(w.reshape(cout, 16, cin).permute(0, 2, 1).contiguous()).to(device)
+        st.tc_pack = p.tensors['tc_pack'].data_ptr()
+    else:
+        st.tc_pack = None
     p.put('fc1', _mat(sd, name + '.fc1.weight'), device)
     p.put('fc2', _mat(sd, name + '.fc2.weight'), device)
     p.put('fc3', _mat(sd, name + '.fc3.weight'), device)

@@ -19,7 +19,8 @@ model = ppsurf_b200.PPSurfModel(
 net = model.network
 net.load_state_dict(synthetic.make_state_dict(net, 42))
 model = model.to(dev)
-pts = torch.from_numpy(synthetic.synthetic_cloud(100000, 42).T[None].copy()).to(dev)
+NPTS = 20000 if '--small' in sys.argv else 100000
+pts = torch.from_numpy(synthetic.synthetic_cloud(NPTS, 42).T[None].copy()).to(dev)
 acc = {'spatial_ids': 0.0, 'encode': 0.0}
 orig_ids, orig_enc = net.spatial_ids, net.encode
 
@@ -37,13 +38,13 @@ def wrap(name, fn):
 
 net.spatial_ids = wrap('spatial_ids', orig_ids)
 net.encode = wrap('encode', orig_enc)
-for bp in (16, 16):
+for bp in ((16,) if '--small' in sys.argv else (16, 16)):
     for k in acc:
         acc[k] = 0.0
     net.sampling_seed = 42
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    sched = list(model.latent_schedule(100000, torch.Generator().manual_seed(42)))
+    sched = list(model.latent_schedule(NPTS, torch.Generator().manual_seed(42)))
     t_sched = time.perf_counter() - t0
     t0 = time.perf_counter()
     model.encode_cloud(pts, generator=torch.Generator().manual_seed(42), batch_passes=bp)
