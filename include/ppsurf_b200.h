@@ -302,6 +302,12 @@ typedef struct pps_fkaconv_weights {
      * shared-memory operand layout, K order k = ((c/2)*4 + m/4)*8 + (m%4)*2 + c%2, per slice of min(cout,256) rows;
      * 4*16*cin*cout bytes.  NULL selects the unfused fp32 kernels. */
     const void* tc_pack;
+    /* HOST pointer (the only one in this struct), nullable: fc1 | fc2 | fc3 contiguous, 48 + 512 + 512 floats.  The fused kernels
+     * take the kernel-weight MLP in their parameter block (constant-bank operands); NULL selects the unfused kernels. */
+    const float* mlp_host;
+    /* tc_pack holds cv_w / tc_out_scale (a power of two chosen so that the fp16 lo parts stay normal); the fused kernel multiplies
+     * its accumulator by tc_out_scale */
+    float tc_out_scale;
 } pps_fkaconv_weights;
 
 size_t pps_fkaconv_workspace_bytes(int64_t b, int64_t n_s, int cin); /* upper bound for any layer of that input width */

@@ -42,7 +42,7 @@ class FKAConvWeights(ctypes.Structure):
         ('cin', ctypes.c_int32), ('cout', ctypes.c_int32), ('act', ctypes.c_int32),
         ('alpha', ctypes.c_float), ('beta', ctypes.c_float), ('norm_radius', ctypes.c_float),
         ('fc1', c_f32p), ('fc2', c_f32p), ('fc3', c_f32p), ('in1_w', c_f32p), ('in1_b', c_f32p), ('in2_w', c_f32p),
-        ('in2_b', c_f32p), ('cv_w', c_f32p), ('out_bias', c_f32p), ('out_relu', ctypes.c_int32), ('tc_pack', c_voidp),
+        ('in2_b', c_f32p), ('cv_w', c_f32p), ('out_bias', c_f32p), ('out_relu', ctypes.c_int32), ('tc_pack', c_voidp), ('mlp_host', c_voidp), ('tc_out_scale', ctypes.c_float),
     ]
 
 

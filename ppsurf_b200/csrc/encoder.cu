@@ -16,7 +16,7 @@ int linear_impl(const float* x, const float* w, const float* bias, const float* 
                 float* y, int64_t m, int n, int k, int ldx, int ldy, int act, cudaStream_t st);
 bool fka_fused_supported(const pps_fkaconv_weights* w, int kn, int64_t n_s);
 int fka_fused_impl(const pps_fkaconv_weights* w, const float* x, const float* pts, const float* support, const int32_t* ids,
-                   int64_t b, int64_t n_in, int64_t n_s, const double* stats, float* out, cudaStream_t st);
+                   int64_t b, int64_t n_in, int64_t n_s, double* stats, float* out, cudaStream_t st);
 
 constexpr int kNbr = 16;   // max neighbours per support point (the reference always asks for 16, clamped to n_in)
 constexpr float kInEps = 1e-5f;
@@ -367,6 +367,7 @@ int pps_fkaconv_forward(const pps_fkaconv_weights* w, const float* x, const floa
     double* stats = reinterpret_cast<double*>(base + l.stats);
     float* mat = reinterpret_cast<float*>(base + l.mat);
     float* feat = reinterpret_cast<float*>(base + l.feat);
+    if (fused) return fka_fused_impl(w, x, pts, support, ids, b, n_in, n_s, stats, out, st);
     PPS_CUDA(cudaMemsetAsync(stats, 0, (size_t)b * 64 * sizeof(double), st));
     FkaParams prm{w->alpha, w->beta, 1.f / w->norm_radius, w->act};
     dim3 grid((unsigned)ceil_div(n_s, kFkaPts), (unsigned)b);
@@ -376,8 +377,6 @@ int pps_fkaconv_forward(const pps_fkaconv_weights* w, const float* x, const floa
     fka_weight_kernel<2><<<grid, 256, 0, st>>>(pts, support, ids, (int)n_in, (int)n_s, kn, prm, w->fc1, w->fc2, w->fc3, w->in1_w,
                                                w->in1_b, w->in2_w, w->in2_b, stats, mat);
     PPS_LAUNCH_CHECK();
-    if (fused)
-        return fka_fused_impl(w, x, pts, support, ids, b, n_in, n_s, stats, out, st);
     fka_weight_kernel<3><<<grid, 256, 0, st>>>(pts, support, ids, (int)n_in, (int)n_s, kn, prm, w->fc1, w->fc2, w->fc3, w->in1_w,
                                                w->in1_b, w->in2_w, w->in2_b, stats, mat);
     PPS_LAUNCH_CHECK();

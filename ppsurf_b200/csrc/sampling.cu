@@ -157,6 +157,9 @@ __global__ void sample_mark(const float* __restrict__ pts, const unsigned char* 
                             unsigned int seed, unsigned int* sort_key, int* sort_val) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     bool rep = false;
+    // the random rotation of this round is mixed into the seed: a CUDA-graph replay (seed baked into the launch) with fresh
+    // rotations still draws a fresh random order
+    seed ^= hash32(__float_as_uint(rot[1]) ^ hash32(__float_as_uint(rot[5])));
     if (i < n && !st->done && alive[i]) {
         const unsigned long long key = voxel_key(rot, pts + 3 * (size_t)i, st);
         unsigned int h = key_slot(key, mask);

@@ -62,86 +62,131 @@ class PPSurfModel(_Base):
         self.test_step_outputs = []
 
     # ---- a1: latent averaging loop (source/poco_model.py:200-237) ----------------------------------------------
-    def latent_schedule(self, n: int, generator: typing.Optional[torch.Generator] = None) -> typing.Iterator[torch.Tensor]:
-        """index sets of the latent loop (source/poco_model.py:207-224), lazily.  They depend only on the visit counts,
-        never on network output, so the host draws the next sets while the device still works on the previous batch."""
+    def _schedule_np(self, n: int, generator: typing.Optional[torch.Generator] = None):
+        """index sets of the latent loop (source/poco_model.py:207-224) as ``(ids int64 ndarray, may_repeat)``.  The reference draws,
+        pass after pass, ``sub`` points uniformly without replacement from the points still at the current visit count; consecutive
+        chunks of ONE random permutation of those points are the same distribution, so one ``randperm`` per iteration replaces one per
+        pass (the host schedule was on the critical path of the encoder).  Only the last chunk of an iteration is padded with random
+        points of the whole cloud (``may_repeat``); padded points are visited twice in this iteration and skipped by later ones,
+        exactly like the reference's ``counts == current`` test does."""
         sub = self.gen_subsample_manifold
         counts = np.zeros(n, dtype=np.int64)
         for current in range(self.gen_subsample_manifold_iter):
-            while counts.min() < current + 1:
-                valid = torch.from_numpy(np.nonzero(counts == current)[0])
-                if n >= sub:
-                    ids = valid[torch.randperm(valid.shape[0], generator=generator)[:sub]]
+            while True:
+                valid = np.nonzero(counts == current)[0]
+                if valid.shape[0] == 0:
+                    break
+                if n < sub:
+                    counts += 1
+                    yield np.arange(n), False
+                    continue
+                perm = valid[torch.randperm(valid.shape[0], generator=generator).numpy()]
+                for s0 in range(0, perm.shape[0], sub):
+                    ids = perm[s0:s0 + sub]
                     if ids.shape[0] < sub:
-                        ids = torch.cat([ids, torch.randperm(n, generator=generator)[:sub - ids.shape[0]]])
-                else:
-                    ids = torch.arange(n)
-                counts[np.unique(ids.numpy())] += 1  # `counts[ids] += 1` counts a repeated id once
-                yield ids
+                        ids = np.concatenate([ids, torch.randperm(n, generator=generator)[:sub - ids.shape[0]].numpy()])
+                        counts[np.unique(ids)] += 1  # `counts[ids] += 1` counts a repeated id once
+                        yield ids, True
+                    else:
+                        counts[ids] += 1
+                        yield ids, False
+
+    def latent_schedule(self, n: int, generator: typing.Optional[torch.Generator] = None) -> typing.Iterator[torch.Tensor]:
+        """index sets of the latent loop (source/poco_model.py:207-224), lazily.  They depend only on the visit counts,
+        never on network output, so the host draws the next sets while the device still works on the previous batch."""
+        for ids, _ in self._schedule_np(n, generator):
+            yield torch.from_numpy(ids)
 
     def encode_cloud(self, pts_bcn: torch.Tensor, generator: typing.Optional[torch.Generator] = None,
                      prog_bar=None, batch_passes: int = 16) -> torch.Tensor:
         """``pts_bcn [1,3,N]`` (device) -> latents ``[1,latent,N]``: every point is encoded at least
         ``gen_subsample_manifold_iter`` times on random ``gen_subsample_manifold``-point subsets and averaged
         (source/poco_model.py:200-237).  The passes are independent given the schedule, so ``batch_passes`` of them go
-        through the encoder as one batch (InstanceNorm statistics are per sample); the accumulation keeps pass order."""
+        through the encoder as one batch (InstanceNorm statistics are per sample), replayed from a CUDA graph
+        (``PPSurfNetwork.latents_of_batch``); the accumulation keeps pass order."""
+        from .sampling import ROUNDS, random_rotations
         pts = pts_bcn[0].transpose(0, 1).contiguous()  # [N,3]
         n = pts.shape[0]
         dev = pts.device
+        net = self.network
         latent = torch.zeros((n, self.network_latent_size), dtype=torch.float32, device=dev)
         counts = torch.zeros((n,), dtype=torch.float32, device=dev)
-        schedule = self.latent_schedule(n, generator)
+        schedule = self._schedule_np(n, generator)
         iteration = 0
         sub = min(self.gen_subsample_manifold, n)
+        rot_gen = np.random.default_rng(net.sampling_seed)
 
         def prepare(group):
             # one host->device copy per batch: the point ids of every pass, the first occurrence of every distinct id
             # (torch semantics of `latent[ids] += x` with repeated ids: one writer wins, counted once) as rows of the
-            # batch's point-major output and as destination points
-            ids_np = [ids.numpy() for ids in group]
-            firsts = [np.unique(a, return_index=True)[1] for a in ids_np]
-            rows = np.concatenate([f + k * sub for k, f in enumerate(firsts)]).astype(np.int32)
-            dsts = np.concatenate([a[f] for a, f in zip(ids_np, firsts)]).astype(np.int32)
-            packed = torch.from_numpy(np.concatenate([np.concatenate(ids_np).astype(np.int32), rows, dsts])).pin_memory()
-            return len(group), [f.shape[0] for f in firsts], packed
+            # batch's point-major output and as destination points; plus the random rotations of the support samplings
+            ids_np = [g[0] for g in group]
+            firsts = [np.unique(a, return_index=True)[1] if rep else None for a, rep in group]
+            n_first = [sub if f is None else f.shape[0] for f in firsts]
+            if all(f is None for f in firsts):
+                extra = []  # no repeated id in the whole batch: rows = 0..B*sub-1, destinations = the ids themselves
+            else:
+                rows = np.concatenate([(np.arange(sub) if f is None else f) + k * sub for k, f in enumerate(firsts)]).astype(np.int32)
+                dsts = np.concatenate([a if f is None else a[f] for a, f in zip(ids_np, firsts)]).astype(np.int32)
+                extra = [rows, dsts]
+            packed = torch.from_numpy(np.concatenate([np.concatenate(ids_np).astype(np.int32)] + extra)).pin_memory()
+            rot = torch.from_numpy(random_rotations(rot_gen, len(group) * 4 * ROUNDS).reshape(len(group), 4, ROUNDS, 9)).pin_memory()
+            return len(group), n_first, packed, rot, not extra
 
         # the schedule depends only on the host-side visit counts, never on network output: a producer thread draws and
         # prepares the next batches while the device works on the current one (numpy / torch release the GIL)
         batches: queue.Queue = queue.Queue(maxsize=3)
+        stop = threading.Event()
+
+        def put(item):
+            while not stop.is_set():
+                try:
+                    batches.put(item, timeout=0.1)
+                    return True
+                except queue.Full:
+                    continue
+            return False
 
         def producer():
             try:
-                while True:
-                    group = [ids for _, ids in zip(range(batch_passes), schedule)]
-                    batches.put(prepare(group) if group else None)
-                    if not group:
+                while not stop.is_set():
+                    group = [g for _, g in zip(range(batch_passes), schedule)]
+                    if not put(prepare(group) if group else None) or not group:
                         return
             except BaseException as err:  # surfaces in the consumer
-                batches.put(err)
+                put(err)
 
         thread = threading.Thread(target=producer, daemon=True)
         thread.start()
-        while True:
-            item = batches.get()
-            if item is None:
-                break
-            if isinstance(item, BaseException):
-                raise item
-            b, n_first, packed = item
-            packed = packed.to(dev, non_blocking=True)
-            total_first = sum(n_first)
-            all_ids, rows_dev, dsts_dev = packed[:b * sub], packed[b * sub:b * sub + total_first], packed[b * sub + total_first:]
-            batch = pts[all_ids.long()].view(b, sub, 3).transpose(1, 2).contiguous()  # [B,3,sub]
-            part = self.network.get_latent({'pts': batch})['latents']  # [B,latent,sub], a view of the point-major result
-            part_pm = part.transpose(1, 2).contiguous().view(b * sub, -1)  # no copy when the view is already point-major
-            off = 0
-            for nf in n_first:  # pass order is kept: a point revisited inside the batch accumulates in the reference's order
-                ops.latent_accumulate_rows(part_pm, rows_dev[off:off + nf], dsts_dev[off:off + nf], latent, counts)
-                off += nf
-                iteration += 1
-            if prog_bar is not None:
-                prog_bar.predict_progress_bar.set_postfix_str('get_latent iter: {}'.format(iteration), refresh=True)
-        thread.join()
+        try:
+            while True:
+                item = batches.get()
+                if item is None:
+                    break
+                if isinstance(item, BaseException):
+                    raise item
+                b, n_first, packed, rot, plain = item
+                packed = packed.to(dev, non_blocking=True)
+                rot = rot.to(dev, non_blocking=True)
+                all_ids = packed[:b * sub]
+                batch = torch.index_select(pts, 0, all_ids).view(b, sub, 3)  # [B,sub,3] point-major
+                part_pm = net.latents_of_batch(batch, rot).reshape(b * sub, -1)
+                if plain:
+                    rows_dev = torch.arange(b * sub, device=dev, dtype=torch.int32)
+                    dsts_dev = all_ids
+                else:
+                    total_first = sum(n_first)
+                    rows_dev, dsts_dev = packed[b * sub:b * sub + total_first], packed[b * sub + total_first:]
+                off = 0
+                for nf in n_first:  # pass order is kept: a point revisited inside the batch accumulates in the reference's order
+                    ops.latent_accumulate_rows(part_pm, rows_dev[off:off + nf], dsts_dev[off:off + nf], latent, counts)
+                    off += nf
+                    iteration += 1
+                if prog_bar is not None:
+                    prog_bar.predict_progress_bar.set_postfix_str('get_latent iter: {}'.format(iteration), refresh=True)
+        finally:
+            stop.set()  # a failing consumer must not leave the producer blocked on the bounded queue (ADVICE r1)
+            thread.join()
         ops.latent_finalize(latent, counts)
         return latent.transpose(0, 1).unsqueeze(0)
 

@@ -155,6 +155,9 @@ class PPSurfNetwork(_Base):
         # 1 = tcgen05 split-fp16 kernels (built for latent 256 / k 64 / 64 heads), 0 = fp32 SIMT kernels for every other shape
         self.decode_path = (1 if (latent_size == 256 and k == 64) else 0) if decode_path is None else decode_path
         self.sampling_seed = None  # set for reproducible support sampling
+        self.use_graphs = True     # CUDA-graph replay of the latent loop's batches (latents_of_batch)
+        self.graph_seed = 12345    # baked into the captured launches; the per-round rotations re-randomise it on the device
+        self._graphs = {}
         self._packed = None
         self._decoder_cache = None
         self.register_load_state_dict_post_hook(lambda module, _keys: module.invalidate())
@@ -163,6 +166,7 @@ class PPSurfNetwork(_Base):
     def invalidate(self):
         self._packed = None
         self._decoder_cache = None
+        self._graphs = {}  # captured graphs hold pointers into the packed weights
 
     def _apply(self, fn, *args, **kwargs):
         self.invalidate()
@@ -199,9 +203,13 @@ class PPSurfNetwork(_Base):
     def encode(self, data: dict) -> torch.Tensor:
         """FKAConvNetwork.forward(spectral_only=True) (source/base/nn.py:508-548): needs ``pts``, ``support1-4`` and the
         13 index tensors in ``data`` (reference layouts); returns point-major latents ``[B,N0,latent]``."""
-        enc = self.packed()['encoder']
         pts = [_pm(data['pts'])] + [_pm(data['support%d' % i]) for i in (1, 2, 3, 4)]
         ids = {key: _ids32(val) for key, val in data.items() if key.startswith('ids')}
+        return self._encode_pm(pts, ids)
+
+    def _encode_pm(self, pts: list, ids: dict) -> torch.Tensor:
+        """the encoder on point-major tensors: ``pts[l] [B,N_l,3]`` for the five levels, ``ids`` int32 (the C ABI's layouts)"""
+        enc = self.packed()['encoder']
         b, n0, _ = pts[0].shape
         x = torch.ones_like(pts[0])  # nn.py:517
         cin0 = enc['cv0'].struct.cin  # the packed layer pads its 3 input channels to 4 (zero weights)
@@ -218,35 +226,72 @@ class PPSurfNetwork(_Base):
         x4 = self._resblock(enc['resnetb40'], x3, pts[3], pts[4], ids['ids34'])
         x4 = self._resblock(enc['resnetb41'], x4, pts[4], pts[4], ids['ids44'])
 
-        out = []
-        for s in range(b):  # the U-Net decoder gathers rows, so run it per sample
-            x4s, n4 = x4[s], x4.shape[1]
-            wa, wb = enc['cv5']
-            glob = ops.linear(ops.global_max(x4[s:s + 1]), wb.w, wb.b)  # [1,1024]: W5b . max + b  (x4d_bug_fixed=True)
-            deep = ops.linear(x4s, wa.w, glob.view(-1), relu=True)
-            for stage, skip, key in (('cv3d', x3, 'ids43'), ('cv2d', x2, 'ids32'), ('cv1d', x1, 'ids21'),
-                                     ('cv0d', x0, 'ids10')):
-                wa, wb = enc[stage]
-                up = ids[key][s].reshape(-1).clamp_min(0)  # interpolate(): ids < 0 -> 0, k=1 (nn.py:684-697)
-                t = ops.linear(deep, wa.w, gather=up)
-                deep = ops.linear(skip[s], wb.w, wb.b, residual=t, relu=True)
-            out.append(ops.linear(deep, enc['fcout'].w, enc['fcout'].b))
-        return torch.stack(out, dim=0)
+        # U-Net decoder on the flattened batch: the 1-NN up-sampling gathers rows of the previous (deeper) level, so the row
+        # indices of sample s are offset by s * N_deeper (interpolate(): ids < 0 -> 0, k = 1; nn.py:684-697)
+        n4 = x4.shape[1]
+        wa, wb = enc['cv5']
+        glob = ops.linear(ops.global_max(x4), wb.w, wb.b)  # [B,1024]: W5b . max + b  (x4d_bug_fixed=True)
+        rows4 = torch.arange(b, device=x4.device, dtype=torch.int32).repeat_interleave(n4)
+        deep = ops.linear(x4.reshape(b * n4, -1), wa.w, residual=ops.gather_rows(glob, rows4), relu=True)
+        n_deep = n4
+        for stage, skip, key in (('cv3d', x3, 'ids43'), ('cv2d', x2, 'ids32'), ('cv1d', x1, 'ids21'), ('cv0d', x0, 'ids10')):
+            wa, wb = enc[stage]
+            n_l = skip.shape[1]
+            up = ids[key].reshape(b, n_l).clamp_min(0) + (torch.arange(b, device=x4.device, dtype=torch.int32) * n_deep)[:, None]
+            t = ops.linear(deep, wa.w, gather=up.reshape(-1).contiguous())
+            deep = ops.linear(skip.reshape(b * n_l, -1), wb.w, wb.b, residual=t, relu=True)
+            n_deep = n_l
+        return ops.linear(deep, enc['fcout'].w, enc['fcout'].b).view(b, n0, -1)
+
+    def spatial_ids_pm(self, pts: torch.Tensor, rot: torch.Tensor = None, seed: int = None) -> dict:
+        """get_fkaconv_ids on the device, C-ABI layouts: ``pts [B,N0,3]`` -> point-major supports ``support1..4 [B,N_l,3]`` and int32
+        index tensors.  ``rot [B,4,ROUNDS,9]`` device rotations (drawn from ``sampling_seed`` when absent)."""
+        from .sampling import ROUNDS, random_rotations
+        if rot is None:
+            gen = np.random.default_rng(self.sampling_seed)
+            b = pts.shape[0]
+            rot = torch.from_numpy(random_rotations(gen, b * 4 * ROUNDS).reshape(b, 4, ROUNDS, 9)).to(pts.device)
+            seed = int(gen.integers(0, 2 ** 31))
+        return ops.encoder_ids(pts, rot, 0 if seed is None else seed)
 
     def spatial_ids(self, pts_bcn: torch.Tensor) -> dict:
         """get_fkaconv_ids on the device (source/poco_data_loader.py:137-209): four quantised support samplings at
         ratio 1/4 and the 13 kNN index tensors in ONE C-ABI call per batch; reference layouts on return (supports
         [B,3,Ns], ids int64)."""
-        from .sampling import ROUNDS, random_rotations
-        gen = np.random.default_rng(self.sampling_seed)
-        pts = _pm(pts_bcn)
-        b = pts.shape[0]
-        rot = torch.from_numpy(random_rotations(gen, b * 4 * ROUNDS).reshape(b, 4, ROUNDS, 9)).to(pts.device)
-        res = ops.encoder_ids(pts, rot, int(gen.integers(0, 2 ** 31)))
+        res = self.spatial_ids_pm(_pm(pts_bcn))
         out = {}
         for key, val in res.items():
             out[key] = val.transpose(1, 2).contiguous() if key.startswith('support') else val.long()
         return out
+
+    def latents_of_batch(self, pts: torch.Tensor, rot: torch.Tensor) -> torch.Tensor:
+        """``get_latent`` of the latent loop (source/poco_model.py:227) for a batch of sub-clouds ``pts [B,n,3]`` with the device
+        rotations ``rot [B,4,ROUNDS,9]`` of their support samplings -> point-major latents ``[B,n,latent]``.  With ``use_graphs`` the
+        whole batch (about 6000 small launches: samplings, radix sorts, index builds, 13 kNN queries per sub-cloud, the network) is
+        captured ONCE per shape into a CUDA graph and replayed: the result lives in the graph's static output buffer and is valid
+        until the next call with the same shape."""
+        key = (tuple(pts.shape), pts.device)
+        slot = self._graphs.get(key)
+        if not self.use_graphs or slot is None:
+            # eager: graphs off, or the first batch of this shape (a shape is captured when it comes back: the ragged last batch of
+            # a cloud is not worth a capture unless a second cloud of the same size follows)
+            if self.use_graphs:
+                self._graphs[key] = {'pts': torch.empty_like(pts), 'rot': torch.empty_like(rot), 'graph': None, 'out': None}
+            res = self.spatial_ids_pm(pts, rot, self.graph_seed)
+            return self._encode_pm([pts] + [res['support%d' % i] for i in (1, 2, 3, 4)], res)
+        slot['pts'].copy_(pts)
+        slot['rot'].copy_(rot)
+        if slot['graph'] is None:
+            def body():
+                res = self.spatial_ids_pm(slot['pts'], slot['rot'], self.graph_seed)
+                return self._encode_pm([slot['pts']] + [res['support%d' % i] for i in (1, 2, 3, 4)], res)
+            graph = torch.cuda.CUDAGraph()  # the eager first use of the shape was the warm-up (function attributes, cub temp sizes)
+            # thread-local capture mode: the latent loop's producer thread pins host buffers (cudaHostAlloc) while this thread captures
+            with torch.cuda.graph(graph, capture_error_mode='thread_local'):
+                slot['out'] = body()
+            slot['graph'] = graph
+        slot['graph'].replay()
+        return slot['out']
 
     # ---- reference surface -------------------------------------------------------------------------------------
     def forward(self, data):

@@ -275,6 +275,11 @@ def fkaconv(packed, x, pts, support, ids):
     return out
 
 
+def gather_rows(x, rows):
+    """``x[rows]`` for ``x [N,C]``, ``rows [M]`` int32 (stream-ordered, no index conversion)"""
+    return torch.index_select(x, 0, rows)
+
+
 def gather_max(x, ids):
     b, n_in, c = x.shape
     n_s, kn = ids.shape[1], ids.shape[2]

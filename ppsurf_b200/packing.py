@@ -190,13 +190,24 @@ def pack_fkaconv(sd, name, device, act, bn=None) -> Packed:
     p.put('cv_w', w, device)
     nsl = min(cout, 256)
     if nsl in (32, 64, 128, 256) and cout % nsl == 0:
-        p.tensors['tc_pack'] = fka_tc_pack(w.reshape(cout, 16, cin).permute(0, 2, 1).contiguous()).to(device)
+        # the fp16 hi/lo split needs lo = w - fp16(w) ~ 2^-12 |w| in fp16's NORMAL range (>= 6.1e-5): the kernels of the wide layers
+        # are ~0.01, whose lo parts would be denormals with 2 % precision.  A power-of-two scale (exact) moves max|w| to ~2048; the
+        # fused kernel's epilogue multiplies the accumulator by its inverse.
+        wmax = float(w.abs().max())
+        shift = int(torch.floor(torch.log2(torch.tensor(2048.0 / wmax)))) if wmax > 0 else 0
+        shift = max(-20, min(20, shift))
+        p.tensors['tc_pack'] = fka_tc_pack((w * 2.0 ** shift).reshape(cout, 16, cin).permute(0, 2, 1).contiguous()).to(device)
         st.tc_pack = p.tensors['tc_pack'].data_ptr()
+        st.tc_out_scale = 2.0 ** -shift
     else:
         st.tc_pack = None
+        st.tc_out_scale = 1.0
     p.put('fc1', _mat(sd, name + '.fc1.weight'), device)
     p.put('fc2', _mat(sd, name + '.fc2.weight'), device)
     p.put('fc3', _mat(sd, name + '.fc3.weight'), device)
+    host = torch.cat([_mat(sd, name + '.fc' + i + '.weight').reshape(-1) for i in '123']).to(torch.float32).contiguous()
+    p.tensors['mlp_host'] = host  # stays on the host: passed by value to the fused kernels
+    st.mlp_host = host.data_ptr()
     p.put('in1_w', _f64(sd, name + '.bn1.weight'), device)
     p.put('in1_b', _f64(sd, name + '.bn1.bias'), device)
     p.put('in2_w', _f64(sd, name + '.bn2.weight'), device)

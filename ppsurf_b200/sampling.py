@@ -23,5 +23,15 @@ def random_rotation(gen: np.random.Generator) -> np.ndarray:
 
 
 def random_rotations(gen: np.random.Generator, count: int) -> np.ndarray:
-    """``[count, 9]`` float32 row-major rotation matrices"""
-    return np.stack([random_rotation(gen).reshape(9) for _ in range(count)]).astype(np.float32)
+    """``[count, 9]`` float32 row-major rotation matrices (vectorised ``random_rotation``: same angles in the same order)"""
+    ang = np.radians(gen.uniform(-180.0, 180.0, (count, 3)))
+    c, s = np.cos(ang), np.sin(ang)
+    one, zero = np.ones(count), np.zeros(count)
+
+    def mat(rows):
+        return np.stack([np.stack(r, axis=-1) for r in rows], axis=-2)
+
+    rx = mat([[one, zero, zero], [zero, c[:, 0], s[:, 0]], [zero, -s[:, 0], c[:, 0]]])
+    ry = mat([[c[:, 1], zero, s[:, 1]], [zero, one, zero], [-s[:, 1], zero, c[:, 1]]])
+    rz = mat([[c[:, 2], s[:, 2], zero], [-s[:, 2], c[:, 2], zero], [zero, zero, one]])
+    return (rz @ ry @ rx).reshape(count, 9).astype(np.float32)

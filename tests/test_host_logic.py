@@ -225,3 +225,22 @@ def test_latent_schedule_of_the_module():
     assert len(again) == len(sched) and all(torch.equal(a, b) for a, b in zip(again, sched))  # a seed reproduces the schedule
     small = list(model.latent_schedule(500, torch.Generator().manual_seed(1)))
     assert len(small) == 3 and all(torch.equal(s, torch.arange(500)) for s in small)
+
+
+def test_fka_tc_pack_layout():
+    """operand pack of the fused FKAConv kernel (csrc/fka_tc.cu): k16 stages of [hi kb0 | hi kb1 | lo kb0 | lo kb1] per slice of
+    min(cout, 256) rows, K order k = ((c/2)*4 + m/4)*8 + (m%4)*2 + c%2; hi + lo reproduces the weight to 2^-21"""
+    from ppsurf_b200 import packing
+    gen = torch.Generator().manual_seed(5)
+    for cout, cin in ((32, 4), (64, 32), (512, 8)):
+        w = torch.randn((cout, cin, 16), generator=gen, dtype=torch.float64)  # [o][c][m]
+        pack = packing.fka_tc_pack(w)
+        nsl, k = min(cout, 256), 16 * cin
+        assert pack.numel() == 4 * k * cout
+        halves = pack.view(torch.float16).view(cout // nsl, k // 16, 2, 2, nsl, 8).to(torch.float64)  # [slice][stage][hl][kb][row][8]
+        both = halves[:, :, 0] + halves[:, :, 1]  # hi + lo: [slice][stage][kb][row][8]
+        wk = both.permute(0, 3, 1, 2, 4).reshape(cout, k)  # [o][k]
+        for c in range(cin):
+            for m in (0, 5, 15):
+                kk = ((c // 2) * 4 + m // 4) * 8 + (m % 4) * 2 + c % 2
+                assert torch.allclose(wk[:, kk], w[:, c, m], rtol=2.0 ** -20, atol=1e-7)
