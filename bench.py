@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument('--chunk', type=int, default=37888,
                     help='queries per decode launch; 37888 = 2 x 148 SMs x 128 rows: whole waves for every tensor-core kernel')
     ap.add_argument('--latents', default='encoder', choices=['encoder', 'random'])
+    ap.add_argument('--encoder', default='sharded', choices=['sharded', 'rank0'], help='multi-GPU: who runs the latent loop')
     ap.add_argument('--cpu-sample', type=int, default=65536,
                     help='queries of the CPU baseline sample (about 10-15 s of host work on 16 cores)')
     ap.add_argument('--ref-sample', type=int, default=16384, help='queries per step of the --impl reference arm')
@@ -357,7 +358,7 @@ def predict_block(model, pts_np, dev, args):
     pts_ms = torch.from_numpy(pts_np[None].copy()).to(dev)
     model.network.sampling_seed = 42
     best = None
-    for _ in range(2):
+    for _ in range(3):  # the first two runs also warm the CUDA graphs of the encoder batches
         torch.manual_seed(42)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -371,7 +372,7 @@ def predict_block(model, pts_np, dev, args):
                     'shell_mquery_per_s': st['shell_queries'] / st['volume_s'] / 1e6,
                     'decoded_fraction_of_grid': st['shell_queries'] / float((args.resolution + 2) ** 3)}
     best['what'] = 'PPSurfModel.reconstruct(pts [1,N,3]): encode_cloud (>=10 encodings per point) + decoder_for + create_volume (region ' \
-                   'growing, source/poco_utils.py:178-254), volume returned to the host; best of 2'
+                   'growing, source/poco_utils.py:178-254), volume returned to the host; best of 3'
     return best
 
 
@@ -407,41 +408,49 @@ def run_b200(args):
     pts_np = synthetic.synthetic_cloud(args.points, 42)
     pts_bcn = torch.from_numpy(pts_np.T[None].copy()).to(dev)
 
-    # ---- encode on rank 0, one NCCL broadcast of the latent table (SURVEY.md §8e option A)
+    # ---- encode: the latent loop's passes are dealt to the ranks, ONE all-reduce of the partial sums (SURVEY.md §8e option B);
+    # `--encoder rank0` is option A of the survey: rank 0 encodes alone, one broadcast of the latent table
+    from ppsurf_b200.sharding import Shard
     encoder_s = None
-    latents = torch.empty((1, 256, args.points), dtype=torch.float32, device=dev)
-    if rank == 0:
-        if args.latents == 'encoder':
-            net.sampling_seed = 42
-            model.encode_cloud(pts_bcn[:, :, :20000].contiguous(), generator=torch.Generator().manual_seed(1))  # warm-up
-            gen = torch.Generator().manual_seed(42)
+    collective_ms = collective_first_ms = None
+    sharded = world > 1 and args.encoder == 'sharded'
+    if args.latents == 'encoder':
+        net.sampling_seed = 42
+        if sharded:
+            model.shard = Shard.from_env()
+        latents = torch.empty((1, 256, args.points), dtype=torch.float32, device=dev)
+        if sharded or rank == 0:
+            t0 = time.perf_counter()
+            for _ in range(2):  # warm-up: a batch shape is captured into a CUDA graph on its second use, replayed from the third
+                model.encode_cloud(pts_bcn, generator=torch.Generator().manual_seed(1))
+            torch.cuda.synchronize()
+            collective_first_ms = (time.perf_counter() - t0) * 1e3 if sharded else None  # includes NCCL set-up and the graph captures
+            if sharded:
+                dist.barrier()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            latents = model.encode_cloud(pts_bcn, generator=gen).contiguous()
+            latents = model.encode_cloud(pts_bcn, generator=torch.Generator().manual_seed(42)).contiguous()
             torch.cuda.synchronize()
-            encoder_s = time.perf_counter() - t0  # 10 encodings per point on random 10k-point subsets = ~100 passes
-        else:
-            latents = torch.from_numpy(np.random.default_rng(7).standard_normal((1, 256, args.points)).astype(np.float32)).to(dev)
-    broadcast_ms = broadcast_first_ms = None
+            encoder_s = time.perf_counter() - t0  # 10 encodings per point on random 10k-point subsets = ~100 passes (all-reduce inside)
+        model.shard = Shard()  # the dense decode below is sharded by bench.grid_blocks, not by the model
+    else:
+        latents = torch.from_numpy(np.random.default_rng(7).standard_normal((1, 256, args.points)).astype(np.float32)).to(dev)
     if world > 1:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        dist.barrier()
-        t0 = time.perf_counter()
-        dist.broadcast(latents, src=0)  # the first collective also builds the NCCL channels: reported separately
-        torch.cuda.synchronize()
-        broadcast_first_ms = (time.perf_counter() - t0) * 1e3
-        scratch = torch.empty_like(latents)
-        if rank == 0:
-            scratch.copy_(latents)
-        dist.broadcast(scratch, src=0)
+        if not sharded:
+            dist.broadcast(latents, src=0)
+        t = torch.tensor([encoder_s or 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        encoder_s = float(t[0]) or None
+        scratch = torch.zeros_like(latents)
+        (dist.all_reduce(scratch) if sharded else dist.broadcast(scratch, src=0))
         dist.barrier()
         e0.record()
         for _ in range(5):
-            dist.broadcast(scratch, src=0)
+            (dist.all_reduce(scratch) if sharded else dist.broadcast(scratch, src=0))
         e1.record()
         torch.cuda.synchronize()
-        broadcast_ms = e0.elapsed_time(e1) / 5  # steady state of the same 102 MB table
-        assert torch.equal(scratch, latents)
+        collective_ms = e0.elapsed_time(e1) / 5  # steady state of the one collective on the 102 MB table
         del scratch
 
     net.decoder_for(pts_bcn, latents)  # warm (cub temp storage, first launches)
@@ -521,6 +530,18 @@ def run_b200(args):
         dist.all_reduce(lt, op=dist.ReduceOp.SUM)
         launches = int(lt[0])
 
+    # ---- secondary metric: the whole predict path of one cloud; on N ranks the latent loop and every sweep's queries are sharded
+    predict = None
+    if not args.profile_run and not args.no_predict:
+        model.shard = Shard.from_env() if world > 1 else Shard()
+        predict = predict_block(model, pts_np, dev, args)
+        predict['ranks'] = world
+        model.shard = Shard()
+        if world > 1:
+            t = torch.tensor([predict['total_s'], predict['encoder_s'], predict['shell_decode_s']], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            predict['total_s'], predict['encoder_s'], predict['shell_decode_s'] = (float(v) for v in t)
+
     if rank == 0:
         peaks = measured_peaks()
         ms_per_step = elapsed_ms / args.steps
@@ -556,10 +577,13 @@ def run_b200(args):
                          'flop_per_row_executed': GEMM_FLOP_PER_ROW, 'peak_source': peaks['source'],
                          'whole_decode_tflops_reference_formulation': value * 1e6 * FLOP_PER_QUERY_REFERENCE / 1e12},
             'clocks': clocks.summary(),
-            'encoder_s': encoder_s, 'setup_ms': setup_ms, 'broadcast_ms': broadcast_ms, 'broadcast_first_ms': broadcast_first_ms,
+            'encoder_s': encoder_s, 'setup_ms': setup_ms,
+            'encoder_parallelism': ('passes dealt to {} ranks, one all-reduce(sum) of latent sums + counts'.format(world) if sharded else
+                                    ('rank 0 encodes, one broadcast' if world > 1 else 'single GPU')),
+            'collective_ms': collective_ms, 'encoder_warmup_ms': collective_first_ms,
         }
-        if not args.profile_run and not args.no_predict and world == 1:
-            out['e2e_predict'] = predict_block(model, pts_np, dev, args)
+        if predict is not None:
+            out['e2e_predict'] = predict
         if not args.profile_run:
             out['roofline_fkaconv'] = fkaconv_roofline(net, dev, peaks)
         if not args.no_cpu_baseline and world == 1:

@@ -341,6 +341,28 @@ int pps_latent_accumulate_rows(const float* partial, const int32_t* rows, const 
                                float* counts, void* stream);
 int pps_latent_finalize(float* latent, const float* counts, int64_t n, int c, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * f3  marching cubes + bisection refinement on the device
+ *     replaces  skimage.measure.marching_cubes + the refinement loop   source/poco_utils.py:96,111-168
+ * volume [r,r,r] f32 (NaN = never decoded; cells with a NaN corner emit nothing).  The case table (ppsurf_b200/mc_tables.py,
+ * [256,width] int8, -1 padded, bit i of the case = corner i below the level) and the three cell-edge tables are supplied by the
+ * caller.  One vertex per crossed GRID edge (no duplicate vertices); vert_edge = 3 * linear index of the edge's lower grid vertex
+ * + axis; verts are in volume-index coordinates like skimage's.
+ *   pps_mc_count : counts_out (device int64[2]) = {vertices, triangles}; leaves the scans in `workspace`
+ *   pps_mc_emit  : same arguments and workspace -> verts_out [nv,3] f32, vert_edge_out [nv] i32, faces_out [nt,3] i32
+ *   pps_refine_init / pps_refine_update : bracketing state of the bisection (va, vb [nv,3]; pa, pb [nv]; v [nv,3]; active [nv] =
+ *     vertex strictly inside its edge with both end values decoded) and one sweep given the occupancy `pred` at v
+ * ------------------------------------------------------------------------------------------------------------- */
+int pps_mc_set_edges(const int8_t* edge_corner_host, const int8_t* edge_axis_host, const int8_t* edge_origin_host);
+size_t pps_mc_workspace_bytes(int r);
+int pps_mc_count(const float* volume, int r, float level, const int8_t* tri_table, int width, void* workspace, size_t workspace_bytes,
+                 int64_t* counts_out, void* stream);
+int pps_mc_emit(const float* volume, int r, float level, const int8_t* tri_table, int width, const void* workspace, float* verts_out,
+                int32_t* vert_edge_out, int32_t* faces_out, void* stream);
+int pps_refine_init(const float* volume, int r, const float* verts, const int32_t* vert_edge, int64_t nv, float step, float bmin_pad,
+                    float* va, float* vb, float* pa, float* pb, float* v, unsigned char* active, void* stream);
+int pps_refine_update(const float* pred, int64_t n, float* va, float* vb, float* pa, float* pb, float* v, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -759,3 +759,85 @@ def synthetic_cloud(n: int, seed: int = 42, radius: float = 0.4, noise: float = 
     d = rng.standard_normal((n, 3))
     d /= np.linalg.norm(d, axis=1, keepdims=True)
     return (radius * d + noise * rng.standard_normal((n, 3))).astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# f3: marching cubes (this repo's generated case table, vertices on grid edges like skimage's) and the
+#     bisection refinement of the vertices  (source/poco_utils.py:96, 111-168)
+# --------------------------------------------------------------------------------------------------------------
+
+def marching_cubes(volume: np.ndarray, level: float = 0.0):
+    """numpy restatement of csrc/mcubes.cu: ``volume [r,r,r]`` -> ``verts [nv,3]`` float32 in volume-index coordinates (one per crossed
+    grid edge, ordered by edge number 3 * linear index + axis), ``vert_edge [nv]``, ``faces [nt,3]`` (cells in C order).  The reference
+    uses skimage's Lewiner tables (third party, not installed); both place a vertex by linear interpolation on every crossed grid
+    edge, so the vertex SET is the same, the triangulation of ambiguous cells may differ.  The case table is the product's
+    (ppsurf_b200/mc_tables.py, generated); tests pin it through table-independent properties: closed 2-manifold, orientation, Euler
+    characteristic, vertices exactly on the level set of the trilinear edge interpolant."""
+    from ppsurf_b200 import mc_tables as T
+    vol = np.asarray(volume, dtype=np.float32)
+    r = vol.shape[0]
+    c = np.zeros((r - 1, r - 1, r - 1), dtype=np.int32)
+    nan = np.zeros_like(c, dtype=bool)
+    for i in range(8):
+        ox, oy, oz = i & 1, (i >> 1) & 1, (i >> 2) & 1
+        v = vol[ox:ox + r - 1, oy:oy + r - 1, oz:oz + r - 1]
+        nan |= np.isnan(v)
+        c |= (v < np.float32(level)).astype(np.int32) << i
+    c[nan] = 0
+    cells = np.argwhere(T.TRI_COUNT[c] > 0)
+    tri_edges = []
+    for x, y, z in cells:
+        row = T.TRI_TABLE[c[x, y, z]]
+        for e in row[row >= 0]:
+            o = T.EDGE_ORIGIN[e]
+            g = ((x + o[0]) * r + (y + o[1])) * r + (z + o[2])
+            tri_edges.append(3 * g + T.EDGE_AXIS[e])
+    tri_edges = np.asarray(tri_edges, dtype=np.int64)
+    vert_edge = np.unique(tri_edges)
+    faces = np.searchsorted(vert_edge, tri_edges).reshape(-1, 3).astype(np.int32)
+    g, axis = vert_edge // 3, vert_edge % 3
+    xyz = np.stack([g // (r * r), (g // r) % r, g % r], axis=1)
+    stride = np.where(axis == 0, r * r, np.where(axis == 1, r, 1))
+    flat = vol.reshape(-1)
+    va, vb = flat[g], flat[g + stride]
+    t = np.clip((np.float32(level) - va) / (vb - va), np.float32(0), np.float32(1)).astype(np.float32)
+    verts = xyz.astype(np.float32)
+    verts[np.arange(verts.shape[0]), axis] += t
+    return verts, vert_edge.astype(np.int32), faces
+
+
+def refine_vertices(predict: typing.Callable[[np.ndarray], np.ndarray], volume: np.ndarray, verts: np.ndarray, step, bmin_pad,
+                    refine_iter: int = 10) -> np.ndarray:
+    """source/poco_utils.py:111-168: vertices strictly inside a grid edge are bisected ``refine_iter`` times between the edge's two
+    grid vertices; returns all vertices in model space.  ``verts`` in volume-index coordinates, ``predict(q [n,3] f32) -> [n]``."""
+    step, bmin_pad = np.float32(step), np.float32(bmin_pad)
+    verts = np.asarray(verts, dtype=np.float32)
+    dirs = verts - np.floor(verts)
+    dirs = (dirs > 0).astype(verts.dtype)
+    mask = np.logical_and(dirs.sum(axis=1) > 0, dirs.sum(axis=1) < 2)
+    v = verts[mask]
+    dirs = dirs[mask]
+    v1 = np.floor(v)
+    v2 = v1 + dirs
+    v1 = v1.astype(int)
+    v2 = v2.astype(int)
+    preds1 = np.asarray(volume)[v1[:, 0], v1[:, 1], v1[:, 2]].astype(np.float32)
+    preds2 = np.asarray(volume)[v2[:, 0], v2[:, 1], v2[:, 2]].astype(np.float32)
+    v1 = v1.astype(np.float32) * step + bmin_pad
+    v2 = v2.astype(np.float32) * step + bmin_pad
+    mask_tmp = np.logical_and(~np.isnan(preds1), ~np.isnan(preds2))
+    v, v1, v2, preds1, preds2 = v[mask_tmp], v1[mask_tmp], v2[mask_tmp], preds1[mask_tmp], preds2[mask_tmp]
+    mask[mask] = mask_tmp
+    out = verts * step + bmin_pad
+    v = v * step + bmin_pad
+    for _ in range(refine_iter):
+        preds = np.asarray(predict(v.astype(np.float32)), dtype=np.float32)
+        mask1 = (preds * preds1) > 0
+        v1[mask1] = v[mask1]
+        preds1[mask1] = preds[mask1]
+        mask2 = (preds * preds2) > 0
+        v2[mask2] = v[mask2]
+        preds2[mask2] = preds[mask2]
+        v = (v2 + v1) / 2
+        out[mask] = v
+    return out

@@ -92,6 +92,13 @@ SIGNATURES = {
     'pps_region_scatter': (i32, [c_i32p, c_f32p, i64, c_f32p, c_voidp]),
     'pps_region_frontier': (i32, [c_i32p, i64, i32, i32, c_f32p, c_voidp, c_voidp, size_t, c_i32p, c_voidp, c_voidp]),
     'pps_region_finish': (i32, [c_f32p, i32, i32, ctypes.c_float, c_voidp]),
+    'pps_mc_set_edges': (i32, [c_voidp, c_voidp, c_voidp]),
+    'pps_mc_workspace_bytes': (size_t, [i32]),
+    'pps_mc_count': (i32, [c_f32p, i32, ctypes.c_float, c_voidp, i32, c_voidp, size_t, c_voidp, c_voidp]),
+    'pps_mc_emit': (i32, [c_f32p, i32, ctypes.c_float, c_voidp, i32, c_voidp, c_f32p, c_i32p, c_i32p, c_voidp]),
+    'pps_refine_init': (i32, [c_f32p, i32, c_f32p, c_i32p, i64, ctypes.c_float, ctypes.c_float, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p,
+                              c_voidp, c_voidp]),
+    'pps_refine_update': (i32, [c_f32p, i64, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_voidp]),
     'pps_sample_workspace_bytes': (size_t, [i64]),
     'pps_sample_quantized': (i32, [c_f32p, i64, i64, c_f32p, i32, ctypes.c_uint32, c_voidp, size_t, c_i32p, c_voidp]),
     'pps_encoder_ids_workspace_bytes': (size_t, [i64]),

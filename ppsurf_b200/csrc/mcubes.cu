@@ -133,9 +133,10 @@ __global__ void refine_init_kernel(const float* __restrict__ vol, int r, const f
     pb[i] = fb;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-        va[3 * i + d] = float(c[d]) * step + bmin_pad;
-        vb[3 * i + d] = float(c[d] + (d == axis ? 1 : 0)) * step + bmin_pad;
-        v[3 * i + d] = verts[3 * i + d] * step + bmin_pad;
+        // separately rounded multiply and add like numpy's `idx * step + bmin_pad` (no FMA contraction: bit-equal coordinates)
+        va[3 * i + d] = __fadd_rn(__fmul_rn(float(c[d]), step), bmin_pad);
+        vb[3 * i + d] = __fadd_rn(__fmul_rn(float(c[d] + (d == axis ? 1 : 0)), step), bmin_pad);
+        v[3 * i + d] = __fadd_rn(__fmul_rn(verts[3 * i + d], step), bmin_pad);
     }
 }
 
@@ -152,7 +153,7 @@ __global__ void refine_update_kernel(const float* __restrict__ pred, long long n
         const float a = m1 ? cur : va[3 * i + d], b = m2 ? cur : vb[3 * i + d];
         va[3 * i + d] = a;
         vb[3 * i + d] = b;
-        v[3 * i + d] = (b + a) / 2.f;
+        v[3 * i + d] = __fadd_rn(b, a) * 0.5f;
     }
     if (m1) pa[i] = p;
     if (m2) pb[i] = p;

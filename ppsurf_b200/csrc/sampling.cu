@@ -391,7 +391,7 @@ int pps_encoder_ids(const float* pts, int64_t b, int64_t n0, const float* rotati
         for (int l = 1; l < 5; ++l) {
             float* sup = out->support[l - 1] + s * n[l] * 3;
             PPS_TRY(sample_quantized_impl(lv[l - 1], n[l - 1], n[l], rotations + ((s * 4 + (l - 1)) * n_rot) * 9, n_rot,
-                                          seed + (uint32_t)(s * 4 + l), sample_ws, sample_bytes, sel, st));
+                                          seed + (uint32_t)l, sample_ws, sample_bytes, sel, st));
             gather_points<<<(unsigned)ceil_div(3 * n[l], 256), 256, 0, st>>>(lv[l - 1], sel, (int)n[l], sup);
             PPS_LAUNCH_CHECK();
             lv[l] = sup;

@@ -35,6 +35,55 @@ def _faces():
     return out
 
 
+def _edge_faces(e):
+    """the two cell faces (axis, side) a cell edge lies on"""
+    a, b = EDGE_CORNERS[e]
+    return {(d, (int(a) >> d) & 1) for d in range(3) if ((int(a) >> d) & 1) == ((int(b) >> d) & 1)}
+
+
+def _triangulate(loop, mid):
+    """triangulation of a loop of edge vertices.  A loop that visits an ambiguous face twice must not get a DIAGONAL inside that
+    face: the neighbouring cell could lay the same diagonal into the shared face, which doubles a directed edge or glues the two
+    sheets along a non-manifold edge.  All triangulations of the polygon are enumerated (at most 12 vertices), the ones with an in-face
+    diagonal are dropped, the shortest total diagonal length wins."""
+    n = len(loop)
+    faces_of = [_edge_faces(e) for e in loop]
+
+    def diagonal_in_face(a, b):
+        adjacent = b - a == 1 or (a == 0 and b == n - 1)
+        return not adjacent and bool(faces_of[a] & faces_of[b])
+
+    def in_face(i, k, j):
+        return diagonal_in_face(i, k) or diagonal_in_face(k, j) or diagonal_in_face(i, j)
+
+    best = {}
+
+    def solve(i, j):  # best triangulation of the sub-polygon i..j (indices into loop): (cost, triangles) or None
+        if j - i < 2:
+            return 0.0, []
+        if (i, j) in best:
+            return best[(i, j)]
+        res = None
+        for k in range(i + 1, j):
+            if in_face(i, k, j):
+                continue
+            left, right = solve(i, k), solve(k, j)
+            if left is None or right is None:
+                continue
+            cost = left[0] + right[0]
+            for a, b in ((i, k), (k, j)):
+                if b - a > 1:
+                    cost += float(np.sum((mid[loop[a]] - mid[loop[b]]) ** 2))
+            if res is None or cost < res[0] - 1e-12:
+                res = (cost, left[1] + right[1] + [(loop[i], loop[k], loop[j])])
+        best[(i, j)] = res
+        return res
+
+    res = solve(0, n - 1)
+    assert res is not None, 'no triangulation without an in-face diagonal for loop {}'.format(loop)
+    return res[1]
+
+
 def _case_triangles(case):
     inside = [(case >> i) & 1 for i in range(8)]
     nbr = {}
@@ -66,7 +115,7 @@ def _case_triangles(case):
             loop.append(nxt)
             seen.add(nxt)
             prev, cur = cur, nxt
-        fan = [(loop[0], loop[i], loop[i + 1]) for i in range(1, len(loop) - 1)]
+        fan = _triangulate(loop, mid)
         area = sum(np.cross(mid[b] - mid[a], mid[c] - mid[a]) for a, b, c in fan)
         out_dir = np.zeros(3)
         for e in loop:  # inside corner -> outside corner along every crossed edge of the loop

@@ -17,6 +17,7 @@ import torch
 
 from . import ops
 from .network import PPSurfNetwork, _Base
+from .sharding import Shard
 
 
 class _NullBar:
@@ -60,6 +61,7 @@ class PPSurfModel(_Base):
                                      k=k, num_pts_local=num_pts_local, pointnet_latent_size=pointnet_latent_size,
                                      decode_chunk=min(int(rec_batch_size), ops.DEFAULT_CHUNK))
         self.test_step_outputs = []
+        self.shard = Shard()  # multi-GPU predict: set to Shard.from_env() (one process per GPU), see sharding.py
 
     # ---- a1: latent averaging loop (source/poco_model.py:200-237) ----------------------------------------------
     def _schedule_np(self, n: int, generator: typing.Optional[torch.Generator] = None):
@@ -91,6 +93,14 @@ class PPSurfModel(_Base):
                         counts[ids] += 1
                         yield ids, False
 
+    def _rotated_schedule(self, n: int, generator: typing.Optional[torch.Generator] = None, rot_seed=None):
+        """the schedule with the random rotations of every pass's four support samplings, drawn in pass order from ONE generator: a
+        pass gets the same rotations whichever rank or batch it lands in"""
+        from .sampling import ROUNDS, random_rotations
+        rot_gen = np.random.default_rng(rot_seed)
+        for ids, rep in self._schedule_np(n, generator):
+            yield ids, rep, random_rotations(rot_gen, 4 * ROUNDS).reshape(4, ROUNDS, 9)
+
     def latent_schedule(self, n: int, generator: typing.Optional[torch.Generator] = None) -> typing.Iterator[torch.Tensor]:
         """index sets of the latent loop (source/poco_model.py:207-224), lazily.  They depend only on the visit counts,
         never on network output, so the host draws the next sets while the device still works on the previous batch."""
@@ -104,24 +114,28 @@ class PPSurfModel(_Base):
         (source/poco_model.py:200-237).  The passes are independent given the schedule, so ``batch_passes`` of them go
         through the encoder as one batch (InstanceNorm statistics are per sample), replayed from a CUDA graph
         (``PPSurfNetwork.latents_of_batch``); the accumulation keeps pass order."""
-        from .sampling import ROUNDS, random_rotations
         pts = pts_bcn[0].transpose(0, 1).contiguous()  # [N,3]
         n = pts.shape[0]
         dev = pts.device
         net = self.network
         latent = torch.zeros((n, self.network_latent_size), dtype=torch.float32, device=dev)
         counts = torch.zeros((n,), dtype=torch.float32, device=dev)
-        schedule = self._schedule_np(n, generator)
+        rot_seed = net.sampling_seed
+        if self.shard.world > 1 and (generator is None or rot_seed is None):
+            # every rank must walk the same schedule: without caller-supplied seeds rank 0's random seed is shared
+            seed = self.shard.common_seed(dev)
+            generator = torch.Generator().manual_seed(seed) if generator is None else generator
+            rot_seed = seed if rot_seed is None else rot_seed
+        schedule = self.shard.my_passes(self._rotated_schedule(n, generator, rot_seed))
         iteration = 0
         sub = min(self.gen_subsample_manifold, n)
-        rot_gen = np.random.default_rng(net.sampling_seed)
 
         def prepare(group):
             # one host->device copy per batch: the point ids of every pass, the first occurrence of every distinct id
             # (torch semantics of `latent[ids] += x` with repeated ids: one writer wins, counted once) as rows of the
             # batch's point-major output and as destination points; plus the random rotations of the support samplings
             ids_np = [g[0] for g in group]
-            firsts = [np.unique(a, return_index=True)[1] if rep else None for a, rep in group]
+            firsts = [np.unique(a, return_index=True)[1] if rep else None for a, rep, _ in group]
             n_first = [sub if f is None else f.shape[0] for f in firsts]
             if all(f is None for f in firsts):
                 extra = []  # no repeated id in the whole batch: rows = 0..B*sub-1, destinations = the ids themselves
@@ -130,7 +144,7 @@ class PPSurfModel(_Base):
                 dsts = np.concatenate([a if f is None else a[f] for a, f in zip(ids_np, firsts)]).astype(np.int32)
                 extra = [rows, dsts]
             packed = torch.from_numpy(np.concatenate([np.concatenate(ids_np).astype(np.int32)] + extra)).pin_memory()
-            rot = torch.from_numpy(random_rotations(rot_gen, len(group) * 4 * ROUNDS).reshape(len(group), 4, ROUNDS, 9)).pin_memory()
+            rot = torch.from_numpy(np.stack([g[2] for g in group])).pin_memory()
             return len(group), n_first, packed, rot, not extra
 
         # the schedule depends only on the host-side visit counts, never on network output: a producer thread draws and
@@ -187,6 +201,7 @@ class PPSurfModel(_Base):
         finally:
             stop.set()  # a failing consumer must not leave the producer blocked on the bounded queue
             thread.join()
+        self.shard.reduce_latents(latent, counts)  # multi-GPU: one all-reduce of the partial sums (no-op on one rank)
         ops.latent_finalize(latent, counts)
         return latent.transpose(0, 1).unsqueeze(0)
 
@@ -234,7 +249,7 @@ class PPSurfModel(_Base):
             ids = region.pending(seeds)
             decoded += int(ids.shape[0])
             if ids.shape[0] > 0:
-                region.scatter(ids, self.occupancy(decoder, region.queries(ids, step, bmin_pad)))
+                region.scatter(ids, self.shard.evaluate(lambda q: self.occupancy(decoder, q), region.queries(ids, step, bmin_pad)))
             seeds = region.frontier(seeds, sweep & 1)
             sweep += 1
             if prog_bar is not None:
@@ -243,51 +258,38 @@ class PPSurfModel(_Base):
         self.last_volume_stats = {'shell_queries': decoded, 'sweeps': sweep}
         return region.finish(padding, out_value)
 
-    # ---- mesh extraction (host libraries, "next" rows of SURVEY.md §8f) --------------------------------------------
-    def extract_mesh(self, decoder: ops.Decoder, volume: np.ndarray, step, bmin_pad, refine_iter: int, prog_bar=None,
-                     pc_file_in: str = 'unknown'):
-        """marching cubes + bisection refinement of the vertices on grid edges (source/poco_utils.py:87-175); the
-        occupancy queries of the refinement run on the device.  Needs scikit-image and trimesh like the reference."""
-        try:
-            from skimage import measure
-            import trimesh
-        except ImportError as err:  # pragma: no cover - neither is installed in the build image
-            raise RuntimeError('mesh extraction needs scikit-image and trimesh (reference requirements.txt); '
-                               'the occupancy volume itself is available from create_volume()') from err
-        finite = volume[~np.isnan(volume)]
-        if not (finite.max() > 0 > finite.min()):
+    # ---- f3: marching cubes + bisection refinement on the device, mesh cleaning on the host ------------------------------------
+    def extract_mesh(self, decoder: ops.Decoder, volume, step, bmin_pad, refine_iter: int, prog_bar=None,
+                     pc_file_in: str = 'unknown', level: float = 0.0):
+        """source/poco_utils.py:87-175 without skimage / trimesh: marching cubes of the occupancy volume and the ``refine_iter``
+        bisection sweeps run on the device (``ops.marching_cubes``, ``ops.VertexRefiner``; the volume, the vertices and the bracketing
+        state never leave it), then ONE copy to the host and the reference's mesh cleaning (``ppsurf_b200.mesh``).  Returns
+        ``(vertices [nv,3] float64 in model space, faces [nf,3] int64)`` or ``None`` when the field has no zero crossing.
+
+        Differences from the reference, by construction: (i) vertices are created once per crossed grid edge, i.e. already merged;
+        the reference merges them in its first cleaning pass; (ii) small components are removed once, after the refinement, instead
+        of before and after  --  connectivity does not change in between; (iii) ambiguous cells are triangulated by this repo's
+        generated case table (``mc_tables``), the reference by skimage's Lewiner tables; the vertex positions agree."""
+        vol = volume if isinstance(volume, torch.Tensor) else torch.from_numpy(np.asarray(volume, dtype=np.float32))
+        vol = vol.to(decoder.pts.device, torch.float32).contiguous()
+        finite = vol[~torch.isnan(vol)]
+        if finite.numel() == 0 or not (float(finite.max()) > level > float(finite.min())):
             return None
-        verts, faces, _, _ = measure.marching_cubes(volume=volume.copy(), level=0)
-        mesh = trimesh.Trimesh(vertices=verts, faces=faces)
-        verts, faces = np.asarray(mesh.vertices), np.asarray(mesh.faces)
-        if refine_iter > 0:
-            frac = ((verts - np.floor(verts)) > 0).astype(verts.dtype)
-            on_edge = np.logical_and(frac.sum(axis=1) > 0, frac.sum(axis=1) < 2)
-            v = verts[on_edge]
-            a = np.floor(v).astype(int)
-            b = a + frac[on_edge].astype(int)
-            pa, pb = volume[a[:, 0], a[:, 1], a[:, 2]], volume[b[:, 0], b[:, 1], b[:, 2]]
-            ok = ~np.isnan(pa) & ~np.isnan(pb)
-            on_edge[on_edge] = ok
-            va = a[ok].astype(np.float32) * step + bmin_pad
-            vb = b[ok].astype(np.float32) * step + bmin_pad
-            pa, pb = pa[ok], pb[ok]
-            verts = verts * step + bmin_pad
-            v = v[ok] * step + bmin_pad
-            for it in range(refine_iter):
-                q = torch.tensor(v, dtype=torch.float32, device=decoder.pts.device)
-                pred = self.occupancy(decoder, q).cpu().numpy()
-                ma, mb = (pred * pa) > 0, (pred * pb) > 0
-                va[ma], pa[ma] = v[ma], pred[ma]
-                vb[mb], pb[mb] = v[mb], pred[mb]
-                v = (va + vb) / 2
-                verts[on_edge] = v
-                if prog_bar is not None:
-                    prog_bar.predict_progress_bar.set_postfix_str(
-                        '{}, refine iter {}'.format(os.path.basename(pc_file_in)[:16], it), refresh=True)
-        else:
-            verts = verts * step + bmin_pad
-        return trimesh.Trimesh(vertices=verts, faces=faces)
+        verts, vert_edge, faces = ops.marching_cubes(vol, level)
+        if faces.shape[0] == 0:
+            return None
+        refiner = ops.VertexRefiner(vol, verts, vert_edge, step, bmin_pad)
+        for it in range(refine_iter):
+            if refiner.v.shape[0] > 0:
+                refiner.update(self.shard.evaluate(lambda q: self.occupancy(decoder, q), refiner.v))
+            if prog_bar is not None:
+                prog_bar.predict_progress_bar.set_postfix_str(
+                    '{}, refine iter {}'.format(os.path.basename(pc_file_in)[:16], it), refresh=True)
+        verts_ms = refiner.result().cpu().numpy().astype(np.float64)
+        from . import mesh as mesh_utils
+        v, f = mesh_utils.clean_simple(verts_ms, faces.cpu().numpy())
+        v, f = mesh_utils.remove_small_connected_components(v, f, num_faces=6)
+        return (v, f) if f.shape[0] > 0 else None
 
     # ---- Lightning surface -----------------------------------------------------------------------------------------
     def get_prog_bar(self):
@@ -360,7 +362,7 @@ class PPSurfModel(_Base):
         return results
 
     def reconstruct(self, pts_ms: torch.Tensor, resolution: typing.Optional[int] = None, dense: bool = False,
-                    prog_bar=None, pc_file_in: str = 'unknown') -> dict:
+                    prog_bar=None, pc_file_in: str = 'unknown', keep_on_device: bool = False) -> dict:
         """encoder + occupancy volume for one cloud ``pts_ms [1,N,3]`` on the device; returns the volume, the grid
         definition and the decoder state (``predict_step`` adds meshing and export on top)."""
         resolution = resolution or self.gen_resolution_global
@@ -379,32 +381,41 @@ class PPSurfModel(_Base):
         step, bmin_pad, _ = self.grid_definition(input_points, resolution, 1)
         self.last_volume_stats = {'shell_queries': (resolution + 2) ** 3, 'sweeps': 1}
         if dense:
-            volume = self.dense_volume(decoder, input_points, resolution).cpu().numpy().astype(np.float64)
+            volume = self.dense_volume(decoder, input_points, resolution)
         else:
-            volume = self.create_volume(decoder, input_points, resolution, prog_bar=prog_bar, pc_file_in=pc_file_in)
+            volume = self.create_volume_device(decoder, input_points, resolution, prog_bar=prog_bar, pc_file_in=pc_file_in)
+        if not keep_on_device:  # the reference's volume: float64 on the host
+            volume = volume.cpu().numpy().astype(np.float64)
+        else:
+            torch.cuda.synchronize(dev)
         t3 = time.perf_counter()
         self.last_reconstruct_stats = dict(self.last_volume_stats, encoder_s=t1 - t0, setup_s=t2 - t1, volume_s=t3 - t2)
         return {'volume': volume, 'step': step, 'bmin_pad': bmin_pad, 'decoder': decoder, 'latents': latents}
 
     def predict_step(self, batch: dict, batch_idx, dataloader_idx=0):
         """source/poco_model.py:183-273: one cloud per batch; writes ``<results_dir>/.../<name>.ply``"""
+        from . import mesh as mesh_utils
         if batch['pts_ms'].shape[0] > 1:
             raise NotImplementedError('batch size > 1 not supported')
         prog_bar = self.get_prog_bar()
         pc_file_in = batch['pc_file_in'][0] if 'pc_file_in' in batch else 'unknown'
-        rec = self.reconstruct(batch['pts_ms'], prog_bar=prog_bar, pc_file_in=pc_file_in)
+        rec = self.reconstruct(batch['pts_ms'], prog_bar=prog_bar, pc_file_in=pc_file_in, keep_on_device=True)
         mesh = self.extract_mesh(rec['decoder'], rec['volume'], rec['step'], rec['bmin_pad'], self.gen_refine_iter,
                                  prog_bar=prog_bar, pc_file_in=pc_file_in)
         if mesh is None:
             print('No reconstruction for {}'.format(pc_file_in))
             return 0
+        verts, faces = mesh
         is_dataset = os.path.splitext(str(self.in_file))[1].lower() == '.txt'
         base = os.path.basename(pc_file_in)
         if is_dataset:
             out_file = os.path.join(self.results_dir, self.name, os.path.basename(os.path.dirname(str(self.in_file))),
                                     'meshes', base)
         else:
+            # a single file was normalised on load: the mesh goes back to the input frame (source/poco_model.py:256-263)
+            pts_np = mesh_utils.load_pts(pc_file_in)[:, :3]
+            bb_center, scale = mesh_utils.get_points_normalization_info(pts_np, self.padding_factor)
+            verts = mesh_utils.denormalize_points_with_info(verts, bb_center, scale)
             out_file = os.path.join(self.results_dir, base, base + '.ply')
-        os.makedirs(os.path.dirname(out_file), exist_ok=True)
-        mesh.export(file_obj=out_file)
+        mesh_utils.write_ply(out_file, verts, faces)
         return 0

@@ -136,6 +136,9 @@ class RegionVolume:
         return self.volume.view(self.r, self.r, self.r)
 
 
+_shared_workspace = {}
+
+
 class Decoder:
     """Per-cloud decoder state: kNN index + hoisted fc1 table; decodes query batches through ``pps_decoder_decode``."""
 
@@ -154,17 +157,20 @@ class Decoder:
         self.table = torch.empty((self.n, packed.struct.latent), dtype=torch.float32, device=pts.device)
         check(lib.pps_decoder_point_table(packed.ref, _ptr(self.pts, torch.float32), _ptr(self.latents, torch.float32),
                                           self.n, _ptr(self.table), _stream()))
-        self._ws = None
-        self._ws_chunk = 0
         self._staging = None
         self._copy_stream = None
 
     def workspace(self, chunk):
-        if self._ws is None or self._ws_chunk < chunk:
-            nbytes = lib.pps_decoder_workspace_bytes(self.packed.ref, chunk)
-            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.pts.device)
-            self._ws_chunk = chunk
-        return self._ws
+        """decode scratch (about 3 GB for the default chunk), ONE buffer per device shared by every Decoder: decodes are ordered on
+        the caller's stream, and a per-decoder buffer made every new cloud pay a multi-GB cudaMalloc"""
+        nbytes = lib.pps_decoder_workspace_bytes(self.packed.ref, chunk)
+        key = str(self.pts.device)
+        ws = _shared_workspace.get(key)
+        if ws is None or ws.numel() < nbytes:
+            _shared_workspace.pop(key, None)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=self.pts.device)
+            _shared_workspace[key] = ws
+        return ws
 
     def decode(self, queries: torch.Tensor, want_logits=True, want_occ=False, want_idx=False):
         """``queries [Q,3]`` device -> dict(logits [Q,2], occ [Q], idx [Q,kmax])"""
@@ -310,3 +316,75 @@ def latent_accumulate_rows(partial, rows, ids, latent, counts):
 def latent_finalize(latent, counts):
     check(lib.pps_latent_finalize(_ptr(latent, torch.float32), _ptr(counts, torch.float32), latent.shape[0],
                                   latent.shape[1], _stream()))
+
+
+# ---- f3: marching cubes + bisection refinement on the device (csrc/mcubes.cu) ------------------------------------------------
+
+_mc_state = {}
+
+
+def _mc_tables(device):
+    """case table on the device, cell-edge tables in constant memory (once per device)"""
+    key = str(device)
+    if key not in _mc_state:
+        import numpy as np
+        from . import mc_tables
+        corner = np.ascontiguousarray(mc_tables.EDGE_CORNERS.astype(np.int8))
+        axis = np.ascontiguousarray(mc_tables.EDGE_AXIS.astype(np.int8))
+        origin = np.ascontiguousarray(mc_tables.EDGE_ORIGIN.astype(np.int8))
+        check(lib.pps_mc_set_edges(corner.ctypes.data, axis.ctypes.data, origin.ctypes.data))
+        _mc_state[key] = torch.from_numpy(mc_tables.TRI_TABLE.copy()).to(device)
+    return _mc_state[key]
+
+
+def marching_cubes(volume: torch.Tensor, level: float = 0.0):
+    """``volume [r,r,r]`` fp32 on the device -> ``verts [nv,3]`` fp32 (volume-index coordinates), ``vert_edge [nv]`` int32,
+    ``faces [nt,3]`` int32, all on the device.  One host synchronisation (the two counts)."""
+    r = volume.shape[0]
+    if volume.dim() != 3 or volume.shape[1] != r or volume.shape[2] != r:
+        raise ValueError('marching_cubes: expected a cubic [r,r,r] volume')
+    dev = volume.device
+    table = _mc_tables(dev)
+    ws = torch.empty(lib.pps_mc_workspace_bytes(r), dtype=torch.uint8, device=dev)
+    counts = torch.zeros((2,), dtype=torch.int64, device=dev)
+    vol = volume.contiguous()
+    check(lib.pps_mc_count(_ptr(vol, torch.float32), r, float(level), _ptr(table), table.shape[1], _ptr(ws), ws.numel(), _ptr(counts),
+                           _stream()))
+    nv, nt = (int(c) for c in counts.cpu())
+    verts = torch.empty((nv, 3), dtype=torch.float32, device=dev)
+    vert_edge = torch.empty((nv,), dtype=torch.int32, device=dev)
+    faces = torch.empty((nt, 3), dtype=torch.int32, device=dev)
+    if nt > 0:
+        check(lib.pps_mc_emit(_ptr(vol, torch.float32), r, float(level), _ptr(table), table.shape[1], _ptr(ws), _ptr(verts),
+                              _ptr(vert_edge), _ptr(faces), _stream()))
+    return verts, vert_edge, faces
+
+
+class VertexRefiner:
+    """bisection state of the vertex refinement (source/poco_utils.py:111-168) on the device"""
+
+    def __init__(self, volume: torch.Tensor, verts: torch.Tensor, vert_edge: torch.Tensor, step: float, bmin_pad: float):
+        nv, dev = verts.shape[0], verts.device
+        r = volume.shape[0]
+        self.verts_ms = torch.empty((nv, 3), dtype=torch.float32, device=dev)  # every vertex in model space
+        va, vb = torch.empty_like(self.verts_ms), torch.empty_like(self.verts_ms)
+        pa = torch.empty((nv,), dtype=torch.float32, device=dev)
+        pb = torch.empty_like(pa)
+        active = torch.empty((nv,), dtype=torch.uint8, device=dev)
+        check(lib.pps_refine_init(_ptr(volume.contiguous(), torch.float32), r, _ptr(verts, torch.float32), _ptr(vert_edge, torch.int32), nv,
+                                  float(step), float(bmin_pad), _ptr(va), _ptr(vb), _ptr(pa), _ptr(pb), _ptr(self.verts_ms), _ptr(active),
+                                  _stream()))
+        self.index = torch.nonzero(active).reshape(-1)  # the refined subset, compacted
+        self.va, self.vb = va[self.index].contiguous(), vb[self.index].contiguous()
+        self.pa, self.pb = pa[self.index].contiguous(), pb[self.index].contiguous()
+        self.v = self.verts_ms[self.index].contiguous()
+
+    def update(self, pred: torch.Tensor):
+        """``pred [n_active]`` = occupancy at ``self.v``; moves the bracket and sets ``self.v`` to its midpoint"""
+        check(lib.pps_refine_update(_ptr(pred, torch.float32), self.v.shape[0], _ptr(self.va), _ptr(self.vb), _ptr(self.pa),
+                                    _ptr(self.pb), _ptr(self.v), _stream()))
+
+    def result(self) -> torch.Tensor:
+        out = self.verts_ms.clone()
+        out[self.index] = self.v
+        return out

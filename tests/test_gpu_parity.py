@@ -1,5 +1,7 @@
 """Parity of the CUDA path (through the C ABI) against the CPU oracle and the golden vectors made by the reference.
 Run on the B200 box:  python -m pytest tests -m gpu"""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -708,3 +710,90 @@ def test_fkaconv_fused_vs_oracle(dev, net, oracle, weights, name, n_in, n_s, bat
     # The encoder as a whole is held to 5e-5 of the latent scale by test_encoder_golden with these kernels in place.
     tol = 2e-5 if 16 * cin <= 4096 else 4e-5
     assert np.abs(fused - ref).max() < tol * scale, np.abs(fused - ref).max() / scale
+
+
+# ---- f3: marching cubes + refinement on the device, predict_step end to end ---------------------------------------------------
+
+def _mc_field(r=41):
+    ax = np.linspace(-0.6, 0.6, r, dtype=np.float32)
+    x, y, z = np.meshgrid(ax, ax, ax, indexing='ij')
+    a = np.sqrt((x + 0.15) ** 2 + y ** 2 + z ** 2) - 0.3
+    b = np.sqrt((x - 0.3) ** 2 + (y - 0.1) ** 2 + z ** 2) - 0.2
+    return np.minimum(a, b).astype(np.float32)
+
+
+def test_marching_cubes_device_vs_oracle(dev, oracle):
+    """csrc/mcubes.cu against its numpy restatement: same vertices (bit exact, same order), same edge numbers, same faces; NaN cells
+    emit nothing; a volume without a crossing gives an empty mesh"""
+    from ppsurf_b200 import ops
+    rng = np.random.default_rng(4)
+    for vol in (_mc_field(), rng.standard_normal((12, 12, 12)).astype(np.float32)):
+        for with_nan in (False, True):
+            v = vol.copy()
+            if with_nan:
+                v[: v.shape[0] // 3] = np.nan
+            verts, vert_edge, faces = ops.marching_cubes(cu(v, dev), 0.0)
+            rv, re, rf = oracle.marching_cubes(v, 0.0)
+            np.testing.assert_array_equal(vert_edge.cpu().numpy(), re)
+            np.testing.assert_array_equal(verts.cpu().numpy(), rv)
+            np.testing.assert_array_equal(faces.cpu().numpy(), rf)
+    verts, _, faces = ops.marching_cubes(torch.ones((8, 8, 8), device=dev), 0.0)
+    assert verts.shape == (0, 3) and faces.shape == (0, 3)
+
+
+def test_vertex_refinement_device_vs_oracle(dev, oracle):
+    """ten bisection sweeps on the device (ops.VertexRefiner) against the oracle's restatement of source/poco_utils.py:111-168 with
+    the same analytic occupancy function: identical vertices"""
+    from ppsurf_b200 import ops
+    vol = _mc_field(33)
+    vol[:4, :4, :4] = np.nan
+    step, bmin_pad = np.float32(1.2 / 32), np.float32(-0.6)
+
+    def field(q):
+        q = q.astype(np.float64)
+        a = np.sqrt((q[:, 0] + 0.15) ** 2 + q[:, 1] ** 2 + q[:, 2] ** 2) - 0.3
+        b = np.sqrt((q[:, 0] - 0.3) ** 2 + (q[:, 1] - 0.1) ** 2 + q[:, 2] ** 2) - 0.2
+        return np.minimum(a, b).astype(np.float32)
+
+    verts, vert_edge, faces = ops.marching_cubes(cu(vol, dev), 0.0)
+    ref = oracle.refine_vertices(field, vol, verts.cpu().numpy(), step, bmin_pad, 10)
+    refiner = ops.VertexRefiner(cu(vol, dev), verts, vert_edge, step, bmin_pad)
+    for _ in range(10):
+        refiner.update(cu(field(refiner.v.cpu().numpy()), dev))
+    got = refiner.result().cpu().numpy()
+    np.testing.assert_array_equal(got, ref)
+    assert np.abs(field(got)).max() < 1e-4
+
+
+def test_predict_step_writes_a_mesh(dev, net, oracle, weights, tmp_path):
+    """`pps.py rec` path end to end on the device (source/poco_model.py:183-273): encoder, region-grown volume, marching cubes,
+    refinement, cleaning, de-normalisation of a single-file input, PLY export  --  with an occupancy head whose sign is the analytic
+    sphere (random-init weights have no surface), so that the mesh can be checked: closed, radius 0.4 in the input frame"""
+    import ppsurf_b200
+    from ppsurf_b200 import mesh as mesh_utils
+    pts_file = str(tmp_path / 'sphere.npy')
+    raw = oracle.synthetic_cloud(9000, seed=3) * 3.0 + np.array([10.0, -2.0, 5.0], dtype=np.float32)
+    np.save(pts_file, raw)
+    center, scale = mesh_utils.get_points_normalization_info(raw.astype(np.float64), 0.05)
+    pts_ms = ((raw - center) / scale).astype(np.float32)
+    model = ppsurf_b200.PPSurfModel(256, ['imp_surf_sign'], 3, 2, 64, 0.0, False, pts_file, str(tmp_path / 'results'), 0.05, 't', 256,
+                                    2, 5000, 33, 50, 50000, 10, 0)
+    model.network.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in weights.items()}, strict=True)
+    model = model.to(dev)
+    r_ms = 0.4 * 3.0 / scale
+    real_occupancy = model.occupancy
+    calls = []
+
+    def occupancy(decoder, q):
+        calls.append(int(q.shape[0]))
+        real = real_occupancy(decoder, q)  # the real decode runs (and must be finite); its sign is replaced by the sphere's
+        assert torch.isfinite(real).all()
+        return torch.tanh(40.0 * (q.norm(dim=1) - r_ms))
+
+    model.occupancy = occupancy
+    assert model.predict_step({'pts_ms': cu(pts_ms[None], dev), 'pc_file_in': [pts_file]}, 0) == 0
+    out = os.path.join(str(tmp_path / 'results'), 'sphere.npy', 'sphere.npy.ply')
+    assert os.path.exists(out) and len(calls) > 10
+    verts = mesh_utils.read_ply_vertices(out)
+    radius = np.linalg.norm(verts - center, axis=1)
+    assert verts.shape[0] > 500 and np.abs(radius - 1.2).max() < 2e-3  # bisection: step / 2^10 in model space, times the scale
