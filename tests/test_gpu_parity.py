@@ -797,3 +797,36 @@ def test_predict_step_writes_a_mesh(dev, net, oracle, weights, tmp_path):
     verts = mesh_utils.read_ply_vertices(out)
     radius = np.linalg.norm(verts - center, axis=1)
     assert verts.shape[0] > 500 and np.abs(radius - 1.2).max() < 2e-3  # bisection: step / 2^10 in model space, times the scale
+
+
+def test_prepare_batch_on_device(dev, net, oracle, weights):
+    """f4: the DataLoader workers' per-item CPU work (kd-tree patches, patch normalisation, get_data_poco) for a collated batch of two
+    clouds on the device: labels, exact projection neighbours, bit-exact patches, index tensors equal to the oracle kNN on the
+    sampled supports; the prepared dict drives network.forward like the reference's batch does"""
+    from ppsurf_b200 import data_pipeline
+    rng = np.random.default_rng(31)
+    n, q = 4200, 150
+    pts = np.stack([oracle.synthetic_cloud(n, seed=41), oracle.synthetic_cloud(n, seed=42) * 0.9])
+    raw = np.stack([np.concatenate([p, p[:800] + 0.001]) for p in pts]).astype(np.float32)  # the raw cloud is denser than the subsample
+    qry = np.stack([(p[rng.integers(0, n, q)] + 0.03 * rng.standard_normal((q, 3))).astype(np.float32) for p in pts])
+    dist = (np.linalg.norm(qry, axis=2) - np.array([0.4, 0.36])[:, None]).astype(np.float32)
+    dist[0, :5] = 0.0
+    net.sampling_seed = 5
+    batch = data_pipeline.prepare_batch(net, {'pts_ms': torch.from_numpy(pts), 'pts_query_ms': torch.from_numpy(qry),
+                                              'pts_raw_ms': torch.from_numpy(raw), 'imp_surf_dist_ms': torch.from_numpy(dist)})
+    np.testing.assert_array_equal(batch['occ'].cpu().numpy(), (dist > 0).astype(np.int64))
+    assert tuple(batch['pts'].shape) == (2, 3, n) and tuple(batch['pts_query'].shape) == (2, 3, q)
+    assert batch['proj_ids'].dtype == torch.int64 and tuple(batch['pts_local_ps'].shape) == (2, q, 50, 3)
+    for b in range(2):
+        assert_knn_equal(oracle, pts[b], qry[b], batch['proj_ids'][b].cpu().numpy(), None, oracle.knn(pts[b], qry[b], 64)[0])
+        ref_loc = oracle.get_pts_local_ps(raw[b], qry[b], 50)
+        np.testing.assert_array_equal(np.sort(batch['pts_local_ps'][b].cpu().numpy(), axis=1), np.sort(ref_loc, axis=1))
+        sup1 = batch['support1'][b].T.cpu().numpy()
+        assert_knn_equal(oracle, pts[b], sup1, batch['ids01'][b].cpu().numpy(), None, oracle.knn(pts[b], sup1, 16)[0])
+    logits = net.forward(dict(batch))
+    assert tuple(logits.shape) == (2, 2, q) and torch.isfinite(logits).all()
+    ref_in = {k: v.cpu().numpy() for k, v in batch.items() if isinstance(v, torch.Tensor)
+              and k.startswith(('pts', 'support', 'ids', 'proj_ids'))}
+    ref_in['pts_query'] = qry  # the oracle takes the queries as [B,Q,3]
+    ref = oracle.network_forward(weights, ref_in)
+    assert np.abs(logits.cpu().numpy() - ref).max() < LOGIT_TOL
