@@ -167,7 +167,8 @@ void pps_debug_tc_profile(long long* counters);
 /* retired tuning knob (no-op, kept for ABI stability) */
 void pps_debug_tc_cluster(int cs);
 /* Split-fp16 terms of the tensor-core global branch (pass ablation, profiles/r02_pass_ablation.md): bit 3*layer + t with layer
- * 0 = fc2, 1 = fc3, 2 = fc_query and t = 0: x_hi*w_hi (always on), 1: x_lo*w_hi, 2: x_hi*w_lo.  Default 0x1FF.  mask < 0 only
+ * 0 = fc2, 1 = fc3, 2 = fc_query and t = 0: x_hi*w_hi (always on), 1: x_lo*w_hi, 2: x_hi*w_lo.  Default 0x0FF (fc_query without its
+ * weight-lo term: 1e-6 on the logits, 7 % of the kernel); 0x1FF = three terms everywhere.  mask < 0 only
  * reads.  Returns the previous mask. */
 int pps_decoder_tc_terms(int mask);
 /* debug: number of CTA pairs (2-CTA clusters) of the projection kernel the device holds at once */

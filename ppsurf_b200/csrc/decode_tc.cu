@@ -26,8 +26,16 @@ constexpr int kABytes = kKB * kALbo;        // 66048
 constexpr int kStageBytes = 8192;           // ring slot = what ONE CTA of the pair holds of a k16 step: 128 weight rows, hi 4 KB + lo 4 KB
                                             // (fc2 / fc3: this CTA's half of the 256 output features; fc_query as the M operand:
                                             // 64 zero rows + 64 heads, the same in both CTAs)
-constexpr int kStages = 10;
+constexpr int kSub = 1;                      // k16 steps per ring slot.  2 was measured (one full-wait + one commit per two steps): the
+                                            // one-term ablation kernel gains 20 %, the product kernel LOSES 11 % (30.9 k vs 27.7 k cycles per
+                                            // tile: coarser slot release, later refills) -- the product is bound by MMA execution, not by the loop
+constexpr int kSlotBytes = kSub * kStageBytes;
+constexpr int kStages = 10 / kSub;
 constexpr int kKSteps = kC / 16;            // 16 k16 steps per layer
+// split-fp16 terms the product kernel issues, bit 3*layer + t (t = 0: x_hi w_hi, 1: x_lo w_hi, 2: x_hi w_lo): three terms for fc2 and
+// fc3, two for fc_query (its weight-lo term changes the logits by 1e-6, profiles/r02_pass_ablation.md; the kernel is bound by MMA
+// execution, ~151 cycles per M256 N256 K16 instruction, so one MMA less per fc_query step is 7 % of the tile)
+constexpr uint32_t kProductTerms = 0x0FFu;
 constexpr int kChunks = 4;                  // a layer's K range is released to the MMA warp in 4 chunks of 64 columns
 constexpr int kGWarps = 8;                  // gather + fc2/fc3 epilogues
 constexpr int kSWarps = 6;                  // softmax + attention pooling
@@ -39,7 +47,7 @@ constexpr int kThreads = 64 + kGThreads + kSThreads;  // 512
 constexpr int kOffAhi = 0;
 constexpr int kOffAlo = kOffAhi + kABytes;
 constexpr int kOffRing = kOffAlo + kABytes;                  // 132096
-constexpr int kOffBias = kOffRing + kStages * kStageBytes;   // 214016: b2[256] b3[256] bq[64]
+constexpr int kOffBias = kOffRing + kStages * kSlotBytes;   // 214016: b2[256] b3[256] bq[64]
 constexpr int kOffAttp = kOffBias + (256 + 256 + 64) * 4;    // 216320: [head half][query][64] partial head sums
 constexpr int kOffPool = kOffAttp + 2 * 2 * 64 * 4;          // 217344: [lane group][256] partial pooled sums
 constexpr int kOffW1 = kOffPool + 4 * 256 * 4;               // 221440: fc1 xyz weights [256][3]
@@ -150,11 +158,14 @@ __global__ void __launch_bounds__(kThreads, 1)
                     const uint8_t* src = layer < 2 ? wpack + (size_t)layer * kKSteps * 2 * kStageBytes + crank * kStageBytes
                                                    : wpack + (size_t)2 * kKSteps * 2 * kStageBytes;
                     const uint32_t stride = layer < 2 ? 2 * kStageBytes : kStageBytes;
-                    for (int s = 0; s < kKSteps; ++s) {
+                    for (int s = 0; s < kKSteps / kSub; ++s) {
                         mbar_wait(bar_empty + 8 * slot, phase ^ 1);
-                        mbar_expect_tx(bar_full + 8 * slot, kStageBytes);
-                        bulk_copy(sbase + kOffRing + slot * kStageBytes, src, kStageBytes, bar_full + 8 * slot);
-                        src += stride;
+                        mbar_expect_tx(bar_full + 8 * slot, kSlotBytes);
+#pragma unroll
+                        for (int sub = 0; sub < kSub; ++sub) {
+                            bulk_copy(sbase + kOffRing + slot * kSlotBytes + sub * kStageBytes, src, kStageBytes, bar_full + 8 * slot);
+                            src += stride;
+                        }
                         if (++slot == kStages) {
                             slot = 0;
                             phase ^= 1;
@@ -169,6 +180,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             uint32_t slot = 0, phase = 0, chunk_phase = 0;
             long long t_chunk = 0, t_full = 0, t_dfree = 0, t_total = tick<PROF>();
             for (long long it = 0; it < iters; ++it) {
+#pragma unroll
                 for (int layer = 0; layer < 3; ++layer) {
                     const uint32_t idesc = umma_idesc2(256);
                     const uint32_t dcol = layer == 1 ? 256u : 0u;
@@ -178,10 +190,12 @@ __global__ void __launch_bounds__(kThreads, 1)
                         tc_fence_after();
                         t_dfree += tick<PROF>() - t0;
                     }
-                    for (int s = 0; s < kKSteps; ++s) {
+                    // product kernel: compile-time terms (the layer loop is unrolled); ablation kernel: the runtime mask
+                    const uint32_t lm = ABL ? (term_mask >> (3 * layer)) & 7u : (kProductTerms >> (3 * layer)) & 7u;
+                    for (int sl = 0; sl < kKSteps / kSub; ++sl) {  // one ring slot = kSub k16 steps: one full-wait and one commit per slot
                         long long t0 = tick<PROF>();
-                        if ((s & 3) == 0) {  // operand columns [64c, 64c+64) of BOTH tiles written by the previous stage of the pipeline
-                            mbar_wait_cluster(bar_chunk + 8 * (s >> 2), chunk_phase);
+                        if (((sl * kSub) & 3) == 0) {  // operand columns [64c, 64c+64) of BOTH tiles written by the previous stage of the pipeline
+                            mbar_wait_cluster(bar_chunk + 8 * ((sl * kSub) >> 2), chunk_phase);
                             tc_fence_after();
                         }
                         long long t1 = tick<PROF>();
@@ -189,21 +203,24 @@ __global__ void __launch_bounds__(kThreads, 1)
                                                                         // async proxy -> async proxy, no tcgen05 fence needed)
                         t_chunk += t1 - t0;
                         t_full += tick<PROF>() - t1;
-                        const uint32_t a_off = 2 * s * kALbo;
-                        const uint64_t x_hi = umma_desc(sbase + kOffAhi + a_off, kALbo, 128);
-                        const uint64_t x_lo = umma_desc(sbase + kOffAlo + a_off, kALbo, 128);
-                        const uint32_t wst = sbase + kOffRing + slot * kStageBytes;
-                        const uint64_t w_hi = umma_desc(wst, 128 * 16, 128);
-                        const uint64_t w_lo = umma_desc(wst + 4096, 128 * 16, 128);
-                        const uint32_t lm = ABL ? (term_mask >> (3 * layer)) & 7u : 7u;
-                        if (layer < 2) {  // D[256 rows, 256 features]: B = the two CTAs' 128-feature halves
-                            umma2(tmem + dcol, x_hi, w_hi, idesc, s > 0 ? 1u : 0u);
-                            if (!ABL || (lm & 2u)) umma2(tmem + dcol, x_lo, w_hi, idesc, 1u);
-                            if (!ABL || (lm & 4u)) umma2(tmem + dcol, x_hi, w_lo, idesc, 1u);
-                        } else {  // scores^T[64 + head, row of either tile] = Wq[head, :] . h3[row, :]  (both CTAs compute all 256 columns)
-                            umma2(tmem, w_hi, x_hi, idesc, s > 0 ? 1u : 0u);
-                            if (!ABL || (lm & 2u)) umma2(tmem, w_hi, x_lo, idesc, 1u);
-                            if (!ABL || (lm & 4u)) umma2(tmem, w_lo, x_hi, idesc, 1u);
+#pragma unroll
+                        for (int sub = 0; sub < kSub; ++sub) {
+                            const int s = sl * kSub + sub;
+                            const uint32_t a_off = 2 * s * kALbo;
+                            const uint64_t x_hi = umma_desc(sbase + kOffAhi + a_off, kALbo, 128);
+                            const uint64_t x_lo = umma_desc(sbase + kOffAlo + a_off, kALbo, 128);
+                            const uint32_t wst = sbase + kOffRing + slot * kSlotBytes + sub * kStageBytes;
+                            const uint64_t w_hi = umma_desc(wst, 128 * 16, 128);
+                            const uint64_t w_lo = umma_desc(wst + 4096, 128 * 16, 128);
+                            if (layer < 2) {  // D[256 rows, 256 features]: B = the two CTAs' 128-feature halves
+                                umma2(tmem + dcol, x_hi, w_hi, idesc, s > 0 ? 1u : 0u);
+                                if (lm & 2u) umma2(tmem + dcol, x_lo, w_hi, idesc, 1u);
+                                if (lm & 4u) umma2(tmem + dcol, x_hi, w_lo, idesc, 1u);
+                            } else {  // scores^T[64 + head, row of either tile] = Wq[head, :] . h3[row, :]  (both CTAs compute all 256 columns)
+                                umma2(tmem, w_hi, x_hi, idesc, s > 0 ? 1u : 0u);
+                                if (lm & 2u) umma2(tmem, w_hi, x_lo, idesc, 1u);
+                                if (lm & 4u) umma2(tmem, w_lo, x_hi, idesc, 1u);
+                            }
                         }
                         tc_commit2(bar_empty + 8 * slot);  // frees the ring slot of both CTAs when these MMAs have read it
                         if (++slot == kStages) {
@@ -225,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         } else if (lane == 0) {
             // ---------------------------------------------------------------- peer: tell the leader when my half of a stage is here
             uint32_t slot = 0, phase = 0;
-            for (long long n = 0; n < iters * 3 * kKSteps; ++n) {
+            for (long long n = 0; n < iters * 3 * (kKSteps / kSub); ++n) {
                 mbar_wait(bar_full + 8 * slot, phase);
                 mbar_arrive_cluster(lead_full + 8 * slot);
                 if (++slot == kStages) {
@@ -518,7 +535,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 }  // namespace tc
 
 static long long* g_tc_prof = nullptr;
-static uint32_t g_tc_terms = 0x1FFu;  // split-fp16 terms per layer of projection_tc_kernel (pps_decoder_tc_terms)
+static uint32_t g_tc_terms = tc::kProductTerms;  // split-fp16 terms per layer of projection_tc_kernel (pps_decoder_tc_terms)
 void set_tc_terms(uint32_t m) { g_tc_terms = m & 0x1FFu; }
 uint32_t get_tc_terms() { return g_tc_terms; }  // device buffer of 128 counters, set by pps_debug_tc_profile
 
@@ -535,6 +552,7 @@ int projection_tc_impl(const pps_decoder_weights* w, const float* table, const f
         PPS_CUDA(cudaFuncSetAttribute(tc::projection_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
         PPS_CUDA(cudaFuncSetAttribute(tc::projection_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
         PPS_CUDA(cudaFuncSetAttribute(tc::projection_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+        PPS_CUDA(cudaFuncSetAttribute(tc::projection_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
         configured = true;
     }
     const long long npt = (q + 3) / 4;  // pair-tiles of 4 queries
@@ -555,10 +573,13 @@ int projection_tc_impl(const pps_decoder_weights* w, const float* table, const f
     cfg.numAttrs = 1;
     profile_begin(st);
     const uint32_t mask = g_tc_terms;
-    if (g_tc_prof)  // instrumented build, tools/tc_phase_profile.py only
+    if (g_tc_prof && mask != tc::kProductTerms)  // instrumented ablation build
+        PPS_CUDA(cudaLaunchKernelEx(&cfg, tc::projection_tc_kernel<true, true>, table, queries, idx, k_stride, nq, wp, w->b2, w->b3, w->bq,
+                                    w->w1_xyz, pooled, g_tc_prof, mask));
+    else if (g_tc_prof)  // instrumented build, tools/tc_phase_profile.py only
         PPS_CUDA(cudaLaunchKernelEx(&cfg, tc::projection_tc_kernel<true, false>, table, queries, idx, k_stride, nq, wp, w->b2, w->b3, w->bq,
                                     w->w1_xyz, pooled, g_tc_prof, mask));
-    else if (mask != 0x1FFu)  // pass-ablation build (tools/pass_ablation.py)
+    else if (mask != tc::kProductTerms)  // pass-ablation build (tools/pass_ablation.py)
         PPS_CUDA(cudaLaunchKernelEx(&cfg, tc::projection_tc_kernel<false, true>, table, queries, idx, k_stride, nq, wp, w->b2, w->b3, w->bq,
                                     w->w1_xyz, pooled, g_tc_prof, mask));
     else
@@ -596,7 +617,8 @@ extern "C" int pps_debug_tc_max_clusters(void) {
 // retired debug knob (cluster multicast / weight-stream experiments); kept so that the ABI is stable
 extern "C" void pps_debug_tc_cluster(int) {}
 // split-fp16 terms of the global branch's three GEMM layers: bit 3*layer + t, layer 0 = fc2, 1 = fc3, 2 = fc_query; t = 0: x_hi w_hi
-// (always issued), 1: x_lo w_hi, 2: x_hi w_lo.  0x1FF (default) = three terms everywhere.  Returns the previous mask.
+// (always issued), 1: x_lo w_hi, 2: x_hi w_lo.  Default 0x0FF: three terms for fc2 / fc3, two for fc_query; 0x1FF = three everywhere.
+// Returns the previous mask.
 extern "C" int pps_decoder_tc_terms(int mask) {
     const int old = (int)pps::get_tc_terms();
     if (mask >= 0) pps::set_tc_terms((uint32_t)mask | 0x49u);

@@ -25,8 +25,9 @@ tiles = 18944 // 4 // 74
 names = ['mma_total', 'mma_wait_chunk', 'mma_wait_weights', 'mma_wait_sgroup', 'g_gather', 'g_wait', 'g_E2E3', 's_wait', 's_softmax', 's_pool']
 ref = None
 print('CTA pairs resident at once:', _lib.lib.pps_debug_tc_max_clusters())
-for cs in (0,):
+for cs, mask in ((0, 0x1FF), (0, 0x049), (0, 0x0DB)):  # all three terms, hh only, hh + hl
     _lib.lib.pps_debug_tc_cluster(cs)
+    _lib.lib.pps_decoder_tc_terms(mask)
     for it in range(3):
         _lib.lib.pps_debug_tc_profile(counters.data_ptr())
         out = dec.projection(qry, idx)
@@ -39,10 +40,11 @@ for cs in (0,):
     torch.cuda.synchronize()
     c = counters.cpu().numpy()
     ref = out if ref is None else ref
-    print('cluster size {}: {:.1f} us per chunk (incl. value matrix), max |diff| vs cs=1 {:.2e}'.format(
-        cs, e0.elapsed_time(e1) * 200, float((out - ref).abs().max())))
+    print('term mask {:#x}: {:.1f} us per chunk (incl. value matrix), max |diff| vs all terms {:.2e}'.format(
+        mask, e0.elapsed_time(e1) * 200, float((out - ref).abs().max())))
     print('   ' + '  '.join('{}={:.0f}'.format(k, v / tiles) for k, v in zip(names, c)))
     per_pair = c[32:32 + 74] / tiles
     print('   per-pair cycles per tile: min {:.0f} median {:.0f} max {:.0f}; slowest pairs {}'.format(per_pair.min(), np.median(per_pair), per_pair.max(), np.argsort(per_pair)[-5:]))
 _lib.lib.pps_debug_tc_profile(None)
 _lib.lib.pps_debug_tc_cluster(0)
+_lib.lib.pps_decoder_tc_terms(0x0FF)
