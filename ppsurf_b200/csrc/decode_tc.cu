@@ -57,14 +57,17 @@ constexpr int kNumBars = 2 * kStages + 3 + kChunks + 2;
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmem + 16;
 
-// packed weights in global memory: [fc2: 16 stages x (CTA 0 half, CTA 1 half)][fc3: likewise][fc_query: 16 stages]
-constexpr size_t kPackBytes = size_t(2) * kKSteps * 2 * kStageBytes + size_t(kKSteps) * kStageBytes;
+// packed weights in global memory: [fc2: 16 stages x (CTA 0 half, CTA 1 half)][fc3: likewise][fc_query: 4 slots x (CTA 0: heads 0..31,
+// CTA 1: heads 32..63), a slot = the 4 k16 steps of one 64-column chunk, 2 KB each]
+constexpr int kQSub = 4;                    // k16 steps of fc_query per ring slot (N = 64: 32 weight rows per CTA, 2 KB per step)
+constexpr int kQStep = 2048;
+constexpr size_t kPackBytes = size_t(2) * kKSteps * 2 * kStageBytes + size_t(kChunks) * 2 * kStageBytes;
 
 __device__ __forceinline__ void g_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kGThreads) : "memory"); }
 __device__ __forceinline__ void s_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(kSThreads) : "memory"); }
 
 // Pipeline of one tile (2 queries x 64 neighbours):
-//   gather -> fc2 (D0) -> E2 -> fc3 (D1) -> E3 -> fc_query^T (D0) -> softmax / head mean / pooling from D1
+//   gather -> fc2 (D0) -> E2 -> fc3 (D1) -> E3 -> fc_query (D0, columns 0..63) -> softmax / head mean / pooling from D1
 // The kernel runs as CTA PAIRS (cluster of 2, tcgen05 cta_group::2): every MMA is M=256 = the two CTAs' 128-row tiles, each CTA
 // holds only its half of the weight stage (B operand) and the pair shares it, which halves the shared-memory traffic and the
 // L2 weight stream per row -- with one CTA per MMA the kernel is shared-memory-bandwidth bound (36 KB of operand reads + 16 KB
@@ -79,8 +82,10 @@ __device__ __forceinline__ void s_barrier() { asm volatile("bar.sync 2, %0;" ::"
 //   warps 10..15 S group: softmax over the neighbours, head mean and the attention pooling of tile t run while the G group and
 //                the tensor pipe are already working on tile t+1 (D0 is handed back as soon as the scores are in registers,
 //                D1 when the pooling has read fc3's accumulator).
-// fc_query is computed TRANSPOSED (heads on TMEM lanes 64..127, the tile's rows on the columns): the softmax over a query's
-// 64 neighbours is then a reduction inside one thread; the mean over heads is a recursive halving across lanes.
+// fc_query is a plain M=256 x N=64 product (heads on the accumulator columns; round 1 computed it transposed with the 64 heads
+// padded to M=128 and both CTAs computing all 256 columns -- four times the MMA work of this form, and the kernel is bound by MMA
+// execution).  The softmax over a query's 64 neighbours is then a reduction over TMEM lanes = over the 32 lanes of a warp (recursive
+// halving: lane l ends with heads 2l, 2l+1) and over the two warps of the query (shared memory); the exponentials wait in TMEM.
 // cycle counter of the instrumented build only: the product kernel (PROF = false) carries no clock reads -- the MMA issuer's loop
 // is on the critical path (a stray branch in it cost 8 % of the kernel)
 template <bool PROF>
@@ -154,11 +159,12 @@ __global__ void __launch_bounds__(kThreads, 1)
             uint32_t slot = 0, phase = 0;
             for (long long it = 0; it < iters; ++it) {
                 for (int layer = 0; layer < 3; ++layer) {
-                    // fc2 / fc3: this CTA's half of every stage; fc_query: the whole (128-row) stage
+                    // fc2 / fc3: this CTA's half (128 features) of every k16 stage; fc_query: this CTA's 32 heads, one slot per chunk
+                    const int nslots = layer < 2 ? kKSteps / kSub : kChunks;
                     const uint8_t* src = layer < 2 ? wpack + (size_t)layer * kKSteps * 2 * kStageBytes + crank * kStageBytes
-                                                   : wpack + (size_t)2 * kKSteps * 2 * kStageBytes;
-                    const uint32_t stride = layer < 2 ? 2 * kStageBytes : kStageBytes;
-                    for (int s = 0; s < kKSteps / kSub; ++s) {
+                                                   : wpack + (size_t)2 * kKSteps * 2 * kStageBytes + crank * kStageBytes;
+                    const uint32_t stride = 2 * kStageBytes;
+                    for (int s = 0; s < nslots; ++s) {
                         mbar_wait(bar_empty + 8 * slot, phase ^ 1);
                         mbar_expect_tx(bar_full + 8 * slot, kSlotBytes);
 #pragma unroll
@@ -192,40 +198,68 @@ __global__ void __launch_bounds__(kThreads, 1)
                     }
                     // product kernel: compile-time terms (the layer loop is unrolled); ablation kernel: the runtime mask
                     const uint32_t lm = ABL ? (term_mask >> (3 * layer)) & 7u : (kProductTerms >> (3 * layer)) & 7u;
-                    for (int sl = 0; sl < kKSteps / kSub; ++sl) {  // one ring slot = kSub k16 steps: one full-wait and one commit per slot
-                        long long t0 = tick<PROF>();
-                        if (((sl * kSub) & 3) == 0) {  // operand columns [64c, 64c+64) of BOTH tiles written by the previous stage of the pipeline
-                            mbar_wait_cluster(bar_chunk + 8 * ((sl * kSub) >> 2), chunk_phase);
-                            tc_fence_after();
-                        }
-                        long long t1 = tick<PROF>();
-                        mbar_wait_cluster(bar_full + 8 * slot, phase);  // both halves of the weight stage have landed (TMA writes:
-                                                                        // async proxy -> async proxy, no tcgen05 fence needed)
-                        t_chunk += t1 - t0;
-                        t_full += tick<PROF>() - t1;
+                    if (layer < 2) {
+                        for (int sl = 0; sl < kKSteps / kSub; ++sl) {  // one ring slot = kSub k16 steps: one full-wait and one commit per slot
+                            long long t0 = tick<PROF>();
+                            if (((sl * kSub) & 3) == 0) {  // operand columns [64c, 64c+64) of BOTH tiles written by the previous stage of the pipeline
+                                mbar_wait_cluster(bar_chunk + 8 * ((sl * kSub) >> 2), chunk_phase);
+                                tc_fence_after();
+                            }
+                            long long t1 = tick<PROF>();
+                            mbar_wait_cluster(bar_full + 8 * slot, phase);  // both halves of the weight stage have landed (TMA writes:
+                                                                            // async proxy -> async proxy, no tcgen05 fence needed)
+                            t_chunk += t1 - t0;
+                            t_full += tick<PROF>() - t1;
 #pragma unroll
-                        for (int sub = 0; sub < kSub; ++sub) {
-                            const int s = sl * kSub + sub;
-                            const uint32_t a_off = 2 * s * kALbo;
-                            const uint64_t x_hi = umma_desc(sbase + kOffAhi + a_off, kALbo, 128);
-                            const uint64_t x_lo = umma_desc(sbase + kOffAlo + a_off, kALbo, 128);
-                            const uint32_t wst = sbase + kOffRing + slot * kSlotBytes + sub * kStageBytes;
-                            const uint64_t w_hi = umma_desc(wst, 128 * 16, 128);
-                            const uint64_t w_lo = umma_desc(wst + 4096, 128 * 16, 128);
-                            if (layer < 2) {  // D[256 rows, 256 features]: B = the two CTAs' 128-feature halves
+                            for (int sub = 0; sub < kSub; ++sub) {
+                                const int s = sl * kSub + sub;
+                                const uint32_t a_off = 2 * s * kALbo;
+                                const uint64_t x_hi = umma_desc(sbase + kOffAhi + a_off, kALbo, 128);
+                                const uint64_t x_lo = umma_desc(sbase + kOffAlo + a_off, kALbo, 128);
+                                const uint32_t wst = sbase + kOffRing + slot * kSlotBytes + sub * kStageBytes;
+                                const uint64_t w_hi = umma_desc(wst, 128 * 16, 128);
+                                const uint64_t w_lo = umma_desc(wst + 4096, 128 * 16, 128);
+                                // D[256 rows, 256 features]: B = the two CTAs' 128-feature halves
                                 umma2(tmem + dcol, x_hi, w_hi, idesc, s > 0 ? 1u : 0u);
                                 if (lm & 2u) umma2(tmem + dcol, x_lo, w_hi, idesc, 1u);
                                 if (lm & 4u) umma2(tmem + dcol, x_hi, w_lo, idesc, 1u);
-                            } else {  // scores^T[64 + head, row of either tile] = Wq[head, :] . h3[row, :]  (both CTAs compute all 256 columns)
-                                umma2(tmem, w_hi, x_hi, idesc, s > 0 ? 1u : 0u);
-                                if (lm & 2u) umma2(tmem, w_hi, x_lo, idesc, 1u);
-                                if (lm & 4u) umma2(tmem, w_lo, x_hi, idesc, 1u);
+                            }
+                            tc_commit2(bar_empty + 8 * slot);  // frees the ring slot of both CTAs when these MMAs have read it
+                            if (++slot == kStages) {
+                                slot = 0;
+                                phase ^= 1;
                             }
                         }
-                        tc_commit2(bar_empty + 8 * slot);  // frees the ring slot of both CTAs when these MMAs have read it
-                        if (++slot == kStages) {
-                            slot = 0;
-                            phase ^= 1;
+                    } else {
+                        // fc_query: scores[256 rows, 64 heads] at D0 columns 0..63, B = the two CTAs' 32-head halves; one ring slot per
+                        // 64-column chunk (4 k16 steps of 2 KB)
+                        const uint32_t idesc_q = umma_idesc2(kHeads);
+                        for (int c = 0; c < kChunks; ++c) {
+                            long long t0 = tick<PROF>();
+                            mbar_wait_cluster(bar_chunk + 8 * c, chunk_phase);
+                            tc_fence_after();
+                            long long t1 = tick<PROF>();
+                            mbar_wait_cluster(bar_full + 8 * slot, phase);
+                            t_chunk += t1 - t0;
+                            t_full += tick<PROF>() - t1;
+#pragma unroll
+                            for (int sub = 0; sub < kQSub; ++sub) {
+                                const int s = c * kQSub + sub;
+                                const uint32_t a_off = 2 * s * kALbo;
+                                const uint64_t x_hi = umma_desc(sbase + kOffAhi + a_off, kALbo, 128);
+                                const uint64_t x_lo = umma_desc(sbase + kOffAlo + a_off, kALbo, 128);
+                                const uint32_t wst = sbase + kOffRing + slot * kSlotBytes + sub * kQStep;
+                                const uint64_t w_hi = umma_desc(wst, 32 * 16, 128);
+                                const uint64_t w_lo = umma_desc(wst + kQStep / 2, 32 * 16, 128);
+                                umma2(tmem, x_hi, w_hi, idesc_q, s > 0 ? 1u : 0u);
+                                if (lm & 2u) umma2(tmem, x_lo, w_hi, idesc_q, 1u);
+                                if (lm & 4u) umma2(tmem, x_hi, w_lo, idesc_q, 1u);
+                            }
+                            tc_commit2(bar_empty + 8 * slot);
+                            if (++slot == kStages) {
+                                slot = 0;
+                                phase ^= 1;
+                            }
                         }
                     }
                     tc_commit2(bar_acc + 8 * layer);  // accumulator of this layer complete, in both CTAs
@@ -242,7 +276,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         } else if (lane == 0) {
             // ---------------------------------------------------------------- peer: tell the leader when my half of a stage is here
             uint32_t slot = 0, phase = 0;
-            for (long long n = 0; n < iters * 3 * (kKSteps / kSub); ++n) {
+            for (long long n = 0; n < iters * (2 * (kKSteps / kSub) + kChunks); ++n) {
                 mbar_wait(bar_full + 8 * slot, phase);
                 mbar_arrive_cluster(lead_full + 8 * slot);
                 if (++slot == kStages) {
@@ -397,12 +431,26 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int st = tid - 64 - kGThreads;   // 0..191
         const int lane_grp = warp & 3;
         const int row = lane_grp * 32 + lane;
-        const bool heads = lane_grp >= 2;      // scores^T lives on lanes 64..127: two warps per lane group, one per query
-        const int sq = sw >> 2;                // the query whose softmax this warp computes (heads only)
-        // pooling: rows 0..63 (lane groups 0,1) have one warp each -> all 8 column blocks; rows 64..127 have two warps each
-        const int cb0 = heads ? 4 * sq : 0, cb1 = heads ? 4 * sq + 4 : 8;
+        const bool soft = sw < 4;              // one softmax warp per TMEM lane group (warps 10..13 = lane groups 2, 3, 0, 1)
+        const bool two = lane_grp >= 2;        // lane groups 2, 3 have two warps: they split the pooling's column blocks
+        const int sq = sw >> 2;
+        const int cb0 = two ? 4 * sq : 0, cb1 = two ? 4 * sq + 4 : 8;
+        float* s_red = s_pool;                 // [2][4 lane groups][64 heads]: per-warp maxima, then per-warp sums (free until the pooling)
+        float* s_att = s_attp;                 // [128] attention weight of every row of the tile
+        const uint32_t trow = tmem + ((uint32_t)(lane_grp * 32) << 16);
         long long t_wait = 0, t_soft = 0, t_pool = 0, t_mark = tick<PROF>();
-        const uint32_t score_col = 128u * crank;  // scores^T columns = rows of the pair's two tiles; mine start here
+        auto load64 = [&](float (&e)[64]) {
+            uint32_t v0[32], v1[32];
+            tmem_ld32_issue(trow, v0);
+            tmem_ld32_issue(trow + 32, v1);
+            tmem_ld_wait(v0);
+            tmem_ld_wait(v1);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                e[j] = __uint_as_float(v0[j]);
+                e[32 + j] = __uint_as_float(v1[j]);
+            }
+        };
         for (long long it = 0; it < iters; ++it) {
             const long long tile = tile0 + it * tile_step;
             mbar_wait(bar_acc + 16, (uint32_t)(it & 1));
@@ -412,48 +460,80 @@ __global__ void __launch_bounds__(kThreads, 1)
                 t_wait += now - t_mark;
                 t_mark = now;
             }
-            if (heads) {
-                float e[64];
-                {
-                    uint32_t v0[32], v1[32];
-                    tmem_ld32_issue(tmem + ((uint32_t)(lane_grp * 32) << 16) + score_col + sq * 64, v0);
-                    tmem_ld32_issue(tmem + ((uint32_t)(lane_grp * 32) << 16) + score_col + sq * 64 + 32, v1);
-                    tmem_ld_wait(v0);
-                    tmem_ld_wait(v1);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        e[j] = __uint_as_float(v0[j]);
-                        e[32 + j] = __uint_as_float(v1[j]);
-                    }
-                }
+            // softmax over the 64 neighbours of a query = the 64 rows of lane groups {0,1} or {2,3}; thread = row, 64 heads each (the
+            // head's bias shifts every score of the head alike and cancels).  Reductions over a warp's 32 rows: recursive halving on a
+            // 32-head COPY (lane l ends with head l of the half), so the scores / exponentials stay in registers and D0 is handed back
+            // right after the one TMEM load, as early as in the transposed form
+            float e[64];
+            if (soft) {
+                load64(e);
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(lead_d0free);  // fc2 of the next tile may overwrite the scores
-                // softmax over the 64 neighbours (the head's bias shifts every score alike and cancels)
-                float m = e[0];
+                if (lane == 0) mbar_arrive_cluster(lead_d0free);  // fc2 of the next tile may overwrite D0
 #pragma unroll
-                for (int j = 1; j < 64; ++j) m = fmaxf(m, e[j]);
-                float sum = 0.f;
+                for (int hf = 0; hf < 2; ++hf) {
+                    float t[32];
 #pragma unroll
-                for (int j = 0; j < 64; ++j) {
-                    e[j] = expf(e[j] - m);
-                    sum += e[j];
-                }
-                const float inv = 1.f / sum;
+                    for (int i = 0; i < 32; ++i) t[i] = e[32 * hf + i];
 #pragma unroll
-                for (int j = 0; j < 64; ++j) e[j] *= inv;
-                // sum over this warp's 32 heads: recursive halving, lane l ends with neighbours 2l and 2l+1
+                    for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
+                        const bool upper = (lane & off) != 0;
 #pragma unroll
-                for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
-                    const bool upper = (lane & off) != 0;
-#pragma unroll
-                    for (int i = 0; i < n; ++i) {
-                        const float send = upper ? e[i] : e[i + n];
-                        const float keep = upper ? e[i + n] : e[i];
-                        e[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                        for (int i = 0; i < n; ++i) {
+                            const float send = upper ? t[i] : t[i + n];
+                            const float keep = upper ? t[i + n] : t[i];
+                            t[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, off));
+                        }
                     }
+                    s_red[lane_grp * 64 + 32 * hf + lane] = t[0];
                 }
-                *reinterpret_cast<float2*>(s_attp + ((lane_grp - 2) * 2 + sq) * 64 + 2 * lane) = make_float2(e[0], e[1]);
+            }
+            s_barrier();
+            if (soft) {
+                const float* m0 = s_red + lane_grp * 64;
+                const float* m1 = s_red + (lane_grp ^ 1) * 64;  // the other 32 rows of the same query
+#pragma unroll
+                for (int h = 0; h < 64; h += 4) {
+                    const float4 a = *reinterpret_cast<const float4*>(m0 + h), b = *reinterpret_cast<const float4*>(m1 + h);
+                    // ex2.approx on (score - max) <= 0: relative error 2^-22 plus |x| 2^-24 from the scaling, far inside the contract;
+                    // the accurate expf costs five times the issue slots and this warp has a scheduler to itself
+                    e[h] = __expf(e[h] - fmaxf(a.x, b.x));
+                    e[h + 1] = __expf(e[h + 1] - fmaxf(a.y, b.y));
+                    e[h + 2] = __expf(e[h + 2] - fmaxf(a.z, b.z));
+                    e[h + 3] = __expf(e[h + 3] - fmaxf(a.w, b.w));
+                }
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    float t[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) t[i] = e[32 * hf + i];
+#pragma unroll
+                    for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
+                        const bool upper = (lane & off) != 0;
+#pragma unroll
+                        for (int i = 0; i < n; ++i) {
+                            const float send = upper ? t[i] : t[i + n];
+                            const float keep = upper ? t[i + n] : t[i];
+                            t[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                        }
+                    }
+                    s_red[256 + lane_grp * 64 + 32 * hf + lane] = t[0];
+                }
+            }
+            s_barrier();
+            if (soft) {
+                const float* z0 = s_red + 256 + lane_grp * 64;
+                const float* z1 = s_red + 256 + (lane_grp ^ 1) * 64;
+                float a = 0.f;
+#pragma unroll
+                for (int h = 0; h < 64; h += 4) {
+                    const float4 u = *reinterpret_cast<const float4*>(z0 + h), v = *reinterpret_cast<const float4*>(z1 + h);
+                    a += __fdividef(e[h], u.x + v.x);  // sums are in [1, 64]: rcp.approx + multiply, 1 ulp
+                    a += __fdividef(e[h + 1], u.y + v.y);
+                    a += __fdividef(e[h + 2], u.z + v.z);
+                    a += __fdividef(e[h + 3], u.w + v.w);
+                }
+                s_att[row] = a * (1.f / kHeads);  // mean over the heads of softmax_k
             }
             s_barrier();
             {
@@ -464,7 +544,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             // pooled[q, :] = sum_j att_j * h3[j, :] straight from the fp32 accumulator of fc3 (still in TMEM): every thread
             // scales its row, the 32 rows of a warp are summed by recursive halving (lane l ends with column l of the block)
             {
-                const float a = (s_attp[(row >> 6) * 64 + (row & 63)] + s_attp[(2 + (row >> 6)) * 64 + (row & 63)]) * (1.f / kHeads);
+                const float a = s_att[row];
                 const float* bias = s_bias + 256;
 #pragma unroll 1
                 for (int cb = cb0; cb < cb1; ++cb) {

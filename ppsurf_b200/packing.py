@@ -98,12 +98,17 @@ def pack_decoder(sd, device, k, num_pts_local, prefix='') -> Packed:
     p.put('m2_w', _mat(sd, m + '2.0.weight'), device)
     p.put('m2_b', _f64(sd, m + '2.0.bias'), device)
     if latent == 256 and st.heads == 64:
-        # M operand of the transposed fc_query: 64 zero rows, then the 64 heads (TMEM lanes 64..127)
-        wq_pad = torch.cat([torch.zeros(64, latent, dtype=torch.float64), _mat(sd, g + 'fc_query.weight')])
         def pair_pack(w):  # per k16 stage: [CTA 0: features 0..127 | CTA 1: features 128..255], each hi 4 KB + lo 4 KB
             a, b = tc_pack_matrix(w[:128]).view(16, -1), tc_pack_matrix(w[128:]).view(16, -1)
             return torch.stack([a, b], dim=1).reshape(-1)
-        pack = torch.cat([pair_pack(_mat(sd, g + 'fc2.weight')), pair_pack(_mat(sd, g + 'fc3.weight')), tc_pack_matrix(wq_pad)])
+
+        def query_pack(w):  # fc_query as the N = 64 operand: per 64-column chunk [CTA 0: heads 0..31 | CTA 1: heads 32..63], a CTA's
+            # slot = its 4 k16 steps of 2 KB (hi kb0 | hi kb1 | lo kb0 | lo kb1, 32 rows each)
+            a, b = tc_pack_matrix(w[:32]).view(4, -1), tc_pack_matrix(w[32:]).view(4, -1)
+            return torch.stack([a, b], dim=1).reshape(-1)
+
+        pack = torch.cat([pair_pack(_mat(sd, g + 'fc2.weight')), pair_pack(_mat(sd, g + 'fc3.weight')),
+                          query_pack(_mat(sd, g + 'fc_query.weight'))])
         assert pack.numel() == _lib.lib.pps_decoder_tc_pack_bytes()
         p.tensors['tc_wpack'] = pack.to(device)
         st.tc_wpack = p.tensors['tc_wpack'].data_ptr()

@@ -178,8 +178,9 @@ def test_bench_emits_one_clean_stdout_line():
 def test_tensor_core_pack_layout(weights):
     """The projection kernel's weight pack, decoded on the CPU exactly the way the kernel addresses it: stage s of layer l holds,
     for each CTA r of the pair, rows [128r, 128r+128) of W as [hi k8-block 0 | hi k8-block 1 | lo block 0 | lo block 1] with
-    blocks of [128 rows][8 fp16]; fc_query is ONE 128-row block per stage (64 zero rows, then the 64 heads).  hi + lo must
-    reproduce the fp32 weights to 2^-21 relative."""
+    blocks of [128 rows][8 fp16]; fc_query is the N = 64 operand: slot c (one 64-column chunk) holds, for each CTA r, heads [32r, 32r+32)
+    as four k16 steps of 2 KB [hi block 0 | hi block 1 | lo block 0 | lo block 1], blocks of [32 rows][8 fp16].  hi + lo must reproduce
+    the fp32 weights to 2^-21 relative."""
     from ppsurf_b200 import packing
     sd = {k: torch.from_numpy(np.asarray(v)) for k, v in weights.items()}
     p = packing.pack_decoder(sd, 'cpu', 64, 50)
@@ -201,11 +202,16 @@ def test_tensor_core_pack_layout(weights):
                 assert np.abs(got - ref).max() <= 2.0 ** -20 * np.abs(ref).max()
     wq = np.asarray(weights['projection.fc_query.weight']).reshape(64, 256).astype(np.float32)
     base = 2 * 16 * 2 * stage_elems
-    for s in (0, 9):
-        got = block(base + s * stage_elems, 0)
-        assert np.all(got[:64] == 0.0)
-        assert np.abs(got[64:] - wq[:, 16 * s:16 * s + 16]).max() <= 2.0 ** -20 * np.abs(wq).max()
-    assert pack.size * 2 == 2 * 16 * 16384 + 16 * 8192
+    for c in (0, 3):
+        for r in (0, 1):
+            slot = pack[base + (c * 2 + r) * stage_elems:base + (c * 2 + r + 1) * stage_elems].astype(np.float32)
+            for sub in (0, 2):
+                step = slot[sub * 1024:(sub + 1) * 1024]  # 2 KB = 1024 fp16
+                hi, lo = step[:512].reshape(2, 32, 8), step[512:].reshape(2, 32, 8)
+                got = (hi + lo).transpose(1, 0, 2).reshape(32, 16)
+                k0 = 64 * c + 16 * sub
+                assert np.abs(got - wq[32 * r:32 * r + 32, k0:k0 + 16]).max() <= 2.0 ** -20 * np.abs(wq).max()
+    assert pack.size * 2 == 2 * 16 * 16384 + 4 * 16384
 
 
 def test_latent_schedule_of_the_module():
