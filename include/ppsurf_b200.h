@@ -61,6 +61,10 @@ int pps_profile_read(double* total_ms, long long* brackets);
 size_t pps_knn_index_bytes(int64_t n);
 int pps_knn_build(const float* pts, int64_t n, void* index, size_t index_bytes, void* stream);
 /* idx_out [q,k] int32 (original point numbering), dist2_out [q,k] f32 or NULL */
+/* tuning knob: consecutive queries one warp handles in the seeded search (33 <= k <= 256); returns the previous value */
+int pps_debug_knn_run(int run);
+/* tuning knob: finest octree cells per point of indices built from now on (query an index under the setting it was built with) */
+int pps_debug_knn_cells(int factor);
 int pps_knn_query(const void* index, int64_t n, const float* queries, int64_t q, int k, int32_t* idx_out,
                   float* dist2_out, void* stream);
 

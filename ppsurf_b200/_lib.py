@@ -63,6 +63,8 @@ SIGNATURES = {
     'pps_profile_read': (i32, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]),
     'pps_knn_index_bytes': (size_t, [i64]),
     'pps_knn_build': (i32, [c_f32p, i64, c_voidp, size_t, c_voidp]),
+    'pps_debug_knn_run': (i32, [i32]),
+    'pps_debug_knn_cells': (i32, [i32]),
     'pps_knn_query': (i32, [c_voidp, i64, c_f32p, i64, i32, c_i32p, c_f32p, c_voidp]),
     'pps_patch_normalize': (i32, [c_f32p, c_f32p, c_i32p, c_f32p, i64, i32, i32, c_f32p, c_voidp]),
     'pps_linear': (i32, [c_f32p, c_f32p, c_f32p, c_f32p, c_i32p, c_f32p, i64, i32, i32, i32, i32, i32, c_voidp]),

@@ -30,9 +30,13 @@ struct KnnHeader {
 };
 static_assert(sizeof(KnnHeader) == 64, "header is 64 bytes");
 
+// finest cells per point (pps_debug_knn_cells): the octree depth is the first with 8^l >= factor * n.  Surface clouds occupy a thin
+// shell of the cells: at 16 cells per point (round 1) a leaf of the 100k-point bench cloud holds ~2 points, i.e. 2 of 32 lanes per
+// scan step; 2 cells per point measured 5 % faster on the dense grid (tools/knn_run_probe.py), identical results
+static int g_knn_cell_factor = 2;
 int knn_levels(int64_t n) {
     int l = 2;
-    while (l < kMaxLevels && (int64_t(1) << (3 * l)) < n * 16) ++l;
+    while (l < kMaxLevels && (int64_t(1) << (3 * l)) < n * g_knn_cell_factor) ++l;
     return l;
 }
 
@@ -168,13 +172,13 @@ template <int SLOTS>
 __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restrict__ hdr, const float4* __restrict__ sorted,
                                                        const int* __restrict__ cell_start, const float* __restrict__ queries,
                                                        long long nq, int k, int32_t* __restrict__ idx_out,
-                                                       float* __restrict__ d2_out) {
+                                                       float* __restrict__ d2_out, int run) {
     // per warp: node code, and the node's range in the sorted array (loaded by the parent: no second round trip on the pop)
     __shared__ unsigned int stack_s[8][8 * kMaxLevels + 8];
     __shared__ int stack_lo_s[8][8 * kMaxLevels + 8], stack_hi_s[8][8 * kMaxLevels + 8];
     const unsigned int full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long q_first = ((long long)blockIdx.x * 8 + warp) * kRun;
+    const long long q_first = ((long long)blockIdx.x * 8 + warp) * run;
     if (q_first >= nq) return;
     unsigned int* stack = stack_s[warp];
     int* stack_lo = stack_lo_s[warp];
@@ -190,7 +194,7 @@ __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restri
     int li[SLOTS];    // original point index
     int lp[SLOTS];    // position in the Morton-sorted array (to re-evaluate the list for the next query of the run)
 
-    for (int rq = 0; rq < kRun; ++rq) {
+    for (int rq = 0; rq < run; ++rq) {
         const long long qi = q_first + rq;
         if (qi >= nq) break;
         const float qx = queries[3 * qi], qy = queries[3 * qi + 1], qz = queries[3 * qi + 2];
@@ -464,10 +468,14 @@ __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restri
     }
 }
 
+static int g_knn_run = 16;  // pps_debug_knn_run: 16 measured 5 % faster than 8 on the dense grid, 32 and 64 slower (tools/knn_run_probe.py)
+
 template <int SLOTS>
 static int launch_query(const KnnHeader* hdr, const float4* sorted, const int* cell_start, const float* queries,
                         int64_t q, int k, int32_t* idx_out, float* d2_out, cudaStream_t st) {
-    knn_warp_kernel<SLOTS><<<(unsigned)ceil_div(q, 8 * kRun), 256, 0, st>>>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out);
+    // seeded lists (k in 33..256: the decoder's grid-ordered queries) profit from longer runs, the others have nothing to amortise
+    const int run = (SLOTS == 2 || SLOTS == 4 || SLOTS == 8) ? g_knn_run : kRun;
+    knn_warp_kernel<SLOTS><<<(unsigned)ceil_div(q, 8 * run), 256, 0, st>>>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out, run);
     PPS_LAUNCH_CHECK();
     return PPS_OK;
 }
@@ -529,9 +537,25 @@ int knn_build_impl(const float* pts, int64_t n, void* index, size_t index_bytes,
     return PPS_OK;
 }
 
+int knn_set_cell_factor(int f) {
+    const int old = g_knn_cell_factor;
+    if (f >= 1 && f <= 64) g_knn_cell_factor = f;
+    return old;
+}
+
+int knn_set_run(int run) {
+    const int old = g_knn_run;
+    if (run >= 1 && run <= 256) g_knn_run = run;
+    return old;
+}
+
 }  // namespace pps
 
 extern "C" {
+// queries per warp run of the seeded search (k in 33..256); returns the previous value, run < 1 only reads
+int pps_debug_knn_run(int run) { return pps::knn_set_run(run); }
+// finest octree cells per point (indices built afterwards use it; an index must be queried under the setting it was built with)
+int pps_debug_knn_cells(int factor) { return pps::knn_set_cell_factor(factor); }
 size_t pps_knn_index_bytes(int64_t n) { return n > 0 ? pps::knn_layout(n).total : 0; }
 int pps_knn_build(const float* pts, int64_t n, void* index, size_t index_bytes, void* stream) {
     return pps::knn_build_impl(pts, n, index, index_bytes, static_cast<cudaStream_t>(stream));

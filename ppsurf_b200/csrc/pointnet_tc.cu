@@ -17,8 +17,10 @@ namespace tc {
 
 constexpr int kPnRows = 128;
 constexpr int kPnLbo = kPnRows * 16 + 16;  // 2064: padded k8-block pitch of an activation tile
-constexpr int kPnSlot = 8192;              // ring slot: one k16 step of the widest weight stage
-constexpr int kPnStages = 4;
+constexpr int kPnSlot = 16384;             // ring slot: a whole 64-wide layer (4 k16 steps of 4 KB) or two k16 steps of a 128-wide one: the MMA
+                                           // issuer pays one full-wait and one commit per SLOT (measured on the projection kernel: ~300 cycles
+                                           // per iteration whatever it contains), and these kernels are latency-bound
+constexpr int kPnStages = 2;
 constexpr int kPnThreads = 320;
 constexpr int kPnEpiThreads = 256;
 
@@ -125,12 +127,11 @@ __global__ void __launch_bounds__(kPnThreads, 2)
             uint32_t slot = 0, phase = 0;
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const uint8_t* src = wpack;
-                for (int s = 0; s < 28; ++s) {
-                    const uint32_t bytes = s < 8 ? 4096u : 8192u;
+                for (int s = 0; s < 12; ++s) {  // slots: conv0b, stn1 (4 steps of 4 KB each), stn2 x2, stn3 x8 (2 steps of 8 KB)
                     mbar_wait(bar_empty + 8 * slot, phase ^ 1);
-                    mbar_expect_tx(bar_full + 8 * slot, bytes);
-                    bulk_copy(sbase + kOffRing + slot * kPnSlot, src, bytes, bar_full + 8 * slot);
-                    src += bytes;
+                    mbar_expect_tx(bar_full + 8 * slot, kPnSlot);
+                    bulk_copy(sbase + kOffRing + slot * kPnSlot, src, kPnSlot, bar_full + 8 * slot);
+                    src += kPnSlot;
                     if (++slot == kPnStages) {
                         slot = 0;
                         phase ^= 1;
@@ -150,17 +151,22 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                         // D[rows, n] = X[rows, 64] . W[n, 64]^T
                         const int n = layer < 2 ? 64 : 128;
                         const uint32_t idesc = umma_idesc(n);
-                        for (int s = 0; s < 4; ++s) {
+                        const int per = n == 64 ? 4 : 2;  // k16 steps per ring slot
+                        const uint32_t step_bytes = 64u * n;
+                        for (int s0 = 0; s0 < 4; s0 += per) {
                             mbar_wait(bar_full + 8 * slot, phase);
                             tc_fence_after();
-                            const uint64_t x_hi = umma_desc(sbase + kOffAhi + 2 * s * kPnLbo, kPnLbo, 128);
-                            const uint64_t x_lo = umma_desc(sbase + kOffAlo + 2 * s * kPnLbo, kPnLbo, 128);
-                            const uint32_t bst = sbase + kOffRing + slot * kPnSlot;
-                            const uint64_t w_hi = umma_desc(bst, n * 16, 128);
-                            const uint64_t w_lo = umma_desc(bst + n * 32, n * 16, 128);
-                            umma(tmem, x_hi, w_hi, idesc, s > 0 ? 1u : 0u);
-                            umma(tmem, x_lo, w_hi, idesc, 1u);
-                            umma(tmem, x_hi, w_lo, idesc, 1u);
+                            for (int sub = 0; sub < per; ++sub) {
+                                const int s = s0 + sub;
+                                const uint64_t x_hi = umma_desc(sbase + kOffAhi + 2 * s * kPnLbo, kPnLbo, 128);
+                                const uint64_t x_lo = umma_desc(sbase + kOffAlo + 2 * s * kPnLbo, kPnLbo, 128);
+                                const uint32_t bst = sbase + kOffRing + slot * kPnSlot + sub * step_bytes;
+                                const uint64_t w_hi = umma_desc(bst, n * 16, 128);
+                                const uint64_t w_lo = umma_desc(bst + n * 32, n * 16, 128);
+                                umma(tmem, x_hi, w_hi, idesc, s > 0 ? 1u : 0u);
+                                umma(tmem, x_lo, w_hi, idesc, 1u);
+                                umma(tmem, x_hi, w_lo, idesc, 1u);
+                            }
                             tc_commit(bar_empty + 8 * slot);
                             if (++slot == kPnStages) {
                                 slot = 0;
@@ -171,17 +177,21 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                         // transposed: D^T[features(128 per block), rows(128)] = W[features, 128] . X[rows, 128]^T
                         const uint32_t idesc = umma_idesc(128);
                         for (int fb = 0; fb < 2; ++fb) {
-                            for (int s = 0; s < 8; ++s) {
+                            for (int s0 = 0; s0 < 8; s0 += 2) {
                                 mbar_wait(bar_full + 8 * slot, phase);
                                 tc_fence_after();
-                                const uint64_t x_hi = umma_desc(sbase + kOffAhi + 2 * s * kPnLbo, kPnLbo, 128);
-                                const uint64_t x_lo = umma_desc(sbase + kOffAlo + 2 * s * kPnLbo, kPnLbo, 128);
-                                const uint32_t wst = sbase + kOffRing + slot * kPnSlot;
-                                const uint64_t w_hi = umma_desc(wst, 128 * 16, 128);
-                                const uint64_t w_lo = umma_desc(wst + 4096, 128 * 16, 128);
-                                umma(tmem + fb * 128, w_hi, x_hi, idesc, s > 0 ? 1u : 0u);
-                                umma(tmem + fb * 128, w_hi, x_lo, idesc, 1u);
-                                umma(tmem + fb * 128, w_lo, x_hi, idesc, 1u);
+#pragma unroll
+                                for (int sub = 0; sub < 2; ++sub) {
+                                    const int s = s0 + sub;
+                                    const uint64_t x_hi = umma_desc(sbase + kOffAhi + 2 * s * kPnLbo, kPnLbo, 128);
+                                    const uint64_t x_lo = umma_desc(sbase + kOffAlo + 2 * s * kPnLbo, kPnLbo, 128);
+                                    const uint32_t wst = sbase + kOffRing + slot * kPnSlot + sub * 8192;
+                                    const uint64_t w_hi = umma_desc(wst, 128 * 16, 128);
+                                    const uint64_t w_lo = umma_desc(wst + 4096, 128 * 16, 128);
+                                    umma(tmem + fb * 128, w_hi, x_hi, idesc, s > 0 ? 1u : 0u);
+                                    umma(tmem + fb * 128, w_hi, x_lo, idesc, 1u);
+                                    umma(tmem + fb * 128, w_lo, x_hi, idesc, 1u);
+                                }
                                 tc_commit(bar_empty + 8 * slot);
                                 if (++slot == kPnStages) {
                                     slot = 0;
@@ -381,12 +391,11 @@ __global__ void __launch_bounds__(kPnThreads, 2)
             uint32_t slot = 0, phase = 0;
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const uint8_t* src = wpack;
-                for (int s = 0; s < 8; ++s) {
-                    const uint32_t bytes = s < 4 ? 4096u : 8192u;
+                for (int s = 0; s < 3; ++s) {  // slots: conv1 (4 steps of 4 KB), conv2 x2 (2 steps of 8 KB)
                     mbar_wait(bar_empty + 8 * slot, phase ^ 1);
-                    mbar_expect_tx(bar_full + 8 * slot, bytes);
-                    bulk_copy(sbase + kOffRing + slot * kPnSlot, src, bytes, bar_full + 8 * slot);
-                    src += bytes;
+                    mbar_expect_tx(bar_full + 8 * slot, kPnSlot);
+                    bulk_copy(sbase + kOffRing + slot * kPnSlot, src, kPnSlot, bar_full + 8 * slot);
+                    src += kPnSlot;
                     if (++slot == kPnStages) {
                         slot = 0;
                         phase ^= 1;
@@ -424,17 +433,22 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                     mbar_wait(bar_aready, ready_phase);
                     ready_phase ^= 1;
                     tc_fence_after();
-                    for (int s = 0; s < 4; ++s) {
+                    const int per = n == 64 ? 4 : 2;  // k16 steps per ring slot
+                    const uint32_t step_bytes = 64u * n;
+                    for (int s0 = 0; s0 < 4; s0 += per) {
                         mbar_wait(bar_full + 8 * slot, phase);
                         tc_fence_after();
-                        const uint64_t x_hi = umma_desc(sbase + kOffAhi + 2 * s * kPnLbo, kPnLbo, 128);
-                        const uint64_t x_lo = umma_desc(sbase + kOffAlo + 2 * s * kPnLbo, kPnLbo, 128);
-                        const uint32_t bst = sbase + kOffRing + slot * kPnSlot;
-                        const uint64_t w_hi = umma_desc(bst, n * 16, 128);
-                        const uint64_t w_lo = umma_desc(bst + n * 32, n * 16, 128);
-                        umma(tmem, x_hi, w_hi, idesc, s > 0 ? 1u : 0u);
-                        umma(tmem, x_lo, w_hi, idesc, 1u);
-                        umma(tmem, x_hi, w_lo, idesc, 1u);
+                        for (int sub = 0; sub < per; ++sub) {
+                            const int s = s0 + sub;
+                            const uint64_t x_hi = umma_desc(sbase + kOffAhi + 2 * s * kPnLbo, kPnLbo, 128);
+                            const uint64_t x_lo = umma_desc(sbase + kOffAlo + 2 * s * kPnLbo, kPnLbo, 128);
+                            const uint32_t bst = sbase + kOffRing + slot * kPnSlot + sub * step_bytes;
+                            const uint64_t w_hi = umma_desc(bst, n * 16, 128);
+                            const uint64_t w_lo = umma_desc(bst + n * 32, n * 16, 128);
+                            umma(tmem, x_hi, w_hi, idesc, s > 0 ? 1u : 0u);
+                            umma(tmem, x_lo, w_hi, idesc, 1u);
+                            umma(tmem, x_hi, w_lo, idesc, 1u);
+                        }
                         tc_commit(bar_empty + 8 * slot);
                         if (++slot == kPnStages) {
                             slot = 0;
