@@ -447,11 +447,10 @@ bool chain_tc_supported(const pps_decoder_weights* w) {
 }
 
 static int chain_configure() {
-    static bool configured = false;
-    if (!configured) {
+    static unsigned char configured[kMaxDevices] = {};
+    if (first_use_on_device(configured)) {
         PPS_CUDA(cudaFuncSetAttribute(tc::chain::stn_fc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::chain::kSmemBytes));
         PPS_CUDA(cudaFuncSetAttribute(tc::chain::mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::chain::kSmemBytes));
-        configured = true;
     }
     return PPS_OK;
 }

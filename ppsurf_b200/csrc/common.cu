@@ -13,6 +13,7 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+static std::mutex g_flag_mutex;
 static unsigned long long g_launches = 0;
 void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 
@@ -32,6 +33,15 @@ void profile_begin(cudaStream_t st) {
 }
 void profile_end(cudaStream_t st) {
     if (g_profile) cudaEventRecord(next_event(), st);
+}
+
+bool first_use_on_device(unsigned char* flags) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return true;  // unknown device: (re)configure, harmless
+    std::lock_guard<std::mutex> lock(g_flag_mutex);
+    if (flags[dev]) return false;
+    flags[dev] = 1;
+    return true;
 }
 
 // per-device pool of timing-disabled events for the host-buffer entry points (created once: the C ABI promises no

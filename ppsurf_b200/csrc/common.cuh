@@ -68,4 +68,9 @@ struct Arena {
 
 constexpr int kNumSMs = 148;  // B200
 
+// true the first time it is called for `flags` on the CURRENT device (function attributes such as the dynamic shared-memory limit are
+// per device: a process driving several GPUs must set them on each).  flags: a zero-initialised static array of kMaxDevices bytes.
+constexpr int kMaxDevices = 64;
+bool first_use_on_device(unsigned char* flags);
+
 }  // namespace pps

@@ -627,13 +627,12 @@ int projection_tc_impl(const pps_decoder_weights* w, const float* table, const f
     PPS_CHECK_ARG(w->k == tc::kNbrs && w->latent == tc::kC && w->heads == tc::kHeads,
                   "decoder path 1 is built for k=64, latent=256, heads=64 (got %d, %d, %d)", w->k, w->latent, w->heads);
     if (q == 0) return PPS_OK;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned char configured[kMaxDevices] = {};
+    if (first_use_on_device(configured)) {
         PPS_CUDA(cudaFuncSetAttribute(tc::projection_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
         PPS_CUDA(cudaFuncSetAttribute(tc::projection_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
         PPS_CUDA(cudaFuncSetAttribute(tc::projection_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
         PPS_CUDA(cudaFuncSetAttribute(tc::projection_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
-        configured = true;
     }
     const long long npt = (q + 3) / 4;  // pair-tiles of 4 queries
     const int pairs = (int)(npt < kNumSMs / 2 ? npt : kNumSMs / 2);

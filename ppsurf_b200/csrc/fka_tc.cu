@@ -550,10 +550,9 @@ bool fka_fused_supported(const pps_fkaconv_weights* w, int kn, int64_t n_s) {
 
 template <int ACT>
 static int fka_fused_launch(const tc::fka::Params& p, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static unsigned char configured[kMaxDevices] = {};
+    if (first_use_on_device(configured)) {
         PPS_CUDA(cudaFuncSetAttribute(tc::fka::fka_fused_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::fka::kSmemBytes));
-        configured = true;
     }
     const unsigned sblocks = (unsigned)((p.rows + 15) / 16);
     tc::fka::fka_stats_kernel<ACT, 1><<<sblocks, 256, 0, st>>>(p);

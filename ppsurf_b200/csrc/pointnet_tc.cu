@@ -677,13 +677,12 @@ bool pointnet_tc_supported(const pps_decoder_weights* w) {
 int pointnet_tc_impl(const pps_decoder_weights* w, const float* patches, int64_t q, float* a1, float* g, float* f1, float* f2,
                      float* tmat, float* pooled128, float* partial, cudaStream_t st) {
     if (q == 0) return PPS_OK;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned char configured[kMaxDevices] = {};
+    if (first_use_on_device(configured)) {
         PPS_CUDA(cudaFuncSetAttribute(tc::pn_stn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::stn::kSmemBytes));
         PPS_CUDA(cudaFuncSetAttribute(tc::pn_stn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::stn::kSmemBytes));
         PPS_CUDA(cudaFuncSetAttribute(tc::pn_feat_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::feat::kSmemBytes));
         PPS_CUDA(cudaFuncSetAttribute(tc::pn_feat_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::feat::kSmemBytes));
-        configured = true;
     }
     const int P = w->num_pts_local, S = w->stn_size;
     const int G = (P + 63) / 64;  // 64-row half-tiles per query

@@ -353,16 +353,30 @@ int pps_encoder_ids(const float* pts, int64_t b, int64_t n0, const float* rotati
         return PPS_ERR_WORKSPACE;
     }
     cudaStream_t user = static_cast<cudaStream_t>(stream);
-    // fork: side streams (created once per process) wait for the caller's stream, each owns one workspace slice
-    static cudaStream_t side[kIdStreams] = {};
-    static cudaEvent_t ev_fork = nullptr, ev_join[kIdStreams] = {};
-    if (!ev_fork) {
-        PPS_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    // fork: side streams (created once per DEVICE) wait for the caller's stream, each owns one workspace slice
+    struct DeviceStreams {
+        cudaStream_t side[kIdStreams];
+        cudaEvent_t fork, join[kIdStreams];
+        bool ready;
+    };
+    static DeviceStreams per_device[kMaxDevices] = {};
+    static unsigned char created[kMaxDevices] = {};
+    int device = 0;
+    PPS_CUDA(cudaGetDevice(&device));
+    PPS_CHECK_ARG(device >= 0 && device < kMaxDevices, "pps_encoder_ids: device %d out of range", device);
+    DeviceStreams& ds = per_device[device];
+    if (first_use_on_device(created)) {
+        PPS_CUDA(cudaEventCreateWithFlags(&ds.fork, cudaEventDisableTiming));
         for (int i = 0; i < kIdStreams; ++i) {
-            PPS_CUDA(cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking));
-            PPS_CUDA(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming));
+            PPS_CUDA(cudaStreamCreateWithFlags(&ds.side[i], cudaStreamNonBlocking));
+            PPS_CUDA(cudaEventCreateWithFlags(&ds.join[i], cudaEventDisableTiming));
         }
+        ds.ready = true;
     }
+    PPS_CHECK_ARG(ds.ready, "pps_encoder_ids: the side streams of device %d could not be created", device);
+    cudaStream_t* side = ds.side;
+    cudaEvent_t ev_fork = ds.fork;
+    cudaEvent_t* ev_join = ds.join;
     const int nstreams = b < kIdStreams ? (int)b : kIdStreams;
     PPS_CUDA(cudaEventRecord(ev_fork, user));
     for (int i = 0; i < nstreams; ++i) PPS_CUDA(cudaStreamWaitEvent(side[i], ev_fork, 0));
@@ -371,7 +385,9 @@ int pps_encoder_ids(const float* pts, int64_t b, int64_t n0, const float* rotati
     const size_t slice = encoder_ids_slice_bytes(n0);
     static const int pair16[9][2] = {{0, 0}, {0, 1}, {1, 1}, {1, 2}, {2, 2}, {2, 3}, {3, 3}, {3, 4}, {4, 4}};
     static const int pair1[4][2] = {{4, 3}, {3, 2}, {2, 1}, {1, 0}};
-    for (int64_t s = 0; s < b; ++s) {
+    // the loop body returns through `rc`: the join below must run even after a failure (the side streams still write the
+    // caller's workspace and outputs)
+    auto one_sample = [&](int64_t s) -> int {
         cudaStream_t st = side[s % nstreams];
         char* base = static_cast<char*>(workspace) + (s % nstreams) * slice;
         size_t off = 0;
@@ -406,12 +422,19 @@ int pps_encoder_ids(const float* pts, int64_t b, int64_t n0, const float* rotati
             const int a = pair1[p][0], c = pair1[p][1];
             PPS_TRY(knn_query_impl(index[a], n[a], lv[c], n[c], 1, out->ids1[p] + s * n[c], nullptr, st));
         }
-    }
+        return PPS_OK;
+    };
+    int rc = PPS_OK;
+    for (int64_t s = 0; s < b && rc == PPS_OK; ++s) rc = one_sample(s);
     // join: the caller's stream continues when every side stream is done
     for (int i = 0; i < nstreams; ++i) {
-        PPS_CUDA(cudaEventRecord(ev_join[i], side[i]));
-        PPS_CUDA(cudaStreamWaitEvent(user, ev_join[i], 0));
+        cudaError_t e = cudaEventRecord(ev_join[i], side[i]);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(user, ev_join[i], 0);
+        if (e != cudaSuccess && rc == PPS_OK) {
+            set_error("pps_encoder_ids: join failed: %s", cudaGetErrorString(e));
+            rc = PPS_ERR_CUDA;
+        }
     }
-    return PPS_OK;
+    return rc;
 }
 }

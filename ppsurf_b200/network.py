@@ -152,8 +152,15 @@ class PPSurfNetwork(_Base):
         self.mlp = MLPParams(latent_size, out_channels)
         self.lcp_preprocess = True
         self.decode_chunk = decode_chunk
-        # 1 = tcgen05 split-fp16 kernels (built for latent 256 / k 64 / 64 heads), 0 = fp32 SIMT kernels for every other shape
-        self.decode_path = (1 if (latent_size == 256 and k == 64) else 0) if decode_path is None else decode_path
+        # The decoder kernels (both paths) are built for the PPSurf configuration: latent 256, 64 attention heads, k <= 64
+        # (configs/ppsurf.yaml:7-9, configs/poco.yaml:47); other sizes fail HERE rather than at the first decode.  Path 1 = tcgen05
+        # split-fp16 kernels (k == 64), path 0 = fp32 SIMT kernels (any k <= 64; the reference path of the parity tests).  A cloud needs
+        # at least max(k, num_pts_local) points (the reference would clamp k to the cloud size, source/poco_utils.py:259-260; a
+        # 64-neighbour interpolation of fewer than 64 points is not a case its configs produce).
+        if latent_size != 256 or pointnet_latent_size != 256 or k > 64 or k < 1:
+            raise ValueError('ppsurf_b200 is built for network_latent_size = pointnet_latent_size = 256 and k <= 64 '
+                             '(got {}, {}, {})'.format(latent_size, pointnet_latent_size, k))
+        self.decode_path = (1 if k == 64 else 0) if decode_path is None else decode_path
         self.sampling_seed = None  # set for reproducible support sampling
         self.use_graphs = True     # CUDA-graph replay of the latent loop's batches (latents_of_batch)
         self.graph_seed = 12345    # baked into the captured launches; the per-round rotations re-randomise it on the device
