@@ -368,6 +368,98 @@ int pps_refine_init(const float* volume, int r, const float* verts, const int32_
                     float* va, float* vb, float* pa, float* pb, float* v, unsigned char* active, void* stream);
 int pps_refine_update(const float* pred, int64_t n, float* va, float* vb, float* pa, float* pb, float* v, void* stream);
 
+/* ===============================================================================================================
+ * config 5  --  the training step (`pps.py fit`): forward in TRAIN mode and backward (SURVEY.md §8b "*_bwd")
+ *     replaces  PocoModel.training_step -> network.forward -> cross_entropy -> Lightning backward (torch autograd)
+ *               source/poco_model.py:75-88,108-125, source/ppsurf_model.py:70-117
+ * Train mode differs from the predict path in ways that forbid the folded / fused predict kernels: BatchNorm uses BATCH
+ * statistics (and updates its running statistics), FKAConvLayer updates norm_radius (nn.py:608-613), dropout is active,
+ * and every activation has to be kept for the backward pass.  The training path is therefore a set of PRIMITIVES with
+ * explicit forward / backward entry points; ppsurf_b200/autograd.py wraps each pair in a torch.autograd.Function and
+ * ppsurf_b200/training.py composes the reference's network from them.  All tensors row-major f32 [rows, channels]; a
+ * "group" is a run of consecutive rows.  No entry point allocates; scratch is passed in.
+ * =============================================================================================================== */
+
+/* Strided, batched GEMM:  C_b[m,n] (+)= sum_k A_b[m,k] . B_b[k,n] (+ bias[n])
+ *   A_b[m,k] = a[b*sa_b + m*sa_m + k*sa_k],  B_b[k,n] = b[b*sb_b + k*sb_k + n*sb_n],  C_b[m,n] = c[b*sc_b + m*ldc + n]
+ * Serves Y = X.W^T (Linear / Conv1d / Conv2d 1x1: nn.py, poco_model.py:400-411), dX = dY.W, dW = dY^T.X (k = rows; split over
+ * the grid and reduced with atomics) and the per-query feature transform torch.bmm(trans2, x) (nn.py:347) with its two
+ * gradients.  accumulate != 0 adds into C.  precision 0 = fp32 SIMT, 1 = bf16 operands on tcgen05 with fp32 accumulation
+ * (BASELINE config 5 "bf16"; batch == 1 problems with m >= 64, n >= 16, k >= 32, others fall to fp32). */
+int pps_gemm(const float* a, int64_t sa_b, int64_t sa_m, int64_t sa_k, const float* b, int64_t sb_b, int64_t sb_k, int64_t sb_n,
+             float* c, int64_t sc_b, int64_t ldc, int64_t batch, int64_t m, int n, int64_t k, const float* bias, int accumulate,
+             int precision, void* stream);
+/* out[c] (+)= sum_r x[r*ld + c]   (bias gradients) */
+int pps_colsum(const float* x, int64_t rows, int c, int64_t ld, float* out, int accumulate, void* stream);
+
+/* Normalisation over the rows of each group, per channel, affine, with the following activation fused (act 0 none, 1 ReLU,
+ * 2 SiLU):  y = act((x - mean_g) / sqrt(var_g + eps) * gamma + beta),  x [groups, rows, c].
+ *   groups = 1        BatchNorm1d in train mode (nn.py:162-190,305-373,376-417,438-450,508-548); mean / var [c] feed
+ *                     pps_bn_running_update (momentum 0.1, unbiased variance, like torch)
+ *   groups = samples  InstanceNorm2d(affine=True) of FKAConvLayer (nn.py:586-587,630,638), rows = n_s * 16
+ * mean / var [groups, c] are outputs of the forward and inputs of the backward (biased variance).  Backward: dx, and
+ * dgamma / dbeta [c] summed over the groups.  workspace: pps_norm_workspace_bytes(groups, c). */
+size_t pps_norm_workspace_bytes(int64_t groups, int c);
+int pps_norm_fwd(const float* x, int64_t groups, int64_t rows, int c, const float* gamma, const float* beta, float eps, int act, float* y,
+                 float* mean, float* var, void* workspace, size_t workspace_bytes, void* stream);
+int pps_norm_bwd(const float* x, const float* dy, int64_t groups, int64_t rows, int c, const float* gamma, const float* beta,
+                 const float* mean, const float* var, float eps, int act, float* dx, float* dgamma, float* dbeta, void* workspace,
+                 size_t workspace_bytes, void* stream);
+int pps_bn_running_update(const float* mean, const float* var, int64_t count, float momentum, int c, float* running_mean, float* running_var,
+                          void* stream);
+
+/* element-wise pairs: activation (0 none, 1 ReLU, 2 SiLU; backward takes the PRE-activation x), dropout with a stored keep-mask
+ * (MLP, p = 0.3, nn.py:399), y = x * w[row] (the distance weights of nn.py:631,639,644), concat of per-row and per-group
+ * channels torch.cat([mat, mp.expand], 1) (nn.py:634-635,642-643) */
+int pps_act_fwd(const float* x, int64_t n, int act, float* y, void* stream);
+int pps_act_bwd(const float* x, const float* dy, int64_t n, int act, float* dx, void* stream);
+int pps_dropout_fwd(const float* x, int64_t n, float p, uint32_t seed, float* y, uint8_t* mask, void* stream);
+int pps_dropout_bwd(const float* dy, const uint8_t* mask, int64_t n, float p, float* dx, void* stream);
+int pps_rowscale_fwd(const float* x, const float* w, int64_t rows, int c, float* y, void* stream);
+int pps_rowscale_bwd(const float* x, const float* w, const float* dy, int64_t rows, int c, float* dx, float* dw, void* stream);
+int pps_concat_bcast_fwd(const float* x, const float* v, int64_t groups, int s, int c, float* out, void* stream);
+int pps_concat_bcast_bwd(const float* dout, int64_t groups, int s, int c, float* dx, float* dv, void* stream);
+
+/* batch_gather (nn.py:655-674) as a row gather and its gradient (atomic scatter-add into a caller-zeroed dx) */
+int pps_gather_rows(const float* x, const int32_t* idx, int64_t m, int c, float* y, void* stream);
+int pps_scatter_add_rows(const float* dy, const int32_t* idx, int64_t m, int c, float* dx, void* stream);
+/* y[g,c] = max_s x[g,s,c] * w[g,s] (w nullable), arg = winning s: the STN max over the patch (nn.py:170-172), the weighted
+ * neighbourhood maxima of FKAConvLayer (nn.py:631-633,639-641), the global max of the U-Net (nn.py:535).  Backward fills
+ * dx [groups,s,c] and, when dw is given, dw [groups,s] (gradient of the distance weights). */
+int pps_seg_max_fwd(const float* x, const float* w, int64_t groups, int s, int c, float* y, int32_t* arg, void* stream);
+int pps_seg_max_bwd(const float* dy, const int32_t* arg, const float* x, const float* w, int64_t groups, int s, int c, float* dx, float* dw,
+                    void* stream);
+/* max_pool(x, ids) (nn.py:677-680) with the winning source row kept for the backward (atomic adds into a caller-zeroed dx) */
+int pps_gather_max_fwd(const float* x, const int32_t* ids, int64_t b, int64_t n_in, int64_t n_s, int c, int kn, float* y, int32_t* arg,
+                       void* stream);
+int pps_gather_max_bwd(const float* dy, const int32_t* arg, int64_t rows, int c, float* dx, void* stream);
+
+/* attention pooling: prob = softmax over the s rows of a group per head, a = mean over the h heads, out = sum_s a[s] v[s,:]
+ *     InterpAttentionKHeadsNet (poco_model.py:413-416; h = 64, s = k = 64) and AttentionPoco (nn.py:84-96; h = 1, s = P) */
+int pps_attn_pool_fwd(const float* scores, const float* v, int64_t groups, int s, int h, int c, float* prob, float* a, float* out,
+                      void* stream);
+int pps_attn_pool_bwd(const float* dout, const float* prob, const float* a, const float* v, int64_t groups, int s, int h, int c,
+                      float* dscores, float* dv, void* stream);
+
+/* FKAConvLayer.forward geometry (nn.py:598-624): offs [R,3] = (pts[ids] - support) / norm_radius, dist [R], sig [R] =
+ * sigmoid(-alpha d + beta), dw [R] = normalised distance weights (R = b * n_s * kn rows).  alpha / beta / norm_radius are DEVICE
+ * scalars; with update_radius the norm_radius buffer is first moved towards the mean neighbourhood radius (train mode,
+ * nn.py:608-613).  scratch: one double.  pps_fka_weights_bwd: d loss / d dw -> {d alpha, d beta} (two doubles). */
+int pps_fka_geometry_fwd(const float* pts, const float* support, const int32_t* ids, int64_t b, int64_t n_in, int64_t n_s, int kn,
+                         const float* alpha, const float* beta, float* norm_radius, float momentum, int update_radius, float* offs,
+                         float* dist, float* sig, float* dw, double* scratch, void* stream);
+int pps_fka_weights_bwd(const float* ddw, const float* sig, const float* dist, int64_t points, int kn, double* dalpha_dbeta, void* stream);
+/* feat[p, c*16 + m] = sum_j x[ids[p,j], c] * mat[p,j,m]  (nn.py:647-649; the column order of cv.weight.view(cout, cin*16)) and its
+ * gradients dmat [R,16] and dx [b*n_in, cin] (zero-filled inside, atomic adds) */
+int pps_fka_feat_fwd(const float* x, const int32_t* ids, const float* mat, int64_t b, int64_t n_in, int64_t n_s, int kn, int cin, float* feat,
+                     void* stream);
+int pps_fka_feat_bwd(const float* dfeat, const float* x, const int32_t* ids, const float* mat, int64_t b, int64_t n_in, int64_t n_s, int kn,
+                     int cin, float* dx, float* dmat, void* stream);
+
+/* cross entropy of compute_loss (poco_model.py:75-88): per-row losses and their sum (one double); backward with a per-row scale */
+int pps_ce_fwd(const float* logits, const int64_t* target, int64_t m, int c, float* loss_rows, double* loss_sum, void* stream);
+int pps_ce_bwd(const float* logits, const int64_t* target, const float* scale, int64_t m, int c, float* dlogits, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

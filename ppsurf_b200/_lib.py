@@ -115,6 +115,37 @@ SIGNATURES = {
     'pps_latent_accumulate': (i32, [c_f32p, c_i32p, i64, i32, c_f32p, c_f32p, c_voidp]),
     'pps_latent_accumulate_rows': (i32, [c_f32p, c_i32p, c_i32p, i64, i32, c_f32p, c_f32p, c_voidp]),
     'pps_latent_finalize': (i32, [c_f32p, c_f32p, i64, i32, c_voidp]),
+    # ---- config 5: training primitives (csrc/train_gemm.cu, train_gemm_tc.cu, train_ops.cu)
+    'pps_gemm': (i32, [c_f32p, i64, i64, i64, c_f32p, i64, i64, i64, c_f32p, i64, i64, i64, i64, i32, i64, c_f32p, i32, i32, c_voidp]),
+    'pps_colsum': (i32, [c_f32p, i64, i32, i64, c_f32p, i32, c_voidp]),
+    'pps_norm_workspace_bytes': (size_t, [i64, i32]),
+    'pps_norm_fwd': (i32, [c_f32p, i64, i64, i32, c_f32p, c_f32p, ctypes.c_float, i32, c_f32p, c_f32p, c_f32p, c_voidp, size_t, c_voidp]),
+    'pps_norm_bwd': (i32, [c_f32p, c_f32p, i64, i64, i32, c_f32p, c_f32p, c_f32p, c_f32p, ctypes.c_float, i32, c_f32p, c_f32p, c_f32p,
+                           c_voidp, size_t, c_voidp]),
+    'pps_bn_running_update': (i32, [c_f32p, c_f32p, i64, ctypes.c_float, i32, c_f32p, c_f32p, c_voidp]),
+    'pps_act_fwd': (i32, [c_f32p, i64, i32, c_f32p, c_voidp]),
+    'pps_act_bwd': (i32, [c_f32p, c_f32p, i64, i32, c_f32p, c_voidp]),
+    'pps_dropout_fwd': (i32, [c_f32p, i64, ctypes.c_float, ctypes.c_uint32, c_f32p, c_voidp, c_voidp]),
+    'pps_dropout_bwd': (i32, [c_f32p, c_voidp, i64, ctypes.c_float, c_f32p, c_voidp]),
+    'pps_rowscale_fwd': (i32, [c_f32p, c_f32p, i64, i32, c_f32p, c_voidp]),
+    'pps_rowscale_bwd': (i32, [c_f32p, c_f32p, c_f32p, i64, i32, c_f32p, c_f32p, c_voidp]),
+    'pps_concat_bcast_fwd': (i32, [c_f32p, c_f32p, i64, i32, i32, c_f32p, c_voidp]),
+    'pps_concat_bcast_bwd': (i32, [c_f32p, i64, i32, i32, c_f32p, c_f32p, c_voidp]),
+    'pps_gather_rows': (i32, [c_f32p, c_i32p, i64, i32, c_f32p, c_voidp]),
+    'pps_scatter_add_rows': (i32, [c_f32p, c_i32p, i64, i32, c_f32p, c_voidp]),
+    'pps_seg_max_fwd': (i32, [c_f32p, c_f32p, i64, i32, i32, c_f32p, c_i32p, c_voidp]),
+    'pps_seg_max_bwd': (i32, [c_f32p, c_i32p, c_f32p, c_f32p, i64, i32, i32, c_f32p, c_f32p, c_voidp]),
+    'pps_gather_max_fwd': (i32, [c_f32p, c_i32p, i64, i64, i64, i32, i32, c_f32p, c_i32p, c_voidp]),
+    'pps_gather_max_bwd': (i32, [c_f32p, c_i32p, i64, i32, c_f32p, c_voidp]),
+    'pps_attn_pool_fwd': (i32, [c_f32p, c_f32p, i64, i32, i32, i32, c_f32p, c_f32p, c_f32p, c_voidp]),
+    'pps_attn_pool_bwd': (i32, [c_f32p, c_f32p, c_f32p, c_f32p, i64, i32, i32, i32, c_f32p, c_f32p, c_voidp]),
+    'pps_fka_geometry_fwd': (i32, [c_f32p, c_f32p, c_i32p, i64, i64, i64, i32, c_f32p, c_f32p, c_f32p, ctypes.c_float, i32, c_f32p, c_f32p,
+                                   c_f32p, c_f32p, c_voidp, c_voidp]),
+    'pps_fka_weights_bwd': (i32, [c_f32p, c_f32p, c_f32p, i64, i32, c_voidp, c_voidp]),
+    'pps_fka_feat_fwd': (i32, [c_f32p, c_i32p, c_f32p, i64, i64, i64, i32, i32, c_f32p, c_voidp]),
+    'pps_fka_feat_bwd': (i32, [c_f32p, c_f32p, c_i32p, c_f32p, i64, i64, i64, i32, i32, c_f32p, c_f32p, c_voidp]),
+    'pps_ce_fwd': (i32, [c_f32p, c_voidp, i64, i32, c_f32p, c_voidp, c_voidp]),
+    'pps_ce_bwd': (i32, [c_f32p, c_voidp, c_f32p, i64, i32, c_f32p, c_voidp]),
 }
 
 

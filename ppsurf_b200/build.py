@@ -7,7 +7,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.path.join(HERE, 'libppsurf_b200.so')
-SOURCES = ['common.cu', 'knn.cu', 'linear.cu', 'decode.cu', 'decode_tc.cu', 'pointnet_tc.cu', 'chain_tc.cu', 'encoder.cu', 'fka_tc.cu', 'sampling.cu', 'volume.cu', 'mcubes.cu']
+SOURCES = ['common.cu', 'knn.cu', 'linear.cu', 'decode.cu', 'decode_tc.cu', 'pointnet_tc.cu', 'chain_tc.cu', 'encoder.cu', 'fka_tc.cu', 'sampling.cu', 'volume.cu', 'mcubes.cu', 'train_gemm.cu', 'train_gemm_tc.cu',
+           'train_ops.cu']
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 FLAGS = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr', '-Wno-deprecated-gpu-targets']
 

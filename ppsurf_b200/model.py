@@ -343,8 +343,28 @@ class PPSurfModel(_Base):
         return loss
 
     def training_step(self, batch, batch_idx):
-        raise NotImplementedError('ppsurf_b200 implements the inference hot path (predict / test); the backward pass of '
-                                  'BASELINE config 5 (fit) is not built yet -- train with the reference module')
+        """source/poco_model.py:120-125 (default_step_dict 108-118): train-mode forward through ``ppsurf_b200.training``, mean cross
+        entropy over all query points; returns the loss tensor whose ``backward()`` runs the CUDA ``*_bwd`` entry points.  Works
+        under Lightning's automatic optimisation, ``torch.autocast(bfloat16)`` (bf16 tensor-core GEMMs) and DDP."""
+        from . import autograd as ag
+        if not self.network.training:
+            self.network.train()
+        pred = self.network.forward(batch)  # [B,2,Q]
+        b, c, q = pred.shape
+        loss, _rows = ag.cross_entropy(pred.transpose(1, 2).reshape(b * q, c), batch['occ'].reshape(-1).to(pred.device, torch.int64))
+        self.last_train_pred = pred.detach()
+        if float(self.lambda_l1) != 0.0:
+            raise NotImplementedError('lambda_l1 != 0 (PocoModel.regularize) is not part of the PPSurf configurations')
+        if hasattr(self, 'log') and getattr(self, '_trainer', None) is not None:
+            self.log('loss/train/00_all', loss, on_step=True, on_epoch=True, sync_dist=True)
+        return loss
+
+    def configure_optimizers(self):
+        """configs/poco.yaml:60-77: AdamW(lr 1e-3, betas (0.9, 0.999), eps 1e-5, weight_decay 1e-2) + MultiStepLR([75, 125], 0.1)
+        (LightningCLI instantiates them from the yaml; this is the same pair for drivers without the CLI)"""
+        opt = torch.optim.AdamW(self.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-5, weight_decay=1e-2, amsgrad=False)
+        sched = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=[75, 125], gamma=0.1)
+        return {'optimizer': opt, 'lr_scheduler': sched}
 
     def test_step(self, batch, batch_idx):
         """source/poco_model.py:134-162: forward on the stored query points, loss and classification metrics"""

@@ -36,6 +36,7 @@ class FKAConvLayerParams(_Base):
         super().__init__()
         self.cv = nn.Conv2d(cin, cout, (1, ks), bias=False)
         self.register_buffer('norm_radius', torch.ones(1))
+        self.norm_radius_momentum = 0.1  # train-mode update of norm_radius (source/base/nn.py:575,608-613)
         self.alpha = nn.Parameter(torch.ones(1))
         self.beta = nn.Parameter(torch.ones(1))
         self.fc1 = nn.Conv2d(3, ks, 1, bias=False)
@@ -302,8 +303,18 @@ class PPSurfNetwork(_Base):
 
     # ---- reference surface -------------------------------------------------------------------------------------
     def forward(self, data):
-        """train/test path (source/ppsurf_model.py:70-74): ids and ``proj_ids`` come with the batch"""
+        """train/test path (source/ppsurf_model.py:70-74): ids and ``proj_ids`` come with the batch.  In TRAIN mode (``.train()``)
+        the step runs through the autograd Functions of ``ppsurf_b200.training`` (batch-statistic BatchNorm, norm_radius update,
+        dropout, a backward pass); in eval mode through the packed predict kernels."""
         self._decoder_cache = None
+        if self.training:
+            from . import training
+            if 'proj_ids' not in data:  # the reference recomputes them in from_latent (ppsurf_model.py:83, has_proj_ids=False)
+                pts_pm, qry = _pm(data['pts']), data['pts_query'].to(data['pts'].device, torch.float32)
+                qry = qry if qry.shape[-1] == 3 else qry.transpose(1, 2)
+                data['proj_ids'] = torch.stack([ops.knn(pts_pm[s], qry[s].contiguous(), self.k) for s in range(pts_pm.shape[0])]).long()
+            self.invalidate()  # the optimiser is about to change the parameters the packed predict weights were built from
+            return training.forward(self, data, training=True)
         data['latents'] = self.encode(data).transpose(1, 2)
         return self.from_latent(data, has_proj_ids='proj_ids' in data)
 

@@ -1,5 +1,7 @@
 """Pins the CPU oracle against outputs of the UNMODIFIED reference (tests/golden/*.npz, made by
 tests/golden/make_golden.py in the build container).  CPU only."""
+import os
+
 import numpy as np
 import pytest
 
@@ -151,3 +153,43 @@ def test_real_cloud_region_grown_volume(oracle, weights, weights_digest):
     finite = vol[~np.isnan(vol)]
     assert np.isnan(vol).any() and finite.min() < -0.5 and finite.max() > 0.5  # region-grown, with an inside and an outside
     assert np.nanmax(np.abs(vol - g['volume'])) < 2e-5
+
+
+def test_train_oracle_twin_matches_the_reference_training_step(weights, weights_digest):
+    """config 5: the torch twin of the TRAINING step (oracle/ppsurf_train_oracle.py, the checker of the CUDA backward) against the
+    golden vectors of the unmodified reference in train mode (tests/golden/make_golden_train.py): loss, logits, gradient norms / sums /
+    sampled entries of all 298 parameter tensors in float64, and the buffers the step updates"""
+    import sys
+    import torch
+    from oracle import ppsurf_train_oracle as T
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    from make_golden_train import sample_positions
+    g = load_golden('train_step')
+    assert str(g['digest']) == weights_digest
+
+    def batch(dtype):
+        out = {}
+        for key in g:
+            if key.startswith('in_'):
+                t = torch.from_numpy(g[key])
+                out[key[3:]] = t.long() if t.dtype == torch.int32 else t.to(dtype)
+        return out
+
+    s = T.State(weights, dtype=torch.float64)
+    loss, logits = T.training_step(s, batch(torch.float64), dropout=0.0)
+    assert abs(float(loss) - float(g['loss64'])) < 1e-12
+    assert np.abs(logits.numpy() - g['logits64']).max() < 1e-6
+    grads = s.grads()
+    assert list(grads) == [str(n) for n in g['grad_names']]
+    for i, (name, gr) in enumerate(grads.items()):
+        flat = gr.numpy().reshape(-1)
+        scale = max(float(g['grad_norm'][i]), 1e-12)
+        assert abs(np.sqrt((flat * flat).sum()) - g['grad_norm'][i]) <= 1e-9 * scale + 1e-15, name
+        assert np.abs(flat[sample_positions(i, flat.size)] - g['grad_samples'][i]).max() <= 1e-9 * scale + 1e-15, name
+    # the float32 run of the twin reproduces the reference's float32 loss and buffers (BatchNorm running statistics, norm_radius)
+    s32 = T.State(weights)
+    loss32, _ = T.training_step(s32, batch(torch.float32), dropout=0.0)
+    assert abs(float(loss32) - float(g['loss'])) < 1e-6
+    for key in g:
+        if key.startswith('buf_'):
+            assert np.abs(s32.b[key[4:]].numpy() - g[key]).max() < 1e-5, key
