@@ -54,6 +54,14 @@ def parse_args():
     ap.add_argument('--no-reference-gpu', action='store_true', help='skip the reference-modules-on-this-B200 leg of the b200 arm')
     ap.add_argument('--no-predict', action='store_true', help='skip the e2e_predict block (encoder + region-grown shell)')
     ap.add_argument('--refgpu-batches', type=int, default=2, help='50 000-query batches the reference-on-GPU leg times')
+    ap.add_argument('--workload', default='decode', choices=['decode', 'fit'],
+                    help="decode = BASELINE metric (default); fit = BASELINE config 5: one training step (bf16, batch 16 over 8 GPUs)")
+    ap.add_argument('--fit-clouds-per-gpu', type=int, default=2, help='config 5: 16 clouds over 8 GPUs (weak scaling: fixed per GPU)')
+    ap.add_argument('--fit-points', type=int, default=10000, help='manifold points per cloud (configs/poco.yaml:34)')
+    ap.add_argument('--fit-queries', type=int, default=2000, help='query points per cloud (as in abc_minimal)')
+    ap.add_argument('--fit-precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--fit-eager', action='store_true', help='config 5: eager launches + torch DDP instead of the captured CUDA graphs')
+    ap.add_argument('--no-fit', action='store_true', help='skip the fit block (config 5 training step) of the default line')
     ap.add_argument('--profile-run', action='store_true', help='for ncu captures only: no minimum warm-up, no e2e leg')
     ap.add_argument('--shard-of', type=int, default=0,
                     help='debug: decode only the share rank 0 would get in a job of this many ranks (single process)')
@@ -617,6 +625,167 @@ def run_b200(args):
                 ref_gpu, _ = time_reference_gpu(args, dev, pts_np, lat_cn, grid_np, args.refgpu_batches)
                 ref_gpu['speedup_of_this_repo'] = {'device_resident': value / ref_gpu['value'], 'e2e_host_buffers': e2e_value / ref_gpu['value']}
                 out['reference_gpu'] = ref_gpu
+        if not args.profile_run and not args.no_fit and world == 1:
+            # BASELINE config 5 next to the headline: a short measurement of the training step (own line: --workload fit)
+            del dec, ws
+            ops._shared_workspace.clear()
+            torch.cuda.empty_cache()
+            out['fit'] = fit_measure(model, args, dev, 1, 3, 3, reference_twin=not args.no_reference_gpu)
+            model.eval()
+        quiet.emit(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ---- BASELINE config 5: the training step ------------------------------------------------------------------------------------------
+
+def fit_batch(n_clouds, n_pts, n_qry, seed):
+    """synthetic training batch in the reference's collated layout (PPSurfDataset.__getitem__, source/ppsurf_data_loader.py:61-81):
+    noisy-sphere clouds, query points half near the surface and half uniform, signed distance to the sphere as the label source"""
+    from ppsurf_b200 import synthetic
+    rng = np.random.default_rng(seed)
+    pts = np.stack([synthetic.synthetic_cloud(n_pts, seed * 1000 + i) for i in range(n_clouds)])
+    near = pts[:, rng.integers(0, n_pts, n_qry // 2)] + 0.03 * rng.standard_normal((n_clouds, n_qry // 2, 3))
+    far = rng.uniform(-0.5, 0.5, (n_clouds, n_qry - n_qry // 2, 3))
+    qry = np.concatenate([near, far], axis=1).astype(np.float32)
+    dist = (np.linalg.norm(qry, axis=2) - 0.4).astype(np.float32)
+    return {'pts_ms': pts.astype(np.float32), 'pts_query_ms': qry, 'imp_surf_dist_ms': dist}
+
+
+def fit_measure(model, args, dev, world, steps, warmup, reference_twin=False):
+    """times `steps` training steps (forward, loss, backward, DDP gradient all-reduce when world > 1, AdamW update) with CUDA
+    events, max over ranks.  value: batch prepared and resident; e2e: pinned host batch -> H2D -> prepare_batch (kd-tree work of
+    the reference's DataLoader workers, on the device) -> step -> loss to the host."""
+    import torch
+    import torch.distributed as dist
+    from ppsurf_b200 import _lib, autograd as ag, data_pipeline
+    net = model.network
+    rank = int(os.environ.get('RANK', '0'))
+    host = {k: torch.from_numpy(v).pin_memory() for k, v in fit_batch(args.fit_clouds_per_gpu, args.fit_points, args.fit_queries,
+                                                                       100 + rank).items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    model.train()
+    net.sampling_seed = 7
+    from ppsurf_b200 import training
+    ag.set_precision(args.fit_precision)
+    ag.manual_seed(1234 + rank)
+
+    def prepare():
+        with torch.no_grad():
+            return data_pipeline.prepare_batch(net, {k: v.to(dev, non_blocking=True) for k, v in host.items()})
+
+    batch = prepare()
+    if args.fit_eager:
+        module = net
+        if world > 1:
+            from torch.nn.parallel import DistributedDataParallel as DDP
+            module = DDP(net, device_ids=[dev.index], gradient_as_bucket_view=True)
+        opt = torch.optim.AdamW(net.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-5, weight_decay=1e-2)
+
+        def step(batch):
+            opt.zero_grad(set_to_none=True)
+            pred = module(dict(batch))
+            b, c, q = pred.shape
+            loss, _ = ag.cross_entropy(pred.transpose(1, 2).reshape(b * q, c), batch['occ'].reshape(-1))
+            loss.backward()
+            opt.step()
+            return loss
+    else:
+        opt = torch.optim.AdamW(net.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-5, weight_decay=1e-2, capturable=True)
+        step = training.GraphedTrainStep(net, opt, batch, world=world)
+
+    def timed(fn, n):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    losses = [float(step(batch)) for _ in range(max(3, warmup))]
+    launches0 = _lib.lib.pps_launch_count()
+    ms = timed(lambda: step(batch), steps)
+    launches = (_lib.lib.pps_launch_count() - launches0) if args.fit_eager else step.kernels_per_step * steps
+    ms_e2e = timed(lambda: float(step(prepare())), steps)
+    ag.set_precision('fp32')
+    clouds = args.fit_clouds_per_gpu * world
+    out = {'value': clouds * steps / (ms / 1e3), 'unit': 'clouds/s', 'ms_per_step': ms / steps,
+           'e2e': {'value': clouds * steps / (ms_e2e / 1e3), 'unit': 'clouds/s', 'ms_per_step': ms_e2e / steps,
+                   'h2d_bytes_per_step': int(h2d_bytes), 'd2h_bytes_per_step': 4,
+                   'call': 'pinned host batch -> data_pipeline.prepare_batch (supports, 13 kNN index tensors, proj_ids, patches on the '
+                           'device) -> training step -> loss.item()'},
+           'gpu_launches_per_step': int(launches // steps), 'loss_first_last_warmup': [losses[0], losses[-1]],
+           'config': {'workload': 'ppsurf_50nn fit (BASELINE config 5): {} clouds/GPU x {} GPUs, {} manifold points, {} query points, '
+                                  'k=64, P=50, {} GEMMs on tcgen05 (fp32 master weights / activations), AdamW, {}'.format(
+                                      args.fit_clouds_per_gpu, world, args.fit_points, args.fit_queries, args.fit_precision,
+                                      ('one flat NCCL gradient all-reduce' if not args.fit_eager else 'torch DDP') if world > 1 else 'single GPU') +
+                                      (', eager launches' if args.fit_eager else ', step replayed from CUDA graphs'),
+                      'global_batch': clouds}}
+    if reference_twin and world == 1:
+        # the reference's GPU training step: eager torch modules (oracle twin) on this device under autocast(bfloat16) with the same
+        # optimiser and the same prepared batch
+        from oracle import ppsurf_train_oracle as T
+        twin = T.State({k: v.detach().cpu() for k, v in net.state_dict().items()}, device=dev)
+        topt = torch.optim.AdamW(list(twin.p.values()), lr=1e-3, betas=(0.9, 0.999), eps=1e-5, weight_decay=1e-2)
+        torch.backends.cuda.matmul.allow_tf32 = True
+
+        def twin_step():
+            topt.zero_grad(set_to_none=True)
+            with torch.autocast('cuda', dtype=torch.bfloat16):
+                logits = T.forward(twin, batch, True, 0.3)
+            T.loss_of(logits.float(), batch['occ']).backward()
+            topt.step()
+
+        for _ in range(3):
+            twin_step()
+        tms = timed(twin_step, steps)
+        out['reference_gpu'] = {'value': clouds * steps / (tms / 1e3), 'unit': 'clouds/s', 'ms_per_step': tms / steps,
+                                'what': 'torch-eager twin of the reference network (oracle/ppsurf_train_oracle.py) on this B200, '
+                                        'autocast bf16 + TF32, same batch (prepared on the device), same optimiser',
+                                'speedup_of_this_repo': tms / ms}
+        del twin, topt
+    return out
+
+
+def run_fit(args):
+    import torch
+    import torch.distributed as dist
+
+    import ppsurf_b200
+    from ppsurf_b200 import ops, synthetic
+    quiet = QuietStdout()
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    ops.require_device()
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    model = ppsurf_b200.PPSurfModel(256, ['imp_surf_sign'], 3, 2, 64, 0.0, False, 'bench', 'results', 0.05, 'ppsurf_50nn', 256, 10, 10000,
+                                    129, 50, 50000, 10, 8)
+    model.network.load_state_dict(synthetic.make_state_dict(model.network, 42), strict=True)
+    model = model.to(dev)
+    with ClockSampler(local_rank) as clocks:
+        clocks.mark()
+        res = fit_measure(model, args, dev, world, args.steps, args.warmup, reference_twin=not args.no_reference_gpu)
+    if rank == 0:
+        out = {'metric': 'clouds/sec training step, ppsurf_50nn fit (BASELINE config 5)', 'value': res['value'], 'unit': 'clouds/s',
+               'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': res['ms_per_step'],
+               'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+               'dtype': 'bf16 GEMM operands, fp32 accumulate / master weights' if args.fit_precision == 'bf16' else 'f32', 'data': 'synthetic',
+               'config': res['config'], 'e2e': res['e2e'], 'gpu_launches': res['gpu_launches_per_step'] * args.steps,
+               'clocks': clocks.summary(), 'loss_first_last_warmup': res['loss_first_last_warmup']}
+        if 'reference_gpu' in res:
+            out['reference_gpu'] = res['reference_gpu']
         quiet.emit(json.dumps(out))
     if world > 1:
         dist.barrier()
@@ -629,6 +798,8 @@ def main():
         run_reference(args)
     elif args.impl == 'reference-gpu':
         run_reference_gpu(args)
+    elif args.workload == 'fit':
+        run_fit(args)
     else:
         run_b200(args)
 

@@ -413,7 +413,10 @@ int pps_bn_running_update(const float* mean, const float* var, int64_t count, fl
  * channels torch.cat([mat, mp.expand], 1) (nn.py:634-635,642-643) */
 int pps_act_fwd(const float* x, int64_t n, int act, float* y, void* stream);
 int pps_act_bwd(const float* x, const float* dy, int64_t n, int act, float* dx, void* stream);
-int pps_dropout_fwd(const float* x, int64_t n, float p, uint32_t seed, float* y, uint8_t* mask, void* stream);
+/* the mask is a hash of (element, seed + *draw_counter): draw_counter (nullable) is a DEVICE counter the caller advances between draws, so a
+ * captured CUDA graph that is replayed draws a new mask every step */
+int pps_dropout_fwd(const float* x, int64_t n, float p, uint32_t seed, const uint32_t* draw_counter, float* y, uint8_t* mask,
+                    void* stream);
 int pps_dropout_bwd(const float* dy, const uint8_t* mask, int64_t n, float p, float* dx, void* stream);
 int pps_rowscale_fwd(const float* x, const float* w, int64_t rows, int c, float* y, void* stream);
 int pps_rowscale_bwd(const float* x, const float* w, const float* dy, int64_t rows, int c, float* dx, float* dw, void* stream);

@@ -125,7 +125,7 @@ SIGNATURES = {
     'pps_bn_running_update': (i32, [c_f32p, c_f32p, i64, ctypes.c_float, i32, c_f32p, c_f32p, c_voidp]),
     'pps_act_fwd': (i32, [c_f32p, i64, i32, c_f32p, c_voidp]),
     'pps_act_bwd': (i32, [c_f32p, c_f32p, i64, i32, c_f32p, c_voidp]),
-    'pps_dropout_fwd': (i32, [c_f32p, i64, ctypes.c_float, ctypes.c_uint32, c_f32p, c_voidp, c_voidp]),
+    'pps_dropout_fwd': (i32, [c_f32p, i64, ctypes.c_float, ctypes.c_uint32, c_voidp, c_f32p, c_voidp, c_voidp]),
     'pps_dropout_bwd': (i32, [c_f32p, c_voidp, i64, ctypes.c_float, c_f32p, c_voidp]),
     'pps_rowscale_fwd': (i32, [c_f32p, c_f32p, i64, i32, c_f32p, c_voidp]),
     'pps_rowscale_bwd': (i32, [c_f32p, c_f32p, c_f32p, i64, i32, c_f32p, c_f32p, c_voidp]),

@@ -35,6 +35,13 @@ def manual_seed(seed: int):
     _state['seed'] = int(seed) & 0xFFFFFFFF
 
 
+def _draw_counter(device):
+    key = ('counter', str(device))
+    if key not in _state:
+        _state[key] = torch.zeros((1,), dtype=torch.int32, device=device)
+    return _state[key]
+
+
 def _f32(t):
     return t if t.dtype == torch.float32 else t.float()
 
@@ -171,7 +178,9 @@ class Dropout(torch.autograd.Function):
         y = torch.empty_like(x)
         mask = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
         _state['seed'] = (_state['seed'] * 1664525 + 1013904223) & 0xFFFFFFFF
-        check(lib.pps_dropout_fwd(_ptr(x, torch.float32), x.numel(), p, _state['seed'], _ptr(y), _ptr(mask), _stream()))
+        counter = _draw_counter(x.device)
+        check(lib.pps_dropout_fwd(_ptr(x, torch.float32), x.numel(), p, _state['seed'], _ptr(counter), _ptr(y), _ptr(mask), _stream()))
+        counter.add_(1)  # a device op: inside a captured graph every replay advances the draw
         ctx.save_for_backward(mask)
         ctx.p = p
         return y

@@ -173,9 +173,11 @@ __device__ __forceinline__ uint32_t hash32(uint32_t a, uint32_t b) {
     h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
     return h;
 }
-__global__ void dropout_fwd_kernel(const float* __restrict__ x, long long n, float p, uint32_t seed, float* __restrict__ y, uint8_t* mask) {
+__global__ void dropout_fwd_kernel(const float* __restrict__ x, long long n, float p, uint32_t seed, const uint32_t* __restrict__ draw,
+                                   float* __restrict__ y, uint8_t* mask) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (draw) seed += draw[0] * 0x9E3779B9u;  // device-side draw counter: a replayed CUDA graph gets a fresh mask every time
     const uint32_t h = hash32((uint32_t)i ^ seed, (uint32_t)(i >> 32) + seed * 31u);
     const bool keep = (h >> 8) * (1.f / 16777216.f) >= p;
     mask[i] = keep;
@@ -301,37 +303,59 @@ __global__ void gather_max_bwd_kernel(const float* __restrict__ dy, const int32_
 }
 
 // ---- attention pooling ---------------------------------------------------------------------------------------------------------
-// one block per group: prob[s, h] = softmax_s(scores[s, h]); a[s] = mean_h prob; out[c] = sum_s a[s] * v[s, c]
+// one block per group: prob[s, h] = softmax_s(scores[s, h]); a[s] = mean_h prob; out[c] = sum_s a[s] * v[s, c].
+// The group's score tile sits in shared memory; threads are laid out as (head lanes) x (parts of s) for the column-wise softmax,
+// one warp per row for the head mean, one thread per channel for the weighted sum.
 __global__ void __launch_bounds__(kT) attn_pool_fwd_kernel(const float* __restrict__ scores, const float* __restrict__ v, int s, int h, int c,
                                                            float* __restrict__ prob, float* __restrict__ a, float* __restrict__ out) {
-    extern __shared__ float sh[];  // a[s]
+    extern __shared__ float sh[];  // tile[s * h], a[s], red[kT]
+    float* tile = sh;
+    float* sa = sh + s * h;
+    float* red = sa + s;
     const long long g = blockIdx.x;
     const float* sc = scores + g * s * h;
-    float* pr = prob + g * s * h;
-    for (int j = threadIdx.x; j < s; j += blockDim.x) sh[j] = 0.f;
+    for (int i = threadIdx.x; i < s * h; i += kT) tile[i] = sc[i];
     __syncthreads();
-    for (int hh = threadIdx.x; hh < h; hh += blockDim.x) {
+    const int lanes_h = h < kT ? h : kT, parts = kT / lanes_h;
+    const int hl = threadIdx.x % lanes_h, part = threadIdx.x / lanes_h;
+    for (int hh = hl; hh < h; hh += lanes_h) {
         float mx = -INFINITY;
-        for (int j = 0; j < s; ++j) mx = fmaxf(mx, sc[j * h + hh]);
+        for (int j = part; j < s; j += parts) mx = fmaxf(mx, tile[j * h + hh]);
+        red[threadIdx.x] = mx;
+        __syncthreads();
+        for (int q = 0; q < parts; ++q) mx = fmaxf(mx, red[q * lanes_h + hl]);
+        __syncthreads();
         float sum = 0.f;
-        for (int j = 0; j < s; ++j) sum += __expf(sc[j * h + hh] - mx);
+        for (int j = part; j < s; j += parts) {
+            const float e = __expf(tile[j * h + hh] - mx);
+            tile[j * h + hh] = e;
+            sum += e;
+        }
+        red[threadIdx.x] = sum;
+        __syncthreads();
+        sum = 0.f;
+        for (int q = 0; q < parts; ++q) sum += red[q * lanes_h + hl];
         const float inv = 1.f / sum;
-        for (int j = 0; j < s; ++j) {
-            const float p = __expf(sc[j * h + hh] - mx) * inv;
-            pr[j * h + hh] = p;
-            atomicAdd(&sh[j], p);
+        for (int j = part; j < s; j += parts) tile[j * h + hh] *= inv;
+        __syncthreads();
+    }
+    float* pr = prob + g * s * h;
+    for (int i = threadIdx.x; i < s * h; i += kT) pr[i] = tile[i];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int j = warp; j < s; j += kT / 32) {
+        float acc = 0.f;
+        for (int hh = lane; hh < h; hh += 32) acc += tile[j * h + hh];
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+            sa[j] = acc / h;
+            a[g * s + j] = acc / h;
         }
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < s; j += blockDim.x) {
-        sh[j] *= 1.f / h;
-        a[g * s + j] = sh[j];
-    }
-    __syncthreads();
     const float* vg = v + g * s * c;
-    for (int cc = threadIdx.x; cc < c; cc += blockDim.x) {
+    for (int cc = threadIdx.x; cc < c; cc += kT) {
         float acc = 0.f;
-        for (int j = 0; j < s; ++j) acc = fmaf(sh[j], vg[j * c + cc], acc);
+        for (int j = 0; j < s; ++j) acc = fmaf(sa[j], vg[j * c + cc], acc);
         out[g * c + cc] = acc;
     }
 }
@@ -557,6 +581,222 @@ __global__ void __launch_bounds__(kT) colsum_kernel(const float* __restrict__ x,
     }
 }
 
+
+// ---- float4 variants (c % 4 == 0, 16-byte aligned rows): a block streams a slab of rows with its threads laid out as
+// (c / 4 channel quads) x (row lanes); the per-channel constants are loaded once, the row loop has no index division ------------------
+struct Quad {
+    int lanes_c, lanes_r, cq, rl;  // channel-quad lanes, row lanes, this thread's quad lane and row lane
+    __device__ explicit Quad(int c) {
+        const int q = c >> 2;
+        lanes_c = q < kT ? q : kT;
+        lanes_r = kT / lanes_c;
+        cq = threadIdx.x % lanes_c;
+        rl = threadIdx.x / lanes_c;
+    }
+};
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+
+__global__ void __launch_bounds__(kT) norm_stats_v4_kernel(const float* __restrict__ x, long long rows, int c, long long slab, double* sums) {
+    const int g = blockIdx.y;
+    const long long r0 = (long long)blockIdx.x * slab, r1 = min(rows, r0 + slab);
+    const float* xg = x + (long long)g * rows * c;
+    const Quad t(c);
+    __shared__ float sh[2][kT][4];
+    for (int cq = t.cq; cq < (c >> 2); cq += t.lanes_c) {
+        float s[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+        // fp32 partial sums over at most slab / lanes_r rows (tens to hundreds), combined in fp64 below
+        for (long long r = r0 + t.rl; r < r1; r += t.lanes_r) {
+            const float4 v = ld4(xg + r * c + 4 * cq);
+            s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+            s2[0] = fmaf(v.x, v.x, s2[0]); s2[1] = fmaf(v.y, v.y, s2[1]); s2[2] = fmaf(v.z, v.z, s2[2]); s2[3] = fmaf(v.w, v.w, s2[3]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            sh[0][threadIdx.x][j] = s[j];
+            sh[1][threadIdx.x][j] = s2[j];
+        }
+        __syncthreads();
+        if (t.rl == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double a = 0.0, b = 0.0;
+                for (int l = 0; l < t.lanes_r; ++l) {
+                    a += sh[0][l * t.lanes_c + t.cq][j];
+                    b += sh[1][l * t.lanes_c + t.cq][j];
+                }
+                atomicAdd(&sums[((long long)g * c + 4 * cq + j) * 2 + 0], a);
+                atomicAdd(&sums[((long long)g * c + 4 * cq + j) * 2 + 1], b);
+            }
+        }
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(kT) norm_apply_v4_kernel(const float* __restrict__ x, long long rows, int c, long long slab,
+                                                           const float* __restrict__ mean, const float* __restrict__ var,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int act,
+                                                           float* __restrict__ y) {
+    const int g = blockIdx.y;
+    const long long r0 = (long long)blockIdx.x * slab, r1 = min(rows, r0 + slab);
+    const long long base = (long long)g * rows * c;
+    const Quad t(c);
+    for (int cq = t.cq; cq < (c >> 2); cq += t.lanes_c) {
+        float sc[4], sf[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int cc = 4 * cq + j;
+            const float rs = rsqrtf(var[(long long)g * c + cc] + eps);
+            sc[j] = rs * gamma[cc];
+            sf[j] = beta[cc] - mean[(long long)g * c + cc] * sc[j];
+        }
+        for (long long r = r0 + t.rl; r < r1; r += t.lanes_r) {
+            const float4 v = ld4(x + base + r * c + 4 * cq);
+            float4 o;
+            o.x = act_fwd(fmaf(v.x, sc[0], sf[0]), act);
+            o.y = act_fwd(fmaf(v.y, sc[1], sf[1]), act);
+            o.z = act_fwd(fmaf(v.z, sc[2], sf[2]), act);
+            o.w = act_fwd(fmaf(v.w, sc[3], sf[3]), act);
+            st4(y + base + r * c + 4 * cq, o);
+        }
+    }
+}
+__global__ void __launch_bounds__(kT) norm_bwd_reduce_v4_kernel(const float* __restrict__ x, const float* __restrict__ dy, long long rows,
+                                                                int c, long long slab, const float* __restrict__ mean,
+                                                                const float* __restrict__ var, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, float eps, int act, double* red) {
+    const int g = blockIdx.y;
+    const long long r0 = (long long)blockIdx.x * slab, r1 = min(rows, r0 + slab);
+    const long long base = (long long)g * rows * c;
+    const Quad t(c);
+    __shared__ float sh[2][kT][4];
+    for (int cq = t.cq; cq < (c >> 2); cq += t.lanes_c) {
+        float m[4], rs[4], ga[4], be[4], s[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int cc = 4 * cq + j;
+            m[j] = mean[(long long)g * c + cc];
+            rs[j] = rsqrtf(var[(long long)g * c + cc] + eps);
+            ga[j] = gamma[cc];
+            be[j] = beta[cc];
+        }
+        for (long long r = r0 + t.rl; r < r1; r += t.lanes_r) {
+            const float4 v = ld4(x + base + r * c + 4 * cq), d = ld4(dy + base + r * c + 4 * cq);
+            const float xv[4] = {v.x, v.y, v.z, v.w}, dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float xh = (xv[j] - m[j]) * rs[j];
+                const float dz = dv[j] * act_grad(fmaf(xh, ga[j], be[j]), act);
+                s[j] += dz;
+                s2[j] = fmaf(dz, xh, s2[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            sh[0][threadIdx.x][j] = s[j];
+            sh[1][threadIdx.x][j] = s2[j];
+        }
+        __syncthreads();
+        if (t.rl == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double a = 0.0, b = 0.0;
+                for (int l = 0; l < t.lanes_r; ++l) {
+                    a += sh[0][l * t.lanes_c + t.cq][j];
+                    b += sh[1][l * t.lanes_c + t.cq][j];
+                }
+                atomicAdd(&red[((long long)g * c + 4 * cq + j) * 2 + 0], a);
+                atomicAdd(&red[((long long)g * c + 4 * cq + j) * 2 + 1], b);
+            }
+        }
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(kT) norm_bwd_apply_v4_kernel(const float* __restrict__ x, const float* __restrict__ dy, long long rows, int c,
+                                                               long long slab, const float* __restrict__ mean, const float* __restrict__ var,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                               int act, const double* __restrict__ red, float* __restrict__ dx) {
+    const int g = blockIdx.y;
+    const long long r0 = (long long)blockIdx.x * slab, r1 = min(rows, r0 + slab);
+    const long long base = (long long)g * rows * c;
+    const Quad t(c);
+    const double inv = 1.0 / (double)rows;
+    for (int cq = t.cq; cq < (c >> 2); cq += t.lanes_c) {
+        float m[4], rs[4], ga[4], be[4], mdz[4], mdzx[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long long gc = (long long)g * c + 4 * cq + j;
+            m[j] = mean[gc];
+            rs[j] = rsqrtf(var[gc] + eps);
+            ga[j] = gamma[4 * cq + j];
+            be[j] = beta[4 * cq + j];
+            mdz[j] = (float)(red[gc * 2 + 0] * inv);
+            mdzx[j] = (float)(red[gc * 2 + 1] * inv);
+        }
+        for (long long r = r0 + t.rl; r < r1; r += t.lanes_r) {
+            const float4 v = ld4(x + base + r * c + 4 * cq), d = ld4(dy + base + r * c + 4 * cq);
+            const float xv[4] = {v.x, v.y, v.z, v.w}, dv[4] = {d.x, d.y, d.z, d.w};
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float xh = (xv[j] - m[j]) * rs[j];
+                const float dz = dv[j] * act_grad(fmaf(xh, ga[j], be[j]), act);
+                o[j] = ga[j] * rs[j] * (dz - mdz[j] - xh * mdzx[j]);
+            }
+            st4(dx + base + r * c + 4 * cq, make_float4(o[0], o[1], o[2], o[3]));
+        }
+    }
+}
+// dgamma[c] = sum_g red[g,c,1], dbeta[c] = sum_g red[g,c,0]
+__global__ void norm_param_grads_kernel(const double* __restrict__ red, int groups, int c, float* dgamma, float* dbeta) {
+    const int cc = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cc >= c) return;
+    double a = 0.0, b = 0.0;
+    for (int g = 0; g < groups; ++g) {
+        b += red[((long long)g * c + cc) * 2 + 0];
+        a += red[((long long)g * c + cc) * 2 + 1];
+    }
+    dgamma[cc] = (float)a;
+    dbeta[cc] = (float)b;
+}
+__global__ void act_fwd_v4_kernel(const float* __restrict__ x, long long n4, int act, float* __restrict__ y) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = ld4(x + 4 * i);
+    st4(y + 4 * i, make_float4(act_fwd(v.x, act), act_fwd(v.y, act), act_fwd(v.z, act), act_fwd(v.w, act)));
+}
+__global__ void act_bwd_v4_kernel(const float* __restrict__ x, const float* __restrict__ dy, long long n4, int act, float* __restrict__ dx) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = ld4(x + 4 * i), d = ld4(dy + 4 * i);
+    st4(dx + 4 * i, make_float4(d.x * act_grad(v.x, act), d.y * act_grad(v.y, act), d.z * act_grad(v.z, act), d.w * act_grad(v.w, act)));
+}
+__global__ void __launch_bounds__(kT) colsum_v4_kernel(const float* __restrict__ x, long long rows, int c, long long ld, long long slab,
+                                                       float* out) {
+    const long long r0 = (long long)blockIdx.x * slab, r1 = min(rows, r0 + slab);
+    const Quad t(c);
+    __shared__ float sh[kT][4];
+    for (int cq = t.cq; cq < (c >> 2); cq += t.lanes_c) {
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+        for (long long r = r0 + t.rl; r < r1; r += t.lanes_r) {
+            const float4 v = ld4(x + r * ld + 4 * cq);
+            s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sh[threadIdx.x][j] = s[j];
+        __syncthreads();
+        if (t.rl == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float a = 0.f;
+                for (int l = 0; l < t.lanes_r; ++l) a += sh[l * t.lanes_c + t.cq][j];
+                atomicAdd(out + 4 * cq + j, a);
+            }
+        }
+        __syncthreads();
+    }
+}
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 inline unsigned blocks_for(long long n) { return (unsigned)std::max<long long>(1, ceil_div(n, kT)); }
 inline long long slab_for(long long rows, long long groups) {
     // about 4 blocks per SM over all groups, at least 64 rows per block
@@ -586,12 +826,20 @@ int pps_norm_fwd(const float* x, int64_t groups, int64_t rows, int c, const floa
     double* sums = static_cast<double*>(workspace);
     PPS_CUDA(cudaMemsetAsync(sums, 0, pps_norm_workspace_bytes(groups, c), ST));
     const long long slab = slab_for(rows, groups);
-    norm_stats_kernel<<<dim3((unsigned)ceil_div(rows, slab), (unsigned)groups), kT, 0, ST>>>(x, rows, c, slab, sums);
+    const bool v4 = (c & 3) == 0 && aligned16(x) && aligned16(y);
+    const dim3 grid((unsigned)ceil_div(rows, slab), (unsigned)groups);
+    if (v4)
+        norm_stats_v4_kernel<<<grid, kT, 0, ST>>>(x, rows, c, slab, sums);
+    else
+        norm_stats_kernel<<<grid, kT, 0, ST>>>(x, rows, c, slab, sums);
     PPS_LAUNCH_CHECK();
     norm_finalize_kernel<<<blocks_for(groups * c), kT, 0, ST>>>(sums, rows, groups * c, mean, var);
     PPS_LAUNCH_CHECK();
     const long long total = groups * rows * c;
-    norm_apply_kernel<<<blocks_for(total), kT, 0, ST>>>(x, rows, c, mean, var, gamma, beta, eps, act, y, total);
+    if (v4)
+        norm_apply_v4_kernel<<<grid, kT, 0, ST>>>(x, rows, c, slab, mean, var, gamma, beta, eps, act, y);
+    else
+        norm_apply_kernel<<<blocks_for(total), kT, 0, ST>>>(x, rows, c, mean, var, gamma, beta, eps, act, y, total);
     PPS_LAUNCH_CHECK();
     return PPS_OK;
 }
@@ -608,12 +856,21 @@ int pps_norm_bwd(const float* x, const float* dy, int64_t groups, int64_t rows, 
     double* red = static_cast<double*>(workspace);
     PPS_CUDA(cudaMemsetAsync(red, 0, pps_norm_workspace_bytes(groups, c), ST));
     const long long slab = slab_for(rows, groups);
-    norm_bwd_reduce_kernel<<<dim3((unsigned)ceil_div(rows, slab), (unsigned)groups), kT, 0, ST>>>(x, dy, rows, c, slab, mean, var, gamma, beta,
-                                                                                                  eps, act, red);
-    PPS_LAUNCH_CHECK();
+    const bool v4 = (c & 3) == 0 && aligned16(x) && aligned16(dy) && aligned16(dx);
+    const dim3 grid((unsigned)ceil_div(rows, slab), (unsigned)groups);
     const long long total = groups * rows * c;
-    norm_bwd_apply_kernel<<<blocks_for(total), kT, 0, ST>>>(x, dy, rows, c, (int)groups, mean, var, gamma, beta, eps, act, red, dx, dgamma,
-                                                            dbeta, total);
+    if (v4) {
+        norm_bwd_reduce_v4_kernel<<<grid, kT, 0, ST>>>(x, dy, rows, c, slab, mean, var, gamma, beta, eps, act, red);
+        PPS_LAUNCH_CHECK();
+        norm_param_grads_kernel<<<blocks_for(c), kT, 0, ST>>>(red, (int)groups, c, dgamma, dbeta);
+        PPS_LAUNCH_CHECK();
+        norm_bwd_apply_v4_kernel<<<grid, kT, 0, ST>>>(x, dy, rows, c, slab, mean, var, gamma, beta, eps, act, red, dx);
+    } else {
+        norm_bwd_reduce_kernel<<<grid, kT, 0, ST>>>(x, dy, rows, c, slab, mean, var, gamma, beta, eps, act, red);
+        PPS_LAUNCH_CHECK();
+        norm_bwd_apply_kernel<<<blocks_for(total), kT, 0, ST>>>(x, dy, rows, c, (int)groups, mean, var, gamma, beta, eps, act, red, dx, dgamma,
+                                                                dbeta, total);
+    }
     PPS_LAUNCH_CHECK();
     return PPS_OK;
 }
@@ -629,21 +886,27 @@ int pps_bn_running_update(const float* mean, const float* var, int64_t count, fl
 int pps_act_fwd(const float* x, int64_t n, int act, float* y, void* stream) {
     PPS_CHECK_ARG(x && y && n >= 0, "pps_act_fwd: bad argument");
     if (n == 0) return PPS_OK;
-    act_fwd_kernel<<<blocks_for(n), kT, 0, ST>>>(x, n, act, y);
+    if ((n & 3) == 0 && aligned16(x) && aligned16(y))
+        act_fwd_v4_kernel<<<blocks_for(n / 4), kT, 0, ST>>>(x, n / 4, act, y);
+    else
+        act_fwd_kernel<<<blocks_for(n), kT, 0, ST>>>(x, n, act, y);
     PPS_LAUNCH_CHECK();
     return PPS_OK;
 }
 int pps_act_bwd(const float* x, const float* dy, int64_t n, int act, float* dx, void* stream) {
     PPS_CHECK_ARG(x && dy && dx && n >= 0, "pps_act_bwd: bad argument");
     if (n == 0) return PPS_OK;
-    act_bwd_kernel<<<blocks_for(n), kT, 0, ST>>>(x, dy, n, act, dx);
+    if ((n & 3) == 0 && aligned16(x) && aligned16(dy) && aligned16(dx))
+        act_bwd_v4_kernel<<<blocks_for(n / 4), kT, 0, ST>>>(x, dy, n / 4, act, dx);
+    else
+        act_bwd_kernel<<<blocks_for(n), kT, 0, ST>>>(x, dy, n, act, dx);
     PPS_LAUNCH_CHECK();
     return PPS_OK;
 }
-int pps_dropout_fwd(const float* x, int64_t n, float p, uint32_t seed, float* y, uint8_t* mask, void* stream) {
+int pps_dropout_fwd(const float* x, int64_t n, float p, uint32_t seed, const uint32_t* draw_counter, float* y, uint8_t* mask, void* stream) {
     PPS_CHECK_ARG(x && y && mask && n >= 0 && p >= 0.f && p < 1.f, "pps_dropout_fwd: bad argument");
     if (n == 0) return PPS_OK;
-    dropout_fwd_kernel<<<blocks_for(n), kT, 0, ST>>>(x, n, p, seed, y, mask);
+    dropout_fwd_kernel<<<blocks_for(n), kT, 0, ST>>>(x, n, p, seed, draw_counter, y, mask);
     PPS_LAUNCH_CHECK();
     return PPS_OK;
 }
@@ -731,9 +994,10 @@ int pps_gather_max_bwd(const float* dy, const int32_t* arg, int64_t rows, int c,
 }
 int pps_attn_pool_fwd(const float* scores, const float* v, int64_t groups, int s, int h, int c, float* prob, float* a, float* out,
                       void* stream) {
-    PPS_CHECK_ARG(scores && v && prob && a && out && groups >= 0 && s > 0 && s <= 4096 && h > 0 && c > 0, "pps_attn_pool_fwd: bad argument");
+    PPS_CHECK_ARG(scores && v && prob && a && out && groups >= 0 && s > 0 && h > 0 && c > 0, "pps_attn_pool_fwd: bad argument");
+    PPS_CHECK_ARG(((size_t)s * h + s + kT) * sizeof(float) <= 48 * 1024, "pps_attn_pool_fwd: a group of %d rows x %d heads exceeds the shared-memory tile", s, h);
     if (groups == 0) return PPS_OK;
-    attn_pool_fwd_kernel<<<(unsigned)groups, kT, s * sizeof(float), ST>>>(scores, v, s, h, c, prob, a, out);
+    attn_pool_fwd_kernel<<<(unsigned)groups, kT, ((size_t)s * h + s + kT) * sizeof(float), ST>>>(scores, v, s, h, c, prob, a, out);
     PPS_LAUNCH_CHECK();
     return PPS_OK;
 }
@@ -805,7 +1069,10 @@ int pps_colsum(const float* x, int64_t rows, int c, int64_t ld, float* out, int 
     if (!accumulate) PPS_CUDA(cudaMemsetAsync(out, 0, (size_t)c * sizeof(float), ST));
     if (rows == 0) return PPS_OK;
     const long long slab = slab_for(rows, 1);
-    colsum_kernel<<<(unsigned)ceil_div(rows, slab), kT, 0, ST>>>(x, rows, c, ld, slab, out);
+    if ((c & 3) == 0 && (ld & 3) == 0 && aligned16(x))
+        colsum_v4_kernel<<<(unsigned)ceil_div(rows, slab), kT, 0, ST>>>(x, rows, c, ld, slab, out);
+    else
+        colsum_kernel<<<(unsigned)ceil_div(rows, slab), kT, 0, ST>>>(x, rows, c, ld, slab, out);
     PPS_LAUNCH_CHECK();
     return PPS_OK;
 }

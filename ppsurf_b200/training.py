@@ -181,3 +181,71 @@ def forward(network, data, training=True):
         + pointnet(network.point_net, loc.reshape(b * q, loc.shape[2], 3).contiguous(), training)
     logits = mlp(network.mlp, feat, training)
     return logits.view(b, q, -1).transpose(1, 2)
+
+
+BATCH_KEYS = ('pts', 'support1', 'support2', 'support3', 'support4', 'ids00', 'ids01', 'ids11', 'ids12', 'ids22', 'ids23', 'ids33', 'ids34',
+              'ids44', 'ids43', 'ids32', 'ids21', 'ids10', 'pts_query', 'proj_ids', 'pts_local_ps', 'occ')
+
+
+class GraphedTrainStep:
+    """One training step (forward, cross entropy, backward, optimiser update) captured ONCE into CUDA graphs and replayed: the step is
+    about 1200 small launches, which a Python thread cannot issue as fast as the device retires them.  All batches must have the shapes
+    of the first one (fixed ``manifold_points`` / query count, as in the reference's training configuration).
+
+    Data parallel (``world > 1``, one process per GPU): every parameter gradient is a view into ONE flat buffer; the backward graph
+    fills it, a single NCCL all-reduce averages it over the ranks, a second graph runs the optimiser -- the reference's DDP
+    (configs/device_server.yaml) with one bucket.  BatchNorm statistics stay per rank like the reference's (no SyncBatchNorm).
+
+    ``optimizer`` must be constructed with ``capturable=True``."""
+
+    def __init__(self, network, optimizer, batch: dict, world: int = 1, warmup: int = 3):
+        import torch.distributed as dist
+        self.network, self.optimizer, self.world = network, optimizer, world
+        self.dist = dist
+        dev = batch['pts'].device
+        self.static = {k: batch[k].clone() for k in BATCH_KEYS}
+        params = [p for p in network.parameters() if p.requires_grad]
+        self.flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
+        off = 0
+        for p in params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._forward_backward()
+                self._reduce()
+                optimizer.step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(dev)
+        from ._lib import lib
+        launched = lib.pps_launch_count()
+        self.graph_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_fb):
+            self.loss = self._forward_backward()
+        self.kernels_per_step = int(lib.pps_launch_count() - launched)  # library kernels recorded in the graph (replayed every step)
+        self.graph_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_opt):
+            optimizer.step()
+
+    def _forward_backward(self):
+        self.flat.zero_()  # gradients accumulate into the flat buffer (set_to_none would detach the views)
+        pred = self.network.forward(dict(self.static))
+        b, c, q = pred.shape
+        loss, _ = ag.cross_entropy(pred.transpose(1, 2).reshape(b * q, c), self.static['occ'].reshape(-1))
+        loss.backward()
+        return loss.detach()
+
+    def _reduce(self):
+        if self.world > 1:
+            self.dist.all_reduce(self.flat)
+            self.flat.mul_(1.0 / self.world)
+
+    def __call__(self, batch: dict) -> torch.Tensor:
+        for k in BATCH_KEYS:
+            self.static[k].copy_(batch[k], non_blocking=True)
+        self.graph_fb.replay()
+        self._reduce()
+        self.graph_opt.replay()
+        return self.loss
