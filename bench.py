@@ -710,11 +710,11 @@ def fit_measure(model, args, dev, world, steps, warmup, reference_twin=False):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0])
 
-    losses = [float(step(batch)) for _ in range(max(3, warmup))]
+    losses = [float(step(batch).detach()) for _ in range(max(3, warmup))]
     launches0 = _lib.lib.pps_launch_count()
     ms = timed(lambda: step(batch), steps)
     launches = (_lib.lib.pps_launch_count() - launches0) if args.fit_eager else step.kernels_per_step * steps
-    ms_e2e = timed(lambda: float(step(prepare())), steps)
+    ms_e2e = timed(lambda: float(step(prepare()).detach()), steps)
     ag.set_precision('fp32')
     clouds = args.fit_clouds_per_gpu * world
     out = {'value': clouds * steps / (ms / 1e3), 'unit': 'clouds/s', 'ms_per_step': ms / steps,
