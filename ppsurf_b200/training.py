@@ -19,6 +19,17 @@ LEVELS = ((0, 0, 'ids00'), (0, 1, 'ids01'), (1, 1, 'ids11'), (1, 2, 'ids12'), (2
           (3, 4, 'ids34'), (4, 4, 'ids44'))
 
 
+CONCURRENT_BRANCHES = True
+_side_streams = {}
+
+
+def _side_stream(device):
+    key = str(device)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
 def _w2(conv):
     """weight of a 1x1 Conv1d / Conv2d / Linear as a ``[out, in]`` view"""
     w = conv.weight
@@ -168,8 +179,6 @@ def forward(network, data, training=True):
     pts = [pm(data['pts'])] + [pm(data['support%d' % i]) for i in (1, 2, 3, 4)]
     ids = {key: val.to(torch.int32).contiguous() for key, val in data.items() if key.startswith('ids')}
     b, n, _ = pts[0].shape
-    latents = encoder(network.encoder, pts, ids, training)
-    data['latents'] = latents.view(b, n, -1).transpose(1, 2)
     qry = data['pts_query'].to(pts[0].device, torch.float32)
     if qry.shape[-1] != 3:
         qry = qry.transpose(1, 2)
@@ -177,8 +186,25 @@ def forward(network, data, training=True):
     proj_ids = data['proj_ids'].to(torch.int32).contiguous()
     loc = data['pts_local_ps'].to(pts[0].device, torch.float32)
     q = qry.shape[1]
-    feat = projection(network.projection, latents, pts[0], qry, proj_ids) \
-        + pointnet(network.point_net, loc.reshape(b * q, loc.shape[2], 3).contiguous(), training)
+    # the local branch does not depend on the encoder: it runs on a side stream next to encoder + projection (autograd replays the
+    # same fork / join in the backward pass, and a captured graph keeps the two branches parallel).  The encoder is ~800 small
+    # launches over 39..10 000 points that leave most SMs idle; the PointNet layers over B*Q*P rows fill them.
+    main = torch.cuda.current_stream()
+    side = _side_stream(pts[0].device) if CONCURRENT_BRANCHES else main
+    patches = loc.reshape(b * q, loc.shape[2], 3).contiguous()
+    if side is not main:
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            local = pointnet(network.point_net, patches, training)
+    else:
+        local = pointnet(network.point_net, patches, training)
+    latents = encoder(network.encoder, pts, ids, training)
+    data['latents'] = latents.view(b, n, -1).transpose(1, 2)
+    glob = projection(network.projection, latents, pts[0], qry, proj_ids)
+    if side is not main:
+        main.wait_stream(side)  # `local` is consumed below on the main stream; the next side-stream work (the branch's backward) is
+        # ordered after it by autograd's own stream synchronisation, so the allocator cannot hand its block out early
+    feat = glob + local
     logits = mlp(network.mlp, feat, training)
     return logits.view(b, q, -1).transpose(1, 2)
 
