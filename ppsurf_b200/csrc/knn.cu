@@ -10,6 +10,8 @@
 // (dx*dx + dy*dy) + dz*dz, every operation rounded, no FMA.
 #include <cub/device/device_radix_sort.cuh>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace pps {
@@ -474,7 +476,15 @@ template <int SLOTS>
 static int launch_query(const KnnHeader* hdr, const float4* sorted, const int* cell_start, const float* queries,
                         int64_t q, int k, int32_t* idx_out, float* d2_out, cudaStream_t st) {
     // seeded lists (k in 33..256: the decoder's grid-ordered queries) profit from longer runs, the others have nothing to amortise
-    const int run = (SLOTS == 2 || SLOTS == 4 || SLOTS == 8) ? g_knn_run : kRun;
+    int run = (SLOTS == 2 || SLOTS == 4 || SLOTS == 8) ? g_knn_run : kRun;
+    // The run length trades the seeding benefit (a query starts from its predecessor's list) against the serial chain it puts on one
+    // warp: queries deep inside the surface scan most of the cloud (~0.3 ms each), and a launch ends when its slowest warp does.
+    // Measured on the bench grid (tools/knn_run_probe2.py; one rank's dealt blocks at 1 / 2 / 4 / 8 ranks): the best run length is
+    // 16 / 8 / 4 / 2 for 2.25 M / 1.13 M / 564 k / 284 k queries, i.e. whatever gives the launch about 140 000 warps -- 284 k queries
+    // take 7.7 ms instead of 16.6 ms, and the small late sweeps of the region growing (2 366 queries: 19 ms) stop dominating the
+    // shell decode.  The result does not depend on the run length (unique total order).
+    const int64_t want_warps = 140000;
+    run = (int)std::min<int64_t>(run, std::max<int64_t>(1, (q + want_warps / 2) / want_warps));
     knn_warp_kernel<SLOTS><<<(unsigned)ceil_div(q, 8 * run), 256, 0, st>>>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out, run);
     PPS_LAUNCH_CHECK();
     return PPS_OK;
