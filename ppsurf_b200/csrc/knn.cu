@@ -173,15 +173,22 @@ __device__ __forceinline__ bool cand_less(float da, int ia, float db, int ib) { 
 template <int SLOTS>
 __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restrict__ hdr, const float4* __restrict__ sorted,
                                                        const int* __restrict__ cell_start, const float* __restrict__ queries,
-                                                       long long nq, int k, int32_t* __restrict__ idx_out,
-                                                       float* __restrict__ d2_out, int run) {
+                                                       long long nq, int k, int32_t* idx_out,
+                                                       float* __restrict__ d2_out, int run, int pass, int scan_cap) {
     // per warp: node code, and the node's range in the sorted array (loaded by the parent: no second round trip on the pop)
     __shared__ unsigned int stack_s[8][8 * kMaxLevels + 8];
     __shared__ int stack_lo_s[8][8 * kMaxLevels + 8], stack_hi_s[8][8 * kMaxLevels + 8];
     const unsigned int full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // pass 1: runs of `run` consecutive queries.  A run whose scans have exceeded `scan_cap` points hands its REMAINING queries to
+    // pass 2 (marks their first output index with -1) instead of serialising them on this warp: queries deep inside the surface scan
+    // most of the cloud (0.3 .. 1 ms each), and 16 of them in a row set the duration of the whole launch.  pass 2: one warp per
+    // marked query (unseeded; nothing to amortise for a query that scans everything), all of them in parallel.
+    if (pass == 2) run = 1;
     const long long q_first = ((long long)blockIdx.x * 8 + warp) * run;
     if (q_first >= nq) return;
+    if (pass == 2 && idx_out[q_first * k] != -1) return;
+    int scanned = 0;
     unsigned int* stack = stack_s[warp];
     int* stack_lo = stack_lo_s[warp];
     int* stack_hi = stack_hi_s[warp];
@@ -199,6 +206,10 @@ __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restri
     for (int rq = 0; rq < run; ++rq) {
         const long long qi = q_first + rq;
         if (qi >= nq) break;
+        if (pass == 1 && rq > 0 && scanned > scan_cap) {
+            for (long long t = qi + lane; t < min(nq, q_first + run); t += 32) idx_out[t * k] = -1;
+            break;
+        }
         const float qx = queries[3 * qi], qy = queries[3 * qi + 1], qz = queries[3 * qi + 2];
         float worst = INFINITY;
         int worst_i = 0x7fffffff;
@@ -288,6 +299,7 @@ __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restri
 
         // scan the contiguous range [lo, hi) of the Morton-sorted points, 32 at a time
         auto scan_range = [&](int lo, int hi) {
+            scanned += hi - lo;
             float4 pn = make_float4(0.f, 0.f, 0.f, 0.f);
             if (lo + lane < hi) pn = sorted[lo + lane];
             for (int base = lo; base < hi; base += 32) {
@@ -470,6 +482,10 @@ __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restri
     }
 }
 
+// points a run may scan before it defers its remaining queries to the second pass: a surface query scans 300..1000 points, a run of 16
+// stays far below; a query inside the closed surface scans 10^4..10^5
+static int g_knn_scan_cap = 16384;
+static long long g_knn_defer_below = 600000;  // launches of fewer queries use the second pass (see launch_query)
 static int g_knn_run = 16;  // pps_debug_knn_run: 16 measured 5 % faster than 8 on the dense grid, 32 and 64 slower (tools/knn_run_probe.py)
 
 template <int SLOTS>
@@ -477,15 +493,22 @@ static int launch_query(const KnnHeader* hdr, const float4* sorted, const int* c
                         int64_t q, int k, int32_t* idx_out, float* d2_out, cudaStream_t st) {
     // seeded lists (k in 33..256: the decoder's grid-ordered queries) profit from longer runs, the others have nothing to amortise
     int run = (SLOTS == 2 || SLOTS == 4 || SLOTS == 8) ? g_knn_run : kRun;
-    // The run length trades the seeding benefit (a query starts from its predecessor's list) against the serial chain it puts on one
-    // warp: queries deep inside the surface scan most of the cloud (~0.3 ms each), and a launch ends when its slowest warp does.
-    // Measured on the bench grid (tools/knn_run_probe2.py; one rank's dealt blocks at 1 / 2 / 4 / 8 ranks): the best run length is
-    // 16 / 8 / 4 / 2 for 2.25 M / 1.13 M / 564 k / 284 k queries, i.e. whatever gives the launch about 140 000 warps -- 284 k queries
-    // take 7.7 ms instead of 16.6 ms, and the small late sweeps of the region growing (2 366 queries: 19 ms) stop dominating the
-    // shell decode.  The result does not depend on the run length (unique total order).
-    const int64_t want_warps = 140000;
-    run = (int)std::min<int64_t>(run, std::max<int64_t>(1, (q + want_warps / 2) / want_warps));
-    knn_warp_kernel<SLOTS><<<(unsigned)ceil_div(q, 8 * run), 256, 0, st>>>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out, run);
+    // small launches (the late sweeps of the region growing, the encoder's 39..2500-point levels): shorten the run until every SM
+    // is offered 32 warps; the result does not depend on the run length (unique total order), only the seeding benefit does
+    const int64_t want_warps = (int64_t)kNumSMs * 32;
+    if (q < want_warps * run) run = (int)std::max<int64_t>(1, q / want_warps);
+    // Deferral (pass 2) removes the serial chains that set the duration of a launch whose expensive runs are FEW: one rank's dealt
+    // share of the 131^3 grid at 8 / 4 / 2 GPUs takes 7.1 / 11.7 / 22.9 ms instead of 16.6 / 19.5 / 25.6 ms, the late sweeps of the
+    // region growing 1-2 ms instead of 10-19 ms.  A deferred query runs unseeded (~1.5x its seeded cost), so a launch that is work-bound
+    // anyway -- a contiguous 606 k-query super-chunk of the dense grid, whose middle is ALL expensive queries -- is better off without
+    // (whole grid 40 ms without, 45 ms with): deferral is used below that size.
+    const bool defer = run > 1 && q < g_knn_defer_below;
+    knn_warp_kernel<SLOTS><<<(unsigned)ceil_div(q, 8 * run), 256, 0, st>>>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out, run, 1,
+                                                                          defer ? g_knn_scan_cap : 0x7fffffff);
+    PPS_LAUNCH_CHECK();
+    if (defer) {  // the deferred queries (none on surface-hugging query sets: the blocks find no mark and exit)
+        knn_warp_kernel<SLOTS><<<(unsigned)ceil_div(q, 8), 256, 0, st>>>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out, 1, 2, 0);
+    }
     PPS_LAUNCH_CHECK();
     return PPS_OK;
 }
