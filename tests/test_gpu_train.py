@@ -348,6 +348,37 @@ def test_training_step_bf16_and_optimizer(dev, weights):
     assert out.shape == (2, 2, data['occ'].shape[1]) and torch.isfinite(out).all()
 
 
+def test_training_step_small_ragged_cloud_vs_twin(dev, weights, oracle):
+    """one cloud of 700 points and 33 queries: the deep encoder levels hold 10 and 2 points, so the neighbourhoods have 10 / 2 members
+    (kn < 16 paths of the FKAConv primitives, BatchNorm over 2 rows); compared with the float64 twin computed here"""
+    sys.path.insert(0, GOLDEN)
+    from make_golden_train import make_batch
+    from oracle import ppsurf_train_oracle as T
+    from ppsurf_b200 import autograd as ag
+    batch = make_batch(seed=321, b=1, n=700, q=33)
+    assert batch['ids34'].shape[2] == 10 and batch['ids44'].shape[2] == 2
+    data = {k: torch.from_numpy(v).to(dev) for k, v in batch.items()}
+    ag.set_precision('fp32')
+    net = _train_net(dev, weights, dropout=0.0)
+    pred = net.forward(dict(data))
+    loss, _ = ag.cross_entropy(pred.transpose(1, 2).reshape(-1, 2), data['occ'].reshape(-1))
+    loss.backward()
+    s = T.State(weights, dtype=torch.float64)
+    ref_loss, ref_logits = T.training_step(s, {k: (torch.from_numpy(v).double() if v.dtype == np.float32 else torch.from_numpy(v))
+                                               for k, v in batch.items()}, dropout=0.0)
+    assert abs(float(loss.detach()) - float(ref_loss)) < 5e-5
+    assert float((pred.detach().double().cpu() - ref_logits).abs().max()) < 5e-4
+    ref = s.grads()
+    rel = []
+    for name, par in net.named_parameters():
+        want = ref[name].reshape(-1)
+        if float(want.norm()) > 1e-4:
+            rel.append((float((par.grad.detach().double().cpu().reshape(-1) - want).norm() / want.norm()), name))
+    rel.sort(reverse=True)
+    print('small cloud: median relative gradient error {:.2e}, worst {}'.format(np.median([r[0] for r in rel]), rel[:3]))
+    assert np.median([r[0] for r in rel]) < 5e-3 and sum(r[0] > 0.1 for r in rel) <= 3, rel[:6]
+
+
 def _ddp_worker(rank, world, port, tmp):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     import torch.distributed as dist
