@@ -32,10 +32,12 @@ constexpr int kSub = 1;                      // k16 steps per ring slot.  2 was 
 constexpr int kSlotBytes = kSub * kStageBytes;
 constexpr int kStages = 10 / kSub;
 constexpr int kKSteps = kC / 16;            // 16 k16 steps per layer
-// split-fp16 terms the product kernel issues, bit 3*layer + t (t = 0: x_hi w_hi, 1: x_lo w_hi, 2: x_hi w_lo): three terms for fc2 and
-// fc3, two for fc_query (its weight-lo term changes the logits by 1e-6, profiles/r02_pass_ablation.md; the kernel is bound by MMA
-// execution, ~151 cycles per M256 N256 K16 instruction, so one MMA less per fc_query step is 7 % of the tile)
-constexpr uint32_t kProductTerms = 0x0FFu;
+// split-fp16 terms the product kernel issues, bit 3*layer + t (t = 0: x_hi w_hi, 1: x_lo w_hi, 2: x_hi w_lo): all three for every layer.
+// fc_query ran with two terms for a while (on the 4096-query ablation set of profiles/r02_pass_ablation.md its weight-lo term moves the
+// logits by 1e-6), but on the smoke workload a query with attention scores around 17 lost 2.1e-4 in the pooled vector and 1.2e-4 in a
+// logit -- beyond the 1e-4 contract (tools/smoke_debug.py: 5.2e-5 with the term).  As an M=256 x N=64 product the term costs 16 small
+// MMAs per tile.
+constexpr uint32_t kProductTerms = 0x1FFu;
 constexpr int kChunks = 4;                  // a layer's K range is released to the MMA warp in 4 chunks of 64 columns
 constexpr int kGWarps = 8;                  // gather + fc2/fc3 epilogues
 constexpr int kSWarps = 6;                  // softmax + attention pooling
@@ -696,7 +698,7 @@ extern "C" int pps_debug_tc_max_clusters(void) {
 // retired debug knob (cluster multicast / weight-stream experiments); kept so that the ABI is stable
 extern "C" void pps_debug_tc_cluster(int) {}
 // split-fp16 terms of the global branch's three GEMM layers: bit 3*layer + t, layer 0 = fc2, 1 = fc3, 2 = fc_query; t = 0: x_hi w_hi
-// (always issued), 1: x_lo w_hi, 2: x_hi w_lo.  Default 0x0FF: three terms for fc2 / fc3, two for fc_query; 0x1FF = three everywhere.
+// (always issued), 1: x_lo w_hi, 2: x_hi w_lo.  Default 0x1FF: three terms everywhere (0x0FF: two for fc_query).
 // Returns the previous mask.
 extern "C" int pps_decoder_tc_terms(int mask) {
     const int old = (int)pps::get_tc_terms();

@@ -507,7 +507,7 @@ def test_test_step_matches_oracle_forward(dev, oracle, weights):
     model = ppsurf_b200.PPSurfModel(256, ['imp_surf_sign'], 3, 2, 64, 0.0, False, 'x.txt', 'results', 0.05, 'test', 256, 10, 10000,
                                     129, 50, 50000, 10, 0)
     model.network.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in weights.items()}, strict=True)
-    model = model.to(dev)
+    model = model.to(dev).eval()  # Trainer.test puts the module in eval mode; in train mode forward() is the training path
     rng = np.random.default_rng(17)
     pts = oracle.synthetic_cloud(4200, seed=23)
     model.network.sampling_seed = 3

@@ -73,4 +73,4 @@ for fc2, fc3, fcq in ((3, 3, 3), (3, 3, 2), (3, 3, 1), (3, 3, 0), (3, 2, 3), (3,
     _lib.lib.pps_profile_read(ctypes.byref(ms), ctypes.byref(br))
     _lib.lib.pps_profile_enable(0)
     print('| {} | {} | {} | {:.2e} | {:.2e} | {:.2f} |'.format(names[fc2], names[fc3], names[fcq], err, err_o, ms.value), flush=True)
-_lib.lib.pps_decoder_tc_terms(0x0FF)
+_lib.lib.pps_decoder_tc_terms(0x1FF)
