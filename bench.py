@@ -714,14 +714,32 @@ def fit_measure(model, args, dev, world, steps, warmup, reference_twin=False):
     launches0 = _lib.lib.pps_launch_count()
     ms = timed(lambda: step(batch), steps)
     launches = (_lib.lib.pps_launch_count() - launches0) if args.fit_eager else step.kernels_per_step * steps
-    ms_e2e = timed(lambda: float(step(prepare()).detach()), steps)
+    # e2e: the batch of step i+1 is prepared (H2D + prepare_batch) on a side stream while step i runs, like the reference's DataLoader
+    # workers prepare batches while the GPU trains; the loss of every step is read on the host
+    side = torch.cuda.Stream(device=dev)
+
+    def prepare_on_side():
+        with torch.cuda.stream(side):
+            return prepare()
+
+    pending = [prepare_on_side()]
+
+    def e2e_step():
+        cur = pending.pop()
+        torch.cuda.current_stream().wait_stream(side)
+        loss = step(cur)                    # asynchronous (graph replay)
+        pending.append(prepare_on_side())   # overlaps the step
+        return float(loss.detach())         # the one host read of the step
+
+    ms_e2e = timed(e2e_step, steps)
+    torch.cuda.synchronize()
     ag.set_precision('fp32')
     clouds = args.fit_clouds_per_gpu * world
     out = {'value': clouds * steps / (ms / 1e3), 'unit': 'clouds/s', 'ms_per_step': ms / steps,
            'e2e': {'value': clouds * steps / (ms_e2e / 1e3), 'unit': 'clouds/s', 'ms_per_step': ms_e2e / steps,
                    'h2d_bytes_per_step': int(h2d_bytes), 'd2h_bytes_per_step': 4,
-                   'call': 'pinned host batch -> data_pipeline.prepare_batch (supports, 13 kNN index tensors, proj_ids, patches on the '
-                           'device) -> training step -> loss.item()'},
+                   'call': 'pinned host batch -> H2D -> data_pipeline.prepare_batch (supports, 13 kNN index tensors, proj_ids, patches on the '
+                           'device; on a side stream, overlapping the previous step) -> training step -> loss.item()'},
            'gpu_launches_per_step': int(launches // steps), 'loss_first_last_warmup': [losses[0], losses[-1]],
            'config': {'workload': 'ppsurf_50nn fit (BASELINE config 5): {} clouds/GPU x {} GPUs, {} manifold points, {} query points, '
                                   'k=64, P=50, {} GEMMs on tcgen05 (fp32 master weights / activations), AdamW, {}'.format(
