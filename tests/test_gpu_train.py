@@ -50,7 +50,8 @@ def _grad_pair(ours_fn, ref_fn, inputs, tol, what):
 
 # ---- primitives ----------------------------------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize('m,n,k', [(1000, 256, 259), (77, 16, 3), (5000, 64, 256), (300, 4096, 64), (64, 2, 256)])
+@pytest.mark.parametrize('m,n,k', [(1000, 256, 259), (77, 16, 3), (5000, 64, 256), (300, 4096, 64), (64, 2, 256), (5000, 16, 32),
+                                   (5001, 16, 3), (40000, 32, 16)])
 def test_linear_fwd_bwd_fp32(dev, m, n, k):
     from ppsurf_b200 import autograd as ag
     ag.set_precision('fp32')
