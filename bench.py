@@ -575,11 +575,12 @@ def run_b200(args):
             'gpu_launches': int(launches),
             'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
                          'frac': (achieved / peaks['bf16_tflops']) if achieved else None,
-                         # DRAM bytes per launch from the ncu --set full capture under profiles/ (452.8 MB read + written by one
-                         # launch over 300763 queries = 1505 B per query, 1024 of them the pooled output), scaled to this run's
-                         # queries per launch
-                         'traffic': (1505.0 * count * args.steps / max(int(brackets.value), 1)) if args.path == 1 else None,
-                         'traffic_source': 'profiles/r01_projection_tc_full_v15_summary.csv' if args.path == 1 else None,
+                         # DRAM bytes per launch from the ncu --set full capture under profiles/ (272.2 MB read + written by one
+                         # launch over 300763 queries = 905 B per query: the pooled output, 1024 B per query, minus what was still
+                         # in the L2 when the capture ended; the fc1 table and the weights are L2 hits), scaled to this run's queries
+                         # per launch
+                         'traffic': (905.0 * count * args.steps / max(int(brackets.value), 1)) if args.path == 1 else None,
+                         'traffic_source': 'profiles/r02_decode_kernels_full_summary.csv' if args.path == 1 else None,
                          'kernel': kernel, 'kernel_ms_per_step': dom_ms.value / args.steps,
                          'kernel_share_of_step': dom_ms.value / elapsed_ms, 'brackets': int(brackets.value),
                          'flop_per_row_executed': GEMM_FLOP_PER_ROW, 'peak_source': peaks['source'],
