@@ -502,7 +502,8 @@ static int launch_query(const KnnHeader* hdr, const float4* sorted, const int* c
     // region growing 1-2 ms instead of 10-19 ms.  A deferred query runs unseeded (~1.5x its seeded cost), so a launch that is work-bound
     // anyway -- a contiguous 606 k-query super-chunk of the dense grid, whose middle is ALL expensive queries -- is better off without
     // (whole grid 40 ms without, 45 ms with): deferral is used below that size.
-    const bool defer = run > 1 && q < g_knn_defer_below;
+    // (k <= 32 serves the encoder's self-queries -- points of the cloud looking for their neighbours in it, never expensive)
+    const bool defer = SLOTS > 1 && run > 1 && q < g_knn_defer_below;
     knn_warp_kernel<SLOTS><<<(unsigned)ceil_div(q, 8 * run), 256, 0, st>>>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out, run, 1,
                                                                           defer ? g_knn_scan_cap : 0x7fffffff);
     PPS_LAUNCH_CHECK();
