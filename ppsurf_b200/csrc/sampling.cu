@@ -19,7 +19,7 @@ int knn_query_impl(const void* index, int64_t n, const float* queries, int64_t q
                    cudaStream_t st);
 
 constexpr int kSampleRounds = 6;
-constexpr int kIdStreams = 4;  // clouds of a batch are independent chains of small kernels: run them on side streams
+constexpr int kIdStreams = 8;  // clouds of a batch are independent chains of small kernels: run them on side streams
 constexpr unsigned long long kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
 
 struct SampleState {

@@ -107,6 +107,12 @@ class PPSurfModel(_Base):
         for ids, _ in self._schedule_np(n, generator):
             yield torch.from_numpy(ids)
 
+    def _latent_lanes(self, dev):
+        lanes = getattr(self, '_lanes', None)
+        if lanes is None or lanes[0].device != dev:
+            self._lanes = lanes = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+        return lanes
+
     def encode_cloud(self, pts_bcn: torch.Tensor, generator: typing.Optional[torch.Generator] = None,
                      prog_bar=None, batch_passes: int = 16) -> torch.Tensor:
         """``pts_bcn [1,3,N]`` (device) -> latents ``[1,latent,N]``: every point is encoded at least
@@ -172,6 +178,13 @@ class PPSurfModel(_Base):
 
         thread = threading.Thread(target=producer, daemon=True)
         thread.start()
+        # two batches in flight: batch i runs (inputs, index generation, network -- one CUDA-graph replay) on lane i % 2 while the main
+        # stream accumulates batch i-1; a lane is reused once the accumulation that read its output has been issued behind an event.
+        # A batch is ~6000 small kernels over 10 000-point clouds that cannot fill the device on their own.
+        main = torch.cuda.current_stream()
+        lanes = self._latent_lanes(dev)
+        consumed = [None, None]
+        turn = 0
         try:
             while True:
                 item = batches.get()
@@ -180,22 +193,33 @@ class PPSurfModel(_Base):
                 if isinstance(item, BaseException):
                     raise item
                 b, n_first, packed, rot, plain = item
-                packed = packed.to(dev, non_blocking=True)
-                rot = rot.to(dev, non_blocking=True)
-                all_ids = packed[:b * sub]
-                batch = torch.index_select(pts, 0, all_ids).view(b, sub, 3)  # [B,sub,3] point-major
-                part_pm = net.latents_of_batch(batch, rot).reshape(b * sub, -1)
-                if plain:
-                    rows_dev = torch.arange(b * sub, device=dev, dtype=torch.int32)
-                    dsts_dev = all_ids
+                lane = lanes[turn % 2]
+                if consumed[turn % 2] is not None:
+                    lane.wait_event(consumed[turn % 2])
                 else:
-                    total_first = sum(n_first)
-                    rows_dev, dsts_dev = packed[b * sub:b * sub + total_first], packed[b * sub + total_first:]
+                    lane.wait_stream(main)
+                with torch.cuda.stream(lane):
+                    packed = packed.to(dev, non_blocking=True)
+                    rot = rot.to(dev, non_blocking=True)
+                    all_ids = packed[:b * sub]
+                    batch = torch.index_select(pts, 0, all_ids).view(b, sub, 3)  # [B,sub,3] point-major
+                    part_pm = net.latents_of_batch(batch, rot).reshape(b * sub, -1)
+                    if plain:
+                        rows_dev = torch.arange(b * sub, device=dev, dtype=torch.int32)
+                        dsts_dev = all_ids
+                    else:
+                        total_first = sum(n_first)
+                        rows_dev, dsts_dev = packed[b * sub:b * sub + total_first], packed[b * sub + total_first:]
+                main.wait_stream(lane)
                 off = 0
                 for nf in n_first:  # pass order is kept: a point revisited inside the batch accumulates in the reference's order
                     ops.latent_accumulate_rows(part_pm, rows_dev[off:off + nf], dsts_dev[off:off + nf], latent, counts)
                     off += nf
                     iteration += 1
+                done = torch.cuda.Event()
+                done.record(main)
+                consumed[turn % 2] = done
+                turn += 1
                 if prog_bar is not None:
                     prog_bar.predict_progress_bar.set_postfix_str('get_latent iter: {}'.format(iteration), refresh=True)
         finally:

@@ -278,7 +278,8 @@ class PPSurfNetwork(_Base):
         whole batch (about 6000 small launches: samplings, radix sorts, index builds, 13 kNN queries per sub-cloud, the network) is
         captured ONCE per shape into a CUDA graph and replayed: the result lives in the graph's static output buffer and is valid
         until the next call with the same shape."""
-        key = (tuple(pts.shape), pts.device)
+        # one slot per (shape, stream): the latent loop alternates between two streams so that two batches are in flight
+        key = (tuple(pts.shape), pts.device, torch.cuda.current_stream().cuda_stream)
         slot = self._graphs.get(key)
         if not self.use_graphs or slot is None:
             # eager: graphs off, or the first batch of this shape (a shape is captured when it comes back: the ragged last batch of
