@@ -538,7 +538,8 @@ __global__ void __launch_bounds__(kT) ce_fwd_kernel(const float* __restrict__ lo
         for (int j = 0; j < c; ++j) mx = fmaxf(mx, logits[i * c + j]);
         float s = 0.f;
         for (int j = 0; j < c; ++j) s += expf(logits[i * c + j] - mx);
-        l = logf(s) + mx - logits[i * c + target[i]];
+        const long long t = min(max((long long)target[i], 0ll), (long long)c - 1);  // labels outside [0, c) are clamped, never read out of bounds
+        l = logf(s) + mx - logits[i * c + t];
         loss_rows[i] = l;
     }
     __shared__ float sh[kT];
@@ -560,7 +561,8 @@ __global__ void ce_bwd_kernel(const float* __restrict__ logits, const int64_t* _
     float s = 0.f;
     for (int j = 0; j < c; ++j) s += expf(logits[i * c + j] - mx);
     const float g = scale[i];
-    for (int j = 0; j < c; ++j) dlogits[i * c + j] = g * (expf(logits[i * c + j] - mx) / s - (j == target[i] ? 1.f : 0.f));
+    const long long t = min(max((long long)target[i], 0ll), (long long)c - 1);
+    for (int j = 0; j < c; ++j) dlogits[i * c + j] = g * (expf(logits[i * c + j] - mx) / s - (j == t ? 1.f : 0.f));
 }
 // out[c] (+)= sum_r x[r, c]   (bias gradients)
 __global__ void __launch_bounds__(kT) colsum_kernel(const float* __restrict__ x, long long rows, int c, long long ld, long long slab, float* out) {

@@ -380,7 +380,14 @@ class PPSurfModel(_Base):
         if float(self.lambda_l1) != 0.0:
             raise NotImplementedError('lambda_l1 != 0 (PocoModel.regularize) is not part of the PPSurf configurations')
         if hasattr(self, 'log') and getattr(self, '_trainer', None) is not None:
-            self.log('loss/train/00_all', loss, on_step=True, on_epoch=True, sync_dist=True)
+            # do_logging of the reference (source/poco_model.py:302-322): total loss, the classification metrics of the step, F1 only
+            # to the progress bar
+            self.log('loss/train/00_all', loss.detach(), on_step=True, on_epoch=False)
+            metrics = self.calc_metrics(pred.detach(), batch)
+            for key in ('accuracy', 'precision', 'recall', 'f1_score'):
+                value = metrics[key]
+                self.log('metrics/train/{}'.format(key), 0.0 if value != value else value, on_step=True, on_epoch=False)
+            self.log('metrics/train/F1', metrics['f1_score'], on_step=True, on_epoch=False, logger=False, prog_bar=False)
         return loss
 
     def configure_optimizers(self):
