@@ -270,6 +270,10 @@ class GraphedTrainStep:
 
     def __call__(self, batch: dict) -> torch.Tensor:
         for k in BATCH_KEYS:
+            if batch[k].shape != self.static[k].shape:
+                raise ValueError("GraphedTrainStep was captured for '{}' of shape {}, got {}: every batch must have the shapes of the "
+                                 'first one (drop_last, fixed manifold_points / query count)'.format(
+                                     k, tuple(self.static[k].shape), tuple(batch[k].shape)))
             self.static[k].copy_(batch[k], non_blocking=True)
         self.graph_fb.replay()
         self._reduce()
