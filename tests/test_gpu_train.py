@@ -206,6 +206,38 @@ def test_cross_entropy_and_dropout(dev):
     assert not torch.equal(y2 > 0, y > 0), 'every draw uses a fresh mask'
 
 
+def test_training_abi_rejects_bad_arguments(dev):
+    """the training entry points return a status and a message instead of launching on inconsistent arguments"""
+    import ctypes
+    from ppsurf_b200 import _lib, autograd as ag
+    lib = _lib.lib
+    x = torch.zeros(64, 32, device=dev)
+    y = torch.zeros(64, 16, device=dev)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # precision outside {0, 1}; ldc smaller than n; null operand
+    assert lib.pps_gemm(p(x), 0, 32, 1, p(x), 0, 1, 32, p(y), 0, 16, 1, 64, 16, 32, None, 0, 7, st) == -1
+    assert b'precision' in lib.pps_last_error()
+    assert lib.pps_gemm(p(x), 0, 32, 1, p(x), 0, 1, 32, p(y), 0, 8, 1, 64, 16, 32, None, 0, 0, st) == -1
+    assert lib.pps_gemm(None, 0, 32, 1, p(x), 0, 1, 32, p(y), 0, 16, 1, 64, 16, 32, None, 0, 0, st) == -1
+    # norm: workspace too small -> PPS_ERR_WORKSPACE; zero groups -> invalid
+    ws = torch.zeros(8, dtype=torch.uint8, device=dev)
+    g = torch.ones(32, device=dev)
+    m = torch.zeros(32, device=dev)
+    assert lib.pps_norm_fwd(p(x), 1, 64, 32, p(g), p(g), 1e-5, 0, p(x), p(m), p(m), p(ws), ws.numel(), st) == -2
+    assert lib.pps_norm_fwd(p(x), 0, 64, 32, p(g), p(g), 1e-5, 0, p(x), p(m), p(m), p(ws), ws.numel(), st) == -1
+    # attention pooling: a group that does not fit the shared-memory tile
+    assert lib.pps_attn_pool_fwd(p(x), p(x), 1, 4096, 64, 8, p(x), p(x), p(x), st) == -1
+    assert b'shared-memory' in lib.pps_last_error()
+    # dropout probability out of range, more than 16 neighbours per FKAConv neighbourhood
+    assert lib.pps_dropout_fwd(p(x), 10, 1.5, 1, None, p(x), p(ws), st) == -1
+    assert lib.pps_fka_feat_fwd(p(x), p(x), p(x), 1, 4, 4, 17, 8, p(x), st) == -1
+    # the Python layer turns a status into an exception
+    with pytest.raises(_lib.PpsError):
+        ag.gemm(x, x.t()[:, :16].contiguous().t().contiguous()[:8], prec=5)
+    torch.cuda.synchronize()
+
+
 # ---- the whole step against the reference ----------------------------------------------------------------------------------------------
 
 def _fixture_batch(g, dev):
