@@ -43,8 +43,9 @@ def parse_args():
     ap.add_argument('--points', type=int, default=100000)
     ap.add_argument('--resolution', type=int, default=129)
     ap.add_argument('--num-pts-local', type=int, default=50)
-    ap.add_argument('--chunk', type=int, default=37888,
-                    help='queries per decode launch; 37888 = 2 x 148 SMs x 128 rows: whole waves for every tensor-core kernel')
+    ap.add_argument('--chunk', type=int, default=151552,
+                    help='queries per launch of the per-chunk kernels; a multiple of 37888 = 2 x 148 SMs x 128 rows (whole waves for every '
+                         'tensor-core kernel); ppsurf_b200.ops.DEFAULT_CHUNK')
     ap.add_argument('--latents', default='encoder', choices=['encoder', 'random'])
     ap.add_argument('--encoder', default='sharded', choices=['sharded', 'rank0'], help='multi-GPU: who runs the latent loop')
     ap.add_argument('--cpu-sample', type=int, default=65536,

@@ -268,8 +268,12 @@ __global__ void grid_queries_kernel(int r, float step, float bmin_pad, long long
 // host-side pipeline
 // ---------------------------------------------------------------------------------------------------------------
 static inline int kmax_of(const pps_decoder_weights* w) { return w->k > w->num_pts_local ? w->k : w->num_pts_local; }
-// the neighbour search runs over kKnnSuper decode chunks at once: a 16k-query launch cannot fill 148 SMs
+// The neighbour search runs over a SUPER-CHUNK of kKnnSuper decode chunks at once: the larger the launch, the better the search's tail
+// is hidden (the whole 131^3 grid in one launch: 40 ms; in four: 46).  The global branch runs over the super-chunk in slices of at
+// most kProjQueries queries: one launch over 2.25 M queries loses the fc1 table from the L2 (110.8 ms instead of 106).
 constexpr int kKnnSuper = 16;
+constexpr int64_t kProjQueries = 606208;
+static int64_t super_chunks(int64_t) { return kKnnSuper; }
 
 struct DecodeBuffers {
     int32_t* idx;
@@ -301,15 +305,16 @@ static bool carve(const pps_decoder_weights* w, int64_t chunk, void* ws, size_t 
     const int kmax = kmax_of(w);
     size_t rows = (size_t)chunk * (size_t)(K > P ? K : P);
     size_t wide = C > S ? C : S;
-    b.idx = a.take<int32_t>((size_t)chunk * kKnnSuper * kmax);
-    b.d2 = a.take<float>((size_t)chunk * kKnnSuper * kmax);
+    const size_t nsuper = (size_t)chunk * super_chunks(chunk);
+    b.idx = a.take<int32_t>(nsuper * kmax);
+    b.d2 = a.take<float>(nsuper * kmax);
     b.bufA = a.take<float>(rows * wide);
     b.bufB = a.take<float>(rows * wide);
     b.score = a.take<float>((size_t)chunk * K * w->heads);
     b.a1 = a.take<float>((size_t)chunk * ((P + 63) / 64) * 64 * 64 + 8192);  // tensor-core path: tile-major, 64 point slots per half-tile
     b.patches = a.take<float>((size_t)chunk * P * 3);
     b.pooled = a.take<float>((size_t)chunk * C);
-    b.pooled_super = a.take<float>((size_t)chunk * kKnnSuper * C);
+    b.pooled_super = a.take<float>(nsuper * C);
     b.feat_proj = a.take<float>((size_t)chunk * C);
     b.g = a.take<float>((size_t)chunk * S);
     b.f1 = a.take<float>((size_t)chunk * (S / 2));
@@ -422,7 +427,13 @@ static int decode_super(const pps_decoder_weights* w, const void* knn_index, con
     // + the weight pack) then stays in the L2 instead of being evicted between chunks by the local branch, which streams
     // ~0.6 GB of a1 / T per chunk through the cache
     const bool all_tc = path == 1 && pointnet_tc_supported(w) && chain_tc_supported(w);
-    if (all_tc) PPS_TRY(projection_tc_impl(w, table, queries, b.idx, kmax, q, b.tc_ws, b.tc_ws_bytes, b.pooled_super, st));
+    if (all_tc) {
+        for (int64_t s = 0; s < q; s += kProjQueries) {
+            const int64_t c = std::min<int64_t>(kProjQueries, q - s);
+            PPS_TRY(projection_tc_impl(w, table, queries + 3 * s, b.idx + s * kmax, kmax, c, b.tc_ws, b.tc_ws_bytes,
+                                       b.pooled_super + (size_t)s * w->latent, st));
+        }
+    }
     // equal chunks: a super-chunk of 7.4 nominal chunks (one rank's share of the 131^3 grid at 8 GPUs) runs as 8 launches of 93 %
     // instead of 7 full ones and a 42 % tail -- the persistent kernels of a chunk cost nearly the same whatever their fill
     const int64_t pieces = ceil_div(q, chunk);
@@ -499,7 +510,7 @@ int pps_decoder_decode(const pps_decoder_weights* w, const void* knn_index, cons
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int kmax = kmax_of(w);
-    const int64_t super = chunk * kKnnSuper;
+    const int64_t super = chunk * super_chunks(chunk);
     for (int64_t s = 0; s < q; s += super) {
         int64_t c = q - s < super ? q - s : super;
         PPS_TRY(decode_super(w, knn_index, pts, table, n, queries + 3 * s, c, chunk, b, logits_out ? logits_out + 2 * s : nullptr,
@@ -529,7 +540,7 @@ int pps_decoder_decode_host(const pps_decoder_weights* w, const void* knn_index,
     cudaStream_t st = static_cast<cudaStream_t>(stream), cs = static_cast<cudaStream_t>(copy_stream);
     float* dq = static_cast<float*>(staging);
     float* docc = dq + 3 * q;
-    const int64_t super = chunk * kKnnSuper;
+    const int64_t super = chunk * super_chunks(chunk);
     int64_t nchunks = ceil_div(q, super);
     // upload on the copy stream, compute on `stream`, download on the copy stream; the upload of super-chunk i+1 is queued
     // before the download of super-chunk i so that it overlaps the decode.  Four events per device, created once

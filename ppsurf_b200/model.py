@@ -59,7 +59,9 @@ class PPSurfModel(_Base):
         self.pointnet_latent_size = pointnet_latent_size
         self.network = PPSurfNetwork(in_channels=in_channels, latent_size=network_latent_size, out_channels=out_channels,
                                      k=k, num_pts_local=num_pts_local, pointnet_latent_size=pointnet_latent_size,
-                                     decode_chunk=min(int(rec_batch_size), ops.DEFAULT_CHUNK))
+                                     decode_chunk=ops.DEFAULT_CHUNK)
+        # rec_batch_size (50 000 / 25 000 in the reference's configs) bounds the REFERENCE's activation memory per from_latent call; here
+        # it is kept for the interface only: the decode works in its own launch granularity (ops.DEFAULT_CHUNK), sized for a B200
         self.test_step_outputs = []
         self.shard = Shard()  # multi-GPU predict: set to Shard.from_env() (one process per GPU), see sharding.py
 

@@ -10,7 +10,11 @@ from ._lib import check, lib
 
 
 # queries per decode launch: 148 SMs x 128-row tiles, i.e. whole waves for every persistent tensor-core kernel
-DEFAULT_CHUNK = 2 * 148 * 128  # whole waves for every tensor-core kernel (tiles of 2 or 128 queries, 148 or 296 CTAs)
+# queries per launch of the per-chunk kernels: a multiple of 2 * 148 * 128 (whole waves for every tensor-core kernel: tiles of 2 or 128
+# queries on 148 or 296 CTAs).  Four of those units: every launch has a ramp and a tail, and 16 chunks share one neighbour search and one
+# projection launch -- 37 888 / 75 776 / 151 552 / 303 104 queries per chunk decode the 131^3 grid in 276 / 275 / 267 / 266 ms; the scratch
+# buffers are ~80 KB per query of the chunk (12 GB here, one buffer per device shared by all decoders)
+DEFAULT_CHUNK = 4 * 2 * 148 * 128
 
 
 def _stream():
