@@ -3,8 +3,9 @@
 (source/poco_utils.py:26-254) with every per-query step on the device.  Selected from the reference CLI with
 ``--model.class_path ppsurf_b200.PPSurfModel``; ``pps.py`` itself is not edited.
 
-What stays on the host, as in the reference: file I/O, marching cubes (scikit-image) and mesh cleaning (trimesh)  --  rows
-SURVEY.md §8f ranks as "next"; the region-growing masks and frontier lists are on the device (``ops.RegionVolume``).
+On the device: the latent loop, the region-growing masks and frontier lists (``ops.RegionVolume``), marching cubes and the bisection
+refinement (``ops.marching_cubes`` / ``ops.VertexRefiner``), the train / test batch preparation and the training step.  On the host, as in
+the reference: file I/O and the mesh cleaning (``ppsurf_b200.mesh``, no trimesh / scikit-image needed).
 """
 import os
 import queue
@@ -380,7 +381,8 @@ class PPSurfModel(_Base):
         loss, _rows = ag.cross_entropy(pred.transpose(1, 2).reshape(b * q, c), batch['occ'].reshape(-1).to(pred.device, torch.int64))
         self.last_train_pred = pred.detach()
         if float(self.lambda_l1) != 0.0:
-            raise NotImplementedError('lambda_l1 != 0 (PocoModel.regularize) is not part of the PPSurf configurations')
+            raise NotImplementedError('lambda_l1 != 0: the reference calls self.regularize (source/poco_model.py:112-113), a method it does '
+                                      'not define; every PPSurf / POCO configuration sets lambda_l1 = 0')
         if hasattr(self, 'log') and getattr(self, '_trainer', None) is not None:
             # do_logging of the reference (source/poco_model.py:302-322): total loss, the classification metrics of the step, F1 only
             # to the progress bar
