@@ -213,6 +213,27 @@ BATCH_KEYS = ('pts', 'support1', 'support2', 'support3', 'support4', 'ids00', 'i
               'ids44', 'ids43', 'ids32', 'ids21', 'ids10', 'pts_query', 'proj_ids', 'pts_local_ps', 'occ')
 
 
+def flatten_gradients(params, device=None) -> torch.Tensor:
+    """one flat fp32 buffer holding the gradient of every parameter, each ``p.grad`` a view into it (autograd accumulates in place):
+    the data-parallel all-reduce is then a single collective.  Works on any device (the gloo tests run it on the CPU)."""
+    params = [p for p in params if p.requires_grad]
+    device = params[0].device if device is None else device
+    flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=device)
+    off = 0
+    for p in params:
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    return flat
+
+
+def average_gradients(flat: torch.Tensor, world: int, group=None):
+    """mean over the ranks of the flat gradient buffer, in place (no-op for one rank)"""
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.mul_(1.0 / world)
+
+
 class GraphedTrainStep:
     """One training step (forward, cross entropy, backward, optimiser update) captured ONCE into CUDA graphs and replayed: the step is
     about 1200 small launches, which a Python thread cannot issue as fast as the device retires them.  All batches must have the shapes
@@ -222,7 +243,8 @@ class GraphedTrainStep:
     fills it, a single NCCL all-reduce averages it over the ranks, a second graph runs the optimiser -- the reference's DDP
     (configs/device_server.yaml) with one bucket.  BatchNorm statistics stay per rank like the reference's (no SyncBatchNorm).
 
-    ``optimizer`` must be constructed with ``capturable=True``."""
+    ``optimizer`` must be constructed with ``capturable=True``; do not call ``zero_grad(set_to_none=True)`` afterwards (it would detach
+    the gradient views; the step zeroes the flat buffer itself)."""
 
     def __init__(self, network, optimizer, batch: dict, world: int = 1, warmup: int = 3):
         import torch.distributed as dist
@@ -230,12 +252,7 @@ class GraphedTrainStep:
         self.dist = dist
         dev = batch['pts'].device
         self.static = {k: batch[k].clone() for k in BATCH_KEYS}
-        params = [p for p in network.parameters() if p.requires_grad]
-        self.flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
-        off = 0
-        for p in params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        self.flat = flatten_gradients(network.parameters(), dev)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -264,9 +281,7 @@ class GraphedTrainStep:
         return loss.detach()
 
     def _reduce(self):
-        if self.world > 1:
-            self.dist.all_reduce(self.flat)
-            self.flat.mul_(1.0 / self.world)
+        average_gradients(self.flat, self.world)
 
     def __call__(self, batch: dict) -> torch.Tensor:
         for k in BATCH_KEYS:

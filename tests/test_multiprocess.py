@@ -136,6 +136,42 @@ def test_shard_collectives(tmp_path, world):
     assert all(a[0] + a[1] == b[0] for a, b in zip(slices, slices[1:]))
 
 
+def _grad_bucket_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    from ppsurf_b200 import training  # host logic only: nothing here launches a kernel
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.BatchNorm1d(7), torch.nn.Linear(7, 2))
+    flat = training.flatten_gradients(net.parameters())
+    params = list(net.parameters())
+    assert flat.numel() == sum(p.numel() for p in params)
+    assert all(p.grad.data_ptr() >= flat.data_ptr() and p.grad.shape == p.shape for p in params)
+    # autograd accumulates INTO the views: the flat buffer sees the gradients
+    x = torch.randn(11, 5, generator=torch.Generator().manual_seed(100 + rank))
+    net(x).square().sum().backward()
+    assert torch.equal(flat, torch.cat([p.grad.reshape(-1) for p in params])) and float(flat.abs().sum()) > 0
+    local = flat.clone()
+    training.average_gradients(flat, world)
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    assert torch.allclose(flat, torch.stack(gathered).mean(0), rtol=1e-6, atol=1e-7)
+    assert torch.equal(params[0].grad.reshape(-1), flat[:params[0].numel()])  # the parameters see the averaged gradient
+    if rank == 0:
+        np.save(os.path.join(out_dir, 'bucket.npy'), flat.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2])
+def test_training_gradient_bucket_gloo(tmp_path, world):
+    """data-parallel fit (config 5): every gradient is a view into one flat buffer, one all-reduce averages it over the ranks
+    (training.GraphedTrainStep's collective) -- host logic on gloo / CPU"""
+    port = 29000 + (os.getpid() * 11 + world) % 900
+    mp.spawn(_grad_bucket_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert np.load(tmp_path / 'bucket.npy').size == 5 * 7 + 7 + 7 + 7 + 7 * 2 + 2
+
+
 def _nccl_worker(rank, world, port, out_dir):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, ROOT)
