@@ -42,6 +42,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         }
     }
 }
+// One lane of a CONVERGED warp.  The single-thread instructions of the async units (tcgen05.mma / commit, cp.async.bulk) read their
+// operands from uniform registers; inside an `if (lane == 0)` region the control flow is divergent for the compiler and it wraps
+// every one of them in an ELECT / BRA.U.ANY loop with a scoreboard wait (~80 cycles per tcgen05.mma, measured: the MMA issuer of
+// the projection kernel needed 510 cycles per k16 step of three MMAs that execute in 450).  With warp-uniform control flow
+// around an `if (elect_one())` the compiler keeps descriptors and barrier addresses in uniform registers and predicates the
+// instruction itself.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void bulk_copy(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                  "r"(bytes), "r"(bar)

@@ -22,7 +22,7 @@ qry = ops.grid_queries(131, step, bmin_pad, first=131 * 131 * 60, count=18944, d
 idx = dec.index.query(qry, 64)
 counters = torch.zeros(128, dtype=torch.int64, device=dev)
 tiles = 18944 // 4 // 74
-names = ['mma_total', 'mma_wait_chunk', 'mma_wait_weights', 'mma_wait_sgroup', 'g_gather', 'g_wait', 'g_E2E3', 's_wait', 's_softmax', 's_pool']
+names = ['mma_total', 'mma_wait_chunk', 'mma_wait_weights', 'mma_wait_sgroup', 'g_gather', 'g_wait', 'g_E2E3', 's_wait', 's_softmax', 's_pool', 'mma_issue32', 'mma_commit32']
 ref = None
 print('CTA pairs resident at once:', _lib.lib.pps_debug_tc_max_clusters())
 for cs, mask in ((0, 0x1FF), (0, 0x049), (0, 0x0DB)):  # all three terms, hh only, hh + hl
