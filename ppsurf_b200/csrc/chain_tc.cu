@@ -48,12 +48,16 @@ struct Ring {
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 
-// producer: stream `nstages` stages of `bytes` each
+// producer: stream `nstages` stages of `bytes` each.  Like the MMA issuer it is run by ALL lanes of its warp (warp-uniform control flow)
+// and issues through one elected lane: see elect_one in tc_common.cuh
 __device__ __forceinline__ void produce(const Ctx& c, Ring& r, const uint8_t*& src, int nstages, uint32_t bytes) {
     for (int s = 0; s < nstages; ++s) {
         mbar_wait(c.bar_empty + 8 * r.slot, r.phase ^ 1);
-        mbar_expect_tx(c.bar_full + 8 * r.slot, bytes);
-        bulk_copy(c.sbase + kOffRing + r.slot * kSlot, src, bytes, c.bar_full + 8 * r.slot);
+        if (elect_one()) {
+            mbar_expect_tx(c.bar_full + 8 * r.slot, bytes);
+            bulk_copy(c.sbase + kOffRing + r.slot * kSlot, src, bytes, c.bar_full + 8 * r.slot);
+        }
+        __syncwarp();
         src += bytes;
         r.advance();
     }
@@ -70,10 +74,13 @@ __device__ __forceinline__ void mma_layer(const Ctx& c, Ring& r, uint32_t dcol, 
         const uint32_t wst = c.sbase + kOffRing + r.slot * kSlot;
         const uint64_t w_hi = umma_desc(wst, n * 16, 128);
         const uint64_t w_lo = umma_desc(wst + n * 32, n * 16, 128);
-        umma(c.tmem + dcol, x_hi, w_hi, idesc, (s > 0 || accumulate_first) ? 1u : 0u);
-        umma(c.tmem + dcol, x_lo, w_hi, idesc, 1u);
-        umma(c.tmem + dcol, x_hi, w_lo, idesc, 1u);
-        tc_commit(c.bar_empty + 8 * r.slot);
+        if (elect_one()) {
+            umma(c.tmem + dcol, x_hi, w_hi, idesc, (s > 0 || accumulate_first) ? 1u : 0u);
+            umma(c.tmem + dcol, x_lo, w_hi, idesc, 1u);
+            umma(c.tmem + dcol, x_hi, w_lo, idesc, 1u);
+            tc_commit(c.bar_empty + 8 * r.slot);
+        }
+        __syncwarp();
         r.advance();
     }
 }
@@ -89,15 +96,18 @@ __device__ __forceinline__ void mma_layer_t(const Ctx& c, Ring& r, uint32_t dcol
         const uint64_t x_hi = umma_desc(c.sbase + kOffAhi + 2 * s * kLbo, kLbo, 128);
         const uint64_t x_lo = umma_desc(c.sbase + kOffAlo + 2 * s * kLbo, kLbo, 128);
         const uint32_t wst = c.sbase + kOffRing + r.slot * kSlot;  // [hi: 2 k8 blocks x 256 rows x 16 B][lo: likewise]
+        if (elect_one()) {
 #pragma unroll
-        for (int mh = 0; mh < 2; ++mh) {
-            const uint64_t w_hi = umma_desc(wst + mh * 128 * 16, 256 * 16, 128);
-            const uint64_t w_lo = umma_desc(wst + 256 * 32 + mh * 128 * 16, 256 * 16, 128);
-            umma(c.tmem + dcol + 128 * mh, w_hi, x_hi, idesc, s > 0 ? 1u : 0u);
-            umma(c.tmem + dcol + 128 * mh, w_hi, x_lo, idesc, 1u);
-            umma(c.tmem + dcol + 128 * mh, w_lo, x_hi, idesc, 1u);
+            for (int mh = 0; mh < 2; ++mh) {
+                const uint64_t w_hi = umma_desc(wst + mh * 128 * 16, 256 * 16, 128);
+                const uint64_t w_lo = umma_desc(wst + 256 * 32 + mh * 128 * 16, 256 * 16, 128);
+                umma(c.tmem + dcol + 128 * mh, w_hi, x_hi, idesc, s > 0 ? 1u : 0u);
+                umma(c.tmem + dcol + 128 * mh, w_hi, x_lo, idesc, 1u);
+                umma(c.tmem + dcol + 128 * mh, w_lo, x_hi, idesc, 1u);
+            }
+            tc_commit(c.bar_empty + 8 * r.slot);
         }
-        tc_commit(c.bar_empty + 8 * r.slot);
+        __syncwarp();
         r.advance();
     }
 }
@@ -219,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     const long long ntiles = (nq + 127) / 128;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {
             Ring r;
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const uint8_t* src = wpack;
@@ -229,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             Ring r;
             uint32_t ready_phase = 0, tfree_phase[2] = {0, 0};
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -237,12 +247,14 @@ __global__ void __launch_bounds__(kThreads, 1)
                 ready_phase ^= 1;
                 tc_fence_after();
                 mma_layer(c, r, 0, 128, 16, false);
-                tc_commit(c.bar_accum);
+                if (elect_one()) tc_commit(c.bar_accum);
+                __syncwarp();
                 mbar_wait(c.bar_ready, ready_phase);
                 ready_phase ^= 1;
                 tc_fence_after();
                 mma_layer(c, r, 0, 64, 8, false);
-                tc_commit(c.bar_accum);
+                if (elect_one()) tc_commit(c.bar_accum);
+                __syncwarp();
                 mbar_wait(c.bar_ready, ready_phase);
                 ready_phase ^= 1;
                 tc_fence_after();
@@ -255,7 +267,8 @@ __global__ void __launch_bounds__(kThreads, 1)
                     mma_layer_t(c, r, buf * 256, 4);  // fc3 block nb, transposed: coalesced T stores
                     // one completion barrier PER accumulator: the issuer can run a block ahead of the epilogue, and a single
                     // barrier advancing two phases would alias in the parity wait
-                    tc_commit(buf ? c.bar_accum2 : c.bar_accum);
+                    if (elect_one()) tc_commit(buf ? c.bar_accum2 : c.bar_accum);
+                    __syncwarp();
                 }
             }
         }
@@ -339,7 +352,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     const long long ntiles = (nq + 127) / 128;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {
             Ring r;
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const uint8_t* src = wpack;
@@ -350,7 +363,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             Ring r;
             uint32_t ready_phase = 0;
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -358,18 +371,21 @@ __global__ void __launch_bounds__(kThreads, 1)
                 ready_phase ^= 1;
                 tc_fence_after();
                 mma_layer(c, r, 0, 256, 16, false);
-                tc_commit(c.bar_afree);  // the operand tile may be reloaded with the second branch
+                if (elect_one()) tc_commit(c.bar_afree);
+                __syncwarp();  // the operand tile may be reloaded with the second branch
                 mbar_wait(c.bar_ready, ready_phase);
                 ready_phase ^= 1;
                 tc_fence_after();
                 mma_layer(c, r, 0, 256, 8, true);  // accumulates onto the first branch
-                tc_commit(c.bar_accum);
+                if (elect_one()) tc_commit(c.bar_accum);
+                __syncwarp();
                 for (int layer = 0; layer < 2; ++layer) {
                     mbar_wait(c.bar_ready, ready_phase);
                     ready_phase ^= 1;
                     tc_fence_after();
                     mma_layer(c, r, layer == 0 ? 256 : 0, 256, 16, false);
-                    tc_commit(c.bar_accum);
+                    if (elect_one()) tc_commit(c.bar_accum);
+                    __syncwarp();
                 }
             }
         }

@@ -317,22 +317,26 @@ __global__ void __launch_bounds__(kThreads, 1) fka_fused_kernel(const __grid_con
     const uint32_t stage_bytes = 64u * nsl;
     const size_t slice_bytes = (size_t)stage_bytes * 4 * nchunks;
 
+    // warps 0 and 1 run their loops with all lanes (warp-uniform control flow) and issue through one elected lane: see elect_one
     if (warp == 0) {
-        if (lane == 0) {
+        {
             Ring r;
             for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
                 const uint8_t* src = prm.wpack + (size_t)(t % prm.nslices) * slice_bytes;
                 for (int s = 0; s < 4 * nchunks; ++s) {
                     mbar_wait(bar_wempty + 8 * r.slot, r.phase ^ 1);
-                    mbar_expect_tx(bar_wfull + 8 * r.slot, stage_bytes);
-                    bulk_copy(sbase + kOffRing + r.slot * kSlot, src, stage_bytes, bar_wfull + 8 * r.slot);
+                    if (elect_one()) {
+                        mbar_expect_tx(bar_wfull + 8 * r.slot, stage_bytes);
+                        bulk_copy(sbase + kOffRing + r.slot * kSlot, src, stage_bytes, bar_wfull + 8 * r.slot);
+                    }
+                    __syncwarp();
                     src += stage_bytes;
                     r.advance();
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             Ring r;
             const uint32_t idesc = umma_idesc(nsl);
             uint32_t g = 0;
@@ -351,15 +355,20 @@ __global__ void __launch_bounds__(kThreads, 1) fka_fused_kernel(const __grid_con
                         const uint32_t wst = sbase + kOffRing + r.slot * kSlot;
                         const uint64_t w_hi = umma_desc(wst, nsl * 16, 128);
                         const uint64_t w_lo = umma_desc(wst + nsl * 32, nsl * 16, 128);
-                        umma(tmem, a_hi, w_hi, idesc, (kc > 0 || s > 0) ? 1u : 0u);
-                        umma(tmem, a_lo, w_hi, idesc, 1u);
-                        umma(tmem, a_hi, w_lo, idesc, 1u);
-                        tc_commit(bar_wempty + 8 * r.slot);
+                        if (elect_one()) {
+                            umma(tmem, a_hi, w_hi, idesc, (kc > 0 || s > 0) ? 1u : 0u);
+                            umma(tmem, a_lo, w_hi, idesc, 1u);
+                            umma(tmem, a_hi, w_lo, idesc, 1u);
+                            tc_commit(bar_wempty + 8 * r.slot);
+                        }
+                        __syncwarp();
                         r.advance();
                     }
-                    tc_commit(bar_afree + 8 * buf);
+                    if (elect_one()) tc_commit(bar_afree + 8 * buf);
+                    __syncwarp();
                 }
-                tc_commit(bar_accum);
+                if (elect_one()) tc_commit(bar_accum);
+                __syncwarp();
             }
         }
     } else {

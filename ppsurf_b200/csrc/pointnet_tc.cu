@@ -122,15 +122,19 @@ __global__ void __launch_bounds__(kPnThreads, 2)
 
     // weight stages of one tile, in issue order: (bytes per stage, number of stages)
     // conv0b 4x4096, stn1 4x4096, stn2 4x8192, stn3 16x8192
+    // warps 0 and 1 run their loops with all lanes (warp-uniform control flow) and issue through one elected lane: see elect_one
     if (warp == 0) {
-        if (lane == 0) {
+        {
             uint32_t slot = 0, phase = 0;
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const uint8_t* src = wpack;
                 for (int s = 0; s < 12; ++s) {  // slots: conv0b, stn1 (4 steps of 4 KB each), stn2 x2, stn3 x8 (2 steps of 8 KB)
                     mbar_wait(bar_empty + 8 * slot, phase ^ 1);
-                    mbar_expect_tx(bar_full + 8 * slot, kPnSlot);
-                    bulk_copy(sbase + kOffRing + slot * kPnSlot, src, kPnSlot, bar_full + 8 * slot);
+                    if (elect_one()) {
+                        mbar_expect_tx(bar_full + 8 * slot, kPnSlot);
+                        bulk_copy(sbase + kOffRing + slot * kPnSlot, src, kPnSlot, bar_full + 8 * slot);
+                    }
+                    __syncwarp();
                     src += kPnSlot;
                     if (++slot == kPnStages) {
                         slot = 0;
@@ -140,7 +144,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             uint32_t slot = 0, phase = 0, ready_phase = 0;
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 for (int layer = 0; layer < 4; ++layer) {
@@ -156,18 +160,21 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                         for (int s0 = 0; s0 < 4; s0 += per) {
                             mbar_wait(bar_full + 8 * slot, phase);
                             tc_fence_after();
-                            for (int sub = 0; sub < per; ++sub) {
-                                const int s = s0 + sub;
-                                const uint64_t x_hi = umma_desc(sbase + kOffAhi + 2 * s * kPnLbo, kPnLbo, 128);
-                                const uint64_t x_lo = umma_desc(sbase + kOffAlo + 2 * s * kPnLbo, kPnLbo, 128);
-                                const uint32_t bst = sbase + kOffRing + slot * kPnSlot + sub * step_bytes;
-                                const uint64_t w_hi = umma_desc(bst, n * 16, 128);
-                                const uint64_t w_lo = umma_desc(bst + n * 32, n * 16, 128);
-                                umma(tmem, x_hi, w_hi, idesc, s > 0 ? 1u : 0u);
-                                umma(tmem, x_lo, w_hi, idesc, 1u);
-                                umma(tmem, x_hi, w_lo, idesc, 1u);
+                            if (elect_one()) {
+                                for (int sub = 0; sub < per; ++sub) {
+                                    const int s = s0 + sub;
+                                    const uint64_t x_hi = umma_desc(sbase + kOffAhi + 2 * s * kPnLbo, kPnLbo, 128);
+                                    const uint64_t x_lo = umma_desc(sbase + kOffAlo + 2 * s * kPnLbo, kPnLbo, 128);
+                                    const uint32_t bst = sbase + kOffRing + slot * kPnSlot + sub * step_bytes;
+                                    const uint64_t w_hi = umma_desc(bst, n * 16, 128);
+                                    const uint64_t w_lo = umma_desc(bst + n * 32, n * 16, 128);
+                                    umma(tmem, x_hi, w_hi, idesc, s > 0 ? 1u : 0u);
+                                    umma(tmem, x_lo, w_hi, idesc, 1u);
+                                    umma(tmem, x_hi, w_lo, idesc, 1u);
+                                }
+                                tc_commit(bar_empty + 8 * slot);
                             }
-                            tc_commit(bar_empty + 8 * slot);
+                            __syncwarp();
                             if (++slot == kPnStages) {
                                 slot = 0;
                                 phase ^= 1;
@@ -180,19 +187,22 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                             for (int s0 = 0; s0 < 8; s0 += 2) {
                                 mbar_wait(bar_full + 8 * slot, phase);
                                 tc_fence_after();
+                                if (elect_one()) {
 #pragma unroll
-                                for (int sub = 0; sub < 2; ++sub) {
-                                    const int s = s0 + sub;
-                                    const uint64_t x_hi = umma_desc(sbase + kOffAhi + 2 * s * kPnLbo, kPnLbo, 128);
-                                    const uint64_t x_lo = umma_desc(sbase + kOffAlo + 2 * s * kPnLbo, kPnLbo, 128);
-                                    const uint32_t wst = sbase + kOffRing + slot * kPnSlot + sub * 8192;
-                                    const uint64_t w_hi = umma_desc(wst, 128 * 16, 128);
-                                    const uint64_t w_lo = umma_desc(wst + 4096, 128 * 16, 128);
-                                    umma(tmem + fb * 128, w_hi, x_hi, idesc, s > 0 ? 1u : 0u);
-                                    umma(tmem + fb * 128, w_hi, x_lo, idesc, 1u);
-                                    umma(tmem + fb * 128, w_lo, x_hi, idesc, 1u);
+                                    for (int sub = 0; sub < 2; ++sub) {
+                                        const int s = s0 + sub;
+                                        const uint64_t x_hi = umma_desc(sbase + kOffAhi + 2 * s * kPnLbo, kPnLbo, 128);
+                                        const uint64_t x_lo = umma_desc(sbase + kOffAlo + 2 * s * kPnLbo, kPnLbo, 128);
+                                        const uint32_t wst = sbase + kOffRing + slot * kPnSlot + sub * 8192;
+                                        const uint64_t w_hi = umma_desc(wst, 128 * 16, 128);
+                                        const uint64_t w_lo = umma_desc(wst + 4096, 128 * 16, 128);
+                                        umma(tmem + fb * 128, w_hi, x_hi, idesc, s > 0 ? 1u : 0u);
+                                        umma(tmem + fb * 128, w_hi, x_lo, idesc, 1u);
+                                        umma(tmem + fb * 128, w_lo, x_hi, idesc, 1u);
+                                    }
+                                    tc_commit(bar_empty + 8 * slot);
                                 }
-                                tc_commit(bar_empty + 8 * slot);
+                                __syncwarp();
                                 if (++slot == kPnStages) {
                                     slot = 0;
                                     phase ^= 1;
@@ -200,7 +210,8 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                             }
                         }
                     }
-                    tc_commit(bar_accum);
+                    if (elect_one()) tc_commit(bar_accum);
+                    __syncwarp();
                 }
             }
         }
@@ -387,14 +398,17 @@ __global__ void __launch_bounds__(kPnThreads, 2)
     const long long ntiles = (nq * G + 1) / 2;
 
     if (warp == 0) {
-        if (lane == 0) {  // conv1 4x4096, conv2 4x8192 per tile
+        {  // conv1 4x4096, conv2 4x8192 per tile
             uint32_t slot = 0, phase = 0;
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const uint8_t* src = wpack;
                 for (int s = 0; s < 3; ++s) {  // slots: conv1 (4 steps of 4 KB), conv2 x2 (2 steps of 8 KB)
                     mbar_wait(bar_empty + 8 * slot, phase ^ 1);
-                    mbar_expect_tx(bar_full + 8 * slot, kPnSlot);
-                    bulk_copy(sbase + kOffRing + slot * kPnSlot, src, kPnSlot, bar_full + 8 * slot);
+                    if (elect_one()) {
+                        mbar_expect_tx(bar_full + 8 * slot, kPnSlot);
+                        bulk_copy(sbase + kOffRing + slot * kPnSlot, src, kPnSlot, bar_full + 8 * slot);
+                    }
+                    __syncwarp();
                     src += kPnSlot;
                     if (++slot == kPnStages) {
                         slot = 0;
@@ -404,15 +418,16 @@ __global__ void __launch_bounds__(kPnThreads, 2)
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             uint32_t slot = 0, phase = 0, ready_phase = 0;
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 // feature transform: D[rows, ql*64 + i] = a1[rows, :] . T_ql[i, :]   (operand built by the epilogue warps)
                 mbar_wait(bar_aready, ready_phase);
                 ready_phase ^= 1;
                 tc_fence_after();
-                {
+                if (elect_one()) {
                     const uint32_t idesc = umma_idesc(64);
+#pragma unroll
                     for (int ql = 0; ql < 2; ++ql) {
                         const uint32_t t_hi = sbase + kOffT + (2 * ql) * kTBytes, t_lo = t_hi + kTBytes;
                         for (int s = 0; s < 4; ++s) {
@@ -427,6 +442,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                     }
                     tc_commit(bar_accum);
                 }
+                __syncwarp();
                 for (int layer = 0; layer < 2; ++layer) {  // conv1 (64 wide), conv2 (128 wide)
                     const int n = layer == 0 ? 64 : 128;
                     const uint32_t idesc = umma_idesc(n);
@@ -438,24 +454,28 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                     for (int s0 = 0; s0 < 4; s0 += per) {
                         mbar_wait(bar_full + 8 * slot, phase);
                         tc_fence_after();
-                        for (int sub = 0; sub < per; ++sub) {
-                            const int s = s0 + sub;
-                            const uint64_t x_hi = umma_desc(sbase + kOffAhi + 2 * s * kPnLbo, kPnLbo, 128);
-                            const uint64_t x_lo = umma_desc(sbase + kOffAlo + 2 * s * kPnLbo, kPnLbo, 128);
-                            const uint32_t bst = sbase + kOffRing + slot * kPnSlot + sub * step_bytes;
-                            const uint64_t w_hi = umma_desc(bst, n * 16, 128);
-                            const uint64_t w_lo = umma_desc(bst + n * 32, n * 16, 128);
-                            umma(tmem, x_hi, w_hi, idesc, s > 0 ? 1u : 0u);
-                            umma(tmem, x_lo, w_hi, idesc, 1u);
-                            umma(tmem, x_hi, w_lo, idesc, 1u);
+                        if (elect_one()) {
+                            for (int sub = 0; sub < per; ++sub) {
+                                const int s = s0 + sub;
+                                const uint64_t x_hi = umma_desc(sbase + kOffAhi + 2 * s * kPnLbo, kPnLbo, 128);
+                                const uint64_t x_lo = umma_desc(sbase + kOffAlo + 2 * s * kPnLbo, kPnLbo, 128);
+                                const uint32_t bst = sbase + kOffRing + slot * kPnSlot + sub * step_bytes;
+                                const uint64_t w_hi = umma_desc(bst, n * 16, 128);
+                                const uint64_t w_lo = umma_desc(bst + n * 32, n * 16, 128);
+                                umma(tmem, x_hi, w_hi, idesc, s > 0 ? 1u : 0u);
+                                umma(tmem, x_lo, w_hi, idesc, 1u);
+                                umma(tmem, x_hi, w_lo, idesc, 1u);
+                            }
+                            tc_commit(bar_empty + 8 * slot);
                         }
-                        tc_commit(bar_empty + 8 * slot);
+                        __syncwarp();
                         if (++slot == kPnStages) {
                             slot = 0;
                             phase ^= 1;
                         }
                     }
-                    tc_commit(bar_accum);
+                    if (elect_one()) tc_commit(bar_accum);
+                    __syncwarp();
                 }
             }
         }

@@ -130,16 +130,19 @@ __global__ void __launch_bounds__(kThreads) gemm_bf16_kernel(Operand a, Operand 
         }
         fence_async_smem();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {  // the whole warp (warp-uniform control flow), one elected lane issues: see elect_one in tc_common.cuh
             tc_fence_after();
+            if (elect_one()) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const uint64_t ad = umma_desc(sbase + s * kTile + 2 * q * kLbo, kLbo, 128);
-                const uint64_t bd = umma_desc(sbase + kOffB + s * tileb + 2 * q * lbo, lbo, 128);
-                umma(tmem, ad, bd, idesc, (kt > 0 || q > 0) ? 1u : 0u);
+                for (int q = 0; q < 4; ++q) {
+                    const uint64_t ad = umma_desc(sbase + s * kTile + 2 * q * kLbo, kLbo, 128);
+                    const uint64_t bd = umma_desc(sbase + kOffB + s * tileb + 2 * q * lbo, lbo, 128);
+                    umma(tmem, ad, bd, idesc, (kt > 0 || q > 0) ? 1u : 0u);
+                }
+                tc_commit(sbase + obar + 8 * s);
+                if (kt == nk - 1) tc_commit(sbase + obar + 16);
             }
-            tc_commit(sbase + obar + 8 * s);
-            if (kt == nk - 1) tc_commit(sbase + obar + 16);
+            __syncwarp();
         }
     }
     if (nk > 0) {
