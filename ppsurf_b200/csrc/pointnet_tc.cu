@@ -17,10 +17,6 @@ namespace tc {
 
 constexpr int kPnRows = 128;
 constexpr int kPnLbo = kPnRows * 16 + 16;  // 2064: padded k8-block pitch of an activation tile
-constexpr int kPnSlot = 16384;             // ring slot: a whole 64-wide layer (4 k16 steps of 4 KB) or two k16 steps of a 128-wide one: the MMA
-                                           // issuer pays one full-wait and one commit per SLOT (measured on the projection kernel: ~300 cycles
-                                           // per iteration whatever it contains), and these kernels are latency-bound
-constexpr int kPnStages = 2;
 constexpr int kPnThreads = 320;
 constexpr int kPnEpiThreads = 256;
 
@@ -59,11 +55,17 @@ constexpr int kOffAhi = 0;
 constexpr int kABytes = 16 * kPnLbo;                 // up to 128 columns
 constexpr int kOffAlo = kOffAhi + kABytes;           // 33024
 constexpr int kOffRing = kOffAlo + kABytes;          // 66048
-constexpr int kOffPar = kOffRing + kPnStages * kPnSlot;  // 98816: w0a[192] b0a[64] b0b[64] bs1[64] bs2[128] bs3[256]
+// Weight ring: 2 slots of 16 KB (a whole 64-wide layer, or two k16 steps of a 128-wide layer / of a stn.conv3 feature block).  Measured
+// with the elect.sync issue path: 5 slots of 8 KB (more bytes in flight for stn.conv3's 128 KB per tile) are SLOWER, 52.6 vs 49.8 ms per
+// 131^3 grid -- every slot costs the issuer and the producer an mbarrier round trip (>= 90 cycles each) against 192 tensor cycles of work
+constexpr int kSlot = 16384;
+constexpr int kStages = 2;
+constexpr int kOffPar = kOffRing + kStages * kSlot;  // 98816: w0a[192] b0a[64] b0b[64] bs1[64] bs2[128] bs3[256]
 constexpr int kParFloats = 192 + 64 + 64 + 64 + 128 + 256;
-constexpr int kOffBar = kOffPar + kParFloats * 4;    // full[4] empty[4] accum aready
-constexpr int kOffTmem = kOffBar + 10 * 8;
-constexpr int kSmemBytes = kOffTmem + 16 + 1024;     // ~103 KB -> two CTAs per SM
+constexpr int kOffBar = kOffPar + kParFloats * 4;    // full[kStages] empty[kStages] accum aready
+constexpr int kOffTmem = kOffBar + (2 * kStages + 2) * 8;
+constexpr int kSmemBytes = kOffTmem + 16 + 1024;     // ~101 KB -> two CTAs per SM
+static_assert(2 * (kSmemBytes + 1024) <= 233472, "two CTAs per SM");
 constexpr int kTmemCols = 256;
 }  // namespace stn
 
@@ -87,7 +89,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
     float* s_bs2 = s_bs1 + 64;
     float* s_bs3 = s_bs2 + 128;
     volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + kOffTmem);
-    const uint32_t bar_full = sbase + kOffBar, bar_empty = bar_full + 8 * kPnStages, bar_accum = bar_empty + 8 * kPnStages,
+    const uint32_t bar_full = sbase + kOffBar, bar_empty = bar_full + 8 * kStages, bar_accum = bar_empty + 8 * kStages,
                    bar_aready = bar_accum + 8;
 
     for (int e = tid; e < 256; e += kPnThreads) {
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
         s_bs3[e] = bs3[e];
     }
     if (tid == 0) {
-        for (int i = 0; i < kPnStages; ++i) {
+        for (int i = 0; i < kStages; ++i) {
             mbar_init(bar_full + 8 * i, 1);
             mbar_init(bar_empty + 8 * i, 1);
         }
@@ -128,15 +130,15 @@ __global__ void __launch_bounds__(kPnThreads, 2)
             uint32_t slot = 0, phase = 0;
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const uint8_t* src = wpack;
-                for (int s = 0; s < 12; ++s) {  // slots: conv0b, stn1 (4 steps of 4 KB each), stn2 x2, stn3 x8 (2 steps of 8 KB)
+                for (int s = 0; s < (4 * 4096 * 2 + 4 * 8192 + 16 * 8192) / kSlot; ++s) {  // conv0b, stn1 (4 KB per k16 step), stn2, stn3 (8 KB)
                     mbar_wait(bar_empty + 8 * slot, phase ^ 1);
                     if (elect_one()) {
-                        mbar_expect_tx(bar_full + 8 * slot, kPnSlot);
-                        bulk_copy(sbase + kOffRing + slot * kPnSlot, src, kPnSlot, bar_full + 8 * slot);
+                        mbar_expect_tx(bar_full + 8 * slot, kSlot);
+                        bulk_copy(sbase + kOffRing + slot * kSlot, src, kSlot, bar_full + 8 * slot);
                     }
                     __syncwarp();
-                    src += kPnSlot;
-                    if (++slot == kPnStages) {
+                    src += kSlot;
+                    if (++slot == kStages) {
                         slot = 0;
                         phase ^= 1;
                     }
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                         // D[rows, n] = X[rows, 64] . W[n, 64]^T
                         const int n = layer < 2 ? 64 : 128;
                         const uint32_t idesc = umma_idesc(n);
-                        const int per = n == 64 ? 4 : 2;  // k16 steps per ring slot
+                        const int per = kSlot / (64 * n);  // k16 steps per ring slot
                         const uint32_t step_bytes = 64u * n;
                         for (int s0 = 0; s0 < 4; s0 += per) {
                             mbar_wait(bar_full + 8 * slot, phase);
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                                     const int s = s0 + sub;
                                     const uint64_t x_hi = umma_desc(sbase + kOffAhi + 2 * s * kPnLbo, kPnLbo, 128);
                                     const uint64_t x_lo = umma_desc(sbase + kOffAlo + 2 * s * kPnLbo, kPnLbo, 128);
-                                    const uint32_t bst = sbase + kOffRing + slot * kPnSlot + sub * step_bytes;
+                                    const uint32_t bst = sbase + kOffRing + slot * kSlot + sub * step_bytes;
                                     const uint64_t w_hi = umma_desc(bst, n * 16, 128);
                                     const uint64_t w_lo = umma_desc(bst + n * 32, n * 16, 128);
                                     umma(tmem, x_hi, w_hi, idesc, s > 0 ? 1u : 0u);
@@ -175,7 +177,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                                 tc_commit(bar_empty + 8 * slot);
                             }
                             __syncwarp();
-                            if (++slot == kPnStages) {
+                            if (++slot == kStages) {
                                 slot = 0;
                                 phase ^= 1;
                             }
@@ -184,16 +186,17 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                         // transposed: D^T[features(128 per block), rows(128)] = W[features, 128] . X[rows, 128]^T
                         const uint32_t idesc = umma_idesc(128);
                         for (int fb = 0; fb < 2; ++fb) {
-                            for (int s0 = 0; s0 < 8; s0 += 2) {
+                            constexpr int per3 = kSlot / 8192;  // k16 steps of a feature block per ring slot
+                            for (int s0 = 0; s0 < 8; s0 += per3) {
                                 mbar_wait(bar_full + 8 * slot, phase);
                                 tc_fence_after();
                                 if (elect_one()) {
 #pragma unroll
-                                    for (int sub = 0; sub < 2; ++sub) {
+                                    for (int sub = 0; sub < per3; ++sub) {
                                         const int s = s0 + sub;
                                         const uint64_t x_hi = umma_desc(sbase + kOffAhi + 2 * s * kPnLbo, kPnLbo, 128);
                                         const uint64_t x_lo = umma_desc(sbase + kOffAlo + 2 * s * kPnLbo, kPnLbo, 128);
-                                        const uint32_t wst = sbase + kOffRing + slot * kPnSlot + sub * 8192;
+                                        const uint32_t wst = sbase + kOffRing + slot * kSlot + sub * 8192;
                                         const uint64_t w_hi = umma_desc(wst, 128 * 16, 128);
                                         const uint64_t w_lo = umma_desc(wst + 4096, 128 * 16, 128);
                                         umma(tmem + fb * 128, w_hi, x_hi, idesc, s > 0 ? 1u : 0u);
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                                     tc_commit(bar_empty + 8 * slot);
                                 }
                                 __syncwarp();
-                                if (++slot == kPnStages) {
+                                if (++slot == kStages) {
                                     slot = 0;
                                     phase ^= 1;
                                 }
@@ -221,7 +224,8 @@ __global__ void __launch_bounds__(kPnThreads, 2)
         const int row = lane_grp * 32 + lane;  // TMEM lane of this thread
         uint32_t accum_phase = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            // ---- gather + conv0a (SIMT, K=3): thread = (row, half of the 64 channels)
+            // ---- gather + conv0a (SIMT, K=3): thread = (row, half of the 64 channels).  (Fetching the next tile's point a whole tile
+            // ahead into three registers was measured and is slower: 52.6 vs 49.8 ms per 131^3 grid.)
             {
                 const int r = et & 127, hf = et >> 7;
                 const PnRow pr = pn_row(tile, r, G);
@@ -333,28 +337,35 @@ __global__ void __launch_bounds__(kPnThreads, 2)
 // kernel C: feature transform, conv1, conv2, attention pooling
 // ---------------------------------------------------------------------------------------------------------------------
 namespace feat {
+// Three CTAs per SM (round 2: two; the kernel is a serial chain load -> transform -> conv1 -> conv2 -> pooling per tile and bound by its
+// latencies, so what counts is the number of chains in flight).  Shared memory per CTA: the 64-column operand tile (33 KB) and ONE more
+// 33 KB region R that holds the per-query transforms until their MMAs are done and the conv1 / conv2 weights afterwards -- no weight ring:
+//   transform MMAs complete -> conv1 (16 KB) -> R+0, conv2 k-steps 0,1 (16 KB) -> R+16 KB   (lands while the epilogue converts x')
+//   conv1 MMAs complete     -> conv2 k-steps 2,3 (16 KB) -> R+0                            (lands while the epilogue converts conv1)
+// One control warp issues the MMAs and these copies (it waits for its own commits), eight epilogue warps: 288 threads, <= 72 registers.
+constexpr int kThreads = 288;
+constexpr int kEpiThreads = 256;
 constexpr int kOffAhi = 0;
 constexpr int kABytes = 8 * kPnLbo;                       // 64-column operand tile (a1, x', conv1 output)
 constexpr int kOffAlo = kOffAhi + kABytes;                // 16512
 constexpr int kTLbo = 64 * 16 + 16;                       // 1040: k8-block pitch of a per-query 64x64 transform
 constexpr int kTBytes = 8 * kTLbo;                        // 8320 per (query, hi/lo)
-constexpr int kOffT = kOffAlo + kABytes;                  // 33024: [query][hi,lo]; dead after the transform MMAs, so
-                                                          // the upper 64 columns of conv2's output are parked here
-constexpr int kOffRing = kOffT + 4 * kTBytes;             // 66304
-constexpr int kOffPar = kOffRing + kPnStages * kPnSlot;   // 99072: b1[64] b2[128] wq[128] part[2][128] att[128]
-constexpr int kParFloats = 64 + 128 + 128 + 256 + 128;
-constexpr int kOffBar = kOffPar + kParFloats * 4;
-constexpr int kOffTmem = kOffBar + 10 * 8;
-constexpr int kSmemBytes = kOffTmem + 16 + 1024;          // ~103 KB -> two CTAs per SM
+constexpr int kOffT = kOffAlo + kABytes;                  // 33024: region R: [query][hi,lo] transforms, then the weights
+constexpr int kWBytes = 16384;                            // conv1, or two k16 steps of conv2
+static_assert(2 * kWBytes <= 4 * kTBytes, "conv1 and half of conv2 must fit into the transform region");
+constexpr int kOffPar = kOffT + 4 * kTBytes;              // 66304: b1[64] b2[128] wq[128] part[2][128] pool[4][128]
+constexpr int kParFloats = 64 + 128 + 128 + 256 + 512;
+constexpr int kOffBar = kOffPar + kParFloats * 4;         // full[2] accum aready
+constexpr int kOffTmem = kOffBar + 4 * 8;
+constexpr int kSmemBytes = kOffTmem + 16 + 1024;          // ~70 KB
 constexpr int kTmemCols = 128;
-static_assert(2 * kABytes <= 4 * kTBytes, "conv2's upper half must fit into the transform buffers");
-// byte offset of k8 block `kblk` (0..15) of the 128-column conv2 output
-__device__ __forceinline__ int c2_hi(int kblk) { return kblk < 8 ? kOffAhi + kblk * kPnLbo : kOffT + (kblk - 8) * kPnLbo; }
-__device__ __forceinline__ int c2_lo(int kblk) { return kblk < 8 ? kOffAlo + kblk * kPnLbo : kOffT + kABytes + (kblk - 8) * kPnLbo; }
+constexpr int kCtasPerSm = 3;
+static_assert(kCtasPerSm * (kSmemBytes + 1024) <= 233472, "three CTAs per SM");
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 }  // namespace feat
 
 template <bool MULTI>
-__global__ void __launch_bounds__(kPnThreads, 2)
+__global__ void __launch_bounds__(feat::kThreads, feat::kCtasPerSm)
     pn_feat_kernel(const float* __restrict__ a1, const float* __restrict__ tmat, long long nq, int P, int G_arg,
                    const uint8_t* __restrict__ wpack, const float* __restrict__ b1, const float* __restrict__ b2,
                    const float* __restrict__ wq, float* __restrict__ pooled, float* __restrict__ partial) {
@@ -366,27 +377,24 @@ __global__ void __launch_bounds__(kPnThreads, 2)
     float* s_b1 = reinterpret_cast<float*>(smem + kOffPar);
     float* s_b2 = s_b1 + 64;
     float* s_wq = s_b2 + 128;
-    float* s_part = s_wq + 128;  // [2][128] partial attention logits of the two column halves
-    float* s_att = s_part + 256;
+    float* s_part = s_wq + 128;    // [2][128] partial attention logits of the two column halves
+    float* s_pool = s_part + 256;  // [4 lane groups][128] partial pooled sums of the warps' 32 rows
     volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + kOffTmem);
-    const uint32_t bar_full = sbase + kOffBar, bar_empty = bar_full + 8 * kPnStages, bar_accum = bar_empty + 8 * kPnStages,
-                   bar_aready = bar_accum + 8;
+    const uint32_t bar_full = sbase + kOffBar, bar_accum = bar_full + 16, bar_aready = bar_accum + 8;
 
-    for (int e = tid; e < 128; e += kPnThreads) {
+    for (int e = tid; e < 128; e += kThreads) {
         if (e < 64) s_b1[e] = b1[e];
         s_b2[e] = b2[e];
         s_wq[e] = wq[e];
     }
     if (tid == 0) {
-        for (int i = 0; i < kPnStages; ++i) {
-            mbar_init(bar_full + 8 * i, 1);
-            mbar_init(bar_empty + 8 * i, 1);
-        }
+        mbar_init(bar_full, 1);
+        mbar_init(bar_full + 8, 1);
         mbar_init(bar_accum, 1);
-        mbar_init(bar_aready, kPnEpiThreads / 32);  // one elected arrival per warp
+        mbar_init(bar_aready, kEpiThreads / 32);  // one elected arrival per warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kOffTmem), "r"((uint32_t)kTmemCols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -398,89 +406,119 @@ __global__ void __launch_bounds__(kPnThreads, 2)
     const long long ntiles = (nq * G + 1) / 2;
 
     if (warp == 0) {
-        {  // conv1 4x4096, conv2 4x8192 per tile
-            uint32_t slot = 0, phase = 0;
-            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const uint8_t* src = wpack;
-                for (int s = 0; s < 3; ++s) {  // slots: conv1 (4 steps of 4 KB), conv2 x2 (2 steps of 8 KB)
-                    mbar_wait(bar_empty + 8 * slot, phase ^ 1);
-                    if (elect_one()) {
-                        mbar_expect_tx(bar_full + 8 * slot, kPnSlot);
-                        bulk_copy(sbase + kOffRing + slot * kPnSlot, src, kPnSlot, bar_full + 8 * slot);
-                    }
-                    __syncwarp();
-                    src += kPnSlot;
-                    if (++slot == kPnStages) {
-                        slot = 0;
-                        phase ^= 1;
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        {
-            uint32_t slot = 0, phase = 0, ready_phase = 0;
-            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                // feature transform: D[rows, ql*64 + i] = a1[rows, :] . T_ql[i, :]   (operand built by the epilogue warps)
-                mbar_wait(bar_aready, ready_phase);
-                ready_phase ^= 1;
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t idesc = umma_idesc(64);
+        // ---- control warp: all lanes run the loop (warp-uniform control flow), one elected lane issues (see elect_one)
+        uint32_t ready_phase = 0, accum_phase = 0, full0_phase = 0, full1_phase = 0;
+        const uint32_t w_r0 = sbase + kOffT, w_r1 = sbase + kOffT + kWBytes;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            // feature transform: D[rows, ql*64 + i] = a1[rows, :] . T_ql[i, :]   (operands built by the epilogue warps)
+            mbar_wait(bar_aready, ready_phase);
+            ready_phase ^= 1;
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t idesc = umma_idesc(64);
 #pragma unroll
-                    for (int ql = 0; ql < 2; ++ql) {
-                        const uint32_t t_hi = sbase + kOffT + (2 * ql) * kTBytes, t_lo = t_hi + kTBytes;
-                        for (int s = 0; s < 4; ++s) {
-                            const uint64_t x_hi = umma_desc(sbase + kOffAhi + 2 * s * kPnLbo, kPnLbo, 128);
-                            const uint64_t x_lo = umma_desc(sbase + kOffAlo + 2 * s * kPnLbo, kPnLbo, 128);
-                            const uint64_t w_hi = umma_desc(t_hi + 2 * s * kTLbo, kTLbo, 128);
-                            const uint64_t w_lo = umma_desc(t_lo + 2 * s * kTLbo, kTLbo, 128);
-                            umma(tmem + ql * 64, x_hi, w_hi, idesc, s > 0 ? 1u : 0u);
-                            umma(tmem + ql * 64, x_lo, w_hi, idesc, 1u);
-                            umma(tmem + ql * 64, x_hi, w_lo, idesc, 1u);
-                        }
+                for (int ql = 0; ql < 2; ++ql) {
+                    const uint32_t t_hi = sbase + kOffT + (2 * ql) * kTBytes, t_lo = t_hi + kTBytes;
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        const uint64_t x_hi = umma_desc(sbase + kOffAhi + 2 * s * kPnLbo, kPnLbo, 128);
+                        const uint64_t x_lo = umma_desc(sbase + kOffAlo + 2 * s * kPnLbo, kPnLbo, 128);
+                        const uint64_t w_hi = umma_desc(t_hi + 2 * s * kTLbo, kTLbo, 128);
+                        const uint64_t w_lo = umma_desc(t_lo + 2 * s * kTLbo, kTLbo, 128);
+                        umma(tmem + ql * 64, x_hi, w_hi, idesc, s > 0 ? 1u : 0u);
+                        umma(tmem + ql * 64, x_lo, w_hi, idesc, 1u);
+                        umma(tmem + ql * 64, x_hi, w_lo, idesc, 1u);
                     }
-                    tc_commit(bar_accum);
                 }
-                __syncwarp();
-                for (int layer = 0; layer < 2; ++layer) {  // conv1 (64 wide), conv2 (128 wide)
-                    const int n = layer == 0 ? 64 : 128;
-                    const uint32_t idesc = umma_idesc(n);
-                    mbar_wait(bar_aready, ready_phase);
-                    ready_phase ^= 1;
-                    tc_fence_after();
-                    const int per = n == 64 ? 4 : 2;  // k16 steps per ring slot
-                    const uint32_t step_bytes = 64u * n;
-                    for (int s0 = 0; s0 < 4; s0 += per) {
-                        mbar_wait(bar_full + 8 * slot, phase);
-                        tc_fence_after();
-                        if (elect_one()) {
-                            for (int sub = 0; sub < per; ++sub) {
-                                const int s = s0 + sub;
-                                const uint64_t x_hi = umma_desc(sbase + kOffAhi + 2 * s * kPnLbo, kPnLbo, 128);
-                                const uint64_t x_lo = umma_desc(sbase + kOffAlo + 2 * s * kPnLbo, kPnLbo, 128);
-                                const uint32_t bst = sbase + kOffRing + slot * kPnSlot + sub * step_bytes;
-                                const uint64_t w_hi = umma_desc(bst, n * 16, 128);
-                                const uint64_t w_lo = umma_desc(bst + n * 32, n * 16, 128);
-                                umma(tmem, x_hi, w_hi, idesc, s > 0 ? 1u : 0u);
-                                umma(tmem, x_lo, w_hi, idesc, 1u);
-                                umma(tmem, x_hi, w_lo, idesc, 1u);
-                            }
-                            tc_commit(bar_empty + 8 * slot);
-                        }
-                        __syncwarp();
-                        if (++slot == kPnStages) {
-                            slot = 0;
-                            phase ^= 1;
-                        }
-                    }
-                    if (elect_one()) tc_commit(bar_accum);
-                    __syncwarp();
+                tc_commit(bar_accum);
+            }
+            __syncwarp();
+            // the transforms have been read: conv1 and the first half of conv2 take their place
+            mbar_wait(bar_accum, accum_phase);
+            accum_phase ^= 1;
+            if (elect_one()) {
+                mbar_expect_tx(bar_full, kWBytes);
+                bulk_copy(w_r0, wpack, kWBytes, bar_full);
+                mbar_expect_tx(bar_full + 8, kWBytes);
+                bulk_copy(w_r1, wpack + kWBytes, kWBytes, bar_full + 8);
+            }
+            __syncwarp();
+            // conv1 (64 wide): 4 k16 steps of 4 KB
+            mbar_wait(bar_aready, ready_phase);
+            ready_phase ^= 1;
+            mbar_wait(bar_full, full0_phase);
+            full0_phase ^= 1;
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t idesc = umma_idesc(64);
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const uint64_t x_hi = umma_desc(sbase + kOffAhi + 2 * s * kPnLbo, kPnLbo, 128);
+                    const uint64_t x_lo = umma_desc(sbase + kOffAlo + 2 * s * kPnLbo, kPnLbo, 128);
+                    const uint32_t bst = w_r0 + s * 4096;
+                    const uint64_t w_hi = umma_desc(bst, 64 * 16, 128);
+                    const uint64_t w_lo = umma_desc(bst + 64 * 32, 64 * 16, 128);
+                    umma(tmem, x_hi, w_hi, idesc, s > 0 ? 1u : 0u);
+                    umma(tmem, x_lo, w_hi, idesc, 1u);
+                    umma(tmem, x_hi, w_lo, idesc, 1u);
+                }
+                tc_commit(bar_accum);
+            }
+            __syncwarp();
+            // conv1's weights have been read: the second half of conv2 takes their place
+            mbar_wait(bar_accum, accum_phase);
+            accum_phase ^= 1;
+            if (elect_one()) {
+                mbar_expect_tx(bar_full, kWBytes);
+                bulk_copy(w_r0, wpack + 2 * kWBytes, kWBytes, bar_full);
+            }
+            __syncwarp();
+            // conv2 (128 wide): k16 steps 0,1 from R+16 KB, steps 2,3 from R+0 (8 KB per step)
+            mbar_wait(bar_aready, ready_phase);
+            ready_phase ^= 1;
+            mbar_wait(bar_full + 8, full1_phase);
+            full1_phase ^= 1;
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t idesc = umma_idesc(128);
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const uint64_t x_hi = umma_desc(sbase + kOffAhi + 2 * s * kPnLbo, kPnLbo, 128);
+                    const uint64_t x_lo = umma_desc(sbase + kOffAlo + 2 * s * kPnLbo, kPnLbo, 128);
+                    const uint32_t bst = w_r1 + s * 8192;
+                    const uint64_t w_hi = umma_desc(bst, 128 * 16, 128);
+                    const uint64_t w_lo = umma_desc(bst + 128 * 32, 128 * 16, 128);
+                    umma(tmem, x_hi, w_hi, idesc, s > 0 ? 1u : 0u);
+                    umma(tmem, x_lo, w_hi, idesc, 1u);
+                    umma(tmem, x_hi, w_lo, idesc, 1u);
                 }
             }
+            __syncwarp();
+            mbar_wait(bar_full, full0_phase);
+            full0_phase ^= 1;
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t idesc = umma_idesc(128);
+#pragma unroll
+                for (int s = 2; s < 4; ++s) {
+                    const uint64_t x_hi = umma_desc(sbase + kOffAhi + 2 * s * kPnLbo, kPnLbo, 128);
+                    const uint64_t x_lo = umma_desc(sbase + kOffAlo + 2 * s * kPnLbo, kPnLbo, 128);
+                    const uint32_t bst = w_r0 + (s - 2) * 8192;
+                    const uint64_t w_hi = umma_desc(bst, 128 * 16, 128);
+                    const uint64_t w_lo = umma_desc(bst + 128 * 32, 128 * 16, 128);
+                    umma(tmem, x_hi, w_hi, idesc, 1u);
+                    umma(tmem, x_lo, w_hi, idesc, 1u);
+                    umma(tmem, x_hi, w_lo, idesc, 1u);
+                }
+                tc_commit(bar_accum);
+            }
+            __syncwarp();
+            // third completion of the tile: keeps this warp's phase in step (the epilogue warps hold R until they have seen it)
+            mbar_wait(bar_accum, accum_phase);
+            accum_phase ^= 1;
         }
     } else {
-        const int ew = warp - 2, et = tid - 64;
+        const int ew = warp - 1, et = tid - 32;  // epilogue warps 1..8: TMEM lane groups 1,2,3,0,1,2,3,0
         const int lane_grp = warp & 3, half = ew >> 2;
         const int row = lane_grp * 32 + lane;
         uint32_t accum_phase = 0;
@@ -509,7 +547,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                 *reinterpret_cast<uint4*>(smem + kOffAlo + kb * kPnLbo + r * 16) = lo;
             }
             // ---- per-query transforms T_q [i][j] -> K-major operand (row i, k = j), values may be negative: plain split
-#pragma unroll
+#pragma unroll 2
             for (int t = 0; t < 4; ++t) {
                 const int e = et + 256 * t;
                 const int ql = e >> 9, i = (e >> 3) & 63, kb = e & 7;
@@ -524,8 +562,24 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                 *reinterpret_cast<uint4*>(smem + kOffT + (2 * ql + 1) * kTBytes + kb * kTLbo + i * 16) = lo;
             }
             warp_arrive(bar_aready, lane);
+            // the next tile's a1 rows and transforms come from HBM (written by the kernels before): pull them into the L2 now, one
+            // 32-byte sector per load instruction of the loops above
+            {
+                const long long nt = tile + gridDim.x;
+                if (nt < ntiles) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) prefetch_l2(a1 + ((nt * 8 + ew) * 128 + i * 32 + lane) * 8);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const int e = et + 256 * t;
+                        const int ql = e >> 9, i = (e >> 3) & 63, kb = e & 7;
+                        long long q = G == 1 ? 2 * nt + ql : (2 * nt + ql) / G;
+                        q = q < nq ? q : nq - 1;
+                        prefetch_l2(tmat + q * 4096 + i * 64 + 8 * kb);
+                    }
+                }
+            }
 
-            const long long q_row = 2 * tile + (row >> 6);
             // ---- x' = T . a1 (no bias, no activation; may be negative) -> operand tile
             mbar_wait(bar_accum, accum_phase);
             accum_phase ^= 1;
@@ -565,12 +619,14 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                 }
             }
             warp_arrive(bar_aready, lane);
-            // ---- conv2: bias + ReLU -> c2 (hi/lo tile for the pooling) and this thread's share of the attention logit
+            // ---- conv2: bias + ReLU; this thread's share (its 64 columns) of the attention logit of its row.  The activations stay in
+            // TMEM: the pooling below reads the accumulator a second time instead of a shared-memory copy
             mbar_wait(bar_accum, accum_phase);
             accum_phase ^= 1;
             tc_fence_after();
             {
                 float logit = 0.f;
+#pragma unroll 1
                 for (int cb = 0; cb < 2; ++cb) {
                     const int col0 = half * 64 + cb * 32;
                     float v[32];
@@ -578,84 +634,77 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                     bias_relu32(v, s_b2 + col0);
 #pragma unroll
                     for (int c = 0; c < 32; ++c) logit = fmaf(v[c], s_wq[col0 + c], logit);
-#pragma unroll
-                    for (int kb = 0; kb < 4; ++kb) {
-                        float x8[8];
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) x8[c] = v[kb * 8 + c];
-                        uint4 hi, lo;
-                        split8(x8, hi, lo);
-                        const int kblk = (col0 >> 3) + kb;
-                        *reinterpret_cast<uint4*>(smem + c2_hi(kblk) + row * 16) = hi;
-                        *reinterpret_cast<uint4*>(smem + c2_lo(kblk) + row * 16) = lo;
-                    }
                 }
                 s_part[half * 128 + row] = logit;
             }
-            tc_fence_before();
-            pn_epi_barrier();
-            // ---- softmax over the patch's points: thread per row
-            if (et < 128) {
-                const int r0 = (et >> 6) * 64, pj = et & 63;
+            epi_barrier();
+            // ---- softmax over the points of the half-tile (64 rows = the lane groups {0,1} or {2,3}): every warp reduces the 64 logits
+            // on its own, lane l holds rows l and 32 + l (the query bias cancels in the softmax)
+            float att;
+            {
+                const int r0 = (row >> 6) * 64;
                 const PnRow ph = pn_row(tile, r0, G);       // first row of this half-tile: its query and first point
                 const int nv = min(64, max(P - ph.p, 0));  // valid points of the half-tile
-                float m = -INFINITY;
-                for (int j = 0; j < nv; ++j) m = fmaxf(m, s_part[r0 + j] + s_part[128 + r0 + j]);
-                float sum = 0.f;
-                for (int j = 0; j < nv; ++j) sum += expf(s_part[r0 + j] + s_part[128 + r0 + j] - m);
-                const float e = pj < nv ? expf(s_part[et] + s_part[128 + et] - m) : 0.f;  // the query bias cancels in the softmax
+                const float la = lane < nv ? s_part[r0 + lane] + s_part[128 + r0 + lane] : -INFINITY;
+                const float lb = 32 + lane < nv ? s_part[r0 + 32 + lane] + s_part[128 + r0 + 32 + lane] : -INFINITY;
+                float m = fmaxf(la, lb);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                const float ea = lane < nv ? expf(la - m) : 0.f, eb = 32 + lane < nv ? expf(lb - m) : 0.f;
+                float sum = ea + eb;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                const float own = (lane_grp & 1) ? eb : ea;
                 // one half-tile per query: normalise here.  Several: keep exp(l - m_h), the combine kernel merges the half-tiles'
                 // (m_h, sum_h, pooled_h) like an online softmax
-                s_att[et] = G == 1 ? e / sum : e;
-                if (G > 1 && pj == 0 && ph.q < nq) {
+                att = nv > 0 ? (G == 1 ? own / sum : own) : 0.f;
+                if (G > 1 && half == 0 && (row & 63) == 0 && ph.q < nq) {
                     float* dst = partial + (ph.q * G + ph.p / 64) * kPartialStride;
                     dst[128] = m;
                     dst[129] = sum;
                 }
             }
-            pn_epi_barrier();
-            // ---- pooled[q, 8kb..] = sum_p att_p c2[p, .]: warp ew owns k8 blocks ew and ew + 8
+            // ---- pooled[q, c] = sum_p att_p c2[p, c]: every thread scales its row of the accumulator, the 32 rows of a warp are summed
+            // by recursive halving (lane l ends with column l of the block), the two warps of a half-tile meet in shared memory
 #pragma unroll 1
-            for (int t = 0; t < 2; ++t) {
-                const int kb = ew + 8 * t;
+            for (int cb = 0; cb < 2; ++cb) {
+                const int col0 = half * 64 + cb * 32;
+                float v[32];
+                tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + col0, v);
+                bias_relu32(v, s_b2 + col0);
 #pragma unroll
-                for (int ql = 0; ql < 2; ++ql) {
-                    float acc[8];
+                for (int c = 0; c < 32; ++c) v[c] *= att;
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+                for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
+                    const bool upper = (lane & off) != 0;
 #pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        const int r = ql * 64 + hh * 32 + lane;
-                        const float a = s_att[r];
-                        const uint4 hi = *reinterpret_cast<const uint4*>(smem + c2_hi(kb) + r * 16);
-                        const uint4 lo = *reinterpret_cast<const uint4*>(smem + c2_lo(kb) + r * 16);
-                        const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
-                            const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&lw[i]));
-                            acc[2 * i] = fmaf(a, fh.x + fl.x, acc[2 * i]);
-                            acc[2 * i + 1] = fmaf(a, fh.y + fl.y, acc[2 * i + 1]);
-                        }
-                    }
-#pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
-                    const PnRow ph = pn_row(tile, ql * 64, G);
-                    if (lane == 0 && ph.q < nq) {
-                        float4* dst = G == 1 ? reinterpret_cast<float4*>(pooled + ph.q * 128 + kb * 8)
-                                             : reinterpret_cast<float4*>(partial + (ph.q * G + ph.p / 64) * kPartialStride + kb * 8);
-                        dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                        dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+                    for (int i = 0; i < n; ++i) {
+                        const float send = upper ? v[i] : v[i + n];
+                        const float keep = upper ? v[i + n] : v[i];
+                        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
                     }
                 }
+                s_pool[lane_grp * 128 + col0 + lane] = v[0];
             }
-            pn_epi_barrier();  // all warps are done with the tile before the next gather overwrites it
+            tc_fence_before();
+            epi_barrier();
+            {
+                const int ql = et >> 7, c = et & 127;
+                const PnRow ph = pn_row(tile, ql * 64, G);
+                if (ph.q < nq) {
+                    const float val = s_pool[(2 * ql) * 128 + c] + s_pool[(2 * ql + 1) * 128 + c];
+                    if (G == 1)
+                        pooled[ph.q * 128 + c] = val;
+                    else
+                        partial[(ph.q * G + ph.p / 64) * kPartialStride + c] = val;
+                }
+            }
+            // s_part / s_pool are next written behind mbarrier waits that need an arrival of every epilogue warp, i.e. after this point
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 0) {
         __syncwarp();
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)kTmemCols) : "memory");
@@ -725,12 +774,13 @@ int pointnet_tc_impl(const pps_decoder_weights* w, const float* patches, int64_t
         PPS_TRY(linear_impl(f2, w->stnf3_w, w->stnf3_b, nullptr, nullptr, tmat, q, 4096, S / 4, S / 4, 4096, 0, st));
     }
     const uint8_t* pack_feat = static_cast<const uint8_t*>(w->tc_pn_feat);
+    const int grid_feat = (int)(ntiles < tc::feat::kCtasPerSm * kNumSMs ? ntiles : tc::feat::kCtasPerSm * kNumSMs);
     if (G > 1)
-        tc::pn_feat_kernel<true><<<grid, tc::kPnThreads, tc::feat::kSmemBytes, st>>>(a1, tmat, q, P, G, pack_feat, w->pn1_b, w->pn2_b,
-                                                                                    w->pnq_w, pooled128, partial);
+        tc::pn_feat_kernel<true><<<grid_feat, tc::feat::kThreads, tc::feat::kSmemBytes, st>>>(a1, tmat, q, P, G, pack_feat, w->pn1_b,
+                                                                                             w->pn2_b, w->pnq_w, pooled128, partial);
     else
-        tc::pn_feat_kernel<false><<<grid, tc::kPnThreads, tc::feat::kSmemBytes, st>>>(a1, tmat, q, P, 1, pack_feat, w->pn1_b, w->pn2_b,
-                                                                                     w->pnq_w, pooled128, partial);
+        tc::pn_feat_kernel<false><<<grid_feat, tc::feat::kThreads, tc::feat::kSmemBytes, st>>>(a1, tmat, q, P, 1, pack_feat, w->pn1_b,
+                                                                                              w->pn2_b, w->pnq_w, pooled128, partial);
     PPS_LAUNCH_CHECK();
     if (G > 1) {
         tc::pn_combine_kernel<<<(unsigned)q, 128, 0, st>>>(partial, q, G, pooled128);
