@@ -51,36 +51,57 @@ constexpr size_t kPackFeatBytes = size_t(4) * 4096 + size_t(4) * 8192;          
 // kernel A: conv0a .. stn.conv3 + max
 // ---------------------------------------------------------------------------------------------------------------------
 namespace stn {
+// The kernel runs as CTA PAIRS (cluster of 2 on one TPC, tcgen05 cta_group::2) like projection_tc_kernel: every MMA is M = 256.
+//   conv0b / stn.conv1 / stn.conv2   D[256 rows, n] = X . W^T: A = the two CTAs' 128-row tiles, B = n/2 weight rows from each CTA
+//   stn.conv3 (transposed)           D^T[256 features, 256 rows] = W . X^T: A = 128 of the 256 features from each CTA, B = the two tiles
+// so a CTA streams HALF of every weight stage through its ring and reads half of the weight operand per MMA.  With one CTA per MMA the
+// kernel was bound by shared-memory bandwidth: an M128 N128 K16 instruction reads 8 KB in its 64 tensor cycles (= the 128 B/clk of the
+// SM), the N = 64 layers need 192 B/clk, and the epilogues' operand stores and the ring refill (192 KB per tile) come on top --
+// ~1 MB of shared-memory traffic per tile for 4.6 k cycles of tensor work.  Pairs: 0.65 MB, ring 96 KB per CTA and tile.
+// After stn.conv3 a CTA holds ITS 128 features of all four queries of the pair-tile: the max over a patch stays a max over
+// accumulator columns inside one thread and nothing crosses the pair.
+// Rank 0 issues the MMAs; the barriers that gate them live in rank 0 and collect arrivals from both CTAs; completions are multicast.
 constexpr int kOffAhi = 0;
 constexpr int kABytes = 16 * kPnLbo;                 // up to 128 columns
 constexpr int kOffAlo = kOffAhi + kABytes;           // 33024
 constexpr int kOffRing = kOffAlo + kABytes;          // 66048
-// Weight ring: 2 slots of 16 KB (a whole 64-wide layer, or two k16 steps of a 128-wide layer / of a stn.conv3 feature block).  Measured
-// with the elect.sync issue path: 5 slots of 8 KB (more bytes in flight for stn.conv3's 128 KB per tile) are SLOWER, 52.6 vs 49.8 ms per
-// 131^3 grid -- every slot costs the issuer and the producer an mbarrier round trip (>= 90 cycles each) against 192 tensor cycles of work
+// Weight ring of one CTA: 2 slots of 16 KB.  Per pair-tile a CTA receives 7 slot fills: conv0b (8 KB: 4 k16 steps x 32 weight rows),
+// stn.conv1 (8 KB), stn.conv2 (16 KB: 4 steps x 64 rows), stn.conv3 (4 x 16 KB: 2 steps x 128 features each)
 constexpr int kSlot = 16384;
 constexpr int kStages = 2;
+constexpr int kFills = 7;
 constexpr int kOffPar = kOffRing + kStages * kSlot;  // 98816: w0a[192] b0a[64] b0b[64] bs1[64] bs2[128] bs3[256]
 constexpr int kParFloats = 192 + 64 + 64 + 64 + 128 + 256;
 constexpr int kOffBar = kOffPar + kParFloats * 4;    // full[kStages] empty[kStages] accum aready
-constexpr int kOffTmem = kOffBar + (2 * kStages + 2) * 8;
-constexpr int kSmemBytes = kOffTmem + 16 + 1024;     // ~101 KB -> two CTAs per SM
-static_assert(2 * (kSmemBytes + 1024) <= 233472, "two CTAs per SM");
-constexpr int kTmemCols = 256;
+constexpr int kSubBytes = ((kOffBar + (2 * kStages + 2) * 8 + 1023) / 1024) * 1024;  // one chain (sub-block): 100 KB
+constexpr int kSmemBytes = 2 * kSubBytes + 16 + 1024;  // two chains per CTA + the TMEM address
+static_assert(kSmemBytes <= 232448, "one CTA per SM");
+constexpr int kTmemCols = 256;                        // per chain
+// packed weights: per fill [CTA 0's slot | CTA 1's slot]
+__device__ __forceinline__ uint32_t fill_bytes(int f) { return f < 2 ? 8192u : 16384u; }
+__device__ __forceinline__ uint32_t fill_offset(int f, uint32_t rank) {  // byte offset of CTA `rank`'s part of fill f
+    const uint32_t base = f < 2 ? 16384u * f : 32768u + 32768u * (f - 2);
+    return base + rank * fill_bytes(f);
+}
 }  // namespace stn
 
 // MULTI = false: every patch fits one half-tile (P <= 64, G == 1): the instantiation carries no divisions and no partials
 template <bool MULTI>
-__global__ void __launch_bounds__(kPnThreads, 2)
+__global__ void __launch_bounds__(2 * kPnThreads, 1)
     pn_stn_kernel(const float* __restrict__ patches, long long nq, int P, int G_arg, const uint8_t* __restrict__ wpack,
                   const float* __restrict__ w0a, const float* __restrict__ b0a, const float* __restrict__ b0b,
                   const float* __restrict__ bs1, const float* __restrict__ bs2, const float* __restrict__ bs3,
                   float* __restrict__ a1_out, float* __restrict__ g_out) {
     using namespace stn;
     const int G = MULTI ? G_arg : 1;
-    extern __shared__ __align__(1024) uint8_t smem[];  // used directly: the compiler keeps the shared address space (LDS/STS)
+    extern __shared__ __align__(1024) uint8_t smem_cta[];  // used directly: the compiler keeps the shared address space (LDS/STS)
+    // Two independent CHAINS per CTA (sub-blocks of 320 threads with their own operand tile, ring, barriers and 256 TMEM columns), one
+    // CTA per SM: two CTAs per SM would each allocate their 256 columns on their own, and nothing makes the two CTAs of a pair receive
+    // the SAME columns on their two SMs -- which cta_group::2 needs (one TMEM address per MMA for both CTAs)
+    const int sub = threadIdx.x >= kPnThreads ? 1 : 0;
+    uint8_t* smem = smem_cta + sub * kSubBytes;
     const uint32_t sbase = smem_u32(smem);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x - sub * kPnThreads, warp = tid >> 5, lane = tid & 31;  // within the sub-block
     float* s_par = reinterpret_cast<float*>(smem + kOffPar);
     float* s_w0a = s_par;
     float* s_b0a = s_par + 192;
@@ -88,9 +109,11 @@ __global__ void __launch_bounds__(kPnThreads, 2)
     float* s_bs1 = s_b0b + 64;
     float* s_bs2 = s_bs1 + 64;
     float* s_bs3 = s_bs2 + 128;
-    volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + kOffTmem);
+    volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem_cta + 2 * kSubBytes);
     const uint32_t bar_full = sbase + kOffBar, bar_empty = bar_full + 8 * kStages, bar_accum = bar_empty + 8 * kStages,
                    bar_aready = bar_accum + 8;
+    const uint32_t crank = cluster_ctarank();  // 0 = leader of the pair
+    const uint32_t lead_full = map_to_cta(bar_full, 0), lead_aready = map_to_cta(bar_aready, 0);
 
     for (int e = tid; e < 256; e += kPnThreads) {
         if (e < 192) s_w0a[e] = w0a[e];
@@ -104,77 +127,101 @@ __global__ void __launch_bounds__(kPnThreads, 2)
     }
     if (tid == 0) {
         for (int i = 0; i < kStages; ++i) {
-            mbar_init(bar_full + 8 * i, 1);
+            mbar_init(bar_full + 8 * i, crank == 0 ? 2 : 1);  // leader: own producer + the peer's relay
             mbar_init(bar_empty + 8 * i, 1);
         }
         mbar_init(bar_accum, 1);
-        mbar_init(bar_aready, kPnEpiThreads / 32);  // one elected arrival per warp
+        mbar_init(bar_aready, 2 * kPnEpiThreads / 32);  // one elected arrival per epilogue warp of the pair (used in the leader)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kOffTmem), "r"((uint32_t)kTmemCols)
+    if (threadIdx.x >> 5 == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_cta + 2 * kSubBytes)),
+                     "r"(512u)
                      : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();  // the barriers of both CTAs are initialised before any remote arrival or multicast commit
     tc_fence_after();
-    const uint32_t tmem = *s_tmem;
-    const long long ntiles = (nq * G + 1) / 2;
+    const uint32_t tmem = *s_tmem + (uint32_t)(sub * kTmemCols);
+    // pair-tile = the two tiles of a pair of sub-blocks; both run the same number of iterations (a tile past the end has no valid row)
+    const long long ntiles = (nq * G + 1) / 2, npt = (ntiles + 1) / 2;
+    const long long pair = (blockIdx.x >> 1) * 2 + sub, npairs = (gridDim.x >> 1) * 2;
+    const long long iters = npt > pair ? (npt - pair + npairs - 1) / npairs : 0;
 
-    // weight stages of one tile, in issue order: (bytes per stage, number of stages)
-    // conv0b 4x4096, stn1 4x4096, stn2 4x8192, stn3 16x8192
     // warps 0 and 1 run their loops with all lanes (warp-uniform control flow) and issue through one elected lane: see elect_one
     if (warp == 0) {
-        {
-            uint32_t slot = 0, phase = 0;
-            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const uint8_t* src = wpack;
-                for (int s = 0; s < (4 * 4096 * 2 + 4 * 8192 + 16 * 8192) / kSlot; ++s) {  // conv0b, stn1 (4 KB per k16 step), stn2, stn3 (8 KB)
-                    mbar_wait(bar_empty + 8 * slot, phase ^ 1);
-                    if (elect_one()) {
-                        mbar_expect_tx(bar_full + 8 * slot, kSlot);
-                        bulk_copy(sbase + kOffRing + slot * kSlot, src, kSlot, bar_full + 8 * slot);
-                    }
-                    __syncwarp();
-                    src += kSlot;
-                    if (++slot == kStages) {
-                        slot = 0;
-                        phase ^= 1;
-                    }
+        uint32_t slot = 0, phase = 0;
+        for (long long it = 0; it < iters; ++it) {
+            for (int f = 0; f < kFills; ++f) {
+                mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+                if (elect_one()) {
+                    mbar_expect_tx(bar_full + 8 * slot, fill_bytes(f));
+                    bulk_copy(sbase + kOffRing + slot * kSlot, wpack + fill_offset(f, crank), fill_bytes(f), bar_full + 8 * slot);
+                }
+                __syncwarp();
+                if (++slot == kStages) {
+                    slot = 0;
+                    phase ^= 1;
                 }
             }
         }
     } else if (warp == 1) {
-        {
+        if (crank == 0) {
+            // ---- MMA issuer of the pair
             uint32_t slot = 0, phase = 0, ready_phase = 0;
-            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (long long it = 0; it < iters; ++it) {
                 for (int layer = 0; layer < 4; ++layer) {
-                    mbar_wait(bar_aready, ready_phase);
+                    mbar_wait_cluster(bar_aready, ready_phase);
                     ready_phase ^= 1;
                     tc_fence_after();
                     if (layer < 3) {
-                        // D[rows, n] = X[rows, 64] . W[n, 64]^T
+                        // D[256 rows, n] = X[rows, 64] . W[n, 64]^T: one ring slot, 4 k16 steps of n/2 weight rows per CTA
                         const int n = layer < 2 ? 64 : 128;
-                        const uint32_t idesc = umma_idesc(n);
-                        const int per = kSlot / (64 * n);  // k16 steps per ring slot
-                        const uint32_t step_bytes = 64u * n;
-                        for (int s0 = 0; s0 < 4; s0 += per) {
-                            mbar_wait(bar_full + 8 * slot, phase);
+                        const uint32_t idesc = umma_idesc2(n);
+                        const uint32_t step_bytes = 32u * n;
+                        mbar_wait_cluster(bar_full + 8 * slot, phase);
+                        tc_fence_after();
+                        if (elect_one()) {
+#pragma unroll
+                            for (int s = 0; s < 4; ++s) {
+                                const uint64_t x_hi = umma_desc(sbase + kOffAhi + 2 * s * kPnLbo, kPnLbo, 128);
+                                const uint64_t x_lo = umma_desc(sbase + kOffAlo + 2 * s * kPnLbo, kPnLbo, 128);
+                                const uint32_t bst = sbase + kOffRing + slot * kSlot + s * step_bytes;
+                                const uint64_t w_hi = umma_desc(bst, n * 8, 128);
+                                const uint64_t w_lo = umma_desc(bst + n * 16, n * 8, 128);
+                                umma2(tmem, x_hi, w_hi, idesc, s > 0 ? 1u : 0u);
+                                umma2(tmem, x_lo, w_hi, idesc, 1u);
+                                umma2(tmem, x_hi, w_lo, idesc, 1u);
+                            }
+                            tc_commit2(bar_empty + 8 * slot);
+                        }
+                        __syncwarp();
+                        if (++slot == kStages) {
+                            slot = 0;
+                            phase ^= 1;
+                        }
+                    } else {
+                        // transposed: D^T[256 features, 256 rows] = W[features, 128] . X[rows, 128]^T, 2 k16 steps per ring slot
+                        const uint32_t idesc = umma_idesc2(256);
+                        for (int s0 = 0; s0 < 8; s0 += 2) {
+                            mbar_wait_cluster(bar_full + 8 * slot, phase);
                             tc_fence_after();
                             if (elect_one()) {
-                                for (int sub = 0; sub < per; ++sub) {
+#pragma unroll
+                                for (int sub = 0; sub < 2; ++sub) {
                                     const int s = s0 + sub;
                                     const uint64_t x_hi = umma_desc(sbase + kOffAhi + 2 * s * kPnLbo, kPnLbo, 128);
                                     const uint64_t x_lo = umma_desc(sbase + kOffAlo + 2 * s * kPnLbo, kPnLbo, 128);
-                                    const uint32_t bst = sbase + kOffRing + slot * kSlot + sub * step_bytes;
-                                    const uint64_t w_hi = umma_desc(bst, n * 16, 128);
-                                    const uint64_t w_lo = umma_desc(bst + n * 32, n * 16, 128);
-                                    umma(tmem, x_hi, w_hi, idesc, s > 0 ? 1u : 0u);
-                                    umma(tmem, x_lo, w_hi, idesc, 1u);
-                                    umma(tmem, x_hi, w_lo, idesc, 1u);
+                                    const uint32_t wst = sbase + kOffRing + slot * kSlot + sub * 8192;
+                                    const uint64_t w_hi = umma_desc(wst, 128 * 16, 128);
+                                    const uint64_t w_lo = umma_desc(wst + 4096, 128 * 16, 128);
+                                    umma2(tmem, w_hi, x_hi, idesc, s > 0 ? 1u : 0u);
+                                    umma2(tmem, w_hi, x_lo, idesc, 1u);
+                                    umma2(tmem, w_lo, x_hi, idesc, 1u);
                                 }
-                                tc_commit(bar_empty + 8 * slot);
+                                tc_commit2(bar_empty + 8 * slot);
                             }
                             __syncwarp();
                             if (++slot == kStages) {
@@ -182,48 +229,30 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                                 phase ^= 1;
                             }
                         }
-                    } else {
-                        // transposed: D^T[features(128 per block), rows(128)] = W[features, 128] . X[rows, 128]^T
-                        const uint32_t idesc = umma_idesc(128);
-                        for (int fb = 0; fb < 2; ++fb) {
-                            constexpr int per3 = kSlot / 8192;  // k16 steps of a feature block per ring slot
-                            for (int s0 = 0; s0 < 8; s0 += per3) {
-                                mbar_wait(bar_full + 8 * slot, phase);
-                                tc_fence_after();
-                                if (elect_one()) {
-#pragma unroll
-                                    for (int sub = 0; sub < per3; ++sub) {
-                                        const int s = s0 + sub;
-                                        const uint64_t x_hi = umma_desc(sbase + kOffAhi + 2 * s * kPnLbo, kPnLbo, 128);
-                                        const uint64_t x_lo = umma_desc(sbase + kOffAlo + 2 * s * kPnLbo, kPnLbo, 128);
-                                        const uint32_t wst = sbase + kOffRing + slot * kSlot + sub * 8192;
-                                        const uint64_t w_hi = umma_desc(wst, 128 * 16, 128);
-                                        const uint64_t w_lo = umma_desc(wst + 4096, 128 * 16, 128);
-                                        umma(tmem + fb * 128, w_hi, x_hi, idesc, s > 0 ? 1u : 0u);
-                                        umma(tmem + fb * 128, w_hi, x_lo, idesc, 1u);
-                                        umma(tmem + fb * 128, w_lo, x_hi, idesc, 1u);
-                                    }
-                                    tc_commit(bar_empty + 8 * slot);
-                                }
-                                __syncwarp();
-                                if (++slot == kStages) {
-                                    slot = 0;
-                                    phase ^= 1;
-                                }
-                            }
-                        }
                     }
-                    if (elect_one()) tc_commit(bar_accum);
+                    if (elect_one()) tc_commit2(bar_accum);  // accumulator of this layer complete, in both CTAs
                     __syncwarp();
+                }
+            }
+        } else if (lane == 0) {
+            // ---- peer: tell the leader when my half of a slot is here
+            uint32_t slot = 0, phase = 0;
+            for (long long n = 0; n < iters * kFills; ++n) {
+                mbar_wait(bar_full + 8 * slot, phase);
+                mbar_arrive_cluster(lead_full + 8 * slot);
+                if (++slot == kStages) {
+                    slot = 0;
+                    phase ^= 1;
                 }
             }
         }
     } else {
         const int ew = warp - 2, et = tid - 64;
-        const int lane_grp = warp & 3, half = ew >> 2;
+        const int lane_grp = (threadIdx.x >> 5) & 3, half = ew >> 2;  // the TMEM lane group follows the warp's index in the CTA
         const int row = lane_grp * 32 + lane;  // TMEM lane of this thread
         uint32_t accum_phase = 0;
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (long long it = 0; it < iters; ++it) {
+            const long long tile = 2 * (pair + it * npairs) + crank;  // a tile >= ntiles has no valid row
             // ---- gather + conv0a (SIMT, K=3): thread = (row, half of the 64 channels).  (Fetching the next tile's point a whole tile
             // ahead into three registers was measured and is slower: 52.6 vs 49.8 ms per 131^3 grid.)
             {
@@ -253,7 +282,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                     *reinterpret_cast<uint4*>(smem + kOffAlo + (hf * 4 + kb) * kPnLbo + r * 16) = lo;
                 }
             }
-            warp_arrive(bar_aready, lane);
+            warp_arrive_cluster(lead_aready, lane);
 
             const PnRow prow = pn_row(tile, row, G);
             const bool row_valid = prow.q < nq && prow.p < P;
@@ -262,7 +291,7 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                 mbar_wait(bar_accum, accum_phase);
                 accum_phase ^= 1;
                 tc_fence_after();
-                    const float* bias = layer == 0 ? s_b0b : (layer == 1 ? s_bs1 : s_bs2);
+                const float* bias = layer == 0 ? s_b0b : (layer == 1 ? s_bs1 : s_bs2);
                 const int nload = layer < 2 ? 1 : 2;  // 32 or 64 columns per thread
                 for (int cb = 0; cb < nload; ++cb) {
                     const int col0 = (layer < 2 ? half * 32 : half * 64) + cb * 32;
@@ -292,31 +321,34 @@ __global__ void __launch_bounds__(kPnThreads, 2)
                         *reinterpret_cast<uint4*>(smem + kOffAlo + kblk * kPnLbo + row * 16) = lo;
                     }
                 }
-                warp_arrive(bar_aready, lane);
-                }
-            // ---- stn.conv3 transposed: TMEM lane = feature, columns = rows of the tile; max over the patch's points
+                warp_arrive_cluster(lead_aready, lane);
+            }
+            // ---- stn.conv3 transposed: TMEM lane = feature 128 * crank + row, columns = the 256 rows of the pair-tile (tile of rank 0,
+            // then tile of rank 1); max over the points of each of the four half-tiles.  This warp takes the tile of rank `half`
             mbar_wait(bar_accum, accum_phase);
             accum_phase ^= 1;
             tc_fence_after();
             {
-                const PnRow ph = pn_row(tile, half * 64, G);  // this warp's column half = one half-tile of one query
-                const long long q = ph.q;
-                for (int fb = 0; fb < 2; ++fb) {
+                const long long ctile = 2 * (pair + it * npairs) + half;
+                const int f = 128 * (int)crank + row;
+                const float bias3 = s_bs3[f];
+#pragma unroll 1
+                for (int hh = 0; hh < 2; ++hh) {
+                    const PnRow ph = pn_row(ctile, hh * 64, G);  // this column block = one half-tile of one query
                     float m = -INFINITY;
                     for (int cb = 0; cb < 2; ++cb) {
                         float v[32];
-                        tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + fb * 128 + half * 64 + cb * 32, v);
+                        tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + half * 128 + hh * 64 + cb * 32, v);
 #pragma unroll
                         for (int c = 0; c < 32; ++c)
                             if (ph.p + cb * 32 + c < P) m = fmaxf(m, v[c]);
                     }
-                    const int f = fb * 128 + row;
-                    if (q < nq) {
-                        const float val = fmaxf(m + s_bs3[f], 0.f);  // ReLU and max commute
+                    if (ph.q < nq) {
+                        const float val = fmaxf(m + bias3, 0.f);  // ReLU and max commute
                         if (G == 1)
-                            g_out[q * 256 + f] = val;
+                            g_out[ph.q * 256 + f] = val;
                         else  // the patch spans several half-tiles: max over them (val >= 0, g zeroed by the host: int order = float order)
-                            atomicMax(reinterpret_cast<int*>(g_out + q * 256 + f), __float_as_int(val));
+                            atomicMax(reinterpret_cast<int*>(g_out + ph.q * 256 + f), __float_as_int(val));
                     }
                 }
             }
@@ -326,10 +358,12 @@ __global__ void __launch_bounds__(kPnThreads, 2)
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    __syncwarp();
+    cluster_sync_all();  // neither CTA exits (or frees its TMEM) while the peer may still arrive on its barriers or read its tile
+    if (threadIdx.x >> 5 == 1) {
         __syncwarp();
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)kTmemCols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
     }
 }
 
@@ -756,15 +790,34 @@ int pointnet_tc_impl(const pps_decoder_weights* w, const float* patches, int64_t
     const int P = w->num_pts_local, S = w->stn_size;
     const int G = (P + 63) / 64;  // 64-row half-tiles per query
     const long long ntiles = (q * G + 1) / 2;
-    const int grid = (int)(ntiles < 2 * kNumSMs ? ntiles : 2 * kNumSMs);
+    // pn_stn: CTA pairs, two chains per CTA -> up to 74 clusters x 2 chains, a pair of chains takes a pair-tile of 2 tiles
+    const long long npt = (ntiles + 1) / 2;
+    const int clusters = (int)((npt + 1) / 2 < kNumSMs / 2 ? (npt + 1) / 2 : kNumSMs / 2);
     if (G > 1) PPS_CUDA(cudaMemsetAsync(g, 0, (size_t)q * 256 * sizeof(float), st));  // the half-tiles' maxima meet in an atomicMax
     const uint8_t* pack_stn = static_cast<const uint8_t*>(w->tc_pn_stn);
-    if (G > 1)
-        tc::pn_stn_kernel<true><<<grid, tc::kPnThreads, tc::stn::kSmemBytes, st>>>(patches, q, P, G, pack_stn, w->pn0a_w, w->pn0a_b,
-                                                                                  w->pn0b_b, w->stn1_b, w->stn2_b, w->stn3_b, a1, g);
-    else
-        tc::pn_stn_kernel<false><<<grid, tc::kPnThreads, tc::stn::kSmemBytes, st>>>(patches, q, P, 1, pack_stn, w->pn0a_w, w->pn0a_b,
-                                                                                   w->pn0b_b, w->stn1_b, w->stn2_b, w->stn3_b, a1, g);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * clusters);
+        cfg.blockDim = dim3(2 * tc::kPnThreads);
+        cfg.dynamicSmemBytes = tc::stn::kSmemBytes;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;  // CTA pairs: the two CTAs of a cluster sit on the two SMs of one TPC
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const long long nq = q;
+        if (G > 1)
+            PPS_CUDA(cudaLaunchKernelEx(&cfg, tc::pn_stn_kernel<true>, patches, nq, P, G, pack_stn, (const float*)w->pn0a_w,
+                                        (const float*)w->pn0a_b, (const float*)w->pn0b_b, (const float*)w->stn1_b,
+                                        (const float*)w->stn2_b, (const float*)w->stn3_b, a1, g));
+        else
+            PPS_CUDA(cudaLaunchKernelEx(&cfg, tc::pn_stn_kernel<false>, patches, nq, P, 1, pack_stn, (const float*)w->pn0a_w,
+                                        (const float*)w->pn0a_b, (const float*)w->pn0b_b, (const float*)w->stn1_b,
+                                        (const float*)w->stn2_b, (const float*)w->stn3_b, a1, g));
+    }
     PPS_LAUNCH_CHECK();
     if (chain_tc_supported(w)) {
         PPS_TRY(stn_fc_tc_impl(w, g, q, tmat, st));

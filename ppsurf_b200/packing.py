@@ -117,8 +117,14 @@ def pack_decoder(sd, device, k, num_pts_local, prefix='') -> Packed:
     if latent == 256 and st.stn_size == 256 and num_pts_local <= 256:
         t = p.tensors
         w3 = t['stn3_w'].to('cpu', torch.float64)
-        stn = torch.cat([tc_pack_matrix(t['pn0b_w'].cpu()), tc_pack_matrix(t['stn1_w'].cpu()), tc_pack_matrix(t['stn2_w'].cpu()),
-                         tc_pack_matrix(w3[:128]), tc_pack_matrix(w3[128:])])
+        def pair_slots(w, nslots):  # pn_stn_kernel runs as CTA pairs: per ring slot [CTA 0: its half of the weight rows | CTA 1]
+            h = w.shape[0] // 2
+            a, b = tc_pack_matrix(w[:h]).view(nslots, -1), tc_pack_matrix(w[h:]).view(nslots, -1)
+            return torch.stack([a, b], dim=1).reshape(-1)
+
+        # conv0b, stn.conv1 (8 KB per CTA), stn.conv2 (16 KB): one slot each; stn.conv3: 4 slots of two k16 steps (16 KB per CTA)
+        stn = torch.cat([pair_slots(t['pn0b_w'].cpu(), 1), pair_slots(t['stn1_w'].cpu(), 1), pair_slots(t['stn2_w'].cpu(), 1),
+                         pair_slots(w3, 4)])
         feat = torch.cat([tc_pack_matrix(t['pn1_w'].cpu()), tc_pack_matrix(t['pn2_w'].cpu())])
         assert stn.numel() == _lib.lib.pps_decoder_tc_pn_stn_bytes() and feat.numel() == _lib.lib.pps_decoder_tc_pn_feat_bytes()
         t['tc_pn_stn'], t['tc_pn_feat'] = stn.to(device), feat.to(device)
