@@ -214,17 +214,19 @@ __global__ void __launch_bounds__(kThreads, 1)
                     const uint32_t lm = ABL ? (term_mask >> (3 * layer)) & 7u : (kProductTerms >> (3 * layer)) & 7u;
                     if (layer < 2) {
                         for (int sl = 0; sl < kKSteps / kSub; ++sl) {  // one ring slot = kSub k16 steps: one full-wait and one commit per slot
+                            // the weights first: they have usually landed long ago, and a wait on a completed mbarrier still costs ~90
+                            // cycles that would otherwise sit between the operand chunk's release and the first MMA that reads it
                             long long t0 = tick<PROF>();
+                            mbar_wait_cluster(bar_full + 8 * slot, phase);  // both halves of the weight stage have landed (TMA writes:
+                                                                            // async proxy -> async proxy, no tcgen05 fence needed)
+                            long long t1 = tick<PROF>();
                             if (((sl * kSub) & 3) == 0) {  // operand columns [64c, 64c+64) of BOTH tiles written by the previous stage of the pipeline
                                 mbar_wait_cluster(bar_chunk + 8 * ((sl * kSub) >> 2), chunk_phase);
                                 tc_fence_after();
                             }
-                            long long t1 = tick<PROF>();
-                            mbar_wait_cluster(bar_full + 8 * slot, phase);  // both halves of the weight stage have landed (TMA writes:
-                                                                            // async proxy -> async proxy, no tcgen05 fence needed)
-                            t_chunk += t1 - t0;
                             const long long t2 = tick<PROF>();
-                            t_full += t2 - t1;
+                            t_full += t1 - t0;
+                            t_chunk += t2 - t1;
                             if (elect_one()) {
 #pragma unroll
                                 for (int sub = 0; sub < kSub; ++sub) {
@@ -255,12 +257,12 @@ __global__ void __launch_bounds__(kThreads, 1)
                         const uint32_t idesc_q = umma_idesc2(kHeads);
                         for (int c = 0; c < kChunks; ++c) {
                             long long t0 = tick<PROF>();
+                            mbar_wait_cluster(bar_full + 8 * slot, phase);
+                            long long t1 = tick<PROF>();
                             mbar_wait_cluster(bar_chunk + 8 * c, chunk_phase);
                             tc_fence_after();
-                            long long t1 = tick<PROF>();
-                            mbar_wait_cluster(bar_full + 8 * slot, phase);
-                            t_chunk += t1 - t0;
-                            t_full += tick<PROF>() - t1;
+                            t_full += t1 - t0;
+                            t_chunk += tick<PROF>() - t1;
                             if (elect_one()) {
 #pragma unroll
                                 for (int sub = 0; sub < kQSub; ++sub) {

@@ -173,6 +173,9 @@ __global__ void __launch_bounds__(2 * kPnThreads, 1)
             uint32_t slot = 0, phase = 0, ready_phase = 0;
             for (long long it = 0; it < iters; ++it) {
                 for (int layer = 0; layer < 4; ++layer) {
+                    // the layer's first weight slot BEFORE the operand tile: it has usually landed long ago, and a wait on a completed
+                    // mbarrier still costs ~90 cycles that would otherwise sit between the tile's release and the first MMA
+                    mbar_wait_cluster(bar_full + 8 * slot, phase);
                     mbar_wait_cluster(bar_aready, ready_phase);
                     ready_phase ^= 1;
                     tc_fence_after();
@@ -181,8 +184,6 @@ __global__ void __launch_bounds__(2 * kPnThreads, 1)
                         const int n = layer < 2 ? 64 : 128;
                         const uint32_t idesc = umma_idesc2(n);
                         const uint32_t step_bytes = 32u * n;
-                        mbar_wait_cluster(bar_full + 8 * slot, phase);
-                        tc_fence_after();
                         if (elect_one()) {
 #pragma unroll
                             for (int s = 0; s < 4; ++s) {
@@ -206,8 +207,10 @@ __global__ void __launch_bounds__(2 * kPnThreads, 1)
                         // transposed: D^T[256 features, 256 rows] = W[features, 128] . X[rows, 128]^T, 2 k16 steps per ring slot
                         const uint32_t idesc = umma_idesc2(256);
                         for (int s0 = 0; s0 < 8; s0 += 2) {
-                            mbar_wait_cluster(bar_full + 8 * slot, phase);
-                            tc_fence_after();
+                            if (s0 > 0) {
+                                mbar_wait_cluster(bar_full + 8 * slot, phase);
+                                tc_fence_after();
+                            }
                             if (elect_one()) {
 #pragma unroll
                                 for (int sub = 0; sub < 2; ++sub) {
@@ -478,10 +481,10 @@ __global__ void __launch_bounds__(feat::kThreads, feat::kCtasPerSm)
             }
             __syncwarp();
             // conv1 (64 wide): 4 k16 steps of 4 KB
+            mbar_wait(bar_full, full0_phase);  // the weights before the operand tile (see pn_stn_kernel)
+            full0_phase ^= 1;
             mbar_wait(bar_aready, ready_phase);
             ready_phase ^= 1;
-            mbar_wait(bar_full, full0_phase);
-            full0_phase ^= 1;
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t idesc = umma_idesc(64);
@@ -508,10 +511,10 @@ __global__ void __launch_bounds__(feat::kThreads, feat::kCtasPerSm)
             }
             __syncwarp();
             // conv2 (128 wide): k16 steps 0,1 from R+16 KB, steps 2,3 from R+0 (8 KB per step)
-            mbar_wait(bar_aready, ready_phase);
-            ready_phase ^= 1;
             mbar_wait(bar_full + 8, full1_phase);
             full1_phase ^= 1;
+            mbar_wait(bar_aready, ready_phase);
+            ready_phase ^= 1;
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t idesc = umma_idesc(128);
