@@ -576,12 +576,12 @@ def run_b200(args):
             'gpu_launches': int(launches),
             'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
                          'frac': (achieved / peaks['bf16_tflops']) if achieved else None,
-                         # DRAM bytes per launch from the ncu --set full capture under profiles/ (272.2 MB read + written by one
-                         # launch over 300763 queries = 905 B per query: the pooled output, 1024 B per query, minus what was still
-                         # in the L2 when the capture ended; the fc1 table and the weights are L2 hits), scaled to this run's queries
-                         # per launch
-                         'traffic': (905.0 * count * args.steps / max(int(brackets.value), 1)) if args.path == 1 else None,
-                         'traffic_source': 'profiles/r02_decode_kernels_full_summary.csv' if args.path == 1 else None,
+                         # DRAM bytes per launch from the ncu --set full capture under profiles/ (185.6 MB read + 267.7 MB written by
+                         # the first launch over 300763 queries = 1507 B per query: the pooled output, 1024 B per query, minus what
+                         # was still in the L2 when the capture ended, plus the cold first read of the fc1 table and the neighbour
+                         # ids; in the timed loop table and weights are L2 hits), scaled to this run's queries per launch
+                         'traffic': (1507.0 * count * args.steps / max(int(brackets.value), 1)) if args.path == 1 else None,
+                         'traffic_source': 'profiles/r02_decode_kernels_full_session3_summary.csv' if args.path == 1 else None,
                          'kernel': kernel, 'kernel_ms_per_step': dom_ms.value / args.steps,
                          'kernel_share_of_step': dom_ms.value / elapsed_ms, 'brackets': int(brackets.value),
                          'flop_per_row_executed': GEMM_FLOP_PER_ROW, 'peak_source': peaks['source'],
