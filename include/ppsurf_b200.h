@@ -65,6 +65,9 @@ int pps_knn_build(const float* pts, int64_t n, void* index, size_t index_bytes, 
 int pps_debug_knn_run(int run);
 /* tuning knob: finest octree cells per point of indices built from now on (query an index under the setting it was built with) */
 int pps_debug_knn_cells(int factor);
+/* tuning knob: an inner octree node of at most this many points per unpruned child is scanned as one contiguous range instead of
+ * being traversed (results do not depend on it); returns the previous value */
+int pps_debug_knn_scan_child(int points);
 int pps_knn_query(const void* index, int64_t n, const float* queries, int64_t q, int k, int32_t* idx_out,
                   float* dist2_out, void* stream);
 

@@ -65,6 +65,7 @@ SIGNATURES = {
     'pps_knn_build': (i32, [c_f32p, i64, c_voidp, size_t, c_voidp]),
     'pps_debug_knn_run': (i32, [i32]),
     'pps_debug_knn_cells': (i32, [i32]),
+    'pps_debug_knn_scan_child': (i32, [i32]),
     'pps_knn_query': (i32, [c_voidp, i64, c_f32p, i64, i32, c_i32p, c_f32p, c_voidp]),
     'pps_patch_normalize': (i32, [c_f32p, c_f32p, c_i32p, c_f32p, i64, i32, i32, c_f32p, c_voidp]),
     'pps_linear': (i32, [c_f32p, c_f32p, c_f32p, c_f32p, c_i32p, c_f32p, i64, i32, i32, i32, i32, i32, c_voidp]),

@@ -174,7 +174,7 @@ template <int SLOTS>
 __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restrict__ hdr, const float4* __restrict__ sorted,
                                                        const int* __restrict__ cell_start, const float* __restrict__ queries,
                                                        long long nq, int k, int32_t* idx_out,
-                                                       float* __restrict__ d2_out, int run, int pass, int scan_cap) {
+                                                       float* __restrict__ d2_out, int run, int pass, int scan_cap, int scan_child) {
     // per warp: node code, and the node's range in the sorted array (loaded by the parent: no second round trip on the pop)
     __shared__ unsigned int stack_s[8][8 * kMaxLevels + 8];
     __shared__ int stack_lo_s[8][8 * kMaxLevels + 8], stack_hi_s[8][8 * kMaxLevels + 8];
@@ -314,6 +314,18 @@ __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restri
                     pi = __float_as_int(p.w);
                 }
                 unsigned int mask = __ballot_sync(full, i < hi && d2 <= bound && cand_less(d2, pi, worst, worst_i));
+                if (kReseed && rq > 0 && mask) {
+                    // points of this step that are already in the list (carried over from the previous query: most of the candidates
+                    // that beat the k-th distance): every lane marks the list entries it holds by their position in the sorted
+                    // array, one warp-wide OR per step replaces a list lookup per candidate
+                    unsigned int mine = 0;
+#pragma unroll
+                    for (int s = 0; s < SLOTS; ++s) {
+                        const unsigned int off = (unsigned int)(lp[s] - base);
+                        if (off < 32u && li[s] != 0x7fffffff) mine |= 1u << off;
+                    }
+                    mask &= ~__reduce_or_sync(full, mine);
+                }
                 while (mask) {
                     const int src = __ffs(mask) - 1;
                     mask &= mask - 1;
@@ -321,12 +333,6 @@ __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restri
                     const int vi = __shfl_sync(full, pi, src);
                     const int vp = base + src;
                     if (!cand_less(vd, vi, worst, worst_i)) continue;  // the bound may have tightened meanwhile
-                    if (kReseed && rq > 0) {  // already in the list (carried over from the previous query)?
-                        bool dup = false;
-#pragma unroll
-                        for (int s = 0; s < SLOTS; ++s) dup |= li[s] == vi;
-                        if (__any_sync(full, dup)) continue;
-                    }
                     int pos = 0;  // number of list elements smaller than the candidate
 #pragma unroll
                     for (int s = 0; s < SLOTS; ++s) pos += __popc(__ballot_sync(full, cand_less(ld[s], li[s], vd, vi)));
@@ -446,7 +452,9 @@ __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restri
                 // no child can be pruned and the node is small: its points are one contiguous range, stream through it
                 // instead of paying the traversal for every grandchild (queries far from the surface see all points at
                 // nearly the same distance and cannot prune)
-                if (cnt <= kScanMax && m == __ballot_sync(full, nonempty)) {
+                // ... or most of them: a child costs ~80 instructions of traversal before its first point is tested (and the leaves of a
+                // surface cloud fill 2 of the 32 lanes of a scan step), a 32-point step of a contiguous range ~20
+                if (cnt <= kScanMax && (m == __ballot_sync(full, nonempty) || cnt <= scan_child * __popc(m))) {
                     scan = true;
                 } else {
                     int rank = 0;  // far children first -> the nearest one ends on top of the stack
@@ -486,6 +494,7 @@ __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restri
 // stays far below; a query inside the closed surface scans 10^4..10^5
 static int g_knn_scan_cap = 16384;
 static long long g_knn_defer_below = 600000;  // launches of fewer queries use the second pass (see launch_query)
+static int g_knn_scan_child = 192;  // pps_debug_knn_scan_child (131^3 grid, k = 64: 42.3 ms at 0, 33.9 at 64, 31.2 at 192, 32.7 at 512; tools/knn_scan_probe.py): a node of at most this many points PER UNPRUNED CHILD is scanned whole
 static int g_knn_run = 16;  // pps_debug_knn_run: 16 measured 5 % faster than 8 on the dense grid, 32 and 64 slower (tools/knn_run_probe.py)
 
 template <int SLOTS>
@@ -505,10 +514,10 @@ static int launch_query(const KnnHeader* hdr, const float4* sorted, const int* c
     // (k <= 32 serves the encoder's self-queries -- points of the cloud looking for their neighbours in it, never expensive)
     const bool defer = SLOTS > 1 && run > 1 && q < g_knn_defer_below;
     knn_warp_kernel<SLOTS><<<(unsigned)ceil_div(q, 8 * run), 256, 0, st>>>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out, run, 1,
-                                                                          defer ? g_knn_scan_cap : 0x7fffffff);
+                                                                          defer ? g_knn_scan_cap : 0x7fffffff, g_knn_scan_child);
     PPS_LAUNCH_CHECK();
     if (defer) {  // the deferred queries (none on surface-hugging query sets: the blocks find no mark and exit)
-        knn_warp_kernel<SLOTS><<<(unsigned)ceil_div(q, 8), 256, 0, st>>>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out, 1, 2, 0);
+        knn_warp_kernel<SLOTS><<<(unsigned)ceil_div(q, 8), 256, 0, st>>>(hdr, sorted, cell_start, queries, q, k, idx_out, d2_out, 1, 2, 0, g_knn_scan_child);
     }
     PPS_LAUNCH_CHECK();
     return PPS_OK;
@@ -577,6 +586,12 @@ int knn_set_cell_factor(int f) {
     return old;
 }
 
+int knn_set_scan_child(int v) {
+    const int old = g_knn_scan_child;
+    if (v >= 0 && v <= kScanMax) g_knn_scan_child = v;
+    return old;
+}
+
 int knn_set_run(int run) {
     const int old = g_knn_run;
     if (run >= 1 && run <= 256) g_knn_run = run;
@@ -590,6 +605,8 @@ extern "C" {
 int pps_debug_knn_run(int run) { return pps::knn_set_run(run); }
 // finest octree cells per point (indices built afterwards use it; an index must be queried under the setting it was built with)
 int pps_debug_knn_cells(int factor) { return pps::knn_set_cell_factor(factor); }
+// points per unpruned child up to which an inner node is scanned as one range instead of being traversed; returns the previous value
+int pps_debug_knn_scan_child(int points) { return pps::knn_set_scan_child(points); }
 size_t pps_knn_index_bytes(int64_t n) { return n > 0 ? pps::knn_layout(n).total : 0; }
 int pps_knn_build(const float* pts, int64_t n, void* index, size_t index_bytes, void* stream) {
     return pps::knn_build_impl(pts, n, index, index_bytes, static_cast<cudaStream_t>(stream));
