@@ -93,6 +93,34 @@ def test_knn_grid_ordered_queries(dev, oracle, k):
     assert_knn_equal(oracle, pts, qry, idx.cpu().numpy(), d2.cpu().numpy(), ref_idx)
 
 
+def test_knn_tuning_knobs_do_not_change_the_result(dev, oracle):
+    """run length, finest cells per point and the scan-whole-node threshold only steer the traversal: indices and distances are bit
+    identical under every setting (unique total order (dist2, index)), and equal to the oracle's"""
+    from ppsurf_b200 import _lib, ops
+    pts = oracle.synthetic_cloud(20000, seed=5)
+    ax = np.linspace(-0.5, 0.5, 20, dtype=np.float32)
+    qry = np.stack(np.meshgrid(ax, ax, ax, indexing='ij'), axis=-1).reshape(-1, 3)
+    lib = _lib.lib
+    old = (lib.pps_debug_knn_run(-1), lib.pps_debug_knn_cells(-1), lib.pps_debug_knn_scan_child(-1))
+    try:
+        ref = None
+        for run, cells, sc in ((16, 2, 192), (1, 2, 0), (8, 1, 32), (32, 8, 1024), (16, 4, 64)):
+            lib.pps_debug_knn_run(run)
+            lib.pps_debug_knn_cells(cells)
+            lib.pps_debug_knn_scan_child(sc)
+            idx, d2 = ops.knn(cu(pts, dev), cu(qry, dev), 64, return_dist=True)
+            got = (idx.cpu().numpy(), d2.cpu().numpy())
+            if ref is None:
+                ref = got
+                assert_knn_equal(oracle, pts, qry, got[0], got[1], oracle.knn(pts, qry, 64)[0])
+            np.testing.assert_array_equal(got[0], ref[0])
+            np.testing.assert_array_equal(got[1], ref[1])
+    finally:
+        lib.pps_debug_knn_run(old[0])
+        lib.pps_debug_knn_cells(old[1])
+        lib.pps_debug_knn_scan_child(old[2])
+
+
 def test_knn_edge_cases(dev, oracle):
     from ppsurf_b200 import ops
     rng = np.random.default_rng(5)
