@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restri
     unsigned int* stack = stack_s[warp];
     int* stack_lo = stack_lo_s[warp];
     int* stack_hi = stack_hi_s[warp];
-    const int L = hdr->levels;
+    const int L = hdr->levels, n_pts = hdr->n;
     const float ox = hdr->origin[0], oy = hdr->origin[1], oz = hdr->origin[2];
     const float cell = hdr->cell;
     const float pad = cell * 1e-3f;
@@ -215,7 +215,25 @@ __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restri
         int worst_i = 0x7fffffff;
         // 32 < k <= 256 (the decoder's grid-ordered queries; list sizes 64 / 128 / 256): the previous list seeds this one
         constexpr bool kReseed = SLOTS == 2 || SLOTS == 4 || SLOTS == 8;
-        if (kReseed && rq > 0) {
+        // A query without a predecessor list (the first of a run, every query of the unseeded list sizes) starts from the SLOTS*32
+        // points around its own position in the Morton order instead of an empty list: real points near the query, so the k-th of
+        // them bounds the search from the first node on, and one sort replaces the one-by-one insertion of everything the first
+        // leaves contain (~350 insertions of ~60 instructions for k = 64)
+        const bool window = !(kReseed && rq > 0) && n_pts >= SLOTS * 32;
+        if (window) {
+            const int top = (1 << L) - 1;
+            const int cx = min(max(int(floorf((qx - ox) / cell)), 0), top), cy = min(max(int(floorf((qy - oy) / cell)), 0), top),
+                      cz = min(max(int(floorf((qz - oz) / cell)), 0), top);
+            const int at = cell_start[morton3(cx, cy, cz)];
+            const int first = min(max(at - SLOTS * 16, 0), n_pts - SLOTS * 32);
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) {
+                lp[s] = first + s * 32 + lane;
+                li[s] = __float_as_int(sorted[lp[s]].w);
+            }
+        }
+        const bool seeded = window || (kReseed && rq > 0);
+        if (seeded) {
             // Consecutive grid queries share most of their neighbours.  Re-evaluate the previous query's list for this query
             // (its entries are real points, so the k-th of them bounds the k-th distance from the first node on) and sort it
             // by (dist2, index) with a bitonic network over the SLOTS*32 entries.  The traversal then only has to find the few
@@ -272,7 +290,7 @@ __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restri
             }
             worst = __shfl_sync(full, ld[wslot < SLOTS ? wslot : SLOTS - 1], wlane);
             worst_i = __shfl_sync(full, li[wslot < SLOTS ? wslot : SLOTS - 1], wlane);
-            bound = INFINITY;
+            if (kReseed) bound = INFINITY;  // (the unseeded list sizes keep the previous k-th distance for the triangle inequality below)
         } else {
 #pragma unroll
             for (int s = 0; s < SLOTS; ++s) {
@@ -314,7 +332,7 @@ __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restri
                     pi = __float_as_int(p.w);
                 }
                 unsigned int mask = __ballot_sync(full, i < hi && d2 <= bound && cand_less(d2, pi, worst, worst_i));
-                if (kReseed && rq > 0 && mask) {
+                if (seeded && mask) {
                     // points of this step that are already in the list (carried over from the previous query: most of the candidates
                     // that beat the k-th distance): every lane marks the list entries it holds by their position in the sorted
                     // array, one warp-wide OR per step replaces a list lookup per candidate
@@ -372,7 +390,7 @@ __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restri
         // touches; at the finest level where that box spans at most 3 cells per axis those are <= 27 cells = 27 contiguous
         // ranges of the sorted array, tested by 27 lanes at once and scanned one after the other
         bool walked = false;
-        if (kReseed && rq > 0 && worst < INFINITY) {
+        if (seeded && worst < INFINITY) {
             const float r = sqrtf(worst) * 1.0001f + pad;
             const int top = (1 << L) - 1;
             int lo_c[3], hi_c[3];
