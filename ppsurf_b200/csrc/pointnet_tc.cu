@@ -286,32 +286,27 @@ __global__ void __launch_bounds__(2 * kPnThreads, 1)
                 }
             }
             warp_arrive_cluster(lead_aready, lane);
+            if ((et & 7) == 0 && it + 1 < iters) {  // the next tile's patch points stream from HBM: one L2 prefetch per 8 rows (96 bytes)
+                const PnRow pn = pn_row(tile + 2 * npairs, et & 127, G);
+                if (pn.q < nq && pn.p < P) prefetch_l2(patches + (pn.q * P + pn.p) * 3);
+            }
 
             const PnRow prow = pn_row(tile, row, G);
             const bool row_valid = prow.q < nq && prow.p < P;
             // ---- conv0b / stn.conv1 (64 wide) and stn.conv2 (128 wide): bias + ReLU -> operand tile (in place)
+#pragma unroll
             for (int layer = 0; layer < 3; ++layer) {
                 mbar_wait(bar_accum, accum_phase);
                 accum_phase ^= 1;
                 tc_fence_after();
                 const float* bias = layer == 0 ? s_b0b : (layer == 1 ? s_bs1 : s_bs2);
                 const int nload = layer < 2 ? 1 : 2;  // 32 or 64 columns per thread
+                float v[32];
+#pragma unroll
                 for (int cb = 0; cb < nload; ++cb) {
                     const int col0 = (layer < 2 ? half * 32 : half * 64) + cb * 32;
-                    float v[32];
                     tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + col0, v);
                     bias_relu32(v, bias + col0);  // padding rows carry finite values nobody reads
-                    if (layer == 0 && row_valid) {
-                        // a1 feeds the feature transform of pn_feat_kernel.  Global layout = the operand tile's: [tile][k8 block]
-                        // [row][8 floats], so the 32 lanes (= 32 consecutive rows) of a store instruction cover 1 KB instead of
-                        // 32 different 256-byte rows (the row-major layout made this epilogue LSU-wavefront bound)
-#pragma unroll
-                        for (int kb = 0; kb < 4; ++kb) {
-                            float4* dst = reinterpret_cast<float4*>(a1_out + ((tile * 8 + (col0 >> 3) + kb) * 128 + row) * 8);
-                            dst[0] = make_float4(v[8 * kb], v[8 * kb + 1], v[8 * kb + 2], v[8 * kb + 3]);
-                            dst[1] = make_float4(v[8 * kb + 4], v[8 * kb + 5], v[8 * kb + 6], v[8 * kb + 7]);
-                        }
-                    }
 #pragma unroll
                     for (int kb = 0; kb < 4; ++kb) {
                         float x8[8];
@@ -325,6 +320,19 @@ __global__ void __launch_bounds__(2 * kPnThreads, 1)
                     }
                 }
                 warp_arrive_cluster(lead_aready, lane);
+                if (layer == 0 && row_valid) {
+                    // a1 feeds the feature transform of pn_feat_kernel -- stored AFTER the hand-off, while stn.conv1's MMAs run.  Global
+                    // layout = the operand tile's: [tile][k8 block][row][8 floats], so the 32 lanes (= 32 consecutive rows) of a store
+                    // instruction cover 1 KB instead of 32 different 256-byte rows (the row-major layout made this epilogue
+                    // LSU-wavefront bound)
+                    const int col0 = half * 32;
+#pragma unroll
+                    for (int kb = 0; kb < 4; ++kb) {
+                        float4* dst = reinterpret_cast<float4*>(a1_out + ((tile * 8 + (col0 >> 3) + kb) * 128 + row) * 8);
+                        dst[0] = make_float4(v[8 * kb], v[8 * kb + 1], v[8 * kb + 2], v[8 * kb + 3]);
+                        dst[1] = make_float4(v[8 * kb + 4], v[8 * kb + 5], v[8 * kb + 6], v[8 * kb + 7]);
+                    }
+                }
             }
             // ---- stn.conv3 transposed: TMEM lane = feature 128 * crank + row, columns = the 256 rows of the pair-tile (tile of rank 0,
             // then tile of rank 1); max over the points of each of the four half-tiles.  This warp takes the tile of rank `half`
