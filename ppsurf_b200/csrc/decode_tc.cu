@@ -332,10 +332,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
             for (int i = 0; i < 4; ++i) src_next[i] = idx[q * ks + ((ew * 16 + 4 * i + rs) & 63)];
         }
-        for (long long it = 0; it < iters; ++it) {
-            const long long tile = tile0 + it * tile_step;
-            // ---- W1_xyz . q for the two queries of the tile.  Every G warp is past the previous tile's gather (this warp saw
-            // fc2's accumulator complete, which needs every warp's chunk arrivals), so s_vq may be overwritten
+        // W1_xyz . q for the two queries of a tile.  Computed for the NEXT tile while this group waits for fc3 (below): at the top of
+        // the tile the query loads' latency would sit between fc_query's completion and the first chunk of the gather
+        auto query_term = [&](long long tile) {
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
                 long long q = 2 * tile + t;
@@ -344,6 +343,10 @@ __global__ void __launch_bounds__(kThreads, 1)
                                      s_w1[3 * gt + 2] * queries[3 * q + 2];
             }
             g_barrier();
+        };
+        if (iters > 0) query_term(tile0);
+        for (long long it = 0; it < iters; ++it) {
+            const long long tile = tile0 + it * tile_step;
             // ---- gather: h1 = relu(U[idx] + W1_xyz.q) -> A_hi/A_lo, one 64-column chunk after the other so that fc2's first
             // k-steps start after a quarter of the gather.  Warp ew owns rows 16*ew .. +15 (all of one query); per chunk a lane
             // owns k8 block (lane & 7) of row 4*i + (lane >> 3): 8 lanes read 256 contiguous bytes of a table row
@@ -407,6 +410,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 
             // ---- fc2 / fc3 epilogues: D -> +bias, ReLU, split -> A in place, released chunk by chunk
             for (int layer = 0; layer < 2; ++layer) {
+                // every G warp is past this tile's gather (fc2's accumulator is complete, which needs every warp's chunk arrivals),
+                // so s_vq may be overwritten: the next tile's query term, in the shadow of fc3
+                if (layer == 1 && it + 1 < iters) query_term(tile + tile_step);
                 mbar_wait(bar_acc + 8 * layer, (uint32_t)(it & 1));
                 tc_fence_after();
                 {
