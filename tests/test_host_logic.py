@@ -214,6 +214,52 @@ def test_tensor_core_pack_layout(weights):
     assert pack.size * 2 == 2 * 16 * 16384 + 4 * 16384
 
 
+def test_pointnet_pack_layouts(weights):
+    """The PointNet kernels' weight packs, decoded the way the kernels address them (csrc/pointnet_tc.cu).
+    pn_stn (CTA pairs): 7 ring-slot fills per pair-tile, each stored as [CTA 0's slot | CTA 1's slot]: conv0b and stn.conv1 (8 KB per
+    CTA: 4 k16 steps x its 32 of the 64 weight rows), stn.conv2 (16 KB: 4 steps x 64 of 128 rows), stn.conv3 (4 fills of 16 KB: 2 steps x
+    its 128 of the 256 features); a step is [hi k8-block 0 | hi block 1 | lo block 0 | lo block 1], blocks of [rows][8 fp16].
+    pn_feat: conv1 (4 steps x 64 rows = 16 KB), conv2 (4 steps x 128 rows, 8 KB each: steps 0,1 at +16 KB, steps 2,3 at +32 KB)."""
+    from ppsurf_b200 import packing
+    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in weights.items()}
+    p = packing.pack_decoder(sd, 'cpu', 64, 50)
+    t = p.tensors
+
+    def steps(buf, rows, nsteps):  # fp16 view of nsteps k16 steps of `rows` weight rows -> [rows, 16 * nsteps] float32 (hi + lo)
+        out = []
+        per = rows * 32  # fp16 elements per step: 4 blocks of rows x 8
+        for s in range(nsteps):
+            st = buf[s * per:(s + 1) * per].astype(np.float32)
+            hi, lo = st[:per // 2].reshape(2, rows, 8), st[per // 2:].reshape(2, rows, 8)
+            out.append((hi + lo).transpose(1, 0, 2).reshape(rows, 16))
+        return np.concatenate(out, axis=1)
+
+    def close(got, ref):
+        assert np.abs(got - ref).max() <= 2.0 ** -20 * max(np.abs(ref).max(), 1e-30)
+
+    stn = t['tc_pn_stn'].numpy().view(np.float16)
+    off = 0  # in fp16 elements
+    for name, n, k, fills in (('pn0b_w', 64, 64, 1), ('stn1_w', 64, 64, 1), ('stn2_w', 128, 64, 1), ('stn3_w', 256, 128, 4)):
+        w = t[name].numpy().astype(np.float32).reshape(n, k)
+        h = n // 2
+        slot = h * 32 * (k // 16) // fills  # fp16 elements of one CTA's slot
+        for f in range(fills):
+            for r in (0, 1):
+                got = steps(stn[off:off + slot], h, (k // 16) // fills)
+                kk = k // fills
+                close(got, w[h * r:h * r + h, kk * f:kk * f + kk])
+                off += slot
+    assert off * 2 == stn.size * 2 == 196608
+
+    feat = t['tc_pn_feat'].numpy().view(np.float16)
+    w1 = t['pn1_w'].numpy().astype(np.float32).reshape(64, 64)
+    w2 = t['pn2_w'].numpy().astype(np.float32).reshape(128, 64)
+    close(steps(feat[:8192], 64, 4), w1)
+    close(steps(feat[8192:16384], 128, 2), w2[:, :32])
+    close(steps(feat[16384:24576], 128, 2), w2[:, 32:])
+    assert feat.size * 2 == 49152
+
+
 def test_latent_schedule_of_the_module():
     """PPSurfModel.latent_schedule (source/poco_model.py:207-224): subsets of gen_subsample_manifold points until every point has
     been visited gen_subsample_manifold_iter times; a cloud smaller than the subset is encoded whole, once per iteration"""
