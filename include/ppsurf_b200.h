@@ -68,6 +68,9 @@ int pps_debug_knn_cells(int factor);
 /* tuning knob: an inner octree node of at most this many points per unpruned child is scanned as one contiguous range instead of
  * being traversed (results do not depend on it); returns the previous value */
 int pps_debug_knn_scan_child(int points);
+/* tuning knob: points a run of consecutive queries may scan before its remaining queries are deferred to a second pass of one warp per
+ * query (results do not depend on it); returns the previous value, points < 1 only reads */
+int pps_debug_knn_scan_cap(int points);
 int pps_knn_query(const void* index, int64_t n, const float* queries, int64_t q, int k, int32_t* idx_out,
                   float* dist2_out, void* stream);
 

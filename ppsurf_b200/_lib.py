@@ -66,6 +66,7 @@ SIGNATURES = {
     'pps_debug_knn_run': (i32, [i32]),
     'pps_debug_knn_cells': (i32, [i32]),
     'pps_debug_knn_scan_child': (i32, [i32]),
+    'pps_debug_knn_scan_cap': (i32, [i32]),
     'pps_knn_query': (i32, [c_voidp, i64, c_f32p, i64, i32, c_i32p, c_f32p, c_voidp]),
     'pps_patch_normalize': (i32, [c_f32p, c_f32p, c_i32p, c_f32p, i64, i32, i32, c_f32p, c_voidp]),
     'pps_linear': (i32, [c_f32p, c_f32p, c_f32p, c_f32p, c_i32p, c_f32p, i64, i32, i32, i32, i32, i32, c_voidp]),

@@ -508,9 +508,9 @@ __global__ void __launch_bounds__(256) knn_warp_kernel(const KnnHeader* __restri
     }
 }
 
-// points a run may scan before it defers its remaining queries to the second pass: a surface query scans 300..1000 points, a run of 16
-// stays far below; a query inside the closed surface scans 10^4..10^5
-static int g_knn_scan_cap = 16384;
+// points a run may scan before it defers its remaining queries to the second pass: a surface query scans 300..1500 points, a run of 16
+// stays below; a query inside the closed surface scans 10^4..10^5
+static int g_knn_scan_cap = 65536;  // (16384 until the nodes were scanned whole: one rank's share at 8 / 4 GPUs 5.6 / 10.8 ms at 16384, 4.7 / 7.9 ms at 65536; tools/knn_shard_probe2.py)
 static long long g_knn_defer_below = 600000;  // launches of fewer queries use the second pass (see launch_query)
 static int g_knn_scan_child = 192;  // pps_debug_knn_scan_child (131^3 grid, k = 64: 42.3 ms at 0, 33.9 at 64, 31.2 at 192, 32.7 at 512; tools/knn_scan_probe.py): a node of at most this many points PER UNPRUNED CHILD is scanned whole
 static int g_knn_run = 16;  // pps_debug_knn_run: 16 measured 5 % faster than 8 on the dense grid, 32 and 64 slower (tools/knn_run_probe.py)
@@ -610,6 +610,12 @@ int knn_set_scan_child(int v) {
     return old;
 }
 
+int knn_set_scan_cap(int v) {
+    const int old = g_knn_scan_cap;
+    if (v >= 1) g_knn_scan_cap = v;
+    return old;
+}
+
 int knn_set_run(int run) {
     const int old = g_knn_run;
     if (run >= 1 && run <= 256) g_knn_run = run;
@@ -625,6 +631,8 @@ int pps_debug_knn_run(int run) { return pps::knn_set_run(run); }
 int pps_debug_knn_cells(int factor) { return pps::knn_set_cell_factor(factor); }
 // points per unpruned child up to which an inner node is scanned as one range instead of being traversed; returns the previous value
 int pps_debug_knn_scan_child(int points) { return pps::knn_set_scan_child(points); }
+// points a run may scan before it hands its remaining queries to the second pass (launches below 600 k queries); returns the previous value
+int pps_debug_knn_scan_cap(int points) { return pps::knn_set_scan_cap(points); }
 size_t pps_knn_index_bytes(int64_t n) { return n > 0 ? pps::knn_layout(n).total : 0; }
 int pps_knn_build(const float* pts, int64_t n, void* index, size_t index_bytes, void* stream) {
     return pps::knn_build_impl(pts, n, index, index_bytes, static_cast<cudaStream_t>(stream));
