@@ -206,6 +206,9 @@ __device__ __forceinline__ void teardown(const Ctx& c, int warp) {
 
 // packed weight bytes: a [n,k] matrix takes 4*n*k bytes (fp16 hi + lo)
 constexpr size_t kPackStnFc = size_t(4) * (128 * 256 + 64 * 128 + 4096 * 64);
+// ... followed by the 4096 fp32 biases of the LAST FC.  That layer is packed MERGED with the local branch's conv1 (packing.py): its
+// output is M_q = W1 (fc3(f2) + I) instead of the transform T_q = fc3(f2) + I, and pn_feat_kernel's first MMA is conv1 with M_q
+constexpr size_t kPackStnFcTotal = kPackStnFc + size_t(4096) * 4;
 constexpr size_t kPackMlp = size_t(4) * (256 * 256 + 256 * 128 + 256 * 256 + 256 * 256);
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -477,7 +480,8 @@ int stn_fc_tc_impl(const pps_decoder_weights* w, const float* g, int64_t q, floa
     const long long ntiles = (q + 127) / 128;
     const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
     tc::chain::stn_fc_tc_kernel<<<grid, tc::chain::kThreads, tc::chain::kSmemBytes, st>>>(
-        g, q, static_cast<const uint8_t*>(w->tc_stn_fc), w->stnf1_b, w->stnf2_b, w->stnf3_b, tmat);
+        g, q, static_cast<const uint8_t*>(w->tc_stn_fc), w->stnf1_b, w->stnf2_b,
+        reinterpret_cast<const float*>(static_cast<const uint8_t*>(w->tc_stn_fc) + tc::chain::kPackStnFc), tmat);
     PPS_LAUNCH_CHECK();
     return PPS_OK;
 }
@@ -498,5 +502,5 @@ int mlp_tc_impl(const pps_decoder_weights* w, const float* pooled_proj, const fl
 
 }  // namespace pps
 
-extern "C" size_t pps_decoder_tc_stn_fc_bytes(void) { return pps::tc::chain::kPackStnFc; }
+extern "C" size_t pps_decoder_tc_stn_fc_bytes(void) { return pps::tc::chain::kPackStnFcTotal; }
 extern "C" size_t pps_decoder_tc_mlp_bytes(void) { return pps::tc::chain::kPackMlp; }

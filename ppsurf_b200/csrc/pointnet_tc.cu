@@ -382,12 +382,14 @@ __global__ void __launch_bounds__(2 * kPnThreads, 1)
 // kernel C: feature transform, conv1, conv2, attention pooling
 // ---------------------------------------------------------------------------------------------------------------------
 namespace feat {
-// Three CTAs per SM (round 2: two; the kernel is a serial chain load -> transform -> conv1 -> conv2 -> pooling per tile and bound by its
-// latencies, so what counts is the number of chains in flight).  Shared memory per CTA: the 64-column operand tile (33 KB) and ONE more
-// 33 KB region R that holds the per-query transforms until their MMAs are done and the conv1 / conv2 weights afterwards -- no weight ring:
-//   transform MMAs complete -> conv1 (16 KB) -> R+0, conv2 k-steps 0,1 (16 KB) -> R+16 KB   (lands while the epilogue converts x')
-//   conv1 MMAs complete     -> conv2 k-steps 2,3 (16 KB) -> R+0                            (lands while the epilogue converts conv1)
-// One control warp issues the MMAs and these copies (it waits for its own commits), eight epilogue warps: 288 threads, <= 72 registers.
+// Three CTAs per SM (round 2: two; the kernel is a serial chain load -> conv1 -> conv2 -> pooling per tile and bound by its
+// latencies, so what counts is the number of chains in flight and the number of hand-offs in a chain).
+// The feature transform is not a layer of its own: conv1(T_q . a1) = (W1 T_q) . a1, and W1 T_q is LINEAR in the output of the STN's
+// last FC, so stn_fc_tc_kernel's fc3 is packed with the merged weights (packing.py) and emits M_q = W1 (T_q) directly -- this kernel's
+// first MMA is conv1 with a per-query weight matrix (one MMA layer, one epilogue and two hand-offs less per tile than transform + conv1).
+// Shared memory per CTA: the 64-column operand tile (33 KB) and ONE more 33 KB region R that holds the per-query matrices until their
+// MMAs are done and the conv2 weights (32 KB) afterwards -- no weight ring: the copy lands while the epilogue converts conv1's output.
+// One control warp issues the MMAs and the copy (it waits for its own commits), eight epilogue warps: 288 threads, <= 72 registers.
 constexpr int kThreads = 288;
 constexpr int kEpiThreads = 256;
 constexpr int kOffAhi = 0;
@@ -395,12 +397,13 @@ constexpr int kABytes = 8 * kPnLbo;                       // 64-column operand t
 constexpr int kOffAlo = kOffAhi + kABytes;                // 16512
 constexpr int kTLbo = 64 * 16 + 16;                       // 1040: k8-block pitch of a per-query 64x64 transform
 constexpr int kTBytes = 8 * kTLbo;                        // 8320 per (query, hi/lo)
-constexpr int kOffT = kOffAlo + kABytes;                  // 33024: region R: [query][hi,lo] transforms, then the weights
-constexpr int kWBytes = 16384;                            // conv1, or two k16 steps of conv2
-static_assert(2 * kWBytes <= 4 * kTBytes, "conv1 and half of conv2 must fit into the transform region");
+constexpr int kOffT = kOffAlo + kABytes;                  // 33024: region R: [query][hi,lo] conv1 matrices M_q, then conv2's weights
+constexpr int kW2Offset = 16384;                          // conv2 in the weight pack (behind the unmerged conv1, which this kernel no longer reads)
+constexpr int kW2Bytes = 32768;                           // conv2: 4 k16 steps of 8 KB
+static_assert(kW2Bytes <= 4 * kTBytes, "conv2 must fit into the region of the per-query matrices");
 constexpr int kOffPar = kOffT + 4 * kTBytes;              // 66304: b1[64] b2[128] wq[128] part[2][128] pool[4][128]
 constexpr int kParFloats = 64 + 128 + 128 + 256 + 512;
-constexpr int kOffBar = kOffPar + kParFloats * 4;         // full[2] accum aready
+constexpr int kOffBar = kOffPar + kParFloats * 4;         // full, (unused), accum, aready
 constexpr int kOffTmem = kOffBar + 4 * 8;
 constexpr int kSmemBytes = kOffTmem + 16 + 1024;          // ~70 KB
 constexpr int kTmemCols = 128;
@@ -452,10 +455,11 @@ __global__ void __launch_bounds__(feat::kThreads, feat::kCtasPerSm)
 
     if (warp == 0) {
         // ---- control warp: all lanes run the loop (warp-uniform control flow), one elected lane issues (see elect_one)
-        uint32_t ready_phase = 0, accum_phase = 0, full0_phase = 0, full1_phase = 0;
-        const uint32_t w_r0 = sbase + kOffT, w_r1 = sbase + kOffT + kWBytes;
+        uint32_t ready_phase = 0, accum_phase = 0, full_phase = 0;
+        const uint32_t w_r = sbase + kOffT;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            // feature transform: D[rows, ql*64 + i] = a1[rows, :] . T_ql[i, :]   (operands built by the epilogue warps)
+            // conv1 with the per-query matrices: D[rows, ql*64 + o] = a1[rows, :] . M_ql[o, :]   (operands built by the epilogue warps;
+            // a row reads the block of ITS query afterwards)
             mbar_wait(bar_aready, ready_phase);
             ready_phase ^= 1;
             tc_fence_after();
@@ -478,31 +482,29 @@ __global__ void __launch_bounds__(feat::kThreads, feat::kCtasPerSm)
                 tc_commit(bar_accum);
             }
             __syncwarp();
-            // the transforms have been read: conv1 and the first half of conv2 take their place
+            // the per-query matrices have been read: conv2's weights take their place (they land while the epilogue converts conv1)
             mbar_wait(bar_accum, accum_phase);
             accum_phase ^= 1;
             if (elect_one()) {
-                mbar_expect_tx(bar_full, kWBytes);
-                bulk_copy(w_r0, wpack, kWBytes, bar_full);
-                mbar_expect_tx(bar_full + 8, kWBytes);
-                bulk_copy(w_r1, wpack + kWBytes, kWBytes, bar_full + 8);
+                mbar_expect_tx(bar_full, kW2Bytes);
+                bulk_copy(w_r, wpack + kW2Offset, kW2Bytes, bar_full);
             }
             __syncwarp();
-            // conv1 (64 wide): 4 k16 steps of 4 KB
-            mbar_wait(bar_full, full0_phase);  // the weights before the operand tile (see pn_stn_kernel)
-            full0_phase ^= 1;
+            // conv2 (128 wide): 4 k16 steps of 8 KB.  The weights before the operand tile (see pn_stn_kernel)
+            mbar_wait(bar_full, full_phase);
+            full_phase ^= 1;
             mbar_wait(bar_aready, ready_phase);
             ready_phase ^= 1;
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t idesc = umma_idesc(64);
+                const uint32_t idesc = umma_idesc(128);
 #pragma unroll
                 for (int s = 0; s < 4; ++s) {
                     const uint64_t x_hi = umma_desc(sbase + kOffAhi + 2 * s * kPnLbo, kPnLbo, 128);
                     const uint64_t x_lo = umma_desc(sbase + kOffAlo + 2 * s * kPnLbo, kPnLbo, 128);
-                    const uint32_t bst = w_r0 + s * 4096;
-                    const uint64_t w_hi = umma_desc(bst, 64 * 16, 128);
-                    const uint64_t w_lo = umma_desc(bst + 64 * 32, 64 * 16, 128);
+                    const uint32_t bst = w_r + s * 8192;
+                    const uint64_t w_hi = umma_desc(bst, 128 * 16, 128);
+                    const uint64_t w_lo = umma_desc(bst + 128 * 32, 128 * 16, 128);
                     umma(tmem, x_hi, w_hi, idesc, s > 0 ? 1u : 0u);
                     umma(tmem, x_lo, w_hi, idesc, 1u);
                     umma(tmem, x_hi, w_lo, idesc, 1u);
@@ -510,55 +512,7 @@ __global__ void __launch_bounds__(feat::kThreads, feat::kCtasPerSm)
                 tc_commit(bar_accum);
             }
             __syncwarp();
-            // conv1's weights have been read: the second half of conv2 takes their place
-            mbar_wait(bar_accum, accum_phase);
-            accum_phase ^= 1;
-            if (elect_one()) {
-                mbar_expect_tx(bar_full, kWBytes);
-                bulk_copy(w_r0, wpack + 2 * kWBytes, kWBytes, bar_full);
-            }
-            __syncwarp();
-            // conv2 (128 wide): k16 steps 0,1 from R+16 KB, steps 2,3 from R+0 (8 KB per step)
-            mbar_wait(bar_full + 8, full1_phase);
-            full1_phase ^= 1;
-            mbar_wait(bar_aready, ready_phase);
-            ready_phase ^= 1;
-            tc_fence_after();
-            if (elect_one()) {
-                const uint32_t idesc = umma_idesc(128);
-#pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    const uint64_t x_hi = umma_desc(sbase + kOffAhi + 2 * s * kPnLbo, kPnLbo, 128);
-                    const uint64_t x_lo = umma_desc(sbase + kOffAlo + 2 * s * kPnLbo, kPnLbo, 128);
-                    const uint32_t bst = w_r1 + s * 8192;
-                    const uint64_t w_hi = umma_desc(bst, 128 * 16, 128);
-                    const uint64_t w_lo = umma_desc(bst + 128 * 32, 128 * 16, 128);
-                    umma(tmem, x_hi, w_hi, idesc, s > 0 ? 1u : 0u);
-                    umma(tmem, x_lo, w_hi, idesc, 1u);
-                    umma(tmem, x_hi, w_lo, idesc, 1u);
-                }
-            }
-            __syncwarp();
-            mbar_wait(bar_full, full0_phase);
-            full0_phase ^= 1;
-            tc_fence_after();
-            if (elect_one()) {
-                const uint32_t idesc = umma_idesc(128);
-#pragma unroll
-                for (int s = 2; s < 4; ++s) {
-                    const uint64_t x_hi = umma_desc(sbase + kOffAhi + 2 * s * kPnLbo, kPnLbo, 128);
-                    const uint64_t x_lo = umma_desc(sbase + kOffAlo + 2 * s * kPnLbo, kPnLbo, 128);
-                    const uint32_t bst = w_r0 + (s - 2) * 8192;
-                    const uint64_t w_hi = umma_desc(bst, 128 * 16, 128);
-                    const uint64_t w_lo = umma_desc(bst + 128 * 32, 128 * 16, 128);
-                    umma(tmem, x_hi, w_hi, idesc, 1u);
-                    umma(tmem, x_lo, w_hi, idesc, 1u);
-                    umma(tmem, x_hi, w_lo, idesc, 1u);
-                }
-                tc_commit(bar_accum);
-            }
-            __syncwarp();
-            // third completion of the tile: keeps this warp's phase in step (the epilogue warps hold R until they have seen it)
+            // second completion of the tile: keeps this warp's phase in step (the epilogue warps hold R until they have seen it)
             mbar_wait(bar_accum, accum_phase);
             accum_phase ^= 1;
         }
@@ -591,7 +545,7 @@ __global__ void __launch_bounds__(feat::kThreads, feat::kCtasPerSm)
                 *reinterpret_cast<uint4*>(smem + kOffAhi + kb * kPnLbo + r * 16) = hi;
                 *reinterpret_cast<uint4*>(smem + kOffAlo + kb * kPnLbo + r * 16) = lo;
             }
-            // ---- per-query transforms T_q [i][j] -> K-major operand (row i, k = j), values may be negative: plain split
+            // ---- per-query conv1 matrices M_q = W1 T_q [o][j] (written by stn_fc_tc_kernel) -> K-major operand (row o, k = j)
 #pragma unroll 2
             for (int t = 0; t < 4; ++t) {
                 const int e = et + 256 * t;
@@ -625,32 +579,14 @@ __global__ void __launch_bounds__(feat::kThreads, feat::kCtasPerSm)
                 }
             }
 
-            // ---- x' = T . a1 (no bias, no activation; may be negative) -> operand tile
+            // ---- conv1 (with the feature transform folded into its per-query matrix): bias + ReLU -> operand tile.  A row reads the
+            // accumulator block of its own query
             mbar_wait(bar_accum, accum_phase);
             accum_phase ^= 1;
             tc_fence_after();
             {
                 float v[32];
                 tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + (row >> 6) * 64 + half * 32, v);
-#pragma unroll
-                for (int kb = 0; kb < 4; ++kb) {
-                    float x8[8];
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) x8[c] = v[kb * 8 + c];
-                    uint4 hi, lo;
-                    split8(x8, hi, lo);
-                    *reinterpret_cast<uint4*>(smem + kOffAhi + (half * 4 + kb) * kPnLbo + row * 16) = hi;
-                    *reinterpret_cast<uint4*>(smem + kOffAlo + (half * 4 + kb) * kPnLbo + row * 16) = lo;
-                }
-            }
-            warp_arrive(bar_aready, lane);
-            // ---- conv1: bias + ReLU -> operand tile
-            mbar_wait(bar_accum, accum_phase);
-            accum_phase ^= 1;
-            tc_fence_after();
-            {
-                float v[32];
-                tmem_ld32(tmem + ((uint32_t)(lane_grp * 32) << 16) + half * 32, v);
                 bias_relu32(v, s_b1 + half * 32);
 #pragma unroll
                 for (int kb = 0; kb < 4; ++kb) {
@@ -783,7 +719,9 @@ bool chain_tc_supported(const pps_decoder_weights* w);
 int stn_fc_tc_impl(const pps_decoder_weights* w, const float* g, int64_t q, float* tmat, cudaStream_t st);
 
 bool pointnet_tc_supported(const pps_decoder_weights* w) {
-    return w->tc_pn_stn != nullptr && w->tc_pn_feat != nullptr && w->num_pts_local <= 256 && w->stn_size == 256 && w->latent == 256;
+    // tc_stn_fc: pn_feat_kernel expects the MERGED matrices M_q = W1 T_q that only stn_fc_tc_kernel's pack produces
+    return w->tc_pn_stn != nullptr && w->tc_pn_feat != nullptr && w->tc_stn_fc != nullptr && w->num_pts_local <= 256 &&
+           w->stn_size == 256 && w->latent == 256;
 }
 
 // local branch on the tensor cores: patches [q,P,3] -> pooled128 [q,128]; scratch: a1 [tiles,8,128,8] (tile-major, 64 point slots per query), g [q,256], f1 [q,128],
@@ -798,7 +736,7 @@ int pointnet_tc_impl(const pps_decoder_weights* w, const float* patches, int64_t
         PPS_CUDA(cudaFuncSetAttribute(tc::pn_feat_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::feat::kSmemBytes));
         PPS_CUDA(cudaFuncSetAttribute(tc::pn_feat_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::feat::kSmemBytes));
     }
-    const int P = w->num_pts_local, S = w->stn_size;
+    const int P = w->num_pts_local;
     const int G = (P + 63) / 64;  // 64-row half-tiles per query
     const long long ntiles = (q * G + 1) / 2;
     // pn_stn: CTA pairs, two chains per CTA -> up to 74 clusters x 2 chains, a pair of chains takes a pair-tile of 2 tiles
@@ -830,13 +768,8 @@ int pointnet_tc_impl(const pps_decoder_weights* w, const float* patches, int64_t
                                         (const float*)w->stn2_b, (const float*)w->stn3_b, a1, g));
     }
     PPS_LAUNCH_CHECK();
-    if (chain_tc_supported(w)) {
-        PPS_TRY(stn_fc_tc_impl(w, g, q, tmat, st));
-    } else {
-        PPS_TRY(linear_impl(g, w->stnf1_w, w->stnf1_b, nullptr, nullptr, f1, q, S / 2, S, S, S / 2, 1, st));
-        PPS_TRY(linear_impl(f1, w->stnf2_w, w->stnf2_b, nullptr, nullptr, f2, q, S / 4, S / 2, S / 2, S / 4, 1, st));
-        PPS_TRY(linear_impl(f2, w->stnf3_w, w->stnf3_b, nullptr, nullptr, tmat, q, 4096, S / 4, S / 4, 4096, 0, st));
-    }
+    PPS_CHECK_ARG(chain_tc_supported(w), "tensor-core PointNet path without the STN FC pack (tc_stn_fc)");
+    PPS_TRY(stn_fc_tc_impl(w, g, q, tmat, st));  // tmat = the per-query conv1 matrices M_q = W1 T_q (merged pack)
     const uint8_t* pack_feat = static_cast<const uint8_t*>(w->tc_pn_feat);
     const int grid_feat = (int)(ntiles < tc::feat::kCtasPerSm * kNumSMs ? ntiles : tc::feat::kCtasPerSm * kNumSMs);
     if (G > 1)

@@ -133,9 +133,18 @@ def pack_decoder(sd, device, k, num_pts_local, prefix='') -> Packed:
         st.tc_pn_stn = st.tc_pn_feat = None
     if latent == 256 and st.stn_size == 256:
         t = p.tensors
-        f3 = t['stnf3_w'].cpu()
+        # The STN's last FC is packed MERGED with the local branch's conv1: conv1(T_q . a1) = (W1 T_q) . a1 and T_q = fc3(f2) + I is
+        # linear in f2, so M_q[o,j] = sum_i W1[o,i] T_q[i,j] = sum_c (sum_i W1[o,i] W3[(i,j),c]) f2[c] + sum_i W1[o,i] (b3 + I)[(i,j)]:
+        # stn_fc_tc_kernel emits M_q (same shape as T_q) and pn_feat_kernel's first MMA is conv1 with a per-query matrix -- exact in
+        # real arithmetic like the reformulations of DESIGN.md section 3, merged in float64.  (The fp32 path keeps the unmerged stnf3 / pn1.)
+        w1f = _fold_bn(sd, n + 'conv1', n + 'bn1')[0]                                        # [64 o, 64 i]
+        w3 = _mat(sd, n + 'stn2.fc3.weight').reshape(64, 64, -1)                             # [i, j, c]
+        b3i = (_f64(sd, n + 'stn2.fc3.bias') + torch.eye(64, dtype=torch.float64).reshape(-1)).reshape(64, 64)
+        f3 = torch.einsum('oi,ijc->ojc', w1f, w3).reshape(4096, -1)
+        b3m = (w1f @ b3i).reshape(-1)
         stn_fc = torch.cat([tc_pack_matrix(t['stnf1_w'].cpu()), tc_pack_matrix(t['stnf2_w'].cpu())] +
-                           [tc_pack_matrix(f3[nb * 256:(nb + 1) * 256]) for nb in range(16)])
+                           [tc_pack_matrix(f3[nb * 256:(nb + 1) * 256]) for nb in range(16)] +
+                           [b3m.to(torch.float32).contiguous().view(torch.uint8)])
         mlp = torch.cat([tc_pack_matrix(t[name].cpu()) for name in ('wv8', 'pnv_w', 'm0_w', 'm1_w')])
         assert stn_fc.numel() == _lib.lib.pps_decoder_tc_stn_fc_bytes() and mlp.numel() == _lib.lib.pps_decoder_tc_mlp_bytes()
         t['tc_stn_fc'], t['tc_mlp'] = stn_fc.to(device), mlp.to(device)

@@ -260,6 +260,40 @@ def test_pointnet_pack_layouts(weights):
     assert feat.size * 2 == 49152
 
 
+def test_merged_stn_fc3_pack_equals_transform_then_conv1(weights):
+    """The tensor-core path packs the STN's last FC merged with the local branch's conv1 (packing.py): the kernel chain
+    f2 -> fc3' -> M_q, conv1 = M_q . a1 must equal the reference's T_q = fc3(f2) + I, x' = T_q . a1, conv1 = W1 x' (nn.py:338-351,
+    162-190) -- checked here on the CPU with the matrices decoded from the pack exactly as the kernels address them."""
+    from ppsurf_b200 import packing
+    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in weights.items()}
+    p = packing.pack_decoder(sd, 'cpu', 64, 50)
+    t = p.tensors
+    raw = t['tc_stn_fc'].numpy()
+    head = 4 * (128 * 256 + 64 * 128)          # fc1, fc2 packs
+    body = raw[head:head + 4 * 4096 * 64].view(np.float16)
+    bias = raw[head + 4 * 4096 * 64:].view(np.float32)
+    assert bias.size == 4096
+    # 16 blocks of 256 output rows, K = 64: 4 k16 steps of [hi kb0 | hi kb1 | lo kb0 | lo kb1], blocks of [256 rows][8 fp16]
+    w3m = np.zeros((4096, 64), np.float64)
+    per = 256 * 32
+    for nb in range(16):
+        for s_ in range(4):
+            st = body[(nb * 4 + s_) * per:(nb * 4 + s_ + 1) * per].astype(np.float64)
+            hi, lo = st[:per // 2].reshape(2, 256, 8), st[per // 2:].reshape(2, 256, 8)
+            w3m[nb * 256:(nb + 1) * 256, 16 * s_:16 * s_ + 16] = (hi + lo).transpose(1, 0, 2).reshape(256, 16)
+    rng = np.random.default_rng(3)
+    f2 = np.abs(rng.standard_normal(64))                      # output of a ReLU layer
+    a1 = np.abs(rng.standard_normal((50, 64)))                # [points, channels]
+    w3 = t['stnf3_w'].numpy().astype(np.float64)              # unmerged, the fp32 path's
+    b3i = t['stnf3_b'].numpy().astype(np.float64)             # bias + identity
+    w1 = t['pn1_w'].numpy().astype(np.float64)
+    T = (w3 @ f2 + b3i).reshape(64, 64)
+    want = (a1 @ T.T) @ w1.T                                  # x'[p,i] = sum_j T[i,j] a1[p,j];  conv1[p,o] = sum_i W1[o,i] x'[p,i]
+    M = (w3m @ f2 + bias).reshape(64, 64)
+    got = a1 @ M.T                                            # conv1[p,o] = sum_j M[o,j] a1[p,j]
+    assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()
+
+
 def test_latent_schedule_of_the_module():
     """PPSurfModel.latent_schedule (source/poco_model.py:207-224): subsets of gen_subsample_manifold points until every point has
     been visited gen_subsample_manifold_iter times; a cloud smaller than the subset is encoded whole, once per iteration"""
